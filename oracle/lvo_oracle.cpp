@@ -1,0 +1,457 @@
+/*
+ * lvo_oracle.cpp -- CPU oracle for the LineVis hot path (tubes + RTAO, PPLL OIT).
+ *
+ * TEST INFRASTRUCTURE ONLY: the checker for tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+ * The product (linevis_b200/) never links or calls this.  PARITY UNPINNED by the reference's own tests
+ * (none exist for this path); see lvo_shaders.hpp for what is pinned instead.
+ *
+ * The shading / intersection / RNG / PPLL arithmetic is restated in lvo_shaders.hpp and lvo_sort.hpp.
+ * This file adds what the reference delegates to the Vulkan driver (BVH build + traversal: the
+ * reference's BVH is an opaque VkAccelerationStructureKHR, src/LineData/LineData.cpp:879-907) with a
+ * plain binned-SAH BVH, and the per-pixel drivers of the ray-gen / compute / resolve shaders.
+ * Result-defining rules the hardware leaves open are fixed here and mirrored by the CUDA side:
+ *   - a candidate is accepted iff its reported hitT lies in [tMin, tMax] (reportIntersectionEXT);
+ *   - closest hit = smallest hitT, ties broken by the lowest segment index.
+ *
+ * Build: g++ -O2 -std=c++17 -fopenmp -ffp-contract=off -shared -fPIC (see oracle/Makefile).
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <atomic>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/linevis_b200.h"
+#include "lvo_shaders.hpp"
+#include "lvo_sort.hpp"
+#ifdef LVO_USE_REFERENCE_BVH
+#include "lvo_bvh_ref.hpp"   // traversal by the reference's submodules/bvh (built into oracle/_ref only)
+#else
+#include "lvo_bvh_own.hpp"
+#endif
+
+using namespace lvo;
+
+extern "C" {
+
+typedef struct lvo_options {
+    int32_t use_capped_tubes;           // LineData::useCappedTubes (LineData.hpp:377)
+    int32_t use_halos;                  // LineData::useHalos (LineData.hpp:378)
+    float ao_strength;                  // ambient_occlusion_strength (LineRenderer.cpp:476)
+    float ao_gamma;                     // ambient_occlusion_gamma
+    float ao_radius;                    // ambient_occlusion_radius (VulkanRayTracedAmbientOcclusion.hpp:151)
+    uint32_t ao_spp;                    // ambient_occlusion_samples_per_frame (:150)
+    int32_t ao_use_distance;            // ambient_occlusion_distance_based (:152)
+    int32_t ao_jitter_primary;          // use_jittered_primary_rays (:153)
+    uint32_t tube_num_subdivisions;     // LineData::tubeNumSubdivisions (LineData.cpp:52)
+    uint32_t num_samples_per_frame;     // num_samples_per_frame (VulkanRayTracer.hpp:137)
+    int32_t use_jittered_rays;          // USE_JITTERED_RAYS (VulkanRayTracer.cpp:421)
+    int32_t use_deterministic_sampling; // DETERMINISTIC_SAMPLING
+    uint32_t max_depth_complexity;      // maxDepthComplexity (VulkanRayTracer.hpp:139)
+    uint32_t tile_w, tile_h;            // LineRenderer::tileWidth/tileHeight (LineRenderer.cpp:739-740)
+} lvo_options;
+
+}  // extern "C"
+
+namespace {
+
+// BVH backend (Scene, buildScene, traceClosest/traceAny/traceAll) comes from the included header.
+
+Uniforms makeUniforms(const Scene& sc, const lv_camera& cam, const lvo_options& o, const float* tf, uint32_t K,
+                      float amin, float amax, const float* aoTex) {
+    Uniforms u{};
+    u.cameraPosition = V3(cam.position[0], cam.position[1], cam.position[2]);
+    u.fieldOfViewY = cam.fov_y;
+    std::memcpy(u.viewMatrix, cam.view, 64); std::memcpy(u.projectionMatrix, cam.proj, 64);
+    std::memcpy(u.inverseViewMatrix, cam.inv_view, 64); std::memcpy(u.inverseProjectionMatrix, cam.inv_proj, 64);
+    u.backgroundColor = vec4{cam.background[0], cam.background[1], cam.background[2], cam.background[3]};
+    // foregroundColor = vec4(1) - backgroundColor -- src/LineData/LineData.cpp:1284-1285
+    u.foregroundColor = vec4{1.0f - cam.background[0], 1.0f - cam.background[1], 1.0f - cam.background[2], 1.0f - cam.background[3]};
+    u.lineWidth = sc.lineWidth;
+    u.ambientOcclusionStrength = o.ao_strength; u.ambientOcclusionGamma = o.ao_gamma;
+    u.viewportW = cam.width; u.viewportH = cam.height;
+    u.tfLut = tf; u.tfK = K; u.minAttributeValue = amin; u.maxAttributeValue = amax;
+    u.useCappedTubes = o.use_capped_tubes != 0; u.useHalos = o.use_halos != 0;
+    u.useAmbientOcclusion = (o.ao_strength > 0.0f) && aoTex != nullptr;
+    u.aoTexture = aoTex;
+    return u;
+}
+
+void paddedSize(uint32_t W, uint32_t H, uint32_t tw, uint32_t th, uint32_t& pw, uint32_t& ph) {
+    // LineRenderer::getScreenSizeWithTiling -- src/Renderers/LineRenderer.cpp:805-812
+    pw = W; ph = H;
+    if (pw % tw != 0) pw = (pw / tw + 1) * tw;
+    if (ph % th != 0) ph = (ph / th + 1) * th;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------ unit helpers
+uint32_t lvo_tea(uint32_t v0, uint32_t v1) { return tea(v0, v1); }
+void lvo_rnd_stream(uint32_t seed, uint32_t n, uint32_t* lcg_out, float* rnd_out) {
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t s2 = seed;
+        float f = rnd(s2);        // advances exactly like lcg(seed)
+        lcg_out[i] = lcg(seed);
+        rnd_out[i] = f;
+    }
+}
+float lvo_det_pow(float x, float y) { return det_pow(x, y); }
+void lvo_det_sincos2pi(float xi, float* c, float* s) { det_sincos2pi(xi, *c, *s); }
+uint32_t lvo_addr_gen(uint32_t x, uint32_t y, uint32_t viewportW, uint32_t tw, uint32_t th) { return addrGen(x, y, viewportW, tw, th); }
+uint32_t lvo_pack_unorm4x8(const float* c) { return packUnorm4x8(vec4{c[0], c[1], c[2], c[3]}); }
+void lvo_sample_hemisphere(float xix, float xiy, float* out3) { vec3 v = sampleHemisphere(xix, xiy); out3[0] = v.x; out3[1] = v.y; out3[2] = v.z; }
+
+// IntersectionTube for one ray / one segment.  Returns 1 if an intersection would be reported.
+int lvo_intersect_tube(const float* ro, const float* rd, const float* p0, const float* p1, float radius, int capped,
+                       float* t_out, int* kind_out) {
+    float t; int k;
+    bool h = intersectionTube(V3(ro[0], ro[1], ro[2]), V3(rd[0], rd[1], rd[2]), V3(p0[0], p0[1], p0[2]), V3(p1[0], p1[1], p1[2]),
+                              radius, capped != 0, t, k);
+    *t_out = t; *kind_out = k;
+    return h ? 1 : 0;
+}
+
+// sort + blend of one pixel's fragment list.  canonical != 0 -> (depth, colour) key order (see lvo_sort.hpp)
+void lvo_sort_blend(const uint32_t* colors, const float* depths, uint32_t n, uint32_t max_frags, int mode, int canonical,
+                    float* rgba_out) {
+    ResolveLists L;
+    L.colorList.assign(colors, colors + n); L.depthList.assign(depths, depths + n);
+    L.colorList.resize(std::max(n, max_frags)); L.depthList.resize(std::max(n, max_frags));
+    vec4 c = canonical ? L.canonical(mode, n) : L.sortingAlgorithm(mode, n, max_frags);
+    rgba_out[0] = c.x; rgba_out[1] = c.y; rgba_out[2] = c.z; rgba_out[3] = c.w;
+}
+
+// Segment list construction -- LineDataFlow::getLinePassTubeAabbRenderData, src/LineData/LineDataFlow.cpp:2140-2236.
+// Input: polylines as (positions, attributes, line_offsets[n_lines+1]).  Output (caller-allocated, worst case sizes):
+// filtered points, attributes, tangents, normals, seg_idx pairs.  Returns counts through n_pt_out / n_seg_out.
+void lvo_segments_from_polylines(const float* pos, const float* attr, const uint64_t* line_offsets, uint64_t n_lines,
+                                 float* pos_out, float* attr_out, float* tangent_out, float* normal_out, uint32_t* seg_idx_out,
+                                 uint64_t* n_pt_out, uint64_t* n_seg_out) {
+    uint64_t npt = 0, nseg = 0;
+    uint32_t lineSegmentIndexCounter = 0;
+    for (uint64_t li = 0; li < n_lines; li++) {
+        uint64_t b = line_offsets[li], e = line_offsets[li + 1];
+        uint64_t n = e - b;
+        if (n < 2) continue;  // a one-point trajectory would read positions[i+1] out of bounds in the reference
+        vec3 lastLineNormal = V3(1.0f, 0.0f, 0.0f);
+        uint32_t numValidLinePoints = 0;
+        auto P = [&](uint64_t i) { return V3(pos[3 * (b + i)], pos[3 * (b + i) + 1], pos[3 * (b + i) + 2]); };
+        for (uint64_t i = 0; i < n; i++) {
+            vec3 tangent;
+            if (i == 0) tangent = P(i + 1) - P(i);
+            else if (i + 1 == n) tangent = P(i) - P(i - 1);
+            else tangent = P(i + 1) - P(i - 1);
+            float tangentLength = length(tangent);
+            if (tangentLength < 0.0001f) continue;
+            tangent = normalize(tangent);
+            vec3 helperAxis = lastLineNormal;
+            if (length(cross(helperAxis, tangent)) < 0.01f) {
+                helperAxis = V3(0.0f, 1.0f, 0.0f);
+                if (length(cross(helperAxis, tangent)) < 0.01f) helperAxis = V3(0.0f, 0.0f, 1.0f);
+            }
+            vec3 normal = normalize(helperAxis - dot(helperAxis, tangent) * tangent);
+            lastLineNormal = normal;
+            vec3 p = P(i);
+            pos_out[3 * npt] = p.x; pos_out[3 * npt + 1] = p.y; pos_out[3 * npt + 2] = p.z;
+            attr_out[npt] = attr[b + i];
+            if (tangent_out) { tangent_out[3 * npt] = tangent.x; tangent_out[3 * npt + 1] = tangent.y; tangent_out[3 * npt + 2] = tangent.z; }
+            if (normal_out) { normal_out[3 * npt] = normal.x; normal_out[3 * npt + 1] = normal.y; normal_out[3 * npt + 2] = normal.z; }
+            npt++;
+            numValidLinePoints++;
+        }
+        if (numValidLinePoints == 1) npt--;
+        if (numValidLinePoints <= 1) continue;
+        for (uint32_t pointIdx = 1; pointIdx < numValidLinePoints; pointIdx++) {
+            seg_idx_out[2 * nseg] = lineSegmentIndexCounter + pointIdx - 1;
+            seg_idx_out[2 * nseg + 1] = lineSegmentIndexCounter + pointIdx;
+            nseg++;
+        }
+        lineSegmentIndexCounter += numValidLinePoints;
+    }
+    *n_pt_out = npt; *n_seg_out = nseg;
+}
+
+// ------------------------------------------------------------------------------------------ scene
+void* lvo_scene_create(const float* pos, const float* attr, const uint32_t* seg_idx, uint64_t n_pt, uint64_t n_seg, float line_width) {
+    (void)n_pt;
+    Scene* sc = new Scene();
+    sc->lineWidth = line_width;
+    sc->segs.resize(n_seg);
+    for (uint64_t i = 0; i < n_seg; i++) {
+        uint32_t a = seg_idx[2 * i], b = seg_idx[2 * i + 1];
+        sc->segs[i] = Segment{V3(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2]), attr[a], V3(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2]), attr[b]};
+    }
+    buildScene(*sc);
+    return sc;
+}
+void lvo_scene_destroy(void* h) { delete static_cast<Scene*>(h); }
+uint64_t lvo_scene_num_nodes(void* h) { return numNodes(*static_cast<Scene*>(h)); }
+const char* lvo_backend_name(void) { return backendName(); }
+
+// Brute-force closest hit (no BVH) for validating the traversal itself on small scenes.
+void lvo_trace_primary_bruteforce(void* h, const lv_camera* cam, const lvo_options* o, lv_hit* hits) {
+    Scene& sc = *static_cast<Scene*>(h);
+    Uniforms u = makeUniforms(sc, *cam, *o, nullptr, 0, 0, 1, nullptr);
+    const float radius = sc.lineWidth * 0.5f;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t y = 0; y < int64_t(cam->height); y++)
+        for (uint32_t x = 0; x < cam->width; x++) {
+            vec3 ro, rd; cameraRay(u, x, uint32_t(y), 0.5f, 0.5f, ro, rd);
+            lv_hit best{0.0f, 0xFFFFFFFFu, 0, 0}; bool found = false;
+            for (size_t p = 0; p < sc.segs.size(); p++) {
+                float t; int k;
+                if (intersectionTube(ro, rd, sc.segs[p].p0, sc.segs[p].p1, radius, u.useCappedTubes, t, k) && t >= 0.0001f && t <= 1000.0f) {
+                    if (!found || t < best.t) { best.t = t; best.prim = uint32_t(p); best.kind = uint32_t(k); found = true; }
+                }
+            }
+            hits[size_t(y) * cam->width + x] = best;
+        }
+}
+
+// S1+S2 closest-hit pass, pixel-centre rays, tMin 1e-4, tMax 1000 (TubeRayTracing.glsl:52-59).  stats = {T, I, rays}
+void lvo_trace_primary(void* h, const lv_camera* cam, const lvo_options* o, lv_hit* hits, uint64_t* stats) {
+    Scene& sc = *static_cast<Scene*>(h);
+    Uniforms u = makeUniforms(sc, *cam, *o, nullptr, 0, 0, 1, nullptr);
+    uint64_t T = 0, I = 0, R = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : T, I, R)
+    for (int64_t y = 0; y < int64_t(cam->height); y++) {
+        RayStats st;
+        for (uint32_t x = 0; x < cam->width; x++) {
+            Ray r; cameraRay(u, x, uint32_t(y), 0.5f, 0.5f, r.o, r.d); r.tmin = 0.0001f; r.tmax = 1000.0f;
+            Hit hit;
+            lv_hit out{0.0f, 0xFFFFFFFFu, 0, 0};
+            if (traceClosest(sc, r, u.useCappedTubes, hit, st)) { out.t = hit.t; out.prim = hit.prim; out.kind = uint32_t(hit.kind); }
+            hits[size_t(y) * cam->width + x] = out;
+        }
+        T += st.steps; I += st.isect; R += st.rays;
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = R; }
+}
+
+// S5: screen-space RTAO against the analytic capsules (VulkanRayTracedAmbientOcclusion.glsl:178-319).
+// ao_inout: W*H floats (x channel of the rgba32f accumulation image).  stats = {T, I, rays_primary, rays_ao, pixels_hit}
+void lvo_render_rtao(void* h, const lv_camera* cam, const lvo_options* o, uint32_t frame_number, float* ao_inout, uint64_t* stats) {
+    Scene& sc = *static_cast<Scene*>(h);
+    Uniforms u = makeUniforms(sc, *cam, *o, nullptr, 0, 0, 1, nullptr);
+    const uint32_t W = cam->width, H = cam->height;
+    const uint32_t globalFrameNumber = frame_number;  // useGlobalFrameNumber == false (VulkanRayTracedAmbientOcclusion.cpp:580-584)
+    // subdivisionCorrectionFactor = cos(pi / tubeNumSubdivisions) -- VulkanRayTracedAmbientOcclusion.cpp:591
+    const float subdivisionCorrectionFactor = float(std::cos(3.14159265358979323846 / double(o->tube_num_subdivisions)));
+    uint64_t T = 0, I = 0, RP = 0, RA = 0, PH = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : T, I, RP, RA, PH)
+    for (int64_t yy = 0; yy < int64_t(H); yy++) {
+        RayStats sp, sa;
+        uint32_t y = uint32_t(yy);
+        for (uint32_t x = 0; x < W; x++) {
+            uint32_t seed = tea(x + y * W, globalFrameNumber);                          // :187
+            float xix = 0.5f, xiy = 0.5f;
+            if (o->ao_jitter_primary) { xix = rnd(seed); xiy = rnd(seed); }            // :189-194
+            Ray r; cameraRay(u, x, y, xix, xiy, r.o, r.d); r.tmin = 0.0001f; r.tmax = 1000.0f;  // :196-203
+            float aoFactor = 1.0f;
+            Hit hit;
+            if (traceClosest(sc, r, u.useCappedTubes, hit, sp)) {
+                PH++;
+                const Segment& s = sc.segs[hit.prim];
+                // analytic replacement of the barycentric vertex fetch (:222-267): position, normal, line centre, tangent
+                vec3 vertexPositionWorld = r.o + r.d * hit.t;
+                vec3 v = s.p1 - s.p0;
+                vec3 linePosition;
+                if (hit.kind == 0) { vec3 uu = vertexPositionWorld - s.p0; float t = dot(v, uu) / dot(v, v); linePosition = s.p0 + t * v; }
+                else if (hit.kind == 1) linePosition = s.p0; else linePosition = s.p1;
+                vec3 surfaceNormal = normalize(vertexPositionWorld - linePosition);
+                vec3 surfaceTangent = normalize(v);
+                vec3 surfaceBitangent = cross(surfaceNormal, surfaceTangent);          // :257
+                const float offsetFactor = length(linePosition - vertexPositionWorld) / subdivisionCorrectionFactor;  // :276
+                aoFactor = 0.0f;
+                for (uint32_t sampleIdx = 0; sampleIdx < o->ao_spp; sampleIdx++) {     // :284-303
+                    uint32_t seed2 = tea(x + y * W, globalFrameNumber * o->ao_spp + sampleIdx);
+                    float a = rnd(seed2), b = rnd(seed2);
+                    vec3 hs = sampleHemisphere(a, b);
+                    vec3 dir = normalize((surfaceTangent * hs.x + surfaceBitangent * hs.y) + surfaceNormal * hs.z);
+                    Ray ar; ar.o = vertexPositionWorld + dir * offsetFactor; ar.d = dir; ar.tmin = 0.0f; ar.tmax = o->ao_radius;
+                    float occ = 1.0f;                                                   // traceAoRay :158-175
+                    if (o->ao_use_distance) { Hit ah; if (traceClosest(sc, ar, u.useCappedTubes, ah, sa)) occ = ah.t / o->ao_radius; }
+                    else { if (traceAny(sc, ar, u.useCappedTubes, sa)) occ = 0.0f; }
+                    aoFactor += occ;
+                }
+                aoFactor /= float(o->ao_spp);
+            }
+            size_t idx = size_t(y) * W + x;
+            if (frame_number != 0) { float prev = ao_inout[idx]; aoFactor = mix(prev, aoFactor, 1.0f / float(frame_number + 1)); }  // :313-317
+            ao_inout[idx] = aoFactor;
+        }
+        T += sp.steps + sa.steps; I += sp.isect + sa.isect; RP += sp.rays; RA += sa.rays;
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = RP; stats[3] = RA; stats[4] = PH; }
+}
+
+// S1 ray-gen with S2/S3/S4: traceRayTransparent loop + running mean (TubeRayTracing.glsl:61-82,198-274).
+// rgba_inout: W*H*4 floats (float stand-in for the rgba8 storage image; quantisation is the caller's).
+// ao_tex: result of lvo_render_rtao or NULL.  stats = {T, I, rays}
+void lvo_render_tubes(void* h, const lv_camera* cam, const lvo_options* o, const float* tf, uint32_t K, float amin, float amax,
+                      const float* ao_tex, uint32_t frame_number, float* rgba_inout, uint64_t* stats) {
+    Scene& sc = *static_cast<Scene*>(h);
+    Uniforms u = makeUniforms(sc, *cam, *o, tf, K, amin, amax, ao_tex);
+    const uint32_t W = cam->width, H = cam->height;
+    uint64_t T = 0, I = 0, R = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : T, I, R)
+    for (int64_t yy = 0; yy < int64_t(H); yy++) {
+        RayStats st;
+        uint32_t y = uint32_t(yy);
+        for (uint32_t x = 0; x < W; x++) {
+            vec4 fragmentColor{0, 0, 0, 0};
+            uint32_t nspp = o->use_jittered_rays ? o->num_samples_per_frame : 1u;
+            for (uint32_t sampleIdx = 0; sampleIdx < nspp; sampleIdx++) {
+                float xix = 0.5f, xiy = 0.5f;
+                if (o->use_jittered_rays) {
+                    uint32_t seed = o->use_deterministic_sampling
+                        ? tea(19u, frame_number * o->num_samples_per_frame + sampleIdx)
+                        : tea(x + y * W, frame_number * o->num_samples_per_frame + sampleIdx);
+                    xix = rnd(seed); xiy = rnd(seed);
+                }
+                vec3 ro, rd; cameraRay(u, x, y, xix, xiy, ro, rd);
+                // traceRayTransparent :61-82
+                vec4 fc{0, 0, 0, 0};
+                float tMin = 0.0001f, tMax = 1000.0f;
+                for (uint32_t hitIdx = 0; hitIdx < o->max_depth_complexity; hitIdx++) {
+                    Ray r; r.o = ro; r.d = rd; r.tmin = tMin; r.tmax = tMax;
+                    Hit hit; HitColor pl;
+                    if (traceClosest(sc, r, u.useCappedTubes, hit, st)) {
+                        const Segment& s = sc.segs[hit.prim];
+                        pl = closestHitTubeAnalytic(u, ro, rd, hit.t, hit.kind, s.p0, s.a0, s.p1, s.a1);
+                    } else pl = missShader(u);
+                    tMin = pl.hitT + fmax_(pl.hitT * 1e-5f, 1e-7f);
+                    fc.x = fc.x + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.x;
+                    fc.y = fc.y + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.y;
+                    fc.z = fc.z + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.z;
+                    fc.w = fc.w + (1.0f - fc.w) * pl.hitColor.w;
+                    if (!pl.hasHit || fc.w > 0.99f) break;
+                }
+                fragmentColor.x += fc.x; fragmentColor.y += fc.y; fragmentColor.z += fc.z; fragmentColor.w += fc.w;
+            }
+            if (o->use_jittered_rays) {
+                float d = float(o->num_samples_per_frame);
+                fragmentColor.x /= d; fragmentColor.y /= d; fragmentColor.z /= d; fragmentColor.w /= d;
+            }
+            float* px = rgba_inout + 4 * (size_t(y) * W + x);
+            if (frame_number != 0) {                                                    // :269-272
+                float a = 1.0f / float(frame_number + 1);
+                fragmentColor = vec4{mix(px[0], fragmentColor.x, a), mix(px[1], fragmentColor.y, a), mix(px[2], fragmentColor.z, a), mix(px[3], fragmentColor.w, a)};
+            }
+            px[0] = fragmentColor.x; px[1] = fragmentColor.y; px[2] = fragmentColor.z; px[3] = fragmentColor.w;
+        }
+        T += st.steps; I += st.isect; R += st.rays;
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = R; }
+}
+
+// ------------------------------------------------------------------------------------------ PPLL
+void lvo_ppll_padded_size(uint32_t W, uint32_t H, uint32_t tw, uint32_t th, uint32_t* pw, uint32_t* ph) { paddedSize(W, H, tw, th, *pw, *ph); }
+
+// S8 + S9: clear + gather.  The fragment source (S11 is a hardware rasteriser) is redefined as: every capsule whose
+// reported hit (S2) along the pixel-centre ray lies in [1e-4, 1000] yields one fragment shaded by S3.
+// heads: paddedW*paddedH u32; nodes: capacity linked_list_size.  Returns fragCounter (may exceed linked_list_size).
+// stats = {T, I, rays, frags_generated}
+uint64_t lvo_ppll_gather(void* h, const lv_camera* cam, const lvo_options* o, const float* tf, uint32_t K, float amin, float amax,
+                         const float* ao_tex, uint64_t linked_list_size, uint32_t* heads, lv_ppll_node* nodes, uint64_t* stats) {
+    Scene& sc = *static_cast<Scene*>(h);
+    Uniforms u = makeUniforms(sc, *cam, *o, tf, K, amin, amax, ao_tex);
+    const uint32_t W = cam->width, H = cam->height;
+    uint32_t pw, ph; paddedSize(W, H, o->tile_w, o->tile_h, pw, ph);
+    for (size_t i = 0; i < size_t(pw) * ph; i++) heads[i] = 0xFFFFFFFFu;               // LinkedListClear.glsl:50
+    uint64_t fragCounter = 0;
+    uint64_t T = 0, I = 0, R = 0;
+    struct Frag { uint32_t color; float depth; };
+    std::vector<std::vector<Frag>> rowFrags(W);
+    for (uint32_t y = 0; y < H; y++) {
+        RayStats stRow;
+#pragma omp parallel
+        {
+            RayStats st;
+#pragma omp for schedule(dynamic, 16) nowait
+            for (int64_t xx = 0; xx < int64_t(W); xx++) {
+                uint32_t x = uint32_t(xx);
+                rowFrags[x].clear();
+                vec3 ro, rd; cameraRay(u, x, y, 0.5f, 0.5f, ro, rd);
+                Ray r; r.o = ro; r.d = rd; r.tmin = 0.0001f; r.tmax = 1000.0f;
+                traceAll(sc, r, u.useCappedTubes, st, [&](uint32_t p, float t, int kind) {
+                    const Segment& s = sc.segs[p];
+                    HitColor pl = closestHitTubeAnalytic(u, ro, rd, t, kind, s.p0, s.a0, s.p1, s.a1);
+                    if (pl.hitColor.w < 0.001f) return;                                 // LinkedListGather.glsl:38
+                    // frag.depth = length(fragmentPositionWorld - cameraPosition) (:52) == payload.hitT
+                    rowFrags[x].push_back(Frag{packUnorm4x8(pl.hitColor), pl.hitT});
+                });
+            }
+#pragma omp critical
+            { stRow.steps += st.steps; stRow.isect += st.isect; stRow.rays += st.rays; }
+        }
+        T += stRow.steps; I += stRow.isect; R += stRow.rays;
+        for (uint32_t x = 0; x < W; x++) {
+            uint32_t pixelIndex = addrGen(x, y, pw, o->tile_w, o->tile_h);
+            for (const Frag& f : rowFrags[x]) {
+                uint64_t insertIndex = fragCounter++;                                   // atomicAdd(fragCounter, 1u) :55
+                if (insertIndex < linked_list_size) {
+                    uint32_t next = heads[pixelIndex]; heads[pixelIndex] = uint32_t(insertIndex);  // atomicExchange :59
+                    nodes[insertIndex] = lv_ppll_node{f.color, f.depth, next};
+                }
+            }
+        }
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = R; stats[3] = fragCounter; }
+    return fragCounter;
+}
+
+// S10: resolve (LinkedListResolve.glsl:57-105) + final BACK_TO_FRONT_STRAIGHT_ALPHA blend over the clear colour
+// (PerPixelLinkedListLineRenderer.cpp:70; dst = src.rgb*src.a + dst*(1-src.a), alpha = src.a + dst.a*(1-src.a)).
+// stats = {frags_sorted, frags_truncated, max_depth_complexity}
+void lvo_ppll_resolve(const lv_camera* cam, const lvo_options* o, const uint32_t* heads, const lv_ppll_node* nodes,
+                      uint32_t max_frags, int sort_mode, int canonical, float* rgba_out, uint64_t* stats) {
+    const uint32_t W = cam->width, H = cam->height;
+    uint32_t pw, ph; paddedSize(W, H, o->tile_w, o->tile_h, pw, ph);
+    uint64_t sorted = 0, trunc = 0, maxdc = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : sorted, trunc) reduction(max : maxdc)
+    for (int64_t yy = 0; yy < int64_t(H); yy++) {
+        ResolveLists L;
+        L.colorList.resize(max_frags); L.depthList.resize(max_frags);
+        uint32_t y = uint32_t(yy);
+        for (uint32_t x = 0; x < W; x++) {
+            uint32_t fragOffset = heads[addrGen(x, y, pw, o->tile_w, o->tile_h)];
+            uint32_t numFrags = 0;
+            for (uint32_t i = 0; i < max_frags; i++) {
+                if (fragOffset == 0xFFFFFFFFu) break;
+                const lv_ppll_node& f = nodes[fragOffset];
+                fragOffset = f.next;
+                L.colorList[i] = f.color; L.depthList[i] = f.depth;
+                numFrags++;
+            }
+            uint64_t rest = 0;
+            while (fragOffset != 0xFFFFFFFFu) { rest++; fragOffset = nodes[fragOffset].next; }
+            sorted += numFrags; trunc += rest; maxdc = std::max<uint64_t>(maxdc, numFrags + rest);
+            float* px = rgba_out + 4 * (size_t(y) * W + x);
+            if (numFrags == 0) { for (int k = 0; k < 4; k++) px[k] = cam->background[k]; continue; }  // discard
+            vec4 c = canonical ? L.canonical(sort_mode, numFrags) : L.sortingAlgorithm(sort_mode, numFrags, max_frags);
+            px[0] = c.x * c.w + cam->background[0] * (1.0f - c.w);
+            px[1] = c.y * c.w + cam->background[1] * (1.0f - c.w);
+            px[2] = c.z * c.w + cam->background[2] * (1.0f - c.w);
+            px[3] = c.w + cam->background[3] * (1.0f - c.w);
+        }
+    }
+    if (stats) { stats[0] = sorted; stats[1] = trunc; stats[2] = maxdc; }
+}
+
+int lvo_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
