@@ -1,0 +1,185 @@
+"""Thin object wrappers over the C ABI: Context (lv_ctx) and Scene (lv_scene).
+
+Buffers handed in may be numpy arrays (host) or torch CUDA tensors (device); the library detects which.
+Every method goes through the C ABI of include/linevis_b200.h -- the same entry points the C++ LineRenderer
+adapter (linevis_b200/host/) binds -- and raises LineVisError on a non-zero status.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import LvStats, LineVisError, HIT_DTYPE, NODE_DTYPE, BVH_NODE_DTYPE, SORT_MODES, _ptr
+
+
+class Context:
+    """One renderer context per GPU (lv_ctx_create; replaces renderer construction in MainApp::setRenderer)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = capi.load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.lv_ctx_create(ctypes.byref(h), int(device), ctypes.c_void_p(stream) if stream else None)
+        if rc != capi.LV_OK:
+            raise LineVisError(rc, self.lib.lv_last_global_error().decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lv_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != capi.LV_OK:
+            raise LineVisError(rc, self.lib.lv_last_error(self.h).decode())
+
+    # -- settings (LineRenderer::setNewSettings keys)
+    def set_option(self, key, value):
+        if isinstance(value, bool):
+            value = "true" if value else "false"
+        self._check(self.lib.lv_set_option(self.h, key.encode(), str(value).encode()))
+
+    def set_new_settings(self, settings):
+        """SettingsMap-style bulk update; same keys as the reference's replay scripts use."""
+        for k, v in settings.items():
+            self.set_option(k, v)
+
+    def get_option(self, key):
+        buf = ctypes.create_string_buffer(256)
+        self._check(self.lib.lv_get_option(self.h, key.encode(), buf, 256))
+        return buf.value.decode()
+
+    def set_transfer_function(self, lut, attr_min=0.0, attr_max=1.0):
+        lut = np.ascontiguousarray(lut, np.float32)
+        assert lut.ndim == 2 and lut.shape[1] == 4
+        self._check(self.lib.lv_set_transfer_function(self.h, _ptr(lut), lut.shape[0], attr_min, attr_max))
+
+    # -- sharding
+    def set_tile_shard(self, rank, world, tile_size=64):
+        self._check(self.lib.lv_set_tile_shard(self.h, rank, world, tile_size))
+
+    def owned_tiles(self, width, height):
+        n = ctypes.c_uint32()
+        self._check(self.lib.lv_get_owned_tiles(self.h, width, height, None, ctypes.byref(n)))
+        t = np.zeros((max(n.value, 1), 2), np.uint32)
+        self._check(self.lib.lv_get_owned_tiles(self.h, width, height, _ptr(t), ctypes.byref(n)))
+        return t[:n.value]
+
+    def pack_owned_tiles(self, image, width, height, packed):
+        self._check(self.lib.lv_pack_owned_tiles(self.h, _ptr(image), width, height, _ptr(packed)))
+
+    def unpack_tiles(self, packed, src_rank, world, width, height, image):
+        self._check(self.lib.lv_unpack_tiles(self.h, _ptr(packed), src_rank, world, width, height, _ptr(image)))
+
+    def synchronize(self):
+        self._check(self.lib.lv_synchronize(self.h))
+
+    # -- scene
+    def create_scene(self, pos, attr, seg_idx, line_width=0.002):
+        return Scene(self, pos, attr, seg_idx, line_width)
+
+    # -- frames
+    def trace_primary(self, scene, cam, out=None):
+        if out is None:
+            out = np.zeros(cam.width * cam.height, HIT_DTYPE)
+        st = LvStats()
+        self._check(self.lib.lv_trace_primary(self.h, scene.h, ctypes.byref(cam), _ptr(out), ctypes.byref(st)))
+        if isinstance(out, np.ndarray):
+            out = out.reshape(cam.height, cam.width)
+        return out, st.as_dict()
+
+    def render_rtao(self, scene, cam, frame_number=0, out=None, stats=True):
+        if out is None:
+            out = np.zeros((cam.height, cam.width), np.float32)
+        st = LvStats()
+        self._check(self.lib.lv_render_rtao(self.h, scene.h, ctypes.byref(cam), frame_number, _ptr(out), ctypes.byref(st) if stats else None))
+        return out, st.as_dict()
+
+    def render_tubes(self, scene, cam, frame_number=0, out=None, stats=True):
+        if out is None:
+            out = np.zeros((cam.height, cam.width, 4), np.float32)
+        st = LvStats()
+        self._check(self.lib.lv_render_tubes(self.h, scene.h, ctypes.byref(cam), frame_number, _ptr(out), ctypes.byref(st) if stats else None))
+        return out, st.as_dict()
+
+    def render_ppll(self, scene, cam, max_frags=100, sort_mode="priority_queue", linked_list_size=0, out=None, stats=True):
+        if out is None:
+            out = np.zeros((cam.height, cam.width, 4), np.float32)
+        mode = SORT_MODES[sort_mode] if isinstance(sort_mode, str) else int(sort_mode)
+        st = LvStats()
+        self._check(self.lib.lv_render_ppll(self.h, scene.h, ctypes.byref(cam), max_frags, mode, linked_list_size, _ptr(out),
+                                            ctypes.byref(st) if stats else None))
+        return out, st.as_dict()
+
+    def ppll_clear(self, cam, linked_list_size=0):
+        self._check(self.lib.lv_ppll_clear(self.h, ctypes.byref(cam), linked_list_size))
+
+    def ppll_gather(self, scene, cam, stats=True):
+        st = LvStats()
+        self._check(self.lib.lv_ppll_gather(self.h, scene.h, ctypes.byref(cam), ctypes.byref(st) if stats else None))
+        return st.as_dict()
+
+    def ppll_resolve(self, cam, max_frags=100, sort_mode="priority_queue", out=None, stats=True):
+        if out is None:
+            out = np.zeros((cam.height, cam.width, 4), np.float32)
+        mode = SORT_MODES[sort_mode] if isinstance(sort_mode, str) else int(sort_mode)
+        st = LvStats()
+        self._check(self.lib.lv_ppll_resolve(self.h, ctypes.byref(cam), max_frags, mode, _ptr(out), ctypes.byref(st) if stats else None))
+        return out, st.as_dict()
+
+    def ppll_read(self):
+        cnt, pw, ph = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self.lib.lv_ppll_read(self.h, ctypes.byref(cnt), None, 0, None, 0, ctypes.byref(pw), ctypes.byref(ph)))
+        heads = np.zeros(pw.value * ph.value, np.uint32)
+        nodes = np.zeros(max(cnt.value, 1), NODE_DTYPE)
+        self._check(self.lib.lv_ppll_read(self.h, ctypes.byref(cnt), _ptr(heads), heads.size, _ptr(nodes), nodes.size, None, None))
+        return dict(counter=cnt.value, heads=heads, nodes=nodes[:cnt.value], padded=(pw.value, ph.value))
+
+
+class Scene:
+    """Device-resident segment soup + BVH (lv_scene_create; replaces getLinePassTubeAabbRenderData + TLAS build)."""
+
+    def __init__(self, ctx, pos, attr, seg_idx, line_width):
+        self.ctx = ctx
+        h = ctypes.c_void_p()
+        if isinstance(pos, np.ndarray):
+            pos = np.ascontiguousarray(pos, np.float32)
+            attr = np.ascontiguousarray(attr, np.float32)
+            seg_idx = np.ascontiguousarray(seg_idx, np.uint32)
+            n_pt, n_seg = pos.shape[0], seg_idx.shape[0]
+            rc = ctx.lib.lv_scene_create(ctx.h, ctypes.byref(h), _ptr(pos), _ptr(attr), _ptr(seg_idx), n_pt, n_seg, line_width)
+        else:  # torch CUDA tensors
+            n_pt, n_seg = pos.shape[0], seg_idx.shape[0]
+            rc = ctx.lib.lv_scene_create_device(ctx.h, ctypes.byref(h), _ptr(pos), _ptr(attr), _ptr(seg_idx), n_pt, n_seg, line_width)
+        ctx._check(rc)
+        self.h = h
+        self.n_seg = n_seg
+
+    def info(self):
+        ns, nn, ms = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_float()
+        bb = np.zeros(6, np.float32)
+        self.ctx._check(self.ctx.lib.lv_scene_info(self.h, ctypes.byref(ns), ctypes.byref(nn), ctypes.byref(ms), _ptr(bb)))
+        return dict(n_seg=ns.value, n_nodes=nn.value, build_ms=ms.value, aabb=bb)
+
+    def bvh_nodes(self):
+        n = self.info()["n_nodes"]
+        nodes = np.zeros(max(n, 1), BVH_NODE_DTYPE)
+        self.ctx._check(self.ctx.lib.lv_scene_copy_bvh(self.h, _ptr(nodes), nodes.nbytes))
+        return nodes[:n]
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.lv_scene_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,781 @@
+// lv_api.cu -- implementation of the C ABI in include/linevis_b200.h on top of the sm_100a kernels.
+// Host orchestration only: option parsing, buffer management, launches, timing, statistics.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/linevis_b200.h"
+#include "lv_bvh.cuh"
+#include "lv_kernels.cuh"
+
+using namespace lv;
+
+namespace {
+
+thread_local std::string g_global_error;
+
+struct Options {
+    // reference defaults: LineData.hpp:377-378, VulkanRayTracedAmbientOcclusion.hpp:108,150-153,
+    // LineData.cpp:52, VulkanRayTracer.hpp:137-142, LineRenderer.cpp:739-740, PerPixelLinkedListLineRenderer.hpp:45-49
+    float line_width = 0.002f;
+    float band_width = 0.005f;
+    float depth_cue_strength = 0.0f;
+    bool use_capped_tubes = true, use_halos = true;
+    float ao_strength = 0.0f, ao_gamma = 1.0f, ao_radius = 0.1f;
+    uint32_t ao_iterations = 64, ao_spp = 4;
+    bool ao_use_distance = true, ao_jitter_primary = true;
+    uint32_t tube_num_subdivisions = 6;
+    uint32_t num_samples_per_frame = 2, num_accumulated_frames = 32;
+    bool use_deterministic_sampling = false;
+    uint32_t max_depth_complexity = 1024;
+    uint32_t tiling_w = 2, tiling_h = 8;
+    uint32_t bvh_leaf_size = 4;
+    uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
+    std::string ao_mode = "RTAO", denoiser = "None", geometry_mode = "AABBs (analytic)";
+};
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct lv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    Options opt;
+    std::string error;
+    // transfer function
+    DevBuf<float4> tf; uint32_t tfK = 0; float amin = 0.0f, amax = 1.0f;
+    // sharding
+    uint32_t rank = 0, world = 1, tile_size = 64;
+    std::vector<uint2> tiles_host; DevBuf<uint2> tiles_dev; uint32_t tiles_w = 0, tiles_h = 0;
+    DevBuf<uint2> tiles_tmp;
+    // frame buffers
+    DevBuf<float4> image; DevBuf<float> ao; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
+    uint32_t ao_w = 0, ao_h = 0;
+    DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[1] = ao work counter
+    // PPLL
+    DevBuf<uint32_t> heads, counts; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
+    unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
+    cudaEvent_t ev[6] = {};
+};
+
+struct lv_scene {
+    lv_ctx* ctx = nullptr;
+    DevBuf<SegRec> segs; DevBuf<uint32_t> prim_ids; DevBuf<Node64> nodes;
+    uint64_t n_seg = 0, n_nodes = 0;
+    float line_width = 0.0f, build_ms = 0.0f;
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    SceneDev dev() const {
+        SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
+        s.n_nodes = uint32_t(n_nodes); s.radius = line_width * 0.5f; s.line_width = line_width;
+        return s;
+    }
+};
+
+namespace {
+
+int fail(lv_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg; else g_global_error = msg;
+    return code;
+}
+#define LV_CUDA(ctx, expr)                                                                                      \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? LV_ERR_OUT_OF_MEMORY : LV_ERR_CUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                                   \
+    } while (0)
+
+bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+bool parse_bool(const char* v) { return !strcmp(v, "true") || !strcmp(v, "1"); }  // SettingsMap::getValueOpt(bool&), InternalState.hpp:67-74
+
+uint32_t morton2(uint32_t x, uint32_t y) {
+    auto part = [](uint32_t v) { v &= 0xffff; v = (v | (v << 8)) & 0x00ff00ff; v = (v | (v << 4)) & 0x0f0f0f0f; v = (v | (v << 2)) & 0x33333333; v = (v | (v << 1)) & 0x55555555; return v; };
+    return part(x) | (part(y) << 1);
+}
+
+// tiles of a W x H frame in Morton order; tile i belongs to rank i % world
+void enumerate_tiles(uint32_t W, uint32_t H, uint32_t ts, uint32_t rank, uint32_t world, std::vector<uint2>& out) {
+    uint32_t tx = (W + ts - 1) / ts, ty = (H + ts - 1) / ts;
+    std::vector<std::pair<uint32_t, uint2>> all;
+    all.reserve(size_t(tx) * ty);
+    for (uint32_t y = 0; y < ty; y++) for (uint32_t x = 0; x < tx; x++) all.push_back({morton2(x, y), make_uint2(x, y)});
+    std::sort(all.begin(), all.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    out.clear();
+    for (size_t i = 0; i < all.size(); i++) if (i % world == rank) out.push_back(all[i].second);
+}
+
+int ensure_tiles(lv_ctx* c, uint32_t W, uint32_t H) {
+    if (c->tiles_w == W && c->tiles_h == H && c->tiles_dev.p) return LV_OK;
+    enumerate_tiles(W, H, c->tile_size, c->rank, c->world, c->tiles_host);
+    LV_CUDA(c, c->tiles_dev.ensure(std::max<size_t>(1, c->tiles_host.size())));
+    if (!c->tiles_host.empty())
+        LV_CUDA(c, cudaMemcpyAsync(c->tiles_dev.p, c->tiles_host.data(), c->tiles_host.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->tiles_w = W; c->tiles_h = H;
+    return LV_OK;
+}
+
+void padded_size(const lv_ctx* c, uint32_t W, uint32_t H, uint32_t& pw, uint32_t& ph) {
+    // LineRenderer::getScreenSizeWithTiling (reference src/Renderers/LineRenderer.cpp:805-812)
+    pw = W; ph = H;
+    if (pw % c->opt.tiling_w) pw = (pw / c->opt.tiling_w + 1) * c->opt.tiling_w;
+    if (ph % c->opt.tiling_h) ph = (ph / c->opt.tiling_h + 1) * c->opt.tiling_h;
+}
+
+int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, FrameParams& P) {
+    if (!cam || cam->width == 0 || cam->height == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "camera: width/height must be > 0");
+    if (uint64_t(cam->width) * cam->height > 0xFFFFFFFFull) return fail(c, LV_ERR_INVALID_ARGUMENT, "frame too large");
+    int rc = ensure_tiles(c, cam->width, cam->height);
+    if (rc) return rc;
+    memset(&P, 0, sizeof(P));
+    memcpy(P.view, cam->view, 64); memcpy(P.proj, cam->proj, 64);
+    memcpy(P.inv_view, cam->inv_view, 64); memcpy(P.inv_proj, cam->inv_proj, 64);
+    memcpy(P.cam_pos, cam->position, 12);
+    P.fov_y = cam->fov_y;
+    for (int k = 0; k < 4; k++) { P.bg[k] = cam->background[k]; P.fg[k] = 1.0f - cam->background[k]; }
+    P.W = cam->width; P.H = cam->height;
+    P.line_width = sc ? sc->line_width : c->opt.line_width;
+    const Options& o = c->opt;
+    P.use_capped = o.use_capped_tubes; P.use_halos = o.use_halos; P.use_ao = 0;
+    P.ao_strength = o.ao_strength; P.ao_gamma = o.ao_gamma; P.ao_radius = o.ao_radius;
+    P.ao_spp = o.ao_spp; P.ao_use_distance = o.ao_use_distance; P.ao_jitter = o.ao_jitter_primary;
+    P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
+    P.spp = o.num_samples_per_frame;
+    // useJitteredSamples = maxNumFrames > 1 || numSamplesPerFrame > 1 (reference VulkanRayTracer.cpp:421)
+    P.use_jitter = (o.num_accumulated_frames > 1 || o.num_samples_per_frame > 1) ? 1 : 0;
+    P.det_sampling = o.use_deterministic_sampling;
+    P.max_depth = o.max_depth_complexity;
+    P.frame_number = frame_number;
+    P.tf = c->tf.p; P.tfK = c->tfK; P.amin = c->amin; P.amax = c->amax;
+    P.ao_tex = nullptr;
+    P.tiles = c->tiles_dev.p; P.n_tiles = uint32_t(c->tiles_host.size()); P.tile_size = c->tile_size;
+    padded_size(c, P.W, P.H, P.padded_w, P.padded_h);
+    P.addr_tw = o.tiling_w; P.addr_th = o.tiling_h;
+    return LV_OK;
+}
+
+uint32_t pixel_grid(const lv_ctx* c, const FrameParams& P) {
+    return P.n_tiles * (c->tile_size / 16) * (c->tile_size / 8);
+}
+
+int reset_counters(lv_ctx* c) {
+    LV_CUDA(c, c->counters.ensure(1));
+    LV_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), c->stream));
+    return LV_OK;
+}
+
+int read_counters(lv_ctx* c, Counters& h) {
+    LV_CUDA(c, cudaMemcpyAsync(&h, c->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
+void fill_stats(lv_stats* s, const Counters& h) {
+    s->rays_primary += h.rays_primary; s->rays_ao += h.rays_ao; s->traversal_steps += h.steps; s->intersections += h.isect;
+    s->pixels_hit += h.pixels_hit ? h.pixels_hit : h.ao_pixels_hit;
+    s->frags_generated += h.frags_generated; s->frags_sorted += h.frags_sorted; s->frags_truncated += h.frags_truncated;
+    s->max_depth_complexity = std::max(s->max_depth_complexity, h.max_depth_complexity);
+}
+
+// copy a device image (W*H elements of `elem` bytes) to the caller's buffer (device or host); sharded + host -> owned tiles only
+int deliver(lv_ctx* c, const void* src, void* dst, uint32_t W, uint32_t H, size_t elem) {
+    if (src == dst) return LV_OK;
+    if (c->world == 1 || is_device_pointer(dst)) {
+        if (c->world == 1) {
+            LV_CUDA(c, cudaMemcpyAsync(dst, src, size_t(W) * H * elem, cudaMemcpyDefault, c->stream));
+        } else {
+            for (const uint2& t : c->tiles_host) {
+                uint32_t x0 = t.x * c->tile_size, y0 = t.y * c->tile_size;
+                uint32_t w = std::min(c->tile_size, W - x0), h = std::min(c->tile_size, H - y0);
+                size_t off = (size_t(y0) * W + x0) * elem;
+                LV_CUDA(c, cudaMemcpy2DAsync((char*)dst + off, size_t(W) * elem, (const char*)src + off, size_t(W) * elem, w * elem, h, cudaMemcpyDefault, c->stream));
+            }
+        }
+    } else {
+        for (const uint2& t : c->tiles_host) {
+            uint32_t x0 = t.x * c->tile_size, y0 = t.y * c->tile_size;
+            uint32_t w = std::min(c->tile_size, W - x0), h = std::min(c->tile_size, H - y0);
+            size_t off = (size_t(y0) * W + x0) * elem;
+            LV_CUDA(c, cudaMemcpy2DAsync((char*)dst + off, size_t(W) * elem, (const char*)src + off, size_t(W) * elem, w * elem, h, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (!is_device_pointer(dst)) LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// ---- RTAO pass (S5) into ctx->ao --------------------------------------------------------------
+int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number) {
+    const size_t npx = size_t(P.W) * P.H;
+    if (c->ao_w != P.W || c->ao_h != P.H || !c->ao.p) {
+        LV_CUDA(c, c->ao.ensure(npx));
+        // untouched (not owned) texels must be finite for the bilinear lookup: initialise to "unoccluded"
+        std::vector<float> ones(npx, 1.0f);
+        LV_CUDA(c, cudaMemcpyAsync(c->ao.p, ones.data(), npx * 4, cudaMemcpyHostToDevice, c->stream));
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->ao_w = P.W; c->ao_h = P.H;
+    }
+    LV_CUDA(c, c->ao_hits.ensure(size_t(P.n_tiles) * c->tile_size * c->tile_size + 1));
+    LV_CUDA(c, c->small.ensure(4));
+    LV_CUDA(c, cudaMemsetAsync(c->small.p, 0, 4 * sizeof(unsigned int), c->stream));
+    P.frame_number = frame_number;
+    const SceneDev S = sc->dev();
+    const uint32_t grid = pixel_grid(c, P);
+    if (grid == 0) return LV_OK;
+    k_rtao_primary<<<grid, kBlockThreads, 0, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p);
+    if (P.ao_spp > 0) {
+        const uint32_t warps = kBlockThreads / 32;
+        const size_t smem = size_t(warps) * std::max<uint32_t>(32u, P.ao_spp) * sizeof(float);
+        if (smem > 48 * 1024) LV_CUDA(c, cudaFuncSetAttribute(k_rtao_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int per_sm = 0;
+        LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtao_rays, kBlockThreads, smem));
+        const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
+        k_rtao_rays<<<pgrid, kBlockThreads, smem, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->small.p + 1, c->counters.p);
+    }
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+int ppll_prepare(lv_ctx* c, const lv_scene* sc, const FrameParams& P, uint64_t linked_list_size) {
+    const size_t npad = size_t(P.padded_w) * P.padded_h;
+    if (linked_list_size == 0) {
+        // expectedAvgDepthComplexity x paddedW x paddedH (reference PerPixelLinkedListLineRenderer.cpp:251-258), 20 / 120 at > 1 M
+        // segments (.hpp:45-49, .cpp:109-126); a shard only stores its own share.
+        uint64_t avg = c->opt.expected_avg_depth_complexity ? c->opt.expected_avg_depth_complexity
+                                                            : ((sc && sc->n_seg > 1000000ull) ? 120ull : 20ull);
+        linked_list_size = (avg * npad + c->world - 1) / c->world;
+    }
+    if (linked_list_size > 0xFFFFFFFEull) linked_list_size = 0xFFFFFFFEull;  // `next` is a u32 and 0xFFFFFFFF terminates
+    LV_CUDA(c, c->heads.ensure(npad));
+    LV_CUDA(c, c->counts.ensure(npad));
+    LV_CUDA(c, c->nodes.ensure(linked_list_size));
+    LV_CUDA(c, c->frag_counter.ensure(1));
+    c->list_size = linked_list_size; c->padded_w = P.padded_w; c->padded_h = P.padded_h;
+    return LV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lv_abi_version(void) { return LV_ABI_VERSION; }
+const char* lv_last_global_error(void) { return g_global_error.c_str(); }
+const char* lv_last_error(const lv_ctx* ctx) { return ctx ? ctx->error.c_str() : g_global_error.c_str(); }
+
+int lv_ctx_create(lv_ctx** out, int device, void* cuda_stream) {
+    if (!out) return fail(nullptr, LV_ERR_INVALID_ARGUMENT, "out == NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(nullptr, LV_ERR_NO_DEVICE, "no CUDA device visible; linevis_b200 has no CPU fallback"); }
+    if (device < 0 || device >= n) return fail(nullptr, LV_ERR_INVALID_ARGUMENT, "device index out of range");
+    LV_CUDA(nullptr, cudaSetDevice(device));
+    lv_ctx* c = new lv_ctx();
+    c->device = device;
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    cudaDeviceProp prop;
+    LV_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    for (auto& e : c->ev) LV_CUDA(nullptr, cudaEventCreate(&e));
+    *out = c;
+    return LV_OK;
+}
+
+int lv_ctx_destroy(lv_ctx* c) {
+    if (!c) return LV_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->hits.release(); c->ao_hits.release();
+    c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->nodes.release(); c->frag_counter.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+    return LV_OK;
+}
+
+int lv_synchronize(lv_ctx* c) {
+    if (!c) return LV_ERR_INVALID_ARGUMENT;
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
+int lv_set_option(lv_ctx* c, const char* key, const char* value) {
+    if (!c || !key || !value) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_set_option: NULL argument");
+    Options& o = c->opt;
+    const std::string k(key);
+    auto f = [&]() { return float(atof(value)); };
+    auto u = [&]() { return uint32_t(strtoul(value, nullptr, 10)); };
+    if (k == "line_width") o.line_width = f();
+    else if (k == "band_width") o.band_width = f();
+    else if (k == "depth_cue_strength") {
+        if (f() > 0.0f) return fail(c, LV_ERR_INVALID_ARGUMENT, "depth cues are not implemented on this path (SURVEY 8a note); use depth_cue_strength = 0");
+        o.depth_cue_strength = 0.0f;
+    } else if (k == "ambient_occlusion_mode") {
+        if (strcmp(value, "RTAO")) return fail(c, LV_ERR_INVALID_ARGUMENT, "only ambient_occlusion_mode = RTAO is implemented");
+        o.ao_mode = value;
+    } else if (k == "ambient_occlusion_strength") o.ao_strength = f();
+    else if (k == "ambient_occlusion_gamma") o.ao_gamma = f();
+    else if (k == "ambient_occlusion_iterations") o.ao_iterations = u();
+    else if (k == "ambient_occlusion_samples_per_frame") { if (u() == 0 || u() > 4096) return fail(c, LV_ERR_INVALID_ARGUMENT, "ambient_occlusion_samples_per_frame must be in [1, 4096]"); o.ao_spp = u(); }
+    else if (k == "ambient_occlusion_radius") o.ao_radius = f();
+    else if (k == "ambient_occlusion_distance_based") o.ao_use_distance = parse_bool(value);
+    else if (k == "use_jittered_primary_rays") o.ao_jitter_primary = parse_bool(value);
+    else if (k == "ambient_occlusion_denoiser") {
+        if (strcmp(value, "None")) return fail(c, LV_ERR_INVALID_ARGUMENT, "denoisers are out of scope; use ambient_occlusion_denoiser = None");
+    } else if (k == "geometry_mode") {
+        if (strcmp(value, "AABBs (analytic)")) return fail(c, LV_ERR_INVALID_ARGUMENT, "only geometry_mode = 'AABBs (analytic)' is implemented");
+    } else if (k == "use_analytic_intersections") {
+        if (!parse_bool(value)) return fail(c, LV_ERR_INVALID_ARGUMENT, "only analytic tube intersections are implemented");
+    } else if (k == "num_samples_per_frame") { if (u() == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "num_samples_per_frame must be >= 1"); o.num_samples_per_frame = u(); }
+    else if (k == "num_accumulated_frames") o.num_accumulated_frames = u();
+    else if (k == "use_deterministic_sampling") o.use_deterministic_sampling = parse_bool(value);
+    else if (k == "use_mlat") { if (parse_bool(value)) return fail(c, LV_ERR_INVALID_ARGUMENT, "MLAT is out of scope"); }
+    else if (k == "mlat_num_nodes") {}
+    else if (k == "use_capped_tubes") o.use_capped_tubes = parse_bool(value);
+    else if (k == "use_halos") o.use_halos = parse_bool(value);
+    else if (k == "tube_num_subdivisions") { if (u() < 3) return fail(c, LV_ERR_INVALID_ARGUMENT, "tube_num_subdivisions must be >= 3"); o.tube_num_subdivisions = u(); }
+    else if (k == "b200_max_depth_complexity") o.max_depth_complexity = u();
+    else if (k == "b200_tiling_width" || k == "b200_tiling_height") {
+        uint32_t v = u();
+        if (v == 0 || (v & (v - 1))) return fail(c, LV_ERR_INVALID_ARGUMENT, "tiling sizes must be powers of two");
+        (k == "b200_tiling_width" ? o.tiling_w : o.tiling_h) = v;
+    } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 32]"); o.bvh_leaf_size = u(); }
+    else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
+    else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
+    return LV_OK;
+}
+
+int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
+    if (!c || !key || !buf || cap == 0) return LV_ERR_INVALID_ARGUMENT;
+    const Options& o = c->opt;
+    const std::string k(key);
+    std::string v;
+    auto b = [](bool x) { return std::string(x ? "true" : "false"); };
+    if (k == "line_width") v = std::to_string(o.line_width);
+    else if (k == "band_width") v = std::to_string(o.band_width);
+    else if (k == "depth_cue_strength") v = std::to_string(o.depth_cue_strength);
+    else if (k == "ambient_occlusion_mode") v = o.ao_mode;
+    else if (k == "ambient_occlusion_strength") v = std::to_string(o.ao_strength);
+    else if (k == "ambient_occlusion_gamma") v = std::to_string(o.ao_gamma);
+    else if (k == "ambient_occlusion_iterations") v = std::to_string(o.ao_iterations);
+    else if (k == "ambient_occlusion_samples_per_frame") v = std::to_string(o.ao_spp);
+    else if (k == "ambient_occlusion_radius") v = std::to_string(o.ao_radius);
+    else if (k == "ambient_occlusion_distance_based") v = b(o.ao_use_distance);
+    else if (k == "use_jittered_primary_rays") v = b(o.ao_jitter_primary);
+    else if (k == "ambient_occlusion_denoiser") v = o.denoiser;
+    else if (k == "geometry_mode") v = o.geometry_mode;
+    else if (k == "use_analytic_intersections") v = "true";
+    else if (k == "num_samples_per_frame") v = std::to_string(o.num_samples_per_frame);
+    else if (k == "num_accumulated_frames") v = std::to_string(o.num_accumulated_frames);
+    else if (k == "use_deterministic_sampling") v = b(o.use_deterministic_sampling);
+    else if (k == "use_mlat") v = "false";
+    else if (k == "use_capped_tubes") v = b(o.use_capped_tubes);
+    else if (k == "use_halos") v = b(o.use_halos);
+    else if (k == "tube_num_subdivisions") v = std::to_string(o.tube_num_subdivisions);
+    else if (k == "b200_max_depth_complexity") v = std::to_string(o.max_depth_complexity);
+    else if (k == "b200_tiling_width") v = std::to_string(o.tiling_w);
+    else if (k == "b200_tiling_height") v = std::to_string(o.tiling_h);
+    else if (k == "b200_bvh_leaf_size") v = std::to_string(o.bvh_leaf_size);
+    else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
+    else return LV_ERR_UNKNOWN_OPTION;
+    snprintf(buf, cap, "%s", v.c_str());
+    return LV_OK;
+}
+
+int lv_set_transfer_function(lv_ctx* c, const float* rgba, uint32_t K, float attr_min, float attr_max) {
+    if (!c || !rgba || K == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_set_transfer_function: need K >= 1 entries");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, c->tf.ensure(K));
+    LV_CUDA(c, cudaMemcpyAsync(c->tf.p, rgba, size_t(K) * 16, cudaMemcpyDefault, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->tfK = K; c->amin = attr_min; c->amax = attr_max;
+    return LV_OK;
+}
+
+int lv_set_tile_shard(lv_ctx* c, uint32_t rank, uint32_t world, uint32_t tile_size) {
+    if (!c || world == 0 || rank >= world) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_set_tile_shard: need rank < world");
+    if (tile_size == 0 || tile_size % 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "tile_size must be a positive multiple of 16");
+    c->rank = rank; c->world = world; c->tile_size = tile_size;
+    c->tiles_w = c->tiles_h = 0;  // re-enumerate on next frame
+    c->ao_w = c->ao_h = 0;
+    return LV_OK;
+}
+
+int lv_get_owned_tiles(const lv_ctx* c, uint32_t width, uint32_t height, uint32_t* tiles_xy, uint32_t* n_owned) {
+    if (!c || !n_owned) return LV_ERR_INVALID_ARGUMENT;
+    std::vector<uint2> t;
+    enumerate_tiles(width, height, c->tile_size, c->rank, c->world, t);
+    *n_owned = uint32_t(t.size());
+    if (tiles_xy) for (size_t i = 0; i < t.size(); i++) { tiles_xy[2 * i] = t[i].x; tiles_xy[2 * i + 1] = t[i].y; }
+    return LV_OK;
+}
+
+int lv_pack_owned_tiles(lv_ctx* c, const float* image, uint32_t W, uint32_t H, float* packed) {
+    if (!c || !image || !packed) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_pack_owned_tiles: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_tiles(c, W, H);
+    if (rc) return rc;
+    if (c->tiles_host.empty()) return LV_OK;
+    const uint32_t tt = c->tile_size * c->tile_size;
+    dim3 grid((tt + 255) / 256, uint32_t(c->tiles_host.size()));
+    k_pack_tiles<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(image), W, H, c->tiles_dev.p, c->tile_size, reinterpret_cast<float4*>(packed));
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+int lv_unpack_tiles(lv_ctx* c, const float* packed, uint32_t src_rank, uint32_t world, uint32_t W, uint32_t H, float* image) {
+    if (!c || !image || !packed || world == 0 || src_rank >= world) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_unpack_tiles: bad argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    std::vector<uint2> t;
+    enumerate_tiles(W, H, c->tile_size, src_rank, world, t);
+    if (t.empty()) return LV_OK;
+    LV_CUDA(c, c->tiles_tmp.ensure(t.size()));
+    LV_CUDA(c, cudaMemcpyAsync(c->tiles_tmp.p, t.data(), t.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t tt = c->tile_size * c->tile_size;
+    dim3 grid((tt + 255) / 256, uint32_t(t.size()));
+    k_unpack_tiles<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(packed), W, H, c->tiles_tmp.p, c->tile_size, reinterpret_cast<float4*>(image));
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));  // `t` (host staging) must outlive the copy
+    return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- scene
+int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const float* d_attr, const uint32_t* d_idx,
+                           uint64_t n_pt, uint64_t n_seg, float line_width) {
+    if (!c || !out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: NULL argument");
+    *out = nullptr;
+    if (n_seg > 0 && (!d_pos || !d_attr || !d_idx || n_pt == 0)) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: NULL array");
+    if (n_seg >= 0x7fffffffull) return fail(c, LV_ERR_INVALID_ARGUMENT, "too many segments (max 2^31-2)");
+    if (line_width <= 0.0f) line_width = c->opt.line_width;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    lv_scene* s = new lv_scene();
+    s->ctx = c; s->n_seg = n_seg; s->line_width = line_width;
+    const int n = int(n_seg);
+    if (n == 0) { *out = s; return LV_OK; }
+    const float r = line_width * 0.5f;
+    cudaStream_t st = c->stream;
+    BuildTmp T{};
+    DevBuf<float> bounds, boxes; DevBuf<unsigned long long> keys, keys2; DevBuf<uint32_t> vals;
+    DevBuf<int2> children, ranges; DevBuf<int> parent; DevBuf<unsigned int> flags; DevBuf<char> cubtmp;
+    auto cleanup = [&]() { bounds.release(); boxes.release(); keys.release(); keys2.release(); vals.release(); children.release(); ranges.release(); parent.release(); flags.release(); cubtmp.release(); };
+#define LV_BUILD(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); delete s; return fail(c, e__ == cudaErrorMemoryAllocation ? LV_ERR_OUT_OF_MEMORY : LV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    LV_BUILD(cudaEventRecord(c->ev[0], st));
+    LV_BUILD(bounds.ensure(6)); LV_BUILD(keys.ensure(n)); LV_BUILD(keys2.ensure(n)); LV_BUILD(vals.ensure(n));
+    LV_BUILD(s->prim_ids.ensure(n)); LV_BUILD(s->segs.ensure(n));
+    k_init_bounds<<<1, 32, 0, st>>>(bounds.p);
+    k_scene_bounds<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p);
+    k_morton<<<(n + 255) / 256, 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p, keys.p, vals.p);
+    size_t cub_bytes = 0;
+    LV_BUILD(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys.p, keys2.p, vals.p, s->prim_ids.p, n, 0, 63, st));
+    LV_BUILD(cubtmp.ensure(cub_bytes + 16));
+    LV_BUILD(cub::DeviceRadixSort::SortPairs(cubtmp.p, cub_bytes, keys.p, keys2.p, vals.p, s->prim_ids.p, n, 0, 63, st));
+    k_pack_segments<<<(n + 255) / 256, 256, 0, st>>>(d_pos, d_attr, d_idx, s->prim_ids.p, uint32_t(n), s->segs.p);
+    const int n_inner = std::max(1, n - 1);
+    LV_BUILD(children.ensure(n_inner)); LV_BUILD(ranges.ensure(n_inner)); LV_BUILD(parent.ensure(2 * size_t(n)));
+    LV_BUILD(boxes.ensure(6 * (2 * size_t(n)))); LV_BUILD(flags.ensure(n_inner));
+    LV_BUILD(cudaMemsetAsync(flags.p, 0, size_t(n_inner) * 4, st));
+    if (n > 1) k_radix_tree<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys2.p, n, children.p, ranges.p, parent.p);
+    k_fit<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, n, r, children.p, parent.p, boxes.p, flags.p);
+    LV_BUILD(s->nodes.ensure(n_inner));
+    k_emit_nodes<<<(n_inner + 255) / 256, 256, 0, st>>>(n, int(c->opt.bvh_leaf_size), children.p, ranges.p, boxes.p, s->nodes.p);
+    LV_BUILD(cudaGetLastError());
+    LV_BUILD(cudaEventRecord(c->ev[1], st));
+    LV_BUILD(cudaMemcpyAsync(s->bounds, bounds.p, 24, cudaMemcpyDeviceToHost, st));
+    LV_BUILD(cudaStreamSynchronize(st));
+    s->build_ms = elapsed(c->ev[0], c->ev[1]);
+    s->n_nodes = uint64_t(n_inner);
+    cleanup();
+#undef LV_BUILD
+    *out = s;
+    return LV_OK;
+}
+
+int lv_scene_create(lv_ctx* c, lv_scene** out, const float* pos, const float* attr, const uint32_t* idx, uint64_t n_pt, uint64_t n_seg, float line_width) {
+    if (!c || !out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: NULL argument");
+    *out = nullptr;
+    if (n_seg > 0 && (!pos || !attr || !idx || n_pt == 0)) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: NULL array");
+    for (uint64_t i = 0; i < 2 * n_seg; i++) if (idx[i] >= n_pt) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: segment index out of range");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    DevBuf<float> dpos, dattr; DevBuf<uint32_t> didx;
+    int rc = LV_OK;
+    auto up = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = dpos.ensure(std::max<uint64_t>(1, 3 * n_pt))) != cudaSuccess) return e;
+        if ((e = dattr.ensure(std::max<uint64_t>(1, n_pt))) != cudaSuccess) return e;
+        if ((e = didx.ensure(std::max<uint64_t>(1, 2 * n_seg))) != cudaSuccess) return e;
+        if (n_seg == 0) return cudaSuccess;
+        if ((e = cudaMemcpyAsync(dpos.p, pos, 12 * n_pt, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(dattr.p, attr, 4 * n_pt, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+        return cudaMemcpyAsync(didx.p, idx, 8 * n_seg, cudaMemcpyHostToDevice, c->stream);
+    };
+    cudaError_t e = up();
+    if (e != cudaSuccess) rc = fail(c, e == cudaErrorMemoryAllocation ? LV_ERR_OUT_OF_MEMORY : LV_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    else rc = lv_scene_create_device(c, out, dpos.p, dattr.p, didx.p, n_pt, n_seg, line_width);
+    cudaStreamSynchronize(c->stream);
+    dpos.release(); dattr.release(); didx.release();
+    return rc;
+}
+
+int lv_scene_destroy(lv_scene* s) {
+    if (!s) return LV_OK;
+    if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
+    s->segs.release(); s->prim_ids.release(); s->nodes.release();
+    delete s;
+    return LV_OK;
+}
+
+int lv_scene_info(const lv_scene* s, uint64_t* n_seg, uint64_t* n_nodes, float* build_ms, float* aabb) {
+    if (!s) return LV_ERR_INVALID_ARGUMENT;
+    if (n_seg) *n_seg = s->n_seg;
+    if (n_nodes) *n_nodes = s->n_nodes;
+    if (build_ms) *build_ms = s->build_ms;
+    if (aabb) memcpy(aabb, s->bounds, 24);
+    return LV_OK;
+}
+
+int lv_scene_copy_bvh(const lv_scene* s, void* nodes_out, size_t cap_bytes) {
+    if (!s || !nodes_out) return LV_ERR_INVALID_ARGUMENT;
+    size_t bytes = std::min(cap_bytes, size_t(s->n_nodes) * sizeof(Node64));
+    if (bytes == 0) return LV_OK;
+    LV_CUDA(s->ctx, cudaSetDevice(s->ctx->device));
+    LV_CUDA(s->ctx, cudaMemcpy(nodes_out, s->nodes.p, bytes, cudaMemcpyDeviceToHost));
+    return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- frames
+int lv_trace_primary(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_hit* hits_out, lv_stats* stats) {
+    if (!c || !sc || !hits_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_trace_primary: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, 0, P);
+    if (rc) return rc;
+    if ((rc = reset_counters(c))) return rc;
+    const size_t npx = size_t(P.W) * P.H;
+    lv_hit* dst = hits_out;
+    const bool dev = is_device_pointer(hits_out);
+    if (!dev) { LV_CUDA(c, c->hits.ensure(npx)); dst = c->hits.p; }
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (P.n_tiles) k_primary<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), dst, c->counters.p);
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (!dev && (rc = deliver(c, dst, hits_out, P.W, P.H, sizeof(lv_hit)))) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->ms_trace = elapsed(c->ev[0], c->ev[1]);
+        stats->ms_total = stats->ms_trace;
+    }
+    return LV_OK;
+}
+
+int lv_render_rtao(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, float* ao_out, lv_stats* stats) {
+    if (!c || !sc) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_render_rtao: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, frame_number, P);
+    if (rc) return rc;
+    if ((rc = reset_counters(c))) return rc;
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = run_rtao(c, sc, P, frame_number))) return rc;
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (ao_out && (rc = deliver(c, c->ao.p, ao_out, P.W, P.H, sizeof(float)))) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
+        stats->ms_total = stats->ms_rtao;
+    }
+    return LV_OK;
+}
+
+int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, float* rgba_out, lv_stats* stats) {
+    if (!c || !sc || !rgba_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_render_tubes: NULL argument");
+    if (!c->tf.p) return fail(c, LV_ERR_STATE, "lv_render_tubes: no transfer function set (lv_set_transfer_function)");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, frame_number, P);
+    if (rc) return rc;
+    if ((rc = reset_counters(c))) return rc;
+    const size_t npx = size_t(P.W) * P.H;
+    const bool dev = is_device_pointer(rgba_out);
+    float4* img = reinterpret_cast<float4*>(rgba_out);
+    if (!dev) { LV_CUDA(c, c->image.ensure(npx)); img = c->image.p; }
+    else if (reinterpret_cast<uintptr_t>(rgba_out) & 15) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 16-byte aligned");
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    const bool use_ao = c->opt.ao_strength > 0.0f;
+    if (use_ao) {
+        // LineRenderer::renderBase -> ambientOcclusionBaker->updateIterative (reference LineRenderer.cpp:259-265): one RTAO
+        // iteration per rendered frame until maxNumAccumulatedFrames (VulkanRayTracedAmbientOcclusion.cpp:89-107).
+        if (frame_number < c->opt.ao_iterations || !c->ao.p || c->ao_w != P.W || c->ao_h != P.H)
+            if ((rc = run_rtao(c, sc, P, frame_number))) return rc;
+        P.use_ao = 1; P.ao_tex = c->ao.p;
+    }
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (P.n_tiles) k_tubes<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if (!dev && (rc = deliver(c, img, rgba_out, P.W, P.H, 16))) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
+        stats->ms_trace = elapsed(c->ev[1], c->ev[2]);
+        stats->ms_total = elapsed(c->ev[0], c->ev[2]);
+    }
+    return LV_OK;
+}
+
+int lv_ppll_clear(lv_ctx* c, const lv_camera* cam, uint64_t linked_list_size) {
+    if (!c) return LV_ERR_INVALID_ARGUMENT;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, nullptr, cam, 0, P);
+    if (rc) return rc;
+    if ((rc = ppll_prepare(c, nullptr, P, linked_list_size))) return rc;
+    const size_t npad = size_t(P.padded_w) * P.padded_h;
+    // LinkedListClear.glsl:50 (startOffset = -1) + fragmentCounterBuffer->fill(0) (PerPixelLinkedListLineRenderer.cpp:431)
+    LV_CUDA(c, cudaMemsetAsync(c->heads.p, 0xFF, npad * 4, c->stream));
+    LV_CUDA(c, cudaMemsetAsync(c->counts.p, 0, npad * 4, c->stream));
+    LV_CUDA(c, cudaMemsetAsync(c->frag_counter.p, 0, 8, c->stream));
+    return LV_OK;
+}
+
+int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats* stats) {
+    if (!c || !sc) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_ppll_gather: NULL argument");
+    if (!c->tf.p) return fail(c, LV_ERR_STATE, "lv_ppll_gather: no transfer function set");
+    if (!c->heads.p || (!c->nodes.p && c->list_size)) return fail(c, LV_ERR_STATE, "lv_ppll_gather: call lv_ppll_clear first");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, 0, P);
+    if (rc) return rc;
+    if (P.padded_w != c->padded_w || P.padded_h != c->padded_h) return fail(c, LV_ERR_STATE, "lv_ppll_gather: resolution changed since lv_ppll_clear");
+    if ((rc = reset_counters(c))) return rc;
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (P.n_tiles)
+        k_ppll_gather<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->frags_stored = std::min<uint64_t>(h.frags_generated, c->list_size);
+        stats->frags_dropped = h.frags_generated - stats->frags_stored;
+        stats->ms_gather = elapsed(c->ev[0], c->ev[1]);
+        stats->ms_total = stats->ms_gather;
+    }
+    return LV_OK;
+}
+
+int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_t sort_mode, float* rgba_out, lv_stats* stats) {
+    if (!c || !rgba_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_ppll_resolve: NULL argument");
+    if (!c->heads.p) return fail(c, LV_ERR_STATE, "lv_ppll_resolve: no gathered fragments");
+    if (max_frags == 0 || max_frags > uint32_t(kResolveCap)) return fail(c, LV_ERR_INVALID_ARGUMENT, "max_frags must be in [1, " + std::to_string(kResolveCap) + "]");
+    if (sort_mode > LV_SORT_QUICKSORT_HYBRID) return fail(c, LV_ERR_INVALID_ARGUMENT, "unknown sort_mode");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, nullptr, cam, 0, P);
+    if (rc) return rc;
+    if (P.padded_w != c->padded_w || P.padded_h != c->padded_h) return fail(c, LV_ERR_STATE, "lv_ppll_resolve: resolution changed since lv_ppll_clear");
+    if ((rc = reset_counters(c))) return rc;
+    const size_t npx = size_t(P.W) * P.H;
+    const bool dev = is_device_pointer(rgba_out);
+    float4* img = reinterpret_cast<float4*>(rgba_out);
+    if (!dev) { LV_CUDA(c, c->image.ensure(npx)); img = c->image.p; }
+    else if (reinterpret_cast<uintptr_t>(rgba_out) & 15) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 16-byte aligned");
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    // All eight modes produce the depth-sorted order; only the priority queue stops blending at alpha >= 0.99
+    // (reference LinkedListSort.glsl:217).  See DESIGN.md for the reference's bitonicSort defect.
+    const int early_out = (sort_mode == LV_SORT_PRIORITY_QUEUE) ? 1 : 0;
+    if (P.n_tiles)
+        k_ppll_resolve<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p);
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (!dev && (rc = deliver(c, img, rgba_out, P.W, P.H, 16))) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->ms_resolve = elapsed(c->ev[0], c->ev[1]);
+        stats->ms_total = stats->ms_resolve;
+    }
+    return LV_OK;
+}
+
+int lv_render_ppll(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t max_frags, uint32_t sort_mode,
+                   uint64_t linked_list_size, float* rgba_out, lv_stats* stats) {
+    if (!c || !sc || !rgba_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_render_ppll: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    lv_stats g{}, r{};
+    LV_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, 0, P);
+    if (rc) return rc;
+    if ((rc = ppll_prepare(c, sc, P, linked_list_size))) return rc;
+    if ((rc = lv_ppll_clear(c, cam, c->list_size))) return rc;
+    LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    if ((rc = lv_ppll_gather(c, sc, cam, stats ? &g : nullptr))) return rc;
+    if ((rc = lv_ppll_resolve(c, cam, max_frags, sort_mode, rgba_out, stats ? &r : nullptr))) return rc;
+    if (stats) {
+        *stats = g;
+        stats->frags_sorted = r.frags_sorted; stats->frags_truncated = r.frags_truncated; stats->max_depth_complexity = r.max_depth_complexity;
+        stats->ms_resolve = r.ms_resolve;
+        stats->ms_clear = elapsed(c->ev[3], c->ev[4]);
+        stats->ms_total = stats->ms_clear + stats->ms_gather + stats->ms_resolve;
+    }
+    return LV_OK;
+}
+
+int lv_ppll_read(lv_ctx* c, uint32_t* frag_counter, uint32_t* start_offset, size_t start_offset_cap, lv_ppll_node* nodes,
+                 size_t nodes_cap, uint32_t* padded_w, uint32_t* padded_h) {
+    if (!c || !c->heads.p) return fail(c, LV_ERR_STATE, "lv_ppll_read: nothing gathered");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long cnt = 0;
+    LV_CUDA(c, cudaMemcpy(&cnt, c->frag_counter.p, 8, cudaMemcpyDeviceToHost));
+    if (frag_counter) *frag_counter = uint32_t(std::min<unsigned long long>(cnt, 0xFFFFFFFFull));
+    if (padded_w) *padded_w = c->padded_w;
+    if (padded_h) *padded_h = c->padded_h;
+    if (start_offset) {
+        size_t n = std::min(start_offset_cap, size_t(c->padded_w) * c->padded_h);
+        LV_CUDA(c, cudaMemcpy(start_offset, c->heads.p, n * 4, cudaMemcpyDeviceToHost));
+    }
+    if (nodes) {
+        size_t n = std::min<size_t>(nodes_cap, size_t(std::min<unsigned long long>(cnt, c->list_size)));
+        if (n) LV_CUDA(c, cudaMemcpy(nodes, c->nodes.p, n * sizeof(lv_ppll_node), cudaMemcpyDeviceToHost));
+    }
+    return LV_OK;
+}
+
+}  // extern "C"

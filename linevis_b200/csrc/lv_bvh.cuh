@@ -1,0 +1,220 @@
+// lv_bvh.cuh -- GPU BVH build over line segments (replaces the driver-built VkAccelerationStructureKHR,
+// reference src/LineData/LineData.cpp:879-907,1057-1075; AABBs as in src/LineData/LineDataFlow.cpp:2230-2233).
+//
+// LBVH: 63-bit Morton codes of the segment-box centres -> radix sort -> Karras' parallel binary radix tree
+// -> bottom-up box fit -> 64-byte child-pair nodes.  Every inner node of a radix tree covers a contiguous
+// range of the sorted records, so a subtree with <= leaf_max records is referenced directly as a leaf
+// (first record, count) and never materialised.
+#pragma once
+#include <cub/cub.cuh>
+#include "lv_types.cuh"
+#include "lv_math.cuh"
+
+namespace lv {
+
+struct BuildTmp {
+    float* bounds;             // 6 floats: scene min xyz, max xyz
+    unsigned long long *keys, *keys_sorted;
+    uint32_t *vals, *vals_sorted;
+    int2* children;            // per inner node: child index, bit31 set = leaf (record index)
+    int2* ranges;              // per inner node: [first, last]
+    int* parent;               // [2N-1]: inner nodes 0..N-2, leaves N-1..2N-2
+    float* boxes;              // [2N-1][6]
+    unsigned int* flags;       // per inner node arrival counter
+    void* cub_tmp; size_t cub_bytes;
+};
+
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(a), __float_as_uint(v));
+}
+
+__global__ void k_init_bounds(float* b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = __int_as_float(0x7f800000);
+    else if (threadIdx.x < 6) b[threadIdx.x] = __int_as_float(0xff800000);
+}
+
+__device__ __forceinline__ void seg_box(const float* pos, const uint32_t* idx, uint32_t i, float r, float* mn, float* mx) {
+    uint32_t a = idx[2 * i], b = idx[2 * i + 1];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float p = pos[3 * size_t(a) + k], q = pos[3 * size_t(b) + k];
+        mn[k] = fminf(p, q) - r; mx[k] = fmaxf(p, q) + r;
+    }
+}
+
+__global__ void k_scene_bounds(const float* pos, const uint32_t* idx, uint32_t n, float r, float* bounds) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float a[3], b[3];
+        seg_box(pos, idx, i, r, a, b);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], a[k]); mx[k] = fmaxf(mx[k], b[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { atomic_min_f(bounds + k, mn[k]); atomic_max_f(bounds + 3 + k, mx[k]); }
+    }
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void k_morton(const float* pos, const uint32_t* idx, uint32_t n, float r, const float* bounds,
+                         unsigned long long* keys, uint32_t* vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float mn[3], mx[3];
+    seg_box(pos, idx, i, r, mn, mx);
+    unsigned long long code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float lo = bounds[k], ext = bounds[3 + k] - lo;
+        float c = 0.5f * (mn[k] + mx[k]);
+        float u = ext > 0.0f ? (c - lo) / ext : 0.0f;
+        u = fminf(fmaxf(u, 0.0f), 1.0f);
+        unsigned long long q = (unsigned long long)(fminf(u * 2097152.0f, 2097151.0f));
+        code |= expand21(q) << (2 - k);
+    }
+    keys[i] = code;
+    vals[i] = i;
+}
+
+__global__ void k_pack_segments(const float* pos, const float* attr, const uint32_t* idx, const uint32_t* order, uint32_t n, SegRec* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = order[i];
+    uint32_t a = idx[2 * size_t(s)], b = idx[2 * size_t(s) + 1];
+    SegRec rec;
+    rec.a = make_float4(pos[3 * size_t(a)], pos[3 * size_t(a) + 1], pos[3 * size_t(a) + 2], attr[a]);
+    rec.b = make_float4(pos[3 * size_t(b)], pos[3 * size_t(b) + 1], pos[3 * size_t(b) + 2], attr[b]);
+    out[i] = rec;
+}
+
+__device__ __forceinline__ int delta_k(const unsigned long long* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll(a ^ b);
+}
+
+// Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees" (HPG 2012), one thread per inner node.
+__global__ void k_radix_tree(const unsigned long long* keys, int n, int2* children, int2* ranges, int* parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta_k(keys, n, i, i + 1) - delta_k(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_k(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta_k(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta_k(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_k(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta_k(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    int lc = gamma, rc = gamma + 1;
+    int lcode = (first == gamma) ? (lc | 0x80000000) : lc;
+    int rcode = (last == gamma + 1) ? (rc | 0x80000000) : rc;
+    children[i] = make_int2(lcode, rcode);
+    ranges[i] = make_int2(first, last);
+    // parent array: inner nodes at [0, n-1), leaves at [n-1, 2n-1)
+    parent[(first == gamma) ? (n - 1 + lc) : lc] = i;
+    parent[(last == gamma + 1) ? (n - 1 + rc) : rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// bottom-up fit: one thread per leaf record; the second thread to arrive at an inner node continues upward.
+__global__ void k_fit(const SegRec* segs, int n, float r, const int2* children, const int* parent, float* boxes, unsigned int* flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SegRec s = segs[i];
+    float b[6] = {fminf(s.a.x, s.b.x) - r, fminf(s.a.y, s.b.y) - r, fminf(s.a.z, s.b.z) - r,
+                  fmaxf(s.a.x, s.b.x) + r, fmaxf(s.a.y, s.b.y) + r, fmaxf(s.a.z, s.b.z) + r};
+    float* mine = boxes + 6 * size_t(n - 1 + i);
+#pragma unroll
+    for (int k = 0; k < 6; k++) mine[k] = b[k];
+    if (n == 1) return;
+    int node = parent[n - 1 + i];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(flags + node, 1u) == 0u) return;  // first arrival: the sibling will finish this node
+        __threadfence();
+        int2 ch = children[node];
+        const volatile float* lb = boxes + 6 * size_t((ch.x < 0) ? (n - 1 + (ch.x & 0x7fffffff)) : ch.x);
+        const volatile float* rb = boxes + 6 * size_t((ch.y < 0) ? (n - 1 + (ch.y & 0x7fffffff)) : ch.y);
+        float* o = boxes + 6 * size_t(node);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { o[k] = fminf(lb[k], rb[k]); o[3 + k] = fmaxf(lb[3 + k], rb[3 + k]); }
+        node = parent[node];
+    }
+}
+
+__device__ __forceinline__ void emit_child(int code, int n, int leaf_max, const int2* ranges, const float* boxes, float4& mnref, float4& mxcnt) {
+    uint32_t ref, cnt; const float* b;
+    if (code < 0) { ref = uint32_t(code & 0x7fffffff); cnt = 1; b = boxes + 6 * size_t(n - 1 + ref); }
+    else {
+        int2 rg = ranges[code];
+        int size = rg.y - rg.x + 1;
+        b = boxes + 6 * size_t(code);
+        if (size <= leaf_max) { ref = uint32_t(rg.x); cnt = uint32_t(size); }
+        else { ref = uint32_t(code); cnt = 0; }
+    }
+    mnref = make_float4(b[0], b[1], b[2], __uint_as_float(ref));
+    mxcnt = make_float4(b[3], b[4], b[5], __uint_as_float(cnt));
+}
+
+__global__ void k_emit_nodes(int n, int leaf_max, const int2* children, const int2* ranges, const float* boxes, Node64* nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 1) {
+        if (i == 0) {
+            const float* b = boxes;
+            Node64 nd;
+            nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0u));
+            nd.l1 = make_float4(b[3], b[4], b[5], __uint_as_float(1u));
+            nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
+            nd.r1 = make_float4(-INFINITY, -INFINITY, -INFINITY, __uint_as_float(0u));
+            nodes[0] = nd;
+        }
+        return;
+    }
+    if (i >= n - 1) return;
+    Node64 nd;
+    if (i == 0 && n <= leaf_max) {  // whole scene fits one leaf
+        const float* b = boxes;
+        nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0u));
+        nd.l1 = make_float4(b[3], b[4], b[5], __uint_as_float(uint32_t(n)));
+        nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
+        nd.r1 = make_float4(-INFINITY, -INFINITY, -INFINITY, __uint_as_float(0u));
+        nodes[0] = nd;
+        return;
+    }
+    int2 ch = children[i];
+    emit_child(ch.x, n, leaf_max, ranges, boxes, nd.l0, nd.l1);
+    emit_child(ch.y, n, leaf_max, ranges, boxes, nd.r0, nd.r1);
+    nodes[i] = nd;
+}
+
+}  // namespace lv

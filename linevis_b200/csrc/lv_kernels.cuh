@@ -1,0 +1,432 @@
+// lv_kernels.cuh -- frame kernels: primary closest hit, tube ray-gen (S1-S4), RTAO (S5), PPLL clear/gather/resolve (S8-S10).
+//
+// Thread mapping shared by all per-pixel kernels: the owned image tiles (tile_size x tile_size, Morton-ordered
+// list in FrameParams) are cut into 16x8-pixel blocks of 128 threads; a warp covers an 8x4 pixel patch so that
+// its primary rays are coherent and its framebuffer / list-head accesses fall into full 32-byte sectors.
+#pragma once
+#include "lv_trace.cuh"
+
+namespace lv {
+
+constexpr int kBlockThreads = 128;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+__device__ __forceinline__ bool thread_pixel(const FrameParams& P, uint32_t& x, uint32_t& y) {
+    const uint32_t bx = P.tile_size >> 4, by = P.tile_size >> 3;
+    const uint32_t bpt = bx * by;
+    const uint32_t tile = blockIdx.x / bpt, sub = blockIdx.x - tile * bpt;
+    const uint2 t = P.tiles[tile];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    x = t.x * P.tile_size + (sub % bx) * 16 + (warp & 1) * 8 + (lane & 7);
+    y = t.y * P.tile_size + (sub / bx) * 8 + (warp >> 1) * 4 + (lane >> 3);
+    return x < P.W && y < P.H;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void flush_counter(unsigned long long* dst, unsigned long long v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+}
+
+// RayGen camera ray (reference TubeRayTracing.glsl:202,219-226)
+__device__ __forceinline__ void camera_ray(const FrameParams& P, uint32_t px, uint32_t py, float xix, float xiy, Vec3& ro, Vec3& rd) {
+    Vec4 o = mat_mul(P.inv_view, v4(0.0f, 0.0f, 0.0f, 1.0f));
+    ro = v3(o.x, o.y, o.z);
+    float nx = 2.0f * ((float(px) + xix) / float(P.W)) - 1.0f;
+    float ny = 2.0f * ((float(py) + xiy) / float(P.H)) - 1.0f;
+    Vec4 tg = mat_mul(P.inv_proj, v4(nx, ny, 1.0f, 1.0f));
+    Vec3 nt = normalize3(v3(tg.x, tg.y, tg.z));
+    Vec4 d = mat_mul(P.inv_view, v4(nt.x, nt.y, nt.z, 0.0f));
+    rd = v3(d.x, d.y, d.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest-hit only (parity / debugging entry point lv_trace_primary)
+__global__ void __launch_bounds__(kBlockThreads)
+k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, lv_hit* hits, Counters* C) {
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    uint32_t steps = 0, isect = 0, nhit = 0;
+    if (valid) {
+        Vec3 ro, rd;
+        camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
+        HitRec h;
+        lv_hit out; out.t = 0.0f; out.prim = kNone; out.kind = 0; out.pad = 0;
+        if (bvh_trace<0>(S, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, steps, isect)) {
+            out.t = h.t; out.prim = h.prim; out.kind = h.kind; nhit = 1;
+        }
+        hits[size_t(y) * P.W + x] = out;
+    }
+    flush_counter(&C->rays_primary, valid ? 1 : 0);
+    flush_counter(&C->steps, steps);
+    flush_counter(&C->isect, isect);
+    flush_counter(&C->pixels_hit, nhit);
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1 ray-gen with the traceRayTransparent loop, S3/S4 shading and the running mean over frames
+// (reference TubeRayTracing.glsl:61-82,198-274).  `image` is the accumulation image (float RGBA).
+__global__ void __launch_bounds__(kBlockThreads)
+k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C) {
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    uint32_t steps = 0, isect = 0, rays = 0, nhit = 0;
+    if (valid) {
+        float fr = 0.0f, fg = 0.0f, fb = 0.0f, fa = 0.0f;
+        const uint32_t nspp = P.use_jitter ? P.spp : 1u;
+        for (uint32_t si = 0; si < nspp; si++) {
+            float xix = 0.5f, xiy = 0.5f;
+            if (P.use_jitter) {
+                uint32_t seed = P.det_sampling ? tea(19u, P.frame_number * P.spp + si)
+                                               : tea(x + y * P.W, P.frame_number * P.spp + si);
+                xix = rnd(seed); xiy = rnd(seed);
+            }
+            Vec3 ro, rd;
+            camera_ray(P, x, y, xix, xiy, ro, rd);
+            float cr = 0.0f, cg = 0.0f, cb = 0.0f, ca = 0.0f;
+            float tmin = 0.0001f;
+            for (uint32_t hi = 0; hi < P.max_depth; hi++) {
+                HitRec h;
+                rays++;
+                Vec4 hc; float hit_t; bool has;
+                if (bvh_trace<0>(S, ro, rd, tmin, 1000.0f, P.use_capped != 0, h, steps, isect)) {
+                    SegRec s = load_seg(S.segs + h.idx);
+                    Shaded sh = shade_hit(P, ro, rd, h.t, h.kind, s);
+                    hc = sh.color; hit_t = sh.hit_t; has = true;
+                    if (hi == 0 && si == 0) nhit = 1;
+                } else {  // Miss (TubeRayTracing.glsl:290-298)
+                    hc = v4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]); hit_t = 0.0f; has = false;
+                }
+                tmin = hit_t + maxf_(hit_t * 1e-5f, 1e-7f);
+                cr = cr + (1.0f - ca) * hc.w * hc.x;
+                cg = cg + (1.0f - ca) * hc.w * hc.y;
+                cb = cb + (1.0f - ca) * hc.w * hc.z;
+                ca = ca + (1.0f - ca) * hc.w;
+                if (!has || ca > 0.99f) break;
+            }
+            fr += cr; fg += cg; fb += cb; fa += ca;
+        }
+        if (P.use_jitter) { float dn = float(P.spp); fr /= dn; fg /= dn; fb /= dn; fa /= dn; }
+        float4* px = image + size_t(y) * P.W + x;
+        if (P.frame_number != 0) {
+            float4 prev = *px;
+            float a = 1.0f / float(P.frame_number + 1);
+            fr = mixf_(prev.x, fr, a); fg = mixf_(prev.y, fg, a); fb = mixf_(prev.z, fb, a); fa = mixf_(prev.w, fa, a);
+        }
+        *px = make_float4(fr, fg, fb, fa);
+    }
+    flush_counter(&C->rays_primary, rays);
+    flush_counter(&C->steps, steps);
+    flush_counter(&C->isect, isect);
+    flush_counter(&C->pixels_hit, nhit);
+}
+
+// ------------------------------------------------------------------------------------------------
+// S5, pass 1: (optionally jittered) primary ray per pixel.  Misses write aoFactor = 1 through the running
+// mean straight away; hits are appended to a compact work list for pass 2.
+struct AoHit { float t; uint32_t idx; uint32_t kind; uint32_t pixel; };  // pixel = y*W + x
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* ao, AoHit* hit_list,
+               unsigned int* hit_count, Counters* C) {
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    uint32_t steps = 0, isect = 0;
+    bool hit = false;
+    AoHit rec;
+    if (valid) {
+        uint32_t seed = tea(x + y * P.W, P.frame_number);
+        float xix = 0.5f, xiy = 0.5f;
+        if (P.ao_jitter) { xix = rnd(seed); xiy = rnd(seed); }
+        Vec3 ro, rd;
+        camera_ray(P, x, y, xix, xiy, ro, rd);
+        HitRec h;
+        hit = bvh_trace<0>(S, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, steps, isect);
+        rec.t = h.t; rec.idx = h.idx; rec.kind = h.kind; rec.pixel = y * P.W + x;
+        if (!hit) {
+            float v = 1.0f;
+            float* p = ao + size_t(y) * P.W + x;
+            if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));
+            *p = v;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        const uint32_t lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(hit_count, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) hit_list[base + __popc(m & ((1u << lane) - 1u))] = rec;
+    }
+    flush_counter(&C->rays_primary, valid ? 1 : 0);
+    flush_counter(&C->steps, steps);
+    flush_counter(&C->isect, isect);
+    flush_counter(&C->ao_pixels_hit, hit ? 1 : 0);
+}
+
+// S5, pass 2: hemisphere AO rays.  A warp takes one work unit at a time from a global counter: one hit pixel
+// (spp >= 32, samples striped over the lanes) or floor(32/spp) hit pixels (spp < 32).  The per-sample occlusion
+// values go through shared memory so that they are summed in sample order, exactly like the shader's loop
+// (VulkanRayTracedAmbientOcclusion.glsl:283-306).
+__global__ void __launch_bounds__(kBlockThreads)
+k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* ao, const AoHit* hit_list,
+            const unsigned int* hit_count, unsigned int* work_counter, Counters* C) {
+    extern __shared__ float s_occ_all[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t spp = P.ao_spp;
+    const uint32_t slots = spp >= 32 ? 1u : 32u / spp;           // pixels per unit
+    const uint32_t per_warp = spp >= 32 ? spp : 32u;
+    float* s_occ = s_occ_all + warp * per_warp;
+    const uint32_t n_hit = *hit_count;
+    const uint32_t n_units = (n_hit + slots - 1) / slots;
+    uint32_t steps = 0, isect = 0, rays = 0;
+    const bool capped = P.use_capped != 0;
+    while (true) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(work_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const uint32_t slot = spp >= 32 ? 0u : lane / spp;
+        const uint32_t hidx = unit * slots + slot;
+        const bool lane_on = slot < slots && hidx < n_hit;
+        Vec3 pos, nrm, tng, btg; float offset = 0.0f; uint32_t pixel = 0;
+        if (lane_on) {
+            const AoHit hr = hit_list[hidx];
+            pixel = hr.pixel;
+            const uint32_t x = pixel % P.W, y = pixel / P.W;
+            uint32_t seed = tea(pixel, P.frame_number);
+            float xix = 0.5f, xiy = 0.5f;
+            if (P.ao_jitter) { xix = rnd(seed); xiy = rnd(seed); }
+            Vec3 ro, rd;
+            camera_ray(P, x, y, xix, xiy, ro, rd);
+            const SegRec s = load_seg(S.segs + hr.idx);
+            const Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
+            pos = ro + rd * hr.t;
+            const Vec3 seg = p1 - p0;
+            Vec3 centre;
+            if (hr.kind == 0) { float u = dot3(seg, pos - p0) / dot3(seg, seg); centre = p0 + u * seg; }
+            else if (hr.kind == 1) centre = p0; else centre = p1;
+            nrm = normalize3(pos - centre);
+            tng = normalize3(seg);
+            btg = cross3(nrm, tng);
+            offset = length3(centre - pos) / P.subdiv_corr;
+        }
+        const uint32_t chunks = spp >= 32 ? (spp + 31) / 32 : 1u;
+        for (uint32_t c = 0; c < chunks; c++) {
+            const uint32_t sample = spp >= 32 ? c * 32 + lane : lane - slot * spp;
+            if (lane_on && sample < spp) {
+                uint32_t seed = tea(pixel, P.frame_number * spp + sample);
+                const float a = rnd(seed), b = rnd(seed);
+                float cs, sn;
+                det_sincos2pi(b, cs, sn);
+                const float rr = sqrtf(1.0f - a * a);
+                const Vec3 hs = v3(cs * rr, sn * rr, a);                          // sampleHemisphere :151-156
+                const Vec3 dir = normalize3((tng * hs.x + btg * hs.y) + nrm * hs.z);
+                const Vec3 org = pos + dir * offset;
+                HitRec h;
+                float occ = 1.0f;
+                rays++;
+                if (P.ao_use_distance) { if (bvh_trace<0>(S, org, dir, 0.0f, P.ao_radius, capped, h, steps, isect)) occ = h.t / P.ao_radius; }
+                else { if (bvh_trace<1>(S, org, dir, 0.0f, P.ao_radius, capped, h, steps, isect)) occ = 0.0f; }
+                s_occ[spp >= 32 ? sample : lane] = occ;
+            }
+        }
+        __syncwarp();
+        if (lane_on && (spp >= 32 ? lane == 0 : lane == slot * spp)) {
+            const float* q = s_occ + (spp >= 32 ? 0 : slot * spp);
+            float sum = 0.0f;
+            for (uint32_t i = 0; i < spp; i++) sum += q[i];
+            float v = sum / float(spp);
+            float* p = ao + pixel;
+            if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));
+            *p = v;
+        }
+        __syncwarp();
+    }
+    flush_counter(&C->rays_ao, rays);
+    flush_counter(&C->steps, steps);
+    flush_counter(&C->isect, isect);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PPLL.  addrGen: reference Data/Shaders/Utils/TiledAddress.glsl:53-85.
+__device__ __forceinline__ uint32_t addr_gen(const FrameParams& P, uint32_t x, uint32_t y) {
+    if (P.addr_tw == 1 && P.addr_th == 1) return x + P.padded_w * y;
+    const uint32_t sw = P.padded_w / P.addr_tw;
+    const uint32_t tx = x / P.addr_tw, ty = y / P.addr_th;
+    const uint32_t base = (tx + sw * ty) * (P.addr_tw * P.addr_th);
+    return base | ((x & (P.addr_tw - 1)) + (y & (P.addr_th - 1)) * P.addr_tw);
+}
+__device__ __forceinline__ uint32_t pack_unorm4x8(Vec4 c) {
+    uint32_t r = uint32_t(floorf(clampf_(c.x, 0.0f, 1.0f) * 255.0f + 0.5f));
+    uint32_t g = uint32_t(floorf(clampf_(c.y, 0.0f, 1.0f) * 255.0f + 0.5f));
+    uint32_t b = uint32_t(floorf(clampf_(c.z, 0.0f, 1.0f) * 255.0f + 0.5f));
+    uint32_t a = uint32_t(floorf(clampf_(c.w, 0.0f, 1.0f) * 255.0f + 0.5f));
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
+// S9 gather.  The fragment source is the all-hits enumeration of the pixel-centre ray: every capsule whose
+// reported hit lies in [1e-4, 1000] is shaded (S3) and appended.  One thread owns one pixel, so the list head lives
+// in a register and is written once (same final startOffset/next structure as the reference's atomicExchange chain);
+// the global fragment counter is bumped once per converged warp group.
+__global__ void __launch_bounds__(kBlockThreads)
+k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
+              lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C) {
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    uint32_t steps = 0, isect = 0, gen = 0;
+    if (valid) {
+        Vec3 ro, rd;
+        camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
+        uint32_t head = kNone, stored = 0;
+        const uint32_t lane = threadIdx.x & 31;
+        bvh_trace_all(S, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, steps, isect,
+                      [&](uint32_t, float t, uint32_t kind, const SegRec& s) {
+                          Shaded sh = shade_hit(P, ro, rd, t, kind, s);
+                          if (sh.color.w < 0.001f) return;                         // LinkedListGather.glsl:38
+                          gen++;
+                          const unsigned m = __activemask();
+                          const int leader = __ffs(m) - 1;
+                          unsigned long long base = 0;
+                          if (int(lane) == leader) base = atomicAdd(frag_counter, (unsigned long long)__popc(m));
+                          base = __shfl_sync(m, base, leader);
+                          const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+                          if (idx < list_size) {
+                              lv_ppll_node nd; nd.color = pack_unorm4x8(sh.color); nd.depth = sh.hit_t; nd.next = head;
+                              nodes[idx] = nd;
+                              head = uint32_t(idx);
+                              stored++;
+                          }
+                      });
+        const uint32_t a = addr_gen(P, x, y);
+        heads[a] = head;
+        counts[a] = stored;
+    }
+    flush_counter(&C->rays_primary, valid ? 1 : 0);
+    flush_counter(&C->steps, steps);
+    flush_counter(&C->isect, isect);
+    flush_counter(&C->frags_generated, gen);
+}
+
+// S10 resolve.  Per warp: 32 pixels.  Lanes walk their own lists (32 independent pointer chases in flight) into a
+// shared-memory tile of kResolveCap 64-bit keys (depth bits << 32 | colour); lists are packed back to back, as many
+// pixels per round as fit.  Each packed list is then sorted by the whole warp with an all-ascending bitonic network
+// and blended front to back by its owning lane, in sorted order, with the reference's arithmetic
+// (LinkedListSort.glsl:45-58; early-out at alpha >= 0.99 for the priority-queue mode, :217-218).
+constexpr int kResolveCap = 1024;     // keys per warp (8 KiB)
+constexpr int kResolveWarps = 4;
+
+__device__ __forceinline__ void cmpxchg(unsigned long long* s, uint32_t i, uint32_t l) {
+    unsigned long long a = s[i], b = s[l];
+    if (a > b) { s[i] = b; s[l] = a; }
+}
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* s, uint32_t n, uint32_t lane) {
+    uint32_t m = 2;
+    while (m < n) m <<= 1;
+    const uint32_t half = m >> 1;
+    for (uint32_t k = 2; k <= m; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t idx = lane; idx < half; idx += 32) {   // flip: i <-> mirrored partner inside the k-block
+            const uint32_t blk = idx / hk, t = idx - blk * hk;
+            const uint32_t i = blk * k + t, l = blk * k + (k - 1 - t);
+            if (l < n) cmpxchg(s, i, l);
+        }
+        __syncwarp();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t idx = lane; idx < half; idx += 32) {
+                const uint32_t i = 2 * idx - (idx & (j - 1)), l = i + j;
+                if (l < n) cmpxchg(s, i, l);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
+               uint32_t max_frags, int early_out, float4* image, Counters* C) {
+    __shared__ unsigned long long s_keys[kResolveWarps * kResolveCap];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long* tile = s_keys + warp * kResolveCap;
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    uint32_t head = kNone, total = 0;
+    if (valid) { const uint32_t a = addr_gen(P, x, y); head = heads[a]; total = counts[a]; }
+    const uint32_t cnt = min(total, max_frags);
+    if (valid && cnt == 0) image[size_t(y) * P.W + x] = make_float4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]);  // discard -> clear colour
+    unsigned remaining = __ballot_sync(0xffffffffu, cnt > 0);
+    while (remaining) {
+        const uint32_t c = ((remaining >> lane) & 1u) ? cnt : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += v; }
+        const uint32_t excl = incl - c;
+        const bool sel = c > 0 && incl <= uint32_t(kResolveCap);
+        if (sel) {
+            uint32_t off = head;
+            for (uint32_t i = 0; i < c; i++) {
+                const lv_ppll_node nd = nodes[off];
+                tile[excl + i] = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
+                off = nd.next;
+            }
+        }
+        __syncwarp();
+        const unsigned selmask = __ballot_sync(0xffffffffu, sel);
+        for (unsigned m = selmask; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const uint32_t n = __shfl_sync(0xffffffffu, c, src), base = __shfl_sync(0xffffffffu, excl, src);
+            if (n > 1) warp_bitonic_sort(tile + base, n, lane);
+        }
+        __syncwarp();
+        if (sel) {
+            float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
+            for (uint32_t i = 0; i < c; i++) {
+                if (early_out && !(a < 0.99f)) break;
+                const uint32_t col = uint32_t(tile[excl + i] & 0xffffffffull);
+                const float sr = float(col & 0xffu) / 255.0f, sg = float((col >> 8) & 0xffu) / 255.0f;
+                const float sb = float((col >> 16) & 0xffu) / 255.0f, sa = float(col >> 24) / 255.0f;
+                r = r + (1.0f - a) * sa * sr;
+                g = g + (1.0f - a) * sa * sg;
+                b = b + (1.0f - a) * sa * sb;
+                a = a + (1.0f - a) * sa;
+            }
+            r = r / a; g = g / a; b = b / a;
+            // BACK_TO_FRONT_STRAIGHT_ALPHA over the clear colour (PerPixelLinkedListLineRenderer.cpp:70)
+            image[size_t(y) * P.W + x] = make_float4(r * a + P.bg[0] * (1.0f - a), g * a + P.bg[1] * (1.0f - a),
+                                                      b * a + P.bg[2] * (1.0f - a), a + P.bg[3] * (1.0f - a));
+        }
+        remaining &= ~selmask;
+        __syncwarp();
+    }
+    flush_counter(&C->frags_sorted, cnt);
+    flush_counter(&C->frags_truncated, total - cnt);
+    unsigned mx = total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx) atomicMax(&C->max_depth_complexity, mx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile pack / unpack around the multi-GPU framebuffer gather
+__global__ void k_pack_tiles(const float4* image, uint32_t W, uint32_t H, const uint2* tiles, uint32_t tile_size, float4* packed) {
+    const uint32_t tile = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tile_size * tile_size) return;
+    const uint32_t x = tiles[tile].x * tile_size + i % tile_size, y = tiles[tile].y * tile_size + i / tile_size;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x < W && y < H) v = image[size_t(y) * W + x];
+    packed[size_t(tile) * tile_size * tile_size + i] = v;
+}
+__global__ void k_unpack_tiles(const float4* packed, uint32_t W, uint32_t H, const uint2* tiles, uint32_t tile_size, float4* image) {
+    const uint32_t tile = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tile_size * tile_size) return;
+    const uint32_t x = tiles[tile].x * tile_size + i % tile_size, y = tiles[tile].y * tile_size + i / tile_size;
+    if (x < W && y < H) image[size_t(y) * W + x] = packed[size_t(tile) * tile_size * tile_size + i];
+}
+
+}  // namespace lv

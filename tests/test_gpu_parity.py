@@ -1,0 +1,246 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars: closest-hit records bit-exact (t bits, segment index, hit kind); AO image and shaded RGBA within
+1e-3 per channel (in practice bit-exact, see DESIGN.md "Float conventions"); PPLL fragment counter, per-pixel list
+lengths and the per-pixel multiset of (depth bits, colour) bit-exact."""
+import numpy as np
+import pytest
+
+import linevis_b200 as lv
+from linevis_b200 import scenes
+from oracle import lvo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3  # per-channel float tolerance of BASELINE.json's north_star
+
+
+def _scene_pair(ctx, oracle, data, width):
+    pos, attr, seg = data
+    return ctx.create_scene(pos, attr, seg, width), oracle.scene(pos, attr, seg, width)
+
+
+DATASETS = {
+    "helix": lambda: (scenes.helix_lines(60, 101), 0.004),
+    "random": lambda: (scenes.random_segments(20000, 0.02, seed=7), 0.003),
+    "single": lambda: ((np.array([[-0.2, 0.0, 0.0], [0.2, 0.05, 0.0]], np.float32), np.array([0.1, 0.9], np.float32),
+                        np.array([[0, 1]], np.uint32)), 0.05),
+}
+
+
+@pytest.mark.parametrize("name", list(DATASETS))
+def test_primary_hits_bit_exact(ctx, oracle, name):
+    data, width = DATASETS[name]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(200, 120)
+    hits, st = ctx.trace_primary(sc, cam)
+    ref, ost = osc.trace_primary(cam)
+    assert np.array_equal(hits["prim"], ref["prim"])
+    assert np.array_equal(hits["kind"], ref["kind"])
+    assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+    assert st["rays_primary"] == 200 * 120
+    assert st["pixels_hit"] == int((ref["prim"] != 0xFFFFFFFF).sum()) > 0
+
+
+def test_primary_empty_scene(ctx):
+    sc = ctx.create_scene(np.zeros((0, 3), np.float32), np.zeros(0, np.float32), np.zeros((0, 2), np.uint32), 0.01)
+    cam = lv.make_camera(64, 48)
+    hits, st = ctx.trace_primary(sc, cam)
+    assert (hits["prim"] == 0xFFFFFFFF).all() and st["pixels_hit"] == 0
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4, 8])
+def test_bvh_leaf_sizes_same_hits(ctx, oracle, leaf):
+    data, width = DATASETS["random"]()
+    ctx.set_option("b200_bvh_leaf_size", leaf)
+    try:
+        sc, osc = _scene_pair(ctx, oracle, data, width)
+    finally:
+        ctx.set_option("b200_bvh_leaf_size", 4)
+    cam = lv.make_camera(160, 96)
+    hits, _ = ctx.trace_primary(sc, cam)
+    ref, _ = osc.trace_primary(cam)
+    assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32)) and np.array_equal(hits["prim"], ref["prim"])
+
+
+def test_bvh_encloses_all_segments(ctx):
+    (pos, attr, seg), width = DATASETS["random"]()
+    sc = ctx.create_scene(pos, attr, seg, width)
+    nodes = sc.bvh_nodes()
+    info = sc.info()
+    assert info["n_nodes"] == len(nodes)
+    # walk from the root; every segment must be referenced exactly once and lie inside its leaf box
+    seen = 0
+    stack = [0]
+    r = width * 0.5
+    lo = np.minimum(pos[seg[:, 0]], pos[seg[:, 1]]) - r
+    hi = np.maximum(pos[seg[:, 0]], pos[seg[:, 1]]) + r
+    glo, ghi = lo.min(0), hi.max(0)
+    assert np.allclose(info["aabb"][:3], glo, atol=1e-6) and np.allclose(info["aabb"][3:], ghi, atol=1e-6)
+    while stack:
+        n = nodes[stack.pop()]
+        for side in ("l", "r"):
+            mn, mx, ref, cnt = n[side + "min"], n[side + "max"], int(n[side + "ref"]), int(n[side + "count"])
+            if not (mn <= mx).all():
+                continue
+            assert (mn >= glo - 1e-6).all() and (mx <= ghi + 1e-6).all()
+            if cnt:
+                seen += cnt
+            else:
+                stack.append(ref)
+    assert seen == seg.shape[0]
+
+
+@pytest.mark.parametrize("jitter,use_distance,spp", [(False, True, 8), (True, True, 4), (False, False, 16), (True, True, 64), (False, True, 5)])
+def test_rtao_parity(ctx, oracle, jitter, use_distance, spp):
+    data, width = DATASETS["helix"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(120, 80)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": use_distance,
+                          "use_jittered_primary_rays": jitter, "ambient_occlusion_radius": 0.1})
+    opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(use_distance), ao_jitter_primary=int(jitter))
+    ao, st = ctx.render_rtao(sc, cam, 0)
+    ref, ost = osc.render_rtao(cam, opts, 0)
+    assert np.abs(ao - ref).max() <= TOL
+    assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32)), "AO image expected bit-exact"
+    assert st["rays_ao"] == ost["rays_ao"] == ost["pixels_hit"] * spp
+    # second accumulated frame (running mean, VulkanRayTracedAmbientOcclusion.glsl:313-317)
+    ao2, _ = ctx.render_rtao(sc, cam, 1, out=ao.copy())
+    ref2, _ = osc.render_rtao(cam, opts, 1, ao=ref.copy())
+    assert np.array_equal(ao2.view(np.uint32), ref2.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,ao", [("helix", False), ("helix", True), ("random", True), ("single", False)])
+def test_tubes_parity(ctx, oracle, name, ao):
+    data, width = DATASETS[name]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(160, 100)
+    tf = scenes.standard_transfer_function(opacity=(0.4, 1.0))
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"ambient_occlusion_strength": 1.0 if ao else 0.0, "ambient_occlusion_samples_per_frame": 4,
+                          "use_jittered_primary_rays": True, "ambient_occlusion_distance_based": True,
+                          "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    opts = lvo.default_options(ao_strength=1.0 if ao else 0.0, ao_spp=4)
+    img, st = ctx.render_tubes(sc, cam, 0)
+    ao_ref = osc.render_rtao(cam, opts, 0)[0] if ao else None
+    ref, ost = osc.render_tubes(cam, opts, tf, ao_tex=ao_ref)
+    assert np.isfinite(img).all()
+    assert np.abs(img - ref).max() <= TOL
+    assert st["rays_primary"] == ost["rays"] + (cam.width * cam.height if ao else 0)
+
+
+def test_tubes_jittered_accumulation(ctx, oracle):
+    data, width = DATASETS["helix"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(96, 64)
+    tf = scenes.standard_transfer_function()
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 2, "num_accumulated_frames": 4})
+    opts = lvo.default_options(num_samples_per_frame=2, use_jittered_rays=1)
+    img = np.zeros((64, 96, 4), np.float32)
+    ref = np.zeros((64, 96, 4), np.float32)
+    for f in range(3):
+        img, _ = ctx.render_tubes(sc, cam, f, out=img)
+        ref, _ = osc.render_tubes(cam, opts, tf, frame_number=f, rgba=ref)
+    assert np.abs(img - ref).max() <= TOL
+    ctx.set_new_settings({"num_samples_per_frame": 1, "num_accumulated_frames": 1})
+
+
+def _lists(heads, nodes, cam, oracle, tw=2, th=8):
+    return lvo.per_pixel_lists(heads, nodes, cam, lvo.default_options(tile_w=tw, tile_h=th), oracle)
+
+
+@pytest.mark.parametrize("name", ["helix", "random"])
+def test_ppll_integer_path_bit_exact(ctx, oracle, name):
+    data, width = DATASETS[name]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(100, 70)   # not a multiple of the 2x8 addressing tile -> padded start-offset buffer
+    tf = scenes.standard_transfer_function(opacity=(0.1, 0.6))
+    ctx.set_transfer_function(tf)
+    ctx.set_option("ambient_occlusion_strength", 0.0)
+    ctx.ppll_clear(cam, 0)
+    st = ctx.ppll_gather(sc, cam)
+    got = ctx.ppll_read()
+    ref = osc.ppll_gather(cam, lvo.default_options(), tf)
+    assert got["counter"] == ref["counter"] == st["frags_generated"] and st["frags_dropped"] == 0
+    assert got["padded"] == ref["padded"]
+    assert np.array_equal(got["heads"] == 0xFFFFFFFF, ref["heads"] == 0xFFFFFFFF)
+    a = _lists(got["heads"], got["nodes"], cam, oracle)
+    b = _lists(ref["heads"], ref["nodes"], cam, oracle)
+    assert a == b, "per-pixel multisets of (depth bits, colour) differ"
+
+
+@pytest.mark.parametrize("mode", ["priority_queue", "bitonic", "insertion", "quicksort_hybrid"])
+def test_ppll_resolve_parity(ctx, oracle, mode):
+    data, width = DATASETS["random"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(128, 96)
+    tf = scenes.standard_transfer_function(opacity=(0.1, 0.6))
+    ctx.set_transfer_function(tf)
+    ctx.set_option("ambient_occlusion_strength", 0.0)
+    img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode=mode)
+    ref = osc.ppll_gather(cam, lvo.default_options(), tf)
+    m = lv.SORT_MODES[mode]
+    ref_img, rst = lvo.ppll_resolve(oracle, cam, lvo.default_options(), ref["heads"], ref["nodes"], 256, m, canonical=True)
+    assert st["frags_sorted"] == rst["frags_sorted"] and st["max_depth_complexity"] == rst["max_depth_complexity"]
+    assert np.abs(img - ref_img).max() <= TOL
+    assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32)), "resolve expected bit-exact vs canonical oracle order"
+
+
+def test_ppll_overflow_is_counted_not_fatal(ctx, oracle):
+    data, width = DATASETS["helix"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(96, 64)
+    tf = scenes.standard_transfer_function(opacity=(0.2, 0.5))
+    ctx.set_transfer_function(tf)
+    ref = osc.ppll_gather(cam, lvo.default_options(), tf)
+    budget = ref["counter"] // 3
+    img, st = ctx.render_ppll(sc, cam, max_frags=64, sort_mode="priority_queue", linked_list_size=budget)
+    assert st["frags_generated"] == ref["counter"] and st["frags_stored"] == budget and st["frags_dropped"] == ref["counter"] - budget
+    assert st["frags_sorted"] + st["frags_truncated"] == budget and np.isfinite(img).all()
+
+
+def test_ppll_truncation_at_max_frags(ctx, oracle):
+    data, width = DATASETS["random"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(64, 48)
+    tf = scenes.standard_transfer_function(opacity=(0.1, 0.3))
+    ctx.set_transfer_function(tf)
+    img, st = ctx.render_ppll(sc, cam, max_frags=4, sort_mode="bitonic")
+    assert st["frags_truncated"] > 0 and st["frags_sorted"] + st["frags_truncated"] == st["frags_stored"]
+    assert np.isfinite(img).all()
+
+
+def test_tile_sharding_reassembles_full_frame(ctx, oracle):
+    """world_size 4 emulated on one GPU: every rank renders its Morton-interleaved tiles; union == unsharded frame."""
+    data, width = DATASETS["helix"]()
+    pos, attr, seg = data
+    cam = lv.make_camera(200, 136)
+    tf = scenes.standard_transfer_function(opacity=(0.4, 1.0))
+    settings = {"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 4, "num_samples_per_frame": 1,
+                "num_accumulated_frames": 1, "use_jittered_primary_rays": False}
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings(settings)
+    sc = ctx.create_scene(pos, attr, seg, width)
+    full, _ = ctx.render_tubes(sc, cam, 0)
+    fullp, _ = ctx.render_ppll(sc, cam, 64, "priority_queue")
+    acc = np.full_like(full, np.nan)
+    accp = np.full_like(full, np.nan)
+    total_rays = 0
+    for r in range(4):
+        c = lv.Context(0)
+        c.set_transfer_function(tf)
+        c.set_new_settings(settings)
+        c.set_tile_shard(r, 4, 32)
+        s = c.create_scene(pos, attr, seg, width)
+        out = np.full_like(full, np.nan)
+        out, st = c.render_tubes(s, cam, 0, out=out)
+        outp = np.full_like(full, np.nan)
+        outp, _ = c.render_ppll(s, cam, 64, "priority_queue", out=outp)
+        m = ~np.isnan(out[..., 0])
+        assert np.isnan(acc[m]).all(), "tiles of different ranks overlap"
+        acc[m] = out[m]
+        accp[m] = outp[m]
+        total_rays += st["rays_primary"]
+        s.close(); c.close()
+    assert not np.isnan(acc).any()
+    assert np.abs(acc - full).max() <= 1e-5 and np.array_equal(accp, fullp)
