@@ -66,8 +66,10 @@ typedef struct lv_camera {
 typedef struct lv_stats {
     uint64_t rays_primary;          /* BVH traversals started for camera rays */
     uint64_t rays_ao;               /* BVH traversals started for AO rays */
-    uint64_t traversal_steps;       /* T: child-pair node visits (64 B each) */
-    uint64_t intersections;         /* I: segment records tested (32 B each) */
+    uint64_t traversal_steps;       /* T: child-pair node visits (64 B each), all rays of the call */
+    uint64_t intersections;         /* I: segment records tested (32 B each), all rays of the call */
+    uint64_t ao_traversal_steps;    /* T of the AO rays alone (the RTAO ray kernel, the dominant one) */
+    uint64_t ao_intersections;      /* I of the AO rays alone */
     uint64_t pixels_hit;            /* pixels whose primary ray hit a tube */
     uint64_t frags_generated;       /* fragments offered to the PPLL gather (alpha >= 0.001) */
     uint64_t frags_stored;          /* min(generated, linkedListSize) */
@@ -77,7 +79,8 @@ typedef struct lv_stats {
     uint32_t max_depth_complexity;  /* longest per-pixel list */
     uint32_t reserved;
     float ms_trace;                 /* CUDA-event time of the tube primary+shade kernel */
-    float ms_rtao;                  /* ... of the RTAO kernels */
+    float ms_rtao;                  /* ... of the RTAO pass (primary + AO ray kernels) */
+    float ms_rtao_rays;             /* ... of the AO ray kernel alone */
     float ms_clear, ms_gather, ms_resolve; /* PPLL stages (PerPixelLinkedListLineRenderer.cpp:411-420) */
     float ms_total;
 } lv_stats;

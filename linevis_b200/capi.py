@@ -33,10 +33,11 @@ ABI_SYMBOLS = [
 class LvStats(ctypes.Structure):
     _fields_ = [
         ("rays_primary", ctypes.c_uint64), ("rays_ao", ctypes.c_uint64), ("traversal_steps", ctypes.c_uint64),
-        ("intersections", ctypes.c_uint64), ("pixels_hit", ctypes.c_uint64), ("frags_generated", ctypes.c_uint64),
+        ("intersections", ctypes.c_uint64), ("ao_traversal_steps", ctypes.c_uint64), ("ao_intersections", ctypes.c_uint64),
+        ("pixels_hit", ctypes.c_uint64), ("frags_generated", ctypes.c_uint64),
         ("frags_stored", ctypes.c_uint64), ("frags_dropped", ctypes.c_uint64), ("frags_sorted", ctypes.c_uint64),
         ("frags_truncated", ctypes.c_uint64), ("max_depth_complexity", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
-        ("ms_trace", ctypes.c_float), ("ms_rtao", ctypes.c_float), ("ms_clear", ctypes.c_float),
+        ("ms_trace", ctypes.c_float), ("ms_rtao", ctypes.c_float), ("ms_rtao_rays", ctypes.c_float), ("ms_clear", ctypes.c_float),
         ("ms_gather", ctypes.c_float), ("ms_resolve", ctypes.c_float), ("ms_total", ctypes.c_float),
     ]
 

@@ -74,7 +74,8 @@ struct lv_ctx {
     // PPLL
     DevBuf<uint32_t> heads, counts; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
     unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[8] = {};
+    bool rtao_rays_timed = false;
 };
 
 struct lv_scene {
@@ -195,7 +196,9 @@ int read_counters(lv_ctx* c, Counters& h) {
 }
 
 void fill_stats(lv_stats* s, const Counters& h) {
-    s->rays_primary += h.rays_primary; s->rays_ao += h.rays_ao; s->traversal_steps += h.steps; s->intersections += h.isect;
+    s->rays_primary += h.rays_primary; s->rays_ao += h.rays_ao;
+    s->traversal_steps += h.steps + h.ao_steps; s->intersections += h.isect + h.ao_isect;
+    s->ao_traversal_steps += h.ao_steps; s->ao_intersections += h.ao_isect;
     s->pixels_hit += h.pixels_hit ? h.pixels_hit : h.ao_pixels_hit;
     s->frags_generated += h.frags_generated; s->frags_sorted += h.frags_sorted; s->frags_truncated += h.frags_truncated;
     s->max_depth_complexity = std::max(s->max_depth_complexity, h.max_depth_complexity);
@@ -232,6 +235,7 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedT
 // ---- RTAO pass (S5) into ctx->ao --------------------------------------------------------------
 int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number) {
     const size_t npx = size_t(P.W) * P.H;
+    c->rtao_rays_timed = false;
     if (c->ao_w != P.W || c->ao_h != P.H || !c->ao.p) {
         LV_CUDA(c, c->ao.ensure(npx));
         // untouched (not owned) texels must be finite for the bilinear lookup: initialise to "unoccluded"
@@ -255,7 +259,10 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
         int per_sm = 0;
         LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtao_rays, kBlockThreads, smem));
         const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
+        LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
         k_rtao_rays<<<pgrid, kBlockThreads, smem, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->small.p + 1, c->counters.p);
+        LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        c->rtao_rays_timed = true;
     }
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
@@ -610,6 +617,7 @@ int lv_render_rtao(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t
         if ((rc = read_counters(c, h))) return rc;
         fill_stats(stats, h);
         stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
+        if (c->rtao_rays_timed) stats->ms_rtao_rays = elapsed(c->ev[4], c->ev[5]);
         stats->ms_total = stats->ms_rtao;
     }
     return LV_OK;
@@ -648,6 +656,7 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
         if ((rc = read_counters(c, h))) return rc;
         fill_stats(stats, h);
         stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
+        if (use_ao && c->rtao_rays_timed) stats->ms_rtao_rays = elapsed(c->ev[4], c->ev[5]);
         stats->ms_trace = elapsed(c->ev[1], c->ev[2]);
         stats->ms_total = elapsed(c->ev[0], c->ev[2]);
     }
@@ -738,20 +747,20 @@ int lv_render_ppll(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t
     if (!c || !sc || !rgba_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_render_ppll: NULL argument");
     LV_CUDA(c, cudaSetDevice(c->device));
     lv_stats g{}, r{};
-    LV_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    LV_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
     FrameParams P;
     int rc = make_params(c, sc, cam, 0, P);
     if (rc) return rc;
     if ((rc = ppll_prepare(c, sc, P, linked_list_size))) return rc;
     if ((rc = lv_ppll_clear(c, cam, c->list_size))) return rc;
-    LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    LV_CUDA(c, cudaEventRecord(c->ev[7], c->stream));
     if ((rc = lv_ppll_gather(c, sc, cam, stats ? &g : nullptr))) return rc;
     if ((rc = lv_ppll_resolve(c, cam, max_frags, sort_mode, rgba_out, stats ? &r : nullptr))) return rc;
     if (stats) {
         *stats = g;
         stats->frags_sorted = r.frags_sorted; stats->frags_truncated = r.frags_truncated; stats->max_depth_complexity = r.max_depth_complexity;
         stats->ms_resolve = r.ms_resolve;
-        stats->ms_clear = elapsed(c->ev[3], c->ev[4]);
+        stats->ms_clear = elapsed(c->ev[6], c->ev[7]);
         stats->ms_total = stats->ms_clear + stats->ms_gather + stats->ms_resolve;
     }
     return LV_OK;

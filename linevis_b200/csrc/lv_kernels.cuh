@@ -248,8 +248,8 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
         __syncwarp();
     }
     flush_counter(&C->rays_ao, rays);
-    flush_counter(&C->steps, steps);
-    flush_counter(&C->isect, isect);
+    flush_counter(&C->ao_steps, steps);
+    flush_counter(&C->ao_isect, isect);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -79,6 +79,9 @@ __device__ __forceinline__ bool bvh_trace(const SceneDev& S, Vec3 o, Vec3 d, flo
         bool hr = box_hit(rb, nd.r0, nd.r1, tmin, best.t, tr);
         uint32_t lref = __float_as_uint(nd.l0.w), lcnt = __float_as_uint(nd.l1.w);
         uint32_t rref = __float_as_uint(nd.r0.w), rcnt = __float_as_uint(nd.r1.w);
+        // an absent child is encoded as inner reference 0 (the root is nobody's child); its inverted box must not be trusted
+        hl = hl && (lcnt | lref);
+        hr = hr && (rcnt | rref);
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             bool h = side ? hr : hl;
@@ -134,6 +137,9 @@ __device__ __forceinline__ void bvh_trace_all(const SceneDev& S, Vec3 o, Vec3 d,
         bool hr = box_hit(rb, nd.r0, nd.r1, tmin, tmax, tr);
         uint32_t lref = __float_as_uint(nd.l0.w), lcnt = __float_as_uint(nd.l1.w);
         uint32_t rref = __float_as_uint(nd.r0.w), rcnt = __float_as_uint(nd.r1.w);
+        // an absent child is encoded as inner reference 0 (the root is nobody's child); its inverted box must not be trusted
+        hl = hl && (lcnt | lref);
+        hr = hr && (rcnt | rref);
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             bool h = side ? hr : hl;

@@ -67,7 +67,7 @@ struct FrameParams {
 
 // per-launch counters accumulated with one atomic per warp
 struct Counters {
-    unsigned long long rays_primary, rays_ao, steps, isect, pixels_hit, ao_pixels_hit;
+    unsigned long long rays_primary, rays_ao, steps, isect, ao_steps, ao_isect, pixels_hit, ao_pixels_hit;
     unsigned long long frags_generated, frags_sorted, frags_truncated;
     unsigned int max_depth_complexity, pad;
 };

@@ -86,7 +86,7 @@ def random_segments(n_seg=1_000_000, seg_len=0.01, seed=2002):
     return pos, attr, seg
 
 
-def curl_noise_streamlines(n_lines=20_000, n_points=501, step=5e-4, seed=3003, modes_per_octave=12):
+def curl_noise_streamlines(n_lines=20_000, n_points=501, step=5e-4, seed=3003, modes_per_octave=12, device=None):
     """Config 5: Rayleigh-Benard-like streamlines.  Velocity = curl(psi), psi = base roll potential
     (0, 0, sin(4 pi x) sin(pi y)) + a 3-octave random vector potential in a 2:1:2 box, integrated with RK4.
     The noise potential is spectral (random Fourier modes per octave, analytic curl) instead of lattice gradient
@@ -105,27 +105,54 @@ def curl_noise_streamlines(n_lines=20_000, n_points=501, step=5e-4, seed=3003, m
     phi = np.concatenate(phases)         # [M]
     kxa = np.cross(kvec, avec)           # curl of a sin(k.x+phi) = (k x a) cos(k.x+phi)
 
-    def vel(p):
-        x, y = p[:, 0], p[:, 1]
-        base = np.stack([math.pi * np.sin(4 * math.pi * x) * np.cos(math.pi * y),
-                         -4 * math.pi * np.cos(4 * math.pi * x) * np.sin(math.pi * y),
-                         np.zeros_like(x)], axis=1) * 0.25
-        c = np.cos(p @ kvec.T + phi[None, :])
-        return base + c @ kxa
+    if device is not None:
+        # same integration on the GPU (torch, float64) -- used by bench.py so that 10 M segments take seconds, not a minute
+        import torch
+        tk, tkxa, tphi = (torch.from_numpy(a).to(device) for a in (kvec, kxa, phi))
 
-    p = rng.random((n_lines, 3)) * np.array([2.0, 1.0, 2.0])
-    traj = np.empty((n_points, n_lines, 3), np.float64)
-    speed = np.empty((n_points, n_lines), np.float64)
-    traj[0] = p
-    for i in range(1, n_points):
-        k1 = vel(p)
-        k2 = vel(p + 0.5 * step * k1)
-        k3 = vel(p + 0.5 * step * k2)
-        k4 = vel(p + step * k3)
-        speed[i - 1] = np.linalg.norm(k1, axis=1)
-        p = p + (step / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
-        traj[i] = p
-    speed[-1] = np.linalg.norm(vel(p), axis=1)
+        def tvel(p):
+            x, y = p[:, 0], p[:, 1]
+            base = torch.stack([math.pi * torch.sin(4 * math.pi * x) * torch.cos(math.pi * y),
+                                -4 * math.pi * torch.cos(4 * math.pi * x) * torch.sin(math.pi * y),
+                                torch.zeros_like(x)], dim=1) * 0.25
+            return base + torch.cos(p @ tk.T + tphi[None, :]) @ tkxa
+
+        p = torch.from_numpy(rng.random((n_lines, 3)) * np.array([2.0, 1.0, 2.0])).to(device)
+        ttraj = torch.empty((n_points, n_lines, 3), dtype=torch.float64, device=device)
+        tspeed = torch.empty((n_points, n_lines), dtype=torch.float64, device=device)
+        ttraj[0] = p
+        for i in range(1, n_points):
+            k1 = tvel(p)
+            k2 = tvel(p + 0.5 * step * k1)
+            k3 = tvel(p + 0.5 * step * k2)
+            k4 = tvel(p + step * k3)
+            tspeed[i - 1] = torch.linalg.norm(k1, dim=1)
+            p = p + (step / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+            ttraj[i] = p
+        tspeed[-1] = torch.linalg.norm(tvel(p), dim=1)
+        traj, speed = ttraj.cpu().numpy(), tspeed.cpu().numpy()
+    else:
+        def vel(p):
+            x, y = p[:, 0], p[:, 1]
+            base = np.stack([math.pi * np.sin(4 * math.pi * x) * np.cos(math.pi * y),
+                             -4 * math.pi * np.cos(4 * math.pi * x) * np.sin(math.pi * y),
+                             np.zeros_like(x)], axis=1) * 0.25
+            c = np.cos(p @ kvec.T + phi[None, :])
+            return base + c @ kxa
+
+        p = rng.random((n_lines, 3)) * np.array([2.0, 1.0, 2.0])
+        traj = np.empty((n_points, n_lines, 3), np.float64)
+        speed = np.empty((n_points, n_lines), np.float64)
+        traj[0] = p
+        for i in range(1, n_points):
+            k1 = vel(p)
+            k2 = vel(p + 0.5 * step * k1)
+            k3 = vel(p + 0.5 * step * k2)
+            k4 = vel(p + step * k3)
+            speed[i - 1] = np.linalg.norm(k1, axis=1)
+            p = p + (step / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+            traj[i] = p
+        speed[-1] = np.linalg.norm(vel(p), axis=1)
     pos = traj.transpose(1, 0, 2).reshape(-1, 3)
     attr = speed.T.reshape(-1)
     attr = (attr - attr.min()) / max(attr.max() - attr.min(), 1e-30)
