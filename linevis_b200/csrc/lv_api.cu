@@ -68,9 +68,9 @@ struct lv_ctx {
     std::vector<uint2> tiles_host; DevBuf<uint2> tiles_dev; uint32_t tiles_w = 0, tiles_h = 0;
     DevBuf<uint2> tiles_tmp;
     // frame buffers
-    DevBuf<float4> image; DevBuf<float> ao; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
+    DevBuf<float4> image; DevBuf<float> ao, occ; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
     uint32_t ao_w = 0, ao_h = 0;
-    DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[1] = ao work counter
+    DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[2..3] = 64-bit ao work counter
     // PPLL
     DevBuf<uint32_t> heads, counts; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
     unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
@@ -83,6 +83,7 @@ struct lv_scene {
     DevBuf<SegRec> segs; DevBuf<uint32_t> prim_ids; DevBuf<Node64> nodes;
     uint64_t n_seg = 0, n_nodes = 0;
     float line_width = 0.0f, build_ms = 0.0f;
+    uint32_t depth = 0;
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     SceneDev dev() const {
         SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
@@ -252,17 +253,19 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     const uint32_t grid = pixel_grid(c, P);
     if (grid == 0) return LV_OK;
     k_rtao_primary<<<grid, kBlockThreads, 0, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p);
-    if (P.ao_spp > 0) {
-        const uint32_t warps = kBlockThreads / 32;
-        const size_t smem = size_t(warps) * std::max<uint32_t>(32u, P.ao_spp) * sizeof(float);
-        if (smem > 48 * 1024) LV_CUDA(c, cudaFuncSetAttribute(k_rtao_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    {
+        // one float per (hit pixel, sample); worst case every owned pixel is hit
+        const size_t max_hits = size_t(P.n_tiles) * c->tile_size * c->tile_size;
+        LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
         int per_sm = 0;
-        LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtao_rays, kBlockThreads, smem));
+        LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtao_rays, kBlockThreads, 0));
         const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
         LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-        k_rtao_rays<<<pgrid, kBlockThreads, smem, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->small.p + 1, c->counters.p);
+        k_rtao_rays<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, c->occ.p, c->ao_hits.p, c->small.p,
+                                                            reinterpret_cast<unsigned long long*>(c->small.p + 2), c->counters.p);
         LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
         c->rtao_rays_timed = true;
+        k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, c->ao.p);
     }
     LV_CUDA(c, cudaGetLastError());
     return LV_OK;
@@ -316,7 +319,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (!c) return LV_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->hits.release(); c->ao_hits.release();
+    c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->occ.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -369,7 +372,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         uint32_t v = u();
         if (v == 0 || (v & (v - 1))) return fail(c, LV_ERR_INVALID_ARGUMENT, "tiling sizes must be powers of two");
         (k == "b200_tiling_width" ? o.tiling_w : o.tiling_h) = v;
-    } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 32]"); o.bvh_leaf_size = u(); }
+    } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
     return LV_OK;
@@ -475,7 +478,7 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     if (!c || !out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: NULL argument");
     *out = nullptr;
     if (n_seg > 0 && (!d_pos || !d_attr || !d_idx || n_pt == 0)) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_create: NULL array");
-    if (n_seg >= 0x7fffffffull) return fail(c, LV_ERR_INVALID_ARGUMENT, "too many segments (max 2^31-2)");
+    if (n_seg >= (1ull << 27)) return fail(c, LV_ERR_INVALID_ARGUMENT, "too many segments (max 2^27-1: leaf references carry 27 index bits)");
     if (line_width <= 0.0f) line_width = c->opt.line_width;
     LV_CUDA(c, cudaSetDevice(c->device));
     lv_scene* s = new lv_scene();
@@ -508,10 +511,18 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     k_fit<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, n, r, children.p, parent.p, boxes.p, flags.p);
     LV_BUILD(s->nodes.ensure(n_inner));
     k_emit_nodes<<<(n_inner + 255) / 256, 256, 0, st>>>(n, int(c->opt.bvh_leaf_size), children.p, ranges.p, boxes.p, s->nodes.p);
+    LV_BUILD(cudaMemsetAsync(flags.p, 0, 4, st));   // reuse flags[0] as the depth accumulator
+    k_tree_depth<<<(n + 255) / 256, 256, 0, st>>>(n, parent.p, flags.p);
     LV_BUILD(cudaGetLastError());
     LV_BUILD(cudaEventRecord(c->ev[1], st));
     LV_BUILD(cudaMemcpyAsync(s->bounds, bounds.p, 24, cudaMemcpyDeviceToHost, st));
+    LV_BUILD(cudaMemcpyAsync(&s->depth, flags.p, 4, cudaMemcpyDeviceToHost, st));
     LV_BUILD(cudaStreamSynchronize(st));
+    if (s->depth + 1 > uint32_t(kStackSize) || s->depth + 1 > uint32_t(kAoStack)) {
+        const uint32_t depth = s->depth;
+        cleanup(); s->segs.release(); s->prim_ids.release(); s->nodes.release(); delete s;
+        return fail(c, LV_ERR_STATE, "BVH depth " + std::to_string(depth) + " exceeds the traversal stack (" + std::to_string(kAoStack) + ")");
+    }
     s->build_ms = elapsed(c->ev[0], c->ev[1]);
     s->n_nodes = uint64_t(n_inner);
     cleanup();

@@ -172,6 +172,19 @@ __global__ void k_fit(const SegRec* segs, int n, float r, const int2* children, 
     }
 }
 
+// upper bound of the traversal stack depth: longest leaf-to-root parent chain
+__global__ void k_tree_depth(int n, const int* parent, unsigned int* max_depth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int d = 0;
+    if (i < n && n > 1) {
+        int node = parent[n - 1 + i];
+        while (node >= 0) { d++; node = parent[node]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d) atomicMax(max_depth, d);
+}
+
 __device__ __forceinline__ void emit_child(int code, int n, int leaf_max, const int2* ranges, const float* boxes, float4& mnref, float4& mxcnt) {
     uint32_t ref, cnt; const float* b;
     if (code < 0) { ref = uint32_t(code & 0x7fffffff); cnt = 1; b = boxes + 6 * size_t(n - 1 + ref); }

@@ -126,9 +126,17 @@ k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev 
 }
 
 // ------------------------------------------------------------------------------------------------
-// S5, pass 1: (optionally jittered) primary ray per pixel.  Misses write aoFactor = 1 through the running
-// mean straight away; hits are appended to a compact work list for pass 2.
-struct AoHit { float t; uint32_t idx; uint32_t kind; uint32_t pixel; };  // pixel = y*W + x
+// S5 (reference Data/Shaders/AO/RTAO/VulkanRayTracedAmbientOcclusion.glsl:178-319) in three kernels:
+//   k_rtao_primary  one (optionally jittered) camera ray per pixel; a miss writes aoFactor = 1 through the running
+//                   mean, a hit appends the shading frame of the hit point to a compact list;
+//   k_rtao_rays     persistent ray-stream kernel over (hit pixel, sample) pairs, see below;
+//   k_rtao_reduce   sums the per-sample occlusion values of each hit pixel IN SAMPLE ORDER (exactly the shader's
+//                   loop, :283-306) and folds the mean into the accumulation image (:313-317).
+struct __align__(16) AoHit {
+    float4 pos_off;   // hit position (vertexPositionWorld), AO ray origin offset |linePos - pos| / cos(pi/N)
+    float4 nrm_px;    // surface normal, as_float(pixel index y*W + x)
+    float4 tng;       // surface tangent (segment direction), unused
+};
 
 __global__ void __launch_bounds__(kBlockThreads)
 k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* ao, AoHit* hit_list,
@@ -146,8 +154,22 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
         camera_ray(P, x, y, xix, xiy, ro, rd);
         HitRec h;
         hit = bvh_trace<0>(S, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, steps, isect);
-        rec.t = h.t; rec.idx = h.idx; rec.kind = h.kind; rec.pixel = y * P.W + x;
-        if (!hit) {
+        if (hit) {
+            // analytic stand-in for the barycentric vertex fetch of the triangle-mesh path (:222-276)
+            const SegRec s = load_seg(S.segs + h.idx);
+            const Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
+            const Vec3 pos = ro + rd * h.t;
+            const Vec3 seg = p1 - p0;
+            Vec3 centre;
+            if (h.kind == 0) { float u = dot3(seg, pos - p0) / dot3(seg, seg); centre = p0 + u * seg; }
+            else if (h.kind == 1) centre = p0; else centre = p1;
+            const Vec3 nrm = normalize3(pos - centre);
+            const Vec3 tng = normalize3(seg);
+            const float offset = length3(centre - pos) / P.subdiv_corr;
+            rec.pos_off = make_float4(pos.x, pos.y, pos.z, offset);
+            rec.nrm_px = make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(y * P.W + x));
+            rec.tng = make_float4(tng.x, tng.y, tng.z, 0.0f);
+        } else {
             float v = 1.0f;
             float* p = ao + size_t(y) * P.W + x;
             if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));
@@ -168,88 +190,155 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
     flush_counter(&C->ao_pixels_hit, hit ? 1 : 0);
 }
 
-// S5, pass 2: hemisphere AO rays.  A warp takes one work unit at a time from a global counter: one hit pixel
-// (spp >= 32, samples striped over the lanes) or floor(32/spp) hit pixels (spp < 32).  The per-sample occlusion
-// values go through shared memory so that they are summed in sample order, exactly like the shader's loop
-// (VulkanRayTracedAmbientOcclusion.glsl:283-306).
+// Persistent ray-stream kernel for the AO rays (the dominant kernel of path (a)).
+//
+// The first version of this kernel gave each warp one pixel's samples and ran an if-if traversal; ncu showed it
+// issue-bound at 3.7 of 32 lanes active (profiles/r1a_*): incoherent short rays finish at very different times and leaf
+// work diverges from box work.  This version keeps every lane busy instead:
+//   - rays are numbered r = hit_slot * spp + sample; a lane whose ray has finished takes the next number from a global
+//     counter (one atomic per warp refill, ranks by ballot/popc) as soon as kRefillBelow lanes of its warp are idle, so
+//     a warp always carries >= 75 % live rays; consecutive numbers share a pixel, i.e. rays start out coherent;
+//   - traversal is while-while with postponed leaves: all lanes first walk inner nodes until each has reached a leaf
+//     (or run out), then all lanes intersect their leaf together; leaves travel on the stack as encoded entries;
+//   - popped entries carry their box entry distance and are skipped when the closest hit found meanwhile is nearer.
+// The per-ray result (4 B) goes to occ[r]; sample-ordered summation happens in k_rtao_reduce.
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kDone = 0x7FFFFFFFu;
+constexpr int kRefillBelow = 24;
+constexpr int kAoStack = 72;
+
+__device__ __forceinline__ uint32_t enc_child(uint32_t ref, uint32_t cnt) {
+    return cnt ? (kLeafBit | ((cnt - 1u) << 27) | ref) : ref;
+}
+
 __global__ void __launch_bounds__(kBlockThreads)
-k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* ao, const AoHit* hit_list,
-            const unsigned int* hit_count, unsigned int* work_counter, Counters* C) {
-    extern __shared__ float s_occ_all[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
+            const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t spp = P.ao_spp;
-    const uint32_t slots = spp >= 32 ? 1u : 32u / spp;           // pixels per unit
-    const uint32_t per_warp = spp >= 32 ? spp : 32u;
-    float* s_occ = s_occ_all + warp * per_warp;
-    const uint32_t n_hit = *hit_count;
-    const uint32_t n_units = (n_hit + slots - 1) / slots;
-    uint32_t steps = 0, isect = 0, rays = 0;
+    const unsigned long long total = (unsigned long long)(*hit_count) * spp;
     const bool capped = P.use_capped != 0;
+    const bool any_mode = P.ao_use_distance == 0;
+    const float radius = S.radius;
+    uint32_t steps = 0, isect = 0, rays = 0;
+
+    uint32_t stk_node[kAoStack];
+    float stk_t[kAoStack];
+    int sp = 0;
+    uint32_t cur = kDone;
+    bool exhausted = false;          // no more rays to fetch
+    unsigned long long ray_id = 0;
+    RayQ rq; RayBox rb;
+    float best = 0.0f;
+    bool found = false;
+    rq.o = v3(0, 0, 0); rq.d = v3(0, 0, 1); rq.dd = 1.0f; rb = make_raybox(rq.o, rq.d);
+
     while (true) {
-        unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd(work_counter, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
-        const uint32_t slot = spp >= 32 ? 0u : lane / spp;
-        const uint32_t hidx = unit * slots + slot;
-        const bool lane_on = slot < slots && hidx < n_hit;
-        Vec3 pos, nrm, tng, btg; float offset = 0.0f; uint32_t pixel = 0;
-        if (lane_on) {
-            const AoHit hr = hit_list[hidx];
-            pixel = hr.pixel;
-            const uint32_t x = pixel % P.W, y = pixel / P.W;
-            uint32_t seed = tea(pixel, P.frame_number);
-            float xix = 0.5f, xiy = 0.5f;
-            if (P.ao_jitter) { xix = rnd(seed); xiy = rnd(seed); }
-            Vec3 ro, rd;
-            camera_ray(P, x, y, xix, xiy, ro, rd);
-            const SegRec s = load_seg(S.segs + hr.idx);
-            const Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
-            pos = ro + rd * hr.t;
-            const Vec3 seg = p1 - p0;
-            Vec3 centre;
-            if (hr.kind == 0) { float u = dot3(seg, pos - p0) / dot3(seg, seg); centre = p0 + u * seg; }
-            else if (hr.kind == 1) centre = p0; else centre = p1;
-            nrm = normalize3(pos - centre);
-            tng = normalize3(seg);
-            btg = cross3(nrm, tng);
-            offset = length3(centre - pos) / P.subdiv_corr;
-        }
-        const uint32_t chunks = spp >= 32 ? (spp + 31) / 32 : 1u;
-        for (uint32_t c = 0; c < chunks; c++) {
-            const uint32_t sample = spp >= 32 ? c * 32 + lane : lane - slot * spp;
-            if (lane_on && sample < spp) {
-                uint32_t seed = tea(pixel, P.frame_number * spp + sample);
-                const float a = rnd(seed), b = rnd(seed);
-                float cs, sn;
-                det_sincos2pi(b, cs, sn);
-                const float rr = sqrtf(1.0f - a * a);
-                const Vec3 hs = v3(cs * rr, sn * rr, a);                          // sampleHemisphere :151-156
-                const Vec3 dir = normalize3((tng * hs.x + btg * hs.y) + nrm * hs.z);
-                const Vec3 org = pos + dir * offset;
-                HitRec h;
-                float occ = 1.0f;
-                rays++;
-                if (P.ao_use_distance) { if (bvh_trace<0>(S, org, dir, 0.0f, P.ao_radius, capped, h, steps, isect)) occ = h.t / P.ao_radius; }
-                else { if (bvh_trace<1>(S, org, dir, 0.0f, P.ao_radius, capped, h, steps, isect)) occ = 0.0f; }
-                s_occ[spp >= 32 ? sample : lane] = occ;
+        // ---- refill idle lanes
+        const bool idle = (cur == kDone) && !exhausted;
+        const unsigned need = __ballot_sync(0xffffffffu, idle);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if (int(lane) == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (idle) {
+                ray_id = base + __popc(need & ((1u << lane) - 1u));
+                if (ray_id >= total) exhausted = true;
+                else {
+                    const uint32_t slot = uint32_t(ray_id / spp), sample = uint32_t(ray_id - (unsigned long long)slot * spp);
+                    const float4* hp = reinterpret_cast<const float4*>(hit_list + slot);
+                    const float4 a = __ldg(hp), b = __ldg(hp + 1), c = __ldg(hp + 2);
+                    const Vec3 pos = v3(a.x, a.y, a.z), nrm = v3(b.x, b.y, b.z), tng = v3(c.x, c.y, c.z);
+                    const Vec3 btg = cross3(nrm, tng);                               // :257
+                    const uint32_t pixel = __float_as_uint(b.w);
+                    uint32_t seed = tea(pixel, P.frame_number * spp + sample);       // :289-292
+                    const float xa = rnd(seed), xb = rnd(seed);
+                    float cs, sn;
+                    det_sincos2pi(xb, cs, sn);
+                    const float rr = sqrtf(1.0f - xa * xa);
+                    const Vec3 hs = v3(cs * rr, sn * rr, xa);                        // sampleHemisphere :151-156
+                    const Vec3 dir = normalize3((tng * hs.x + btg * hs.y) + nrm * hs.z);
+                    const Vec3 org = pos + dir * a.w;                                // :299
+                    rq = make_rayq(org, dir);
+                    rb = make_raybox(org, dir);
+                    best = P.ao_radius; found = false;
+                    sp = 0; cur = 0;                                                 // root
+                    rays++;
+                }
             }
         }
-        __syncwarp();
-        if (lane_on && (spp >= 32 ? lane == 0 : lane == slot * spp)) {
-            const float* q = s_occ + (spp >= 32 ? 0 : slot * spp);
-            float sum = 0.0f;
-            for (uint32_t i = 0; i < spp; i++) sum += q[i];
-            float v = sum / float(spp);
-            float* p = ao + pixel;
-            if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));
-            *p = v;
+        if (__ballot_sync(0xffffffffu, cur != kDone) == 0u) break;
+
+        // ---- trace until too many lanes of the warp are idle again
+        while (true) {
+            // A: inner nodes until this lane holds a leaf (or is done)
+            while (cur != kDone && !(cur & kLeafBit)) {
+                const Node64 nd = load_node(S.nodes + cur);
+                steps++;
+                float tl, tr;
+                bool hl = box_hit(rb, nd.l0, nd.l1, 0.0f, best, tl);
+                bool hr = box_hit(rb, nd.r0, nd.r1, 0.0f, best, tr);
+                const uint32_t lref = __float_as_uint(nd.l0.w), lcnt = __float_as_uint(nd.l1.w);
+                const uint32_t rref = __float_as_uint(nd.r0.w), rcnt = __float_as_uint(nd.r1.w);
+                hl = hl && (lcnt | lref);
+                hr = hr && (rcnt | rref);
+                const uint32_t cl = enc_child(lref, lcnt), cr = enc_child(rref, rcnt);
+                if (hl && hr) {
+                    const bool swap = tr < tl;
+                    if (sp < kAoStack) { stk_node[sp] = swap ? cl : cr; stk_t[sp] = swap ? tl : tr; sp++; }
+                    cur = swap ? cr : cl;
+                } else if (hl) cur = cl;
+                else if (hr) cur = cr;
+                else {
+                    cur = kDone;
+                    while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } }
+                }
+            }
+            // B: the postponed leaf
+            if (cur != kDone) {
+                const uint32_t ref = cur & 0x07FFFFFFu, cnt = ((cur >> 27) & 15u) + 1u;
+                isect += cnt;
+                bool stop = false;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const SegRec s = load_seg(S.segs + ref + i);
+                    float t; uint32_t kind;
+                    if (capsule_hit(rq, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) {
+                        if (!found || t < best) { best = t; found = true; }
+                        if (any_mode) { stop = true; break; }
+                    }
+                }
+                cur = kDone;
+                if (!stop) while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } }
+                else sp = 0;
+            }
+            if (cur == kDone && !exhausted && ray_id < total) {
+                // ray finished: traceAoRay result (:158-175)
+                occ[ray_id] = found ? (any_mode ? 0.0f : best / P.ao_radius) : 1.0f;
+                ray_id = total;   // written
+            }
+            if (__popc(__ballot_sync(0xffffffffu, cur != kDone)) < kRefillBelow) break;
         }
-        __syncwarp();
     }
     flush_counter(&C->rays_ao, rays);
     flush_counter(&C->ao_steps, steps);
     flush_counter(&C->ao_isect, isect);
+}
+
+__global__ void k_rtao_reduce(const __grid_constant__ FrameParams P, const float* occ, const AoHit* hit_list,
+                              const unsigned int* hit_count, float* ao) {
+    const uint32_t n_hit = *hit_count;
+    const uint32_t spp = P.ao_spp;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_hit; slot += gridDim.x * blockDim.x) {
+        const uint32_t pixel = __float_as_uint(hit_list[slot].nrm_px.w);
+        const float* q = occ + size_t(slot) * spp;
+        float sum = 0.0f;
+        for (uint32_t i = 0; i < spp; i++) sum += q[i];
+        float v = sum / float(spp);
+        float* p = ao + pixel;
+        if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));
+        *p = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,6 +408,7 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
 // (LinkedListSort.glsl:45-58; early-out at alpha >= 0.99 for the priority-queue mode, :217-218).
 constexpr int kResolveCap = 1024;     // keys per warp (8 KiB)
 constexpr int kResolveWarps = 4;
+constexpr int kResolveInsertionMax = 32;  // lists up to this length are sorted by their own lane
 
 __device__ __forceinline__ void cmpxchg(unsigned long long* s, uint32_t i, uint32_t l) {
     unsigned long long a = s[i], b = s[l];
@@ -367,19 +457,31 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
         const uint32_t excl = incl - c;
         const bool sel = c > 0 && incl <= uint32_t(kResolveCap);
         if (sel) {
-            uint32_t off = head;
-            for (uint32_t i = 0; i < c; i++) {
-                const lv_ppll_node nd = nodes[off];
-                tile[excl + i] = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
-                off = nd.next;
+            unsigned long long* mine = tile + excl;
+            lv_ppll_node nd = nodes[head];
+            if (c <= uint32_t(kResolveInsertionMax)) {
+                // short list: this lane insertion-sorts its own slice while the next node is in flight (32 lists in parallel)
+                for (uint32_t i = 0; i < c; i++) {
+                    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
+                    if (i + 1 < c) nd = nodes[nd.next];
+                    uint32_t j = i;
+                    while (j > 0 && mine[j - 1] > key) { mine[j] = mine[j - 1]; j--; }
+                    mine[j] = key;
+                }
+            } else {
+                for (uint32_t i = 0; i < c; i++) {
+                    mine[i] = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
+                    if (i + 1 < c) nd = nodes[nd.next];
+                }
             }
         }
         __syncwarp();
         const unsigned selmask = __ballot_sync(0xffffffffu, sel);
-        for (unsigned m = selmask; m; m &= m - 1) {
+        // long lists: cooperative bitonic sort, one list at a time
+        for (unsigned m = __ballot_sync(0xffffffffu, sel && c > uint32_t(kResolveInsertionMax)); m; m &= m - 1) {
             const int src = __ffs(m) - 1;
             const uint32_t n = __shfl_sync(0xffffffffu, c, src), base = __shfl_sync(0xffffffffu, excl, src);
-            if (n > 1) warp_bitonic_sort(tile + base, n, lane);
+            warp_bitonic_sort(tile + base, n, lane);
         }
         __syncwarp();
         if (sel) {

@@ -12,7 +12,7 @@
 
 namespace lv {
 
-constexpr int kStackSize = 128;
+constexpr int kStackSize = 72;
 
 struct RayBox {
     float ix, iy, iz;     // safe 1/d
