@@ -195,7 +195,8 @@ __device__ __forceinline__ void emit_child(int code, int n, int leaf_max, const 
         if (size <= leaf_max) { ref = uint32_t(rg.x); cnt = uint32_t(size); }
         else { ref = uint32_t(code); cnt = 0; }
     }
-    mnref = make_float4(b[0], b[1], b[2], __uint_as_float(ref));
+    // child word: leaf = bit31 | (count-1) << 27 | first record, inner = node index; the count is repeated in the max.w lane
+    mnref = make_float4(b[0], b[1], b[2], __uint_as_float(cnt ? (0x80000000u | ((cnt - 1u) << 27) | ref) : ref));
     mxcnt = make_float4(b[3], b[4], b[5], __uint_as_float(cnt));
 }
 
@@ -205,10 +206,10 @@ __global__ void k_emit_nodes(int n, int leaf_max, const int2* children, const in
         if (i == 0) {
             const float* b = boxes;
             Node64 nd;
-            nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0u));
+            nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0x80000000u));
             nd.l1 = make_float4(b[3], b[4], b[5], __uint_as_float(1u));
-            nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
-            nd.r1 = make_float4(-INFINITY, -INFINITY, -INFINITY, __uint_as_float(0u));
+            nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));   // absent: a point at +inf never passes the slab test
+            nd.r1 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
             nodes[0] = nd;
         }
         return;
@@ -217,10 +218,10 @@ __global__ void k_emit_nodes(int n, int leaf_max, const int2* children, const in
     Node64 nd;
     if (i == 0 && n <= leaf_max) {  // whole scene fits one leaf
         const float* b = boxes;
-        nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0u));
+        nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0x80000000u | ((uint32_t(n) - 1u) << 27)));
         nd.l1 = make_float4(b[3], b[4], b[5], __uint_as_float(uint32_t(n)));
         nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
-        nd.r1 = make_float4(-INFINITY, -INFINITY, -INFINITY, __uint_as_float(0u));
+        nd.r1 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
         nodes[0] = nd;
         return;
     }

@@ -202,14 +202,9 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
 //     (or run out), then all lanes intersect their leaf together; leaves travel on the stack as encoded entries;
 //   - popped entries carry their box entry distance and are skipped when the closest hit found meanwhile is nearer.
 // The per-ray result (4 B) goes to occ[r]; sample-ordered summation happens in k_rtao_reduce.
-constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kDone = 0x7FFFFFFFu;
 constexpr int kRefillBelow = 24;
 constexpr int kAoStack = 72;
-
-__device__ __forceinline__ uint32_t enc_child(uint32_t ref, uint32_t cnt) {
-    return cnt ? (kLeafBit | ((cnt - 1u) << 27) | ref) : ref;
-}
 
 __global__ void __launch_bounds__(kBlockThreads)
 k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
@@ -279,11 +274,7 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                 float tl, tr;
                 bool hl = box_hit(rb, nd.l0, nd.l1, 0.0f, best, tl);
                 bool hr = box_hit(rb, nd.r0, nd.r1, 0.0f, best, tr);
-                const uint32_t lref = __float_as_uint(nd.l0.w), lcnt = __float_as_uint(nd.l1.w);
-                const uint32_t rref = __float_as_uint(nd.r0.w), rcnt = __float_as_uint(nd.r1.w);
-                hl = hl && (lcnt | lref);
-                hr = hr && (rcnt | rref);
-                const uint32_t cl = enc_child(lref, lcnt), cr = enc_child(rref, rcnt);
+                const uint32_t cl = __float_as_uint(nd.l0.w), cr = __float_as_uint(nd.r0.w);
                 if (hl && hr) {
                     const bool swap = tr < tl;
                     if (sp < kAoStack) { stk_node[sp] = swap ? cl : cr; stk_t[sp] = swap ? tl : tr; sp++; }
@@ -297,13 +288,13 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
             }
             // B: the postponed leaf
             if (cur != kDone) {
-                const uint32_t ref = cur & 0x07FFFFFFu, cnt = ((cur >> 27) & 15u) + 1u;
+                const uint32_t ref = cur & kRefMask, cnt = ((cur >> 27) & 15u) + 1u;
                 isect += cnt;
                 bool stop = false;
                 for (uint32_t i = 0; i < cnt; i++) {
                     const SegRec s = load_seg(S.segs + ref + i);
                     float t; uint32_t kind;
-                    if (capsule_hit(rq, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) {
+                    if (seg_box_hit(rb, s, radius, 0.0f, P.ao_radius) && capsule_hit(rq, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) {
                         if (!found || t < best) { best = t; found = true; }
                         if (any_mode) { stop = true; break; }
                     }
@@ -317,7 +308,7 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                 occ[ray_id] = found ? (any_mode ? 0.0f : best / P.ao_radius) : 1.0f;
                 ray_id = total;   // written
             }
-            if (__popc(__ballot_sync(0xffffffffu, cur != kDone)) < kRefillBelow) break;
+            if (__popc(__ballot_sync(0xffffffffu, cur != kDone)) < P.ao_refill_below) break;
         }
     }
     flush_counter(&C->rays_ao, rays);

@@ -5,6 +5,9 @@
 // Result-defining rules (mirrored by the CPU oracle): a candidate is accepted iff its reported hitT lies
 // in [tmin, tmax]; the closest hit is the smallest hitT, ties go to the lowest caller-side segment index.
 //
+// A candidate is accepted iff (1) the ray's [tmin, tmax] interval meets the segment's own AABB under the canonical slab
+// test below, (2) IntersectionTube reports a hit, (3) the reported hitT lies in [tmin, tmax].
+//
 // Cost model: one traversal step = one 64-byte node fetch (4 x LDG.128), one intersection =
 // one 32-byte segment record fetch (2 x LDG.128).  `steps` / `isect` count exactly those.
 #pragma once
@@ -13,10 +16,16 @@
 namespace lv {
 
 constexpr int kStackSize = 72;
+constexpr uint32_t kLeafBit = 0x80000000u;   // child word: leaf = kLeafBit | (count-1) << 27 | first record; inner = node index
+constexpr uint32_t kRefMask = 0x07FFFFFFu;
 
+// Canonical slab test (DESIGN.md "Result-defining rules"): per axis t0 = (bmin - o) * inv, t1 = (bmax - o) * inv with
+// separately rounded subtract and multiply, inv = 1/d (|d| clamped to 1e-30); hit iff
+// max(lo_x, lo_y, lo_z, tmin) <= min(hi_x, hi_y, hi_z, tmax).  Rounding is monotone, so a box that encloses another can
+// never be missed when the inner one is hit: the set of accepted candidates does not depend on the BVH topology.
 struct RayBox {
     float ix, iy, iz;     // safe 1/d
-    float ox, oy, oz;     // -o/d
+    float ox, oy, oz;     // origin
 };
 
 __device__ __forceinline__ float safe_inv(float d) {
@@ -27,18 +36,28 @@ __device__ __forceinline__ float safe_inv(float d) {
 __device__ __forceinline__ RayBox make_raybox(Vec3 o, Vec3 d) {
     RayBox b;
     b.ix = safe_inv(d.x); b.iy = safe_inv(d.y); b.iz = safe_inv(d.z);
-    b.ox = -(o.x * b.ix); b.oy = -(o.y * b.iy); b.oz = -(o.z * b.iz);
+    b.ox = o.x; b.oy = o.y; b.oz = o.z;
     return b;
 }
-// slab test; entry distance in tn.  Slightly widened so the box test never rejects what the capsule test accepts.
-__device__ __forceinline__ bool box_hit(const RayBox& rb, float4 mn, float4 mx, float tmin, float tmax, float& tn) {
-    float ax = __fmaf_rn(mn.x, rb.ix, rb.ox), bx = __fmaf_rn(mx.x, rb.ix, rb.ox);
-    float ay = __fmaf_rn(mn.y, rb.iy, rb.oy), by = __fmaf_rn(mx.y, rb.iy, rb.oy);
-    float az = __fmaf_rn(mn.z, rb.iz, rb.oz), bz = __fmaf_rn(mx.z, rb.iz, rb.oz);
+__device__ __forceinline__ bool box_hit(const RayBox& rb, float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
+                                        float tmin, float tmax, float& tn) {
+    float ax = (mnx - rb.ox) * rb.ix, bx = (mxx - rb.ox) * rb.ix;
+    float ay = (mny - rb.oy) * rb.iy, by = (mxy - rb.oy) * rb.iy;
+    float az = (mnz - rb.oz) * rb.iz, bz = (mxz - rb.oz) * rb.iz;
     float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
     float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
     tn = lo;
-    return lo * 0.9999995f <= hi * 1.0000005f;
+    return lo <= hi;
+}
+__device__ __forceinline__ bool box_hit(const RayBox& rb, float4 mn, float4 mx, float tmin, float tmax, float& tn) {
+    return box_hit(rb, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, tmin, tmax, tn);
+}
+// the segment's own AABB (min/max(p0,p1) -+ r, reference src/LineData/LineDataFlow.cpp:2230-2233) against the ray's
+// ORIGINAL interval: part of the acceptance rule, and a cheap reject in front of the three quadratics
+__device__ __forceinline__ bool seg_box_hit(const RayBox& rb, const SegRec& s, float r, float tmin, float tmax) {
+    float tn;
+    return box_hit(rb, fminf(s.a.x, s.b.x) - r, fminf(s.a.y, s.b.y) - r, fminf(s.a.z, s.b.z) - r,
+                   fmaxf(s.a.x, s.b.x) + r, fmaxf(s.a.y, s.b.y) + r, fmaxf(s.a.z, s.b.z) + r, tmin, tmax, tn);
 }
 
 __device__ __forceinline__ Node64 load_node(const Node64* p) {
@@ -77,11 +96,9 @@ __device__ __forceinline__ bool bvh_trace(const SceneDev& S, Vec3 o, Vec3 d, flo
         float tl, tr;
         bool hl = box_hit(rb, nd.l0, nd.l1, tmin, best.t, tl);
         bool hr = box_hit(rb, nd.r0, nd.r1, tmin, best.t, tr);
-        uint32_t lref = __float_as_uint(nd.l0.w), lcnt = __float_as_uint(nd.l1.w);
-        uint32_t rref = __float_as_uint(nd.r0.w), rcnt = __float_as_uint(nd.r1.w);
-        // an absent child is encoded as inner reference 0 (the root is nobody's child); its inverted box must not be trusted
-        hl = hl && (lcnt | lref);
-        hr = hr && (rcnt | rref);
+        const uint32_t lw = __float_as_uint(nd.l0.w), rw = __float_as_uint(nd.r0.w);   // absent children have a box that never hits
+        const uint32_t lref = lw & kRefMask, rref = rw & kRefMask;
+        const uint32_t lcnt = (lw & kLeafBit) ? ((lw >> 27) & 15u) + 1u : 0u, rcnt = (rw & kLeafBit) ? ((rw >> 27) & 15u) + 1u : 0u;
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             bool h = side ? hr : hl;
@@ -91,7 +108,7 @@ __device__ __forceinline__ bool bvh_trace(const SceneDev& S, Vec3 o, Vec3 d, flo
                 for (uint32_t i = 0; i < cnt; i++) {
                     SegRec s = load_seg(S.segs + ref + i);
                     float t; uint32_t kind;
-                    if (capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
+                    if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
                         if (MODE == 1) { best.t = t; best.idx = ref + i; best.kind = kind; return true; }
                         if (!found || t <= best.t) {
                             uint32_t prim = __ldg(S.prim_ids + ref + i);
@@ -135,11 +152,9 @@ __device__ __forceinline__ void bvh_trace_all(const SceneDev& S, Vec3 o, Vec3 d,
         float tl, tr;
         bool hl = box_hit(rb, nd.l0, nd.l1, tmin, tmax, tl);
         bool hr = box_hit(rb, nd.r0, nd.r1, tmin, tmax, tr);
-        uint32_t lref = __float_as_uint(nd.l0.w), lcnt = __float_as_uint(nd.l1.w);
-        uint32_t rref = __float_as_uint(nd.r0.w), rcnt = __float_as_uint(nd.r1.w);
-        // an absent child is encoded as inner reference 0 (the root is nobody's child); its inverted box must not be trusted
-        hl = hl && (lcnt | lref);
-        hr = hr && (rcnt | rref);
+        const uint32_t lw = __float_as_uint(nd.l0.w), rw = __float_as_uint(nd.r0.w);   // absent children have a box that never hits
+        const uint32_t lref = lw & kRefMask, rref = rw & kRefMask;
+        const uint32_t lcnt = (lw & kLeafBit) ? ((lw >> 27) & 15u) + 1u : 0u, rcnt = (rw & kLeafBit) ? ((rw >> 27) & 15u) + 1u : 0u;
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             bool h = side ? hr : hl;
@@ -149,7 +164,7 @@ __device__ __forceinline__ void bvh_trace_all(const SceneDev& S, Vec3 o, Vec3 d,
                 for (uint32_t i = 0; i < cnt; i++) {
                     SegRec s = load_seg(S.segs + ref + i);
                     float t; uint32_t kind;
-                    if (capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) f(ref + i, t, kind, s);
+                    if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) f(ref + i, t, kind, s);
                 }
                 if (side) hr = false; else hl = false;
             }

@@ -14,12 +14,13 @@ struct __align__(16) SegRec {
 };
 
 // 64-byte child-pair node: both children's boxes + references in one 64-byte (2-sector) fetch.
-// ref/count: count > 0 -> leaf, `ref` = first record (BVH order), `count` records;
-//            count == 0 -> inner, `ref` = node index.  An absent child has an inverted box.
+// child word: leaf  = bit31 | (count-1) << 27 | first record (BVH order), 1 <= count <= 16, record index < 2^27;
+//             inner = node index.  `count` is repeated in the max.w lane (0 for inner).  An absent child is the point
+//             box (+inf, +inf, +inf), which the canonical slab test can never hit.
 struct __align__(16) Node64 {
-    float4 l0;  // lmin.xyz, as_float(lref)
+    float4 l0;  // lmin.xyz, as_float(left child word)
     float4 l1;  // lmax.xyz, as_float(lcount)
-    float4 r0;  // rmin.xyz, as_float(rref)
+    float4 r0;  // rmin.xyz, as_float(right child word)
     float4 r1;  // rmax.xyz, as_float(rcount)
 };
 
@@ -48,6 +49,7 @@ struct FrameParams {
     uint32_t ao_spp;
     int ao_use_distance, ao_jitter;
     float subdiv_corr;        // cos(pi / tubeNumSubdivisions)
+    int ao_refill_below;      // k_rtao_rays refills a warp once fewer lanes than this are live
     uint32_t spp;             // numSamplesPerFrame
     int use_jitter, det_sampling;
     uint32_t max_depth;       // maxDepthComplexity

@@ -45,7 +45,7 @@ inline Box segmentBox(const Segment& s, float lineWidth) {
     Box b;
     float r = lineWidth * 0.5f;
     const float p0[3] = {s.p0.x, s.p0.y, s.p0.z}, p1[3] = {s.p1.x, s.p1.y, s.p1.z};
-    for (int k = 0; k < 3; k++) { b.mn[k] = std::min(p0[k], p1[k]) - r; b.mx[k] = std::max(p0[k], p1[k]) + r; }
+    for (int k = 0; k < 3; k++) { b.mn[k] = std::fmin(p0[k], p1[k]) - r; b.mx[k] = std::fmax(p0[k], p1[k]) + r; }
     return b;
 }
 
@@ -131,29 +131,12 @@ struct RayStats { uint64_t steps = 0, isect = 0, rays = 0; };
 
 struct Ray {
     vec3 o, d; float tmin, tmax;
-    float inv[3], od[3];
-    void prep() {
-        const float dd[3] = {d.x, d.y, d.z}, oo[3] = {o.x, o.y, o.z};
-        for (int k = 0; k < 3; k++) {
-            float v = dd[k];
-            if (std::fabs(v) < 1e-30f) v = std::signbit(v) ? -1e-30f : 1e-30f;
-            inv[k] = 1.0f / v; od[k] = oo[k] * inv[k];
-        }
-    }
+    RayInv ri;
+    void prep() { ri = makeRayInv(o, d); }
 };
 
 inline bool slab(const Node& n, const Ray& r, float tmax, float& tnear) {
-    float t0 = r.tmin, t1 = tmax;
-    for (int k = 0; k < 3; k++) {
-        float a = n.bmin[k] * r.inv[k] - r.od[k];
-        float b = n.bmax[k] * r.inv[k] - r.od[k];
-        float lo = std::min(a, b), hi = std::max(a, b);
-        // widen by a few ulps so that the box test never rejects a hit the capsule test accepts
-        lo -= std::fabs(lo) * 4e-7f; hi += std::fabs(hi) * 4e-7f;
-        t0 = std::max(t0, lo); t1 = std::min(t1, hi);
-    }
-    tnear = t0;
-    return t0 <= t1;
+    return slabTest(r.ri, n.bmin, n.bmax, r.tmin, tmax, tnear);   // canonical test: conservative w.r.t. acceptCandidate
 }
 
 struct Hit { float t; uint32_t prim; int kind; };
@@ -179,7 +162,7 @@ inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStat
                 uint32_t p = sc.primIdx[n.left + i];
                 const Segment& s = sc.segs[p];
                 float t; int kind;
-                if (intersectionTube(r.o, r.d, s.p0, s.p1, radius, capped, t, kind) && t >= r.tmin && t <= r.tmax) {
+                if (acceptCandidate(r.o, r.d, r.ri, s.p0, s.p1, radius, capped, r.tmin, r.tmax, t, kind)) {
                     if (!found || t < best.t || (t == best.t && p < best.prim)) { best.t = t; best.prim = p; best.kind = kind; found = true; }
                 }
             }
@@ -212,7 +195,7 @@ inline bool traceAny(const Scene& sc, Ray r, bool capped, RayStats& st) {
             for (uint32_t i = 0; i < n.count; i++) {
                 const Segment& s = sc.segs[sc.primIdx[n.left + i]];
                 float t; int kind;
-                if (intersectionTube(r.o, r.d, s.p0, s.p1, radius, capped, t, kind) && t >= r.tmin && t <= r.tmax) return true;
+                if (acceptCandidate(r.o, r.d, r.ri, s.p0, s.p1, radius, capped, r.tmin, r.tmax, t, kind)) return true;
             }
         } else { st.steps++; stack[sp++] = n.left; stack[sp++] = n.left + 1; }
     }
@@ -238,7 +221,7 @@ void traceAll(const Scene& sc, Ray r, bool capped, RayStats& st, F&& f) {
                 uint32_t p = sc.primIdx[n.left + i];
                 const Segment& s = sc.segs[p];
                 float t; int kind;
-                if (intersectionTube(r.o, r.d, s.p0, s.p1, radius, capped, t, kind) && t >= r.tmin && t <= r.tmax) f(p, t, kind);
+                if (acceptCandidate(r.o, r.d, r.ri, s.p0, s.p1, radius, capped, r.tmin, r.tmax, t, kind)) f(p, t, kind);
             }
         } else { st.steps++; stack[sp++] = n.left; stack[sp++] = n.left + 1; }
     }

@@ -52,14 +52,16 @@ struct TubePrimitive {
     BVec3 center() const { return BVec3(0.5f * (p0.x + p1.x), 0.5f * (p0.y + p1.y), 0.5f * (p0.z + p1.z)); }
     // AABB = min/max(p0,p1) -+ lineWidth/2 -- src/LineData/LineDataFlow.cpp:2230-2233
     BBox bounding_box() const {
-        return BBox(BVec3(std::min(p0.x, p1.x) - radius, std::min(p0.y, p1.y) - radius, std::min(p0.z, p1.z) - radius),
-                    BVec3(std::max(p0.x, p1.x) + radius, std::max(p0.y, p1.y) + radius, std::max(p0.z, p1.z) + radius));
+        return BBox(BVec3(std::fmin(p0.x, p1.x) - radius, std::fmin(p0.y, p1.y) - radius, std::fmin(p0.z, p1.z) - radius),
+                    BVec3(std::fmax(p0.x, p1.x) + radius, std::fmax(p0.y, p1.y) + radius, std::fmax(p0.z, p1.z) + radius));
     }
-    // the ray handed in carries the ORIGINAL [tmin, tmax] in (omin, omax); see the intersectors below
-    std::optional<Intersection> intersect(const BRay& ray) const {
+    // acceptance rule of lvo_shaders.hpp (own-AABB slab test on the ORIGINAL interval + IntersectionTube + range check);
+    // ray.tmax has meanwhile been shortened to the best hit by the traverser, which only removes non-improving candidates
+    std::optional<Intersection> intersect(const BRay& ray, float otmin, float otmax) const {
         float t; int kind;
-        if (intersectionTube(V3(ray.origin[0], ray.origin[1], ray.origin[2]), V3(ray.direction[0], ray.direction[1], ray.direction[2]),
-                             p0, p1, radius, capped, t, kind) && t >= ray.tmin && t <= ray.tmax)
+        vec3 ro = V3(ray.origin[0], ray.origin[1], ray.origin[2]), rd = V3(ray.direction[0], ray.direction[1], ray.direction[2]);
+        RayInv ri = makeRayInv(ro, rd);
+        if (acceptCandidate(ro, rd, ri, p0, p1, radius, capped, otmin, otmax, t, kind) && t <= ray.tmax)
             return std::make_optional(Intersection{t, kind});
         return std::nullopt;
     }
@@ -103,13 +105,13 @@ struct TieBreakClosestIntersector {
         BScalar distance() const { return intersection.distance(); }
     };
     static constexpr bool any_hit = false;
-    const Scene& sc; bool capped;
+    const Scene& sc; bool capped; float otmin, otmax;
     bool have = false; float bestT = 0; size_t bestPrim = 0;
-    TieBreakClosestIntersector(const Scene& s, bool c) : sc(s), capped(c) {}
+    TieBreakClosestIntersector(const Scene& s, bool c, float a, float b) : sc(s), capped(c), otmin(a), otmax(b) {}
     std::optional<Result> intersect(size_t index, const BRay& ray) {
         size_t p = sc.bvh.primitive_indices[index];
         TubePrimitive prim = sc.prims[p]; prim.capped = capped;
-        if (auto hit = prim.intersect(ray)) {
+        if (auto hit = prim.intersect(ray, otmin, otmax)) {
             if (!have || hit->t < bestT || (hit->t == bestT && p < bestPrim)) {
                 have = true; bestT = hit->t; bestPrim = p;
                 return std::make_optional(Result{p, *hit});
@@ -122,11 +124,11 @@ struct TieBreakClosestIntersector {
 struct AnyIntersector {
     struct Result { BScalar t; BScalar distance() const { return t; } };
     static constexpr bool any_hit = true;
-    const Scene& sc; bool capped;
-    AnyIntersector(const Scene& s, bool c) : sc(s), capped(c) {}
+    const Scene& sc; bool capped; float otmin, otmax;
+    AnyIntersector(const Scene& s, bool c, float a, float b) : sc(s), capped(c), otmin(a), otmax(b) {}
     std::optional<Result> intersect(size_t index, const BRay& ray) {
         TubePrimitive prim = sc.prims[sc.bvh.primitive_indices[index]]; prim.capped = capped;
-        if (auto hit = prim.intersect(ray)) return std::make_optional(Result{hit->t});
+        if (auto hit = prim.intersect(ray, otmin, otmax)) return std::make_optional(Result{hit->t});
         return std::nullopt;
     }
 };
@@ -135,24 +137,26 @@ template <class F>
 struct AllIntersector {
     struct Result { BScalar t; BScalar distance() const { return t; } };
     static constexpr bool any_hit = false;
-    const Scene& sc; bool capped; F& f;
-    AllIntersector(const Scene& s, bool c, F& fn) : sc(s), capped(c), f(fn) {}
+    const Scene& sc; bool capped; float otmin, otmax; F& f;
+    AllIntersector(const Scene& s, bool c, float a, float b, F& fn) : sc(s), capped(c), otmin(a), otmax(b), f(fn) {}
     std::optional<Result> intersect(size_t index, const BRay& ray) {
         size_t p = sc.bvh.primitive_indices[index];
         TubePrimitive prim = sc.prims[p]; prim.capped = capped;
-        if (auto hit = prim.intersect(ray)) f(uint32_t(p), hit->t, hit->kind);
+        if (auto hit = prim.intersect(ray, otmin, otmax)) f(uint32_t(p), hit->t, hit->kind);
         return std::nullopt;  // never shrink the interval: every candidate must be visited
     }
 };
 
-using Traverser = bvh::SingleRayTraverser<BBvh>;
+// RobustNodeIntersector (include/bvh/node_intersectors.hpp:56-78, T. Ize's robust BVH traversal): the library's box test
+// must not reject a box whose segment the canonical acceptance rule admits.
+using Traverser = bvh::SingleRayTraverser<BBvh, 64, bvh::RobustNodeIntersector<BBvh>>;
 
 inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStats& st) {
     st.rays++;
     best.t = r.tmax; best.prim = 0xFFFFFFFFu; best.kind = 0;
     if (sc.segs.empty()) return false;
     BRay ray(BVec3(r.o.x, r.o.y, r.o.z), BVec3(r.d.x, r.d.y, r.d.z), r.tmin, r.tmax);
-    TieBreakClosestIntersector isect(sc, capped);
+    TieBreakClosestIntersector isect(sc, capped, r.tmin, r.tmax);
     Traverser trav(sc.bvh);
     Traverser::Statistics s;
     auto hit = trav.traverse(ray, isect, s);
@@ -166,7 +170,7 @@ inline bool traceAny(const Scene& sc, Ray r, bool capped, RayStats& st) {
     st.rays++;
     if (sc.segs.empty()) return false;
     BRay ray(BVec3(r.o.x, r.o.y, r.o.z), BVec3(r.d.x, r.d.y, r.d.z), r.tmin, r.tmax);
-    AnyIntersector isect(sc, capped);
+    AnyIntersector isect(sc, capped, r.tmin, r.tmax);
     Traverser trav(sc.bvh);
     Traverser::Statistics s;
     auto hit = trav.traverse(ray, isect, s);
@@ -179,7 +183,7 @@ inline void traceAll(const Scene& sc, Ray r, bool capped, RayStats& st, F&& f) {
     st.rays++;
     if (sc.segs.empty()) return;
     BRay ray(BVec3(r.o.x, r.o.y, r.o.z), BVec3(r.d.x, r.d.y, r.d.z), r.tmin, r.tmax);
-    AllIntersector<F> isect(sc, capped, f);
+    AllIntersector<F> isect(sc, capped, r.tmin, r.tmax, f);
     Traverser trav(sc.bvh);
     Traverser::Statistics s;
     trav.traverse(ray, isect, s);

@@ -205,9 +205,10 @@ void lvo_trace_primary_bruteforce(void* h, const lv_camera* cam, const lvo_optio
         for (uint32_t x = 0; x < cam->width; x++) {
             vec3 ro, rd; cameraRay(u, x, uint32_t(y), 0.5f, 0.5f, ro, rd);
             lv_hit best{0.0f, 0xFFFFFFFFu, 0, 0}; bool found = false;
+            const RayInv ri = makeRayInv(ro, rd);
             for (size_t p = 0; p < sc.segs.size(); p++) {
                 float t; int k;
-                if (intersectionTube(ro, rd, sc.segs[p].p0, sc.segs[p].p1, radius, u.useCappedTubes, t, k) && t >= 0.0001f && t <= 1000.0f) {
+                if (acceptCandidate(ro, rd, ri, sc.segs[p].p0, sc.segs[p].p1, radius, u.useCappedTubes, 0.0001f, 1000.0f, t, k)) {
                     if (!found || t < best.t) { best.t = t; best.prim = uint32_t(p); best.kind = uint32_t(k); found = true; }
                 }
             }

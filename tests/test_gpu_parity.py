@@ -80,10 +80,12 @@ def test_bvh_encloses_all_segments(ctx):
         n = nodes[stack.pop()]
         for side in ("l", "r"):
             mn, mx, ref, cnt = n[side + "min"], n[side + "max"], int(n[side + "ref"]), int(n[side + "count"])
-            if not (mn <= mx).all():
-                continue
-            assert (mn >= glo - 1e-6).all() and (mx <= ghi + 1e-6).all()
+            if not np.isfinite(mn).all():
+                continue                                   # absent child: point box at +inf
+            assert (mn <= mx).all() and (mn >= glo - 1e-6).all() and (mx <= ghi + 1e-6).all()
             if cnt:
+                assert ref >> 31 == 1 and ((ref >> 27) & 15) + 1 == cnt
+                first = ref & 0x07FFFFFF
                 seen += cnt
             else:
                 stack.append(ref)
