@@ -36,7 +36,8 @@ struct Options {
     uint32_t max_depth_complexity = 1024;
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 4;
-    uint32_t ao_refill_below = 24;
+    uint32_t ao_refill_below = 20;
+    uint32_t ao_leaf_vote = 16;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
     std::string ao_mode = "RTAO", denoiser = "None", geometry_mode = "AABBs (analytic)";
 };
@@ -168,6 +169,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.ao_spp = o.ao_spp; P.ao_use_distance = o.ao_use_distance; P.ao_jitter = o.ao_jitter_primary;
     P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
     P.ao_refill_below = int(o.ao_refill_below);
+    P.ao_leaf_vote = int(o.ao_leaf_vote);
     P.spp = o.num_samples_per_frame;
     // useJitteredSamples = maxNumFrames > 1 || numSamplesPerFrame > 1 (reference VulkanRayTracer.cpp:421)
     P.use_jitter = (o.num_accumulated_frames > 1 || o.num_samples_per_frame > 1) ? 1 : 0;
@@ -376,6 +378,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         (k == "b200_tiling_width" ? o.tiling_w : o.tiling_h) = v;
     } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
+    else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
     else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
     else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
     return LV_OK;
@@ -414,6 +417,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_bvh_leaf_size") v = std::to_string(o.bvh_leaf_size);
     else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
+    else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
     return LV_OK;

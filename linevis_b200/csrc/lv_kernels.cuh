@@ -194,13 +194,16 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
 //
 // The first version of this kernel gave each warp one pixel's samples and ran an if-if traversal; ncu showed it
 // issue-bound at 3.7 of 32 lanes active (profiles/r1a_*): incoherent short rays finish at very different times and leaf
-// work diverges from box work.  This version keeps every lane busy instead:
+// work diverges from box work.  This version keeps the lanes busy instead (11.6 of 32, profiles/r1c_*):
 //   - rays are numbered r = hit_slot * spp + sample; a lane whose ray has finished takes the next number from a global
-//     counter (one atomic per warp refill, ranks by ballot/popc) as soon as kRefillBelow lanes of its warp are idle, so
-//     a warp always carries >= 75 % live rays; consecutive numbers share a pixel, i.e. rays start out coherent;
-//   - traversal is while-while with postponed leaves: all lanes first walk inner nodes until each has reached a leaf
-//     (or run out), then all lanes intersect their leaf together; leaves travel on the stack as encoded entries;
+//     counter (one atomic per warp refill, ranks by ballot/popc) as soon as fewer than ao_refill_below lanes of its warp
+//     are live; consecutive numbers share a pixel, i.e. rays start out coherent;
+//   - every iteration all lanes that hold an inner node take ONE step; a lane that reaches a leaf postpones it (leaves
+//     travel as encoded child words, also on the stack) and waits until ao_leaf_vote lanes hold one, then those lanes
+//     intersect their leaves together;
 //   - popped entries carry their box entry distance and are skipped when the closest hit found meanwhile is nearer.
+// Tried and dropped (measured, no gain): sorting the rays of 128 neighbouring hit pixels into 64 direction bins,
+// warp-private chunks of consecutive ray numbers, a second compaction pass over box-test survivors inside the leaf phase.
 // The per-ray result (4 B) goes to occ[r]; sample-ordered summation happens in k_rtao_reduce.
 constexpr uint32_t kDone = 0x7FFFFFFFu;
 constexpr int kRefillBelow = 24;
@@ -267,8 +270,9 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
 
         // ---- trace until too many lanes of the warp are idle again
         while (true) {
-            // A: inner nodes until this lane holds a leaf (or is done)
-            while (cur != kDone && !(cur & kLeafBit)) {
+            // A: ONE inner-node step for every lane that holds an inner node.  Lanes that already hold a leaf wait; waiting
+            // for the slowest lane to reach a leaf (classic while-while) left 3/4 of the lanes idle in this phase.
+            if (cur != kDone && !(cur & kLeafBit)) {
                 const Node64 nd = load_node(S.nodes + cur);
                 steps++;
                 float tl, tr;
@@ -286,8 +290,11 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                     while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } }
                 }
             }
-            // B: the postponed leaf
-            if (cur != kDone) {
+            // B: postponed leaves are intersected once enough lanes hold one (vote), or when nobody can step any more
+            const bool at_leaf = (cur != kDone) && (cur & kLeafBit);
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);
+            const unsigned inner_mask = __ballot_sync(0xffffffffu, cur != kDone && !(cur & kLeafBit));
+            if (at_leaf && (__popc(leaf_mask) >= P.ao_leaf_vote || inner_mask == 0u)) {
                 const uint32_t ref = cur & kRefMask, cnt = ((cur >> 27) & 15u) + 1u;
                 isect += cnt;
                 bool stop = false;

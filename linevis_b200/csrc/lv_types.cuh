@@ -50,6 +50,7 @@ struct FrameParams {
     int ao_use_distance, ao_jitter;
     float subdiv_corr;        // cos(pi / tubeNumSubdivisions)
     int ao_refill_below;      // k_rtao_rays refills a warp once fewer lanes than this are live
+    int ao_leaf_vote;         // ... and intersects postponed leaves once this many lanes hold one
     uint32_t spp;             // numSamplesPerFrame
     int use_jitter, det_sampling;
     uint32_t max_depth;       // maxDepthComplexity
