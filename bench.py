@@ -254,22 +254,14 @@ def main():
 
     frame = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     n_own = len(ctx.owned_tiles(W, H))
-    if world > 1:
-        n_max = torch.tensor([n_own], device=dev)
-        dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
-        n_max = int(n_max.item())
-        packed = torch.zeros((n_max, tile * tile, 4), dtype=torch.float32, device=dev)
-        gathered = torch.zeros((world, n_max, tile * tile, 4), dtype=torch.float32, device=dev)
+    from linevis_b200.sharding import FrameGather
+    fg = FrameGather(W, H, tile, rank, world, dev, ctx=ctx) if world > 1 else None
 
     def step(stats):
         out, st = ctx.render_tubes(scene, cam, 0, out=frame, stats=stats)
-        if world > 1:
-            # the single collective of the frame: all ranks' tile blocks -> every rank (rank 0 assembles)
-            ctx.pack_owned_tiles(frame, W, H, packed)
-            dist.all_gather_into_tensor(gathered, packed)
-            if rank == 0:
-                for r in range(1, world):
-                    ctx.unpack_tiles(gathered[r], r, world, W, H, frame)
+        if fg is not None:
+            # the single collective of the frame: every rank's packed tile block -> all ranks; rank 0 assembles the frame
+            fg.gather(frame, assemble_on=(0,))
         return st
 
     # warm-up (also yields the per-frame ray / T / I counts: the frame is deterministic)
@@ -319,8 +311,8 @@ def main():
 
     def step_e2e():
         ctx.render_tubes(scene, cam, 0, out=host_np, stats=False)   # D2H inside, synchronises
-        if world > 1:
-            ctx.pack_owned_tiles(frame, W, H, packed)               # device copy of the owned tiles for the gather
+        if fg is not None:
+            fg.gather(frame, assemble_on=())                        # the collective stays in the e2e step as well
     for _ in range(2):
         step_e2e()
     if world > 1:

@@ -216,6 +216,37 @@ def test_ppll_truncation_at_max_frags(ctx, oracle):
     assert np.isfinite(img).all()
 
 
+def test_owned_tiles_match_host_enumeration(ctx):
+    """lv_get_owned_tiles (C side) == linevis_b200.sharding.owned_tiles (host side used for the NCCL gather)."""
+    from linevis_b200 import sharding
+    for (W, H, ts, world) in [(3840, 2160, 64, 8), (200, 136, 32, 4), (100, 70, 16, 3)]:
+        for r in range(world):
+            c = lv.Context(0)
+            c.set_tile_shard(r, world, ts)
+            assert np.array_equal(c.owned_tiles(W, H), sharding.owned_tiles(W, H, ts, r, world))
+            c.close()
+
+
+def test_pack_unpack_tiles_kernels(ctx):
+    import torch
+    from linevis_b200 import sharding
+    W, H, ts, world = 200, 136, 32, 3
+    img = torch.rand((H, W, 4), device="cuda")
+    out = torch.zeros_like(img)
+    for r in range(world):
+        c = lv.Context(0)
+        c.set_tile_shard(r, world, ts)
+        n = len(c.owned_tiles(W, H))
+        packed = torch.zeros((n, ts * ts, 4), device="cuda")
+        c.pack_owned_tiles(img, W, H, packed)
+        c.synchronize()
+        ref = sharding.pack_tiles_torch(img, sharding.owned_tiles(W, H, ts, r, world), ts, n)
+        assert torch.equal(packed, ref)
+        c.unpack_tiles(packed, r, world, W, H, out)
+        c.close()
+    assert torch.equal(out, img)
+
+
 def test_tile_sharding_reassembles_full_frame(ctx, oracle):
     """world_size 4 emulated on one GPU: every rank renders its Morton-interleaved tiles; union == unsharded frame."""
     data, width = DATASETS["helix"]()
