@@ -35,9 +35,9 @@ struct Options {
     bool use_deterministic_sampling = false;
     uint32_t max_depth_complexity = 1024;
     uint32_t tiling_w = 2, tiling_h = 8;
-    uint32_t bvh_leaf_size = 4;
-    uint32_t ao_refill_below = 20;
-    uint32_t ao_leaf_vote = 16;
+    uint32_t bvh_leaf_size = 1;
+    uint32_t ao_refill_below = 24;
+    uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
     std::string ao_mode = "RTAO", denoiser = "None", geometry_mode = "AABBs (analytic)";
 };

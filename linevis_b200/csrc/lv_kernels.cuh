@@ -301,7 +301,8 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                 for (uint32_t i = 0; i < cnt; i++) {
                     const SegRec s = load_seg(S.segs + ref + i);
                     float t; uint32_t kind;
-                    if (seg_box_hit(rb, s, radius, 0.0f, P.ao_radius) && capsule_hit(rq, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) {
+                    // a one-record leaf's box in its parent IS the record's own AABB (same float expressions): already tested
+                    if ((cnt == 1u || seg_box_hit(rb, s, radius, 0.0f, P.ao_radius)) && capsule_hit(rq, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) {
                         if (!found || t < best) { best = t; found = true; }
                         if (any_mode) { stop = true; break; }
                     }
@@ -371,30 +372,42 @@ constexpr int kGatherQueue = 16;   // queued hits per lane; >= the largest leaf 
 
 struct GatherState { uint32_t head, stored, gen; };
 
+// Shade the queued hits of all lanes in lockstep rounds, then allocate the surviving fragments of the whole warp with ONE
+// atomicAdd (warp scan of the per-lane counts) so that each pixel's new nodes are CONTIGUOUS in the fragment buffer: the
+// resolve pass then walks runs of up to kGatherQueue adjacent 12-byte nodes instead of one 32-byte sector per node.
 __device__ __forceinline__ void gather_flush(const FrameParams& P, const SceneDev& S, Vec3 ro, Vec3 rd, uint32_t lane,
                                              uint2 (*q)[kBlockThreads], uint32_t& qn, GatherState& g, lv_ppll_node* nodes,
                                              unsigned long long* frag_counter, unsigned long long list_size) {
-    while (__ballot_sync(0xffffffffu, qn != 0u)) {
-        if (qn) {
-            qn--;
-            const uint2 e = q[qn][threadIdx.x];
+    uint32_t kept = 0;
+    for (uint32_t i = 0; __ballot_sync(0xffffffffu, i < qn); i++) {
+        if (i < qn) {
+            const uint2 e = q[i][threadIdx.x];
             const SegRec s = load_seg(S.segs + (e.x & kRefMask));
             const Shaded sh = shade_hit(P, ro, rd, __uint_as_float(e.y), e.x >> 28, s);
             if (!(sh.color.w < 0.001f)) {                                       // LinkedListGather.glsl:38
-                g.gen++;
-                const unsigned m = __activemask();
-                const int leader = __ffs(m) - 1;
-                unsigned long long base = 0;
-                if (int(lane) == leader) base = atomicAdd(frag_counter, (unsigned long long)__popc(m));
-                base = __shfl_sync(m, base, leader);
-                const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
-                if (idx < list_size) {
-                    lv_ppll_node nd; nd.color = pack_unorm4x8(sh.color); nd.depth = sh.hit_t; nd.next = g.head;
-                    nodes[idx] = nd;
-                    g.head = uint32_t(idx);
-                    g.stored++;
-                }
+                q[kept][threadIdx.x] = make_uint2(pack_unorm4x8(sh.color), __float_as_uint(sh.hit_t));   // kept <= i: slot is free
+                kept++;
             }
+        }
+    }
+    qn = 0;
+    uint32_t incl = kept;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(frag_counter, (unsigned long long)total);   // fragCounter, LinkedListGather.glsl:55
+    base = __shfl_sync(0xffffffffu, base, 0) + (incl - kept);
+    g.gen += kept;
+    for (uint32_t j = 0; j < kept; j++) {
+        const unsigned long long idx = base + j;
+        if (idx < list_size) {                                                   // :57
+            const uint2 e = q[j][threadIdx.x];
+            lv_ppll_node nd; nd.color = e.x; nd.depth = __uint_as_float(e.y); nd.next = g.head;
+            nodes[idx] = nd;
+            g.head = uint32_t(idx);
+            g.stored++;
         }
     }
 }
@@ -479,7 +492,7 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
 // (LinkedListSort.glsl:45-58; early-out at alpha >= 0.99 for the priority-queue mode, :217-218).
 constexpr int kResolveCap = 1024;     // keys per warp (8 KiB)
 constexpr int kResolveWarps = 4;
-constexpr int kResolveInsertionMax = 32;  // lists up to this length are sorted by their own lane
+constexpr int kResolveInsertionMax = 64;  // lists up to this length are sorted by their own lane
 
 __device__ __forceinline__ void cmpxchg(unsigned long long* s, uint32_t i, uint32_t l) {
     unsigned long long a = s[i], b = s[l];
@@ -511,6 +524,9 @@ __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
                uint32_t max_frags, int early_out, float4* image, Counters* C) {
     __shared__ unsigned long long s_keys[kResolveWarps * kResolveCap];
+    __shared__ float s_unorm[256];   // unpackUnorm4x8: float(b) / 255.0f, tabulated once (4 IEEE divisions per fragment otherwise)
+    for (uint32_t i = threadIdx.x; i < 256u; i += kBlockThreads) s_unorm[i] = float(i) / 255.0f;
+    __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long* tile = s_keys + warp * kResolveCap;
     uint32_t x, y;
@@ -560,8 +576,8 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
             for (uint32_t i = 0; i < c; i++) {
                 if (early_out && !(a < 0.99f)) break;
                 const uint32_t col = uint32_t(tile[excl + i] & 0xffffffffull);
-                const float sr = float(col & 0xffu) / 255.0f, sg = float((col >> 8) & 0xffu) / 255.0f;
-                const float sb = float((col >> 16) & 0xffu) / 255.0f, sa = float(col >> 24) / 255.0f;
+                const float sr = s_unorm[col & 0xffu], sg = s_unorm[(col >> 8) & 0xffu];
+                const float sb = s_unorm[(col >> 16) & 0xffu], sa = s_unorm[col >> 24];
                 r = r + (1.0f - a) * sa * sr;
                 g = g + (1.0f - a) * sa * sg;
                 b = b + (1.0f - a) * sa * sb;

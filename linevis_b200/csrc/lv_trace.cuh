@@ -19,13 +19,14 @@ constexpr int kStackSize = 72;
 constexpr uint32_t kLeafBit = 0x80000000u;   // child word: leaf = kLeafBit | (count-1) << 27 | first record; inner = node index
 constexpr uint32_t kRefMask = 0x07FFFFFFu;
 
-// Canonical slab test (DESIGN.md "Result-defining rules"): per axis t0 = (bmin - o) * inv, t1 = (bmax - o) * inv with
-// separately rounded subtract and multiply, inv = 1/d (|d| clamped to 1e-30); hit iff
-// max(lo_x, lo_y, lo_z, tmin) <= min(hi_x, hi_y, hi_z, tmax).  Rounding is monotone, so a box that encloses another can
-// never be missed when the inner one is hit: the set of accepted candidates does not depend on the BVH topology.
+// Canonical slab test (DESIGN.md "Result-defining rules"): per plane t = fma(b, inv, c) -- ONE correctly rounded fused
+// multiply-add -- with inv = 1/d (|d| clamped to 1e-30) and c = -(o * inv); hit iff
+// max(lo_x, lo_y, lo_z, tmin) <= min(hi_x, hi_y, hi_z, tmax).  For a fixed ray t is a monotone function of b, so a box
+// that encloses another can never be missed when the inner one is hit: the set of accepted candidates does not depend on
+// the BVH topology.
 struct RayBox {
     float ix, iy, iz;     // safe 1/d
-    float ox, oy, oz;     // origin
+    float cx, cy, cz;     // -(o * inv)
 };
 
 __device__ __forceinline__ float safe_inv(float d) {
@@ -36,14 +37,14 @@ __device__ __forceinline__ float safe_inv(float d) {
 __device__ __forceinline__ RayBox make_raybox(Vec3 o, Vec3 d) {
     RayBox b;
     b.ix = safe_inv(d.x); b.iy = safe_inv(d.y); b.iz = safe_inv(d.z);
-    b.ox = o.x; b.oy = o.y; b.oz = o.z;
+    b.cx = -(o.x * b.ix); b.cy = -(o.y * b.iy); b.cz = -(o.z * b.iz);
     return b;
 }
 __device__ __forceinline__ bool box_hit(const RayBox& rb, float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
                                         float tmin, float tmax, float& tn) {
-    float ax = (mnx - rb.ox) * rb.ix, bx = (mxx - rb.ox) * rb.ix;
-    float ay = (mny - rb.oy) * rb.iy, by = (mxy - rb.oy) * rb.iy;
-    float az = (mnz - rb.oz) * rb.iz, bz = (mxz - rb.oz) * rb.iz;
+    float ax = __fmaf_rn(mnx, rb.ix, rb.cx), bx = __fmaf_rn(mxx, rb.ix, rb.cx);
+    float ay = __fmaf_rn(mny, rb.iy, rb.cy), by = __fmaf_rn(mxy, rb.iy, rb.cy);
+    float az = __fmaf_rn(mnz, rb.iz, rb.cz), bz = __fmaf_rn(mxz, rb.iz, rb.cz);
     float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
     float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
     tn = lo;
@@ -94,8 +95,12 @@ __device__ __forceinline__ bool bvh_trace(const SceneDev& S, Vec3 o, Vec3 d, flo
         const Node64 nd = load_node(S.nodes + node);
         steps++;
         float tl, tr;
-        bool hl = box_hit(rb, nd.l0, nd.l1, tmin, best.t, tl);
-        bool hr = box_hit(rb, nd.r0, nd.r1, tmin, best.t, tr);
+        // Boxes are culled against best.t + one tube diameter, not best.t: the reference's float32 quadratic reports hitT
+        // with an error of up to a few % of r, so a candidate that TIES the current best (adjacent capsules share an end
+        // sphere) may have a box entry slightly beyond it; the tie rule must still see it, whatever the BVH looks like.
+        const float tcull = MODE == 0 ? best.t + S.line_width : best.t;
+        bool hl = box_hit(rb, nd.l0, nd.l1, tmin, tcull, tl);
+        bool hr = box_hit(rb, nd.r0, nd.r1, tmin, tcull, tr);
         const uint32_t lw = __float_as_uint(nd.l0.w), rw = __float_as_uint(nd.r0.w);   // absent children have a box that never hits
         const uint32_t lref = lw & kRefMask, rref = rw & kRefMask;
         const uint32_t lcnt = (lw & kLeafBit) ? ((lw >> 27) & 15u) + 1u : 0u, rcnt = (rw & kLeafBit) ? ((rw >> 27) & 15u) + 1u : 0u;

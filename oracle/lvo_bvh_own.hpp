@@ -155,7 +155,8 @@ inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStat
         uint32_t ni = stack[--sp];
         const Node& n = sc.nodes[ni];
         float tn;
-        if (!slab(n, r, best.t, tn)) continue;
+        // cull against best.t + one tube diameter so that tying candidates are always seen (closest-hit rule)
+        if (!slab(n, r, best.t + sc.lineWidth, tn)) continue;
         if (n.count) {
             st.isect += n.count;
             for (uint32_t i = 0; i < n.count; i++) {
@@ -169,7 +170,7 @@ inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStat
         } else {
             st.steps++;
             float t0, t1;
-            bool h0 = slab(sc.nodes[n.left], r, best.t, t0), h1 = slab(sc.nodes[n.left + 1], r, best.t, t1);
+            bool h0 = slab(sc.nodes[n.left], r, best.t + sc.lineWidth, t0), h1 = slab(sc.nodes[n.left + 1], r, best.t + sc.lineWidth, t1);
             if (h0 && h1) {
                 if (t0 <= t1) { stack[sp++] = n.left + 1; stack[sp++] = n.left; } else { stack[sp++] = n.left; stack[sp++] = n.left + 1; }
             } else if (h0) stack[sp++] = n.left;

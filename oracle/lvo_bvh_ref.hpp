@@ -61,7 +61,7 @@ struct TubePrimitive {
         float t; int kind;
         vec3 ro = V3(ray.origin[0], ray.origin[1], ray.origin[2]), rd = V3(ray.direction[0], ray.direction[1], ray.direction[2]);
         RayInv ri = makeRayInv(ro, rd);
-        if (acceptCandidate(ro, rd, ri, p0, p1, radius, capped, otmin, otmax, t, kind) && t <= ray.tmax)
+        if (acceptCandidate(ro, rd, ri, p0, p1, radius, capped, otmin, otmax, t, kind))
             return std::make_optional(Intersection{t, kind});
         return std::nullopt;
     }
@@ -101,8 +101,10 @@ inline uint64_t numNodes(const Scene& sc) { return sc.bvh.node_count; }
 // include/bvh/primitive_intersectors.hpp:33-55, keeps whichever equal-t candidate it meets last.)
 struct TieBreakClosestIntersector {
     struct Result {
-        size_t primitive_index; TubePrimitive::Intersection intersection;
-        BScalar distance() const { return intersection.distance(); }
+        size_t primitive_index; TubePrimitive::Intersection intersection; BScalar margin;
+        // what the traverser shortens ray.tmax to (single_ray_traverser.hpp:59): one tube diameter beyond the hit, so that
+        // candidates tying the best hit are never culled by the library's node test (closest-hit rule)
+        BScalar distance() const { return intersection.distance() + margin; }
     };
     static constexpr bool any_hit = false;
     const Scene& sc; bool capped; float otmin, otmax;
@@ -114,7 +116,7 @@ struct TieBreakClosestIntersector {
         if (auto hit = prim.intersect(ray, otmin, otmax)) {
             if (!have || hit->t < bestT || (hit->t == bestT && p < bestPrim)) {
                 have = true; bestT = hit->t; bestPrim = p;
-                return std::make_optional(Result{p, *hit});
+                return std::make_optional(Result{p, *hit, sc.lineWidth});
             }
         }
         return std::nullopt;

@@ -240,24 +240,26 @@ static inline bool intersectionTube(vec3 ro, vec3 rd, vec3 p0, vec3 p1, float li
 // hitT in [tMin, tMax].  Fixed here so that the accepted set is a pure function of (ray, segment, radius) and never of
 // the acceleration structure: (1) the ray's [tmin, tmax] meets the segment's own AABB (src/LineData/LineDataFlow.cpp:
 // 2230-2233) under the canonical slab test below, (2) IntersectionTube reports a hit, (3) hitT in [tmin, tmax].
-// Canonical slab test: t = (b - o) * inv per plane, separately rounded; inv = 1/d with |d| clamped to 1e-30.
-// Rounding is monotone, so any box enclosing the segment's AABB passes whenever the segment's AABB does.
+// Canonical slab test: per plane t = fma(b, inv, c), one correctly rounded fused multiply-add, inv = 1/d with |d| clamped to
+// 1e-30 and c = -(o * inv).  For a fixed ray t is monotone in b, so any box enclosing the segment's AABB passes whenever
+// the segment's AABB does.
 // ----------------------------------------------------------------------------------------------
 static inline float safeInv(float d) {
     const float tiny = 1e-30f;
     if (fabsf(d) < tiny) d = std::signbit(d) ? -tiny : tiny;
     return 1.0f / d;
 }
-struct RayInv { float o[3], inv[3]; };
+struct RayInv { float c[3], inv[3]; };
 static inline RayInv makeRayInv(vec3 o, vec3 d) {
-    RayInv r; r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
+    RayInv r;
     r.inv[0] = safeInv(d.x); r.inv[1] = safeInv(d.y); r.inv[2] = safeInv(d.z);
+    r.c[0] = -(o.x * r.inv[0]); r.c[1] = -(o.y * r.inv[1]); r.c[2] = -(o.z * r.inv[2]);
     return r;
 }
 static inline bool slabTest(const RayInv& r, const float* bmin, const float* bmax, float tmin, float tmax, float& tnear) {
     float lo[3], hi[3];
     for (int k = 0; k < 3; k++) {
-        float a = (bmin[k] - r.o[k]) * r.inv[k], b = (bmax[k] - r.o[k]) * r.inv[k];
+        float a = std::fmaf(bmin[k], r.inv[k], r.c[k]), b = std::fmaf(bmax[k], r.inv[k], r.c[k]);
         lo[k] = std::fmin(a, b); hi[k] = std::fmax(a, b);
     }
     float l = std::fmax(std::fmax(lo[0], lo[1]), std::fmax(lo[2], tmin));
