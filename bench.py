@@ -381,7 +381,7 @@ def main():
                                   % (st["ao_traversal_steps"] / max(st["rays_ao"], 1), st["ao_intersections"] / max(st["rays_ao"], 1), st["rays_ao"])},
             "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 316, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera (316 B) in, RGBA32F frame out"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": (4 + (2 + (world - 1) if world > 1 else 0)) * args.steps,   # k_rtao_primary, k_rtao_rays, k_rtao_reduce, k_tubes (+ tile pack / unpack)
             "clocks": clocks,
         }
         if ppll:

@@ -37,6 +37,7 @@ struct Options {
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
     uint32_t ao_refill_below = 24;
+    bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
     std::string ao_mode = "RTAO", denoiser = "None", geometry_mode = "AABBs (analytic)";
@@ -74,7 +75,7 @@ struct lv_ctx {
     uint32_t ao_w = 0, ao_h = 0;
     DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[2..3] = 64-bit ao work counter
     // PPLL
-    DevBuf<uint32_t> heads, counts; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
+    DevBuf<uint32_t> heads, counts, bin_order; DevBuf<unsigned int> bin_hist; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
     unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
     cudaEvent_t ev[8] = {};
     bool rtao_rays_timed = false;
@@ -324,7 +325,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->occ.release(); c->hits.release(); c->ao_hits.release();
-    c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->nodes.release(); c->frag_counter.release();
+    c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
     return LV_OK;
@@ -378,6 +379,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         (k == "b200_tiling_width" ? o.tiling_w : o.tiling_h) = v;
     } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
+    else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
     else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
     else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
@@ -418,6 +420,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
+    else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
     return LV_OK;
@@ -745,8 +748,36 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
     // All eight modes produce the depth-sorted order; only the priority queue stops blending at alpha >= 0.99
     // (reference LinkedListSort.glsl:217).  See DESIGN.md for the reference's bitonicSort defect.
     const int early_out = (sort_mode == LV_SORT_PRIORITY_QUEUE) ? 1 : 0;
-    if (P.n_tiles)
-        k_ppll_resolve<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p);
+    if (P.n_tiles && !c->opt.ppll_binned_resolve)
+        k_ppll_resolve<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img,
+                                                                       c->counters.p, nullptr, nullptr);
+    else if (P.n_tiles) {
+        const size_t n_own = size_t(P.n_tiles) * c->tile_size * c->tile_size;
+        LV_CUDA(c, c->bin_hist.ensure(2 * (size_t(kResolveCap) + 2) + 8));   // hist | offsets | n_sorted[kBinClasses]
+        LV_CUDA(c, c->bin_order.ensure(n_own));
+        unsigned int* hist = c->bin_hist.p; unsigned int* offs = hist + kResolveCap + 2; unsigned int* nsort = offs + kResolveCap + 2;
+        LV_CUDA(c, cudaMemsetAsync(hist, 0, (2 * (size_t(kResolveCap) + 2) + 8) * sizeof(unsigned int), c->stream));
+        const uint32_t grid = pixel_grid(c, P);
+        k_ppll_bin_count<<<grid, kBlockThreads, 0, c->stream>>>(P, c->counts.p, max_frags, hist);
+        k_ppll_bin_scan<<<1, 32, 0, c->stream>>>(max_frags, hist, offs, nsort);
+        k_ppll_bin_scatter<<<grid, kBlockThreads, 0, c->stream>>>(P, c->counts.p, max_frags, offs, c->bin_order.p, img);
+        // lists longer than 256 keys: cooperative kernel over the head of the order array; the launch covers the worst case,
+        // surplus blocks exit on n_sorted[0]
+        if (max_frags > 256u)
+            k_ppll_resolve<<<uint32_t((n_own + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
+                P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, c->bin_order.p, nsort);
+        auto smem = [](int maxn, int warps) { return size_t(warps) * maxn * 32 * 8 + 256 * 4; };
+        static bool attr_set = false;
+        if (!attr_set) {
+            LV_CUDA(c, cudaFuncSetAttribute(k_ppll_resolve_binned<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem(256, 1))));
+            attr_set = true;
+        }
+        const uint32_t pg = uint32_t(c->num_sms) * 6u;
+        if (max_frags > 128u) k_ppll_resolve_binned<256, 1, 1><<<pg, 32, smem(256, 1), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);
+        if (max_frags > 64u) k_ppll_resolve_binned<128, 1, 2><<<pg, 32, smem(128, 1), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);
+        if (max_frags > 32u) k_ppll_resolve_binned<64, 2, 3><<<pg, 64, smem(64, 2), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);
+        k_ppll_resolve_binned<32, 4, 4><<<pg, 128, smem(32, 4), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);
+    }
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (!dev && (rc = deliver(c, img, rgba_out, P.W, P.H, 16))) return rc;

@@ -522,7 +522,7 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* s, uint32_
 
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
-               uint32_t max_frags, int early_out, float4* image, Counters* C) {
+               uint32_t max_frags, int early_out, float4* image, Counters* C, const uint32_t* order, const unsigned int* n_sorted) {
     __shared__ unsigned long long s_keys[kResolveWarps * kResolveCap];
     __shared__ float s_unorm[256];   // unpackUnorm4x8: float(b) / 255.0f, tabulated once (4 IEEE divisions per fragment otherwise)
     for (uint32_t i = threadIdx.x; i < 256u; i += kBlockThreads) s_unorm[i] = float(i) / 255.0f;
@@ -530,7 +530,13 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long* tile = s_keys + warp * kResolveCap;
     uint32_t x, y;
-    const bool valid = thread_pixel(P, x, y);
+    bool valid;
+    if (order) {   // binned mode: this kernel only takes the first n_sorted[0] pixels of `order` (lists longer than 256 keys)
+        const uint32_t slot = blockIdx.x * kBlockThreads + threadIdx.x;
+        valid = slot < n_sorted[0];
+        const uint32_t pixel = valid ? order[slot] : 0u;
+        x = pixel % P.W; y = pixel / P.W;
+    } else valid = thread_pixel(P, x, y);
     uint32_t head = kNone, total = 0;
     if (valid) { const uint32_t a = addr_gen(P, x, y); head = heads[a]; total = counts[a]; }
     const uint32_t cnt = min(total, max_frags);
@@ -594,6 +600,129 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
     flush_counter(&C->frags_sorted, cnt);
     flush_counter(&C->frags_truncated, total - cnt);
     unsigned mx = total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx) atomicMax(&C->max_depth_complexity, mx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// S10 resolve, count-binned variant (default).  Lists of very different lengths in one warp cost max(n)^2 for everybody, so
+// the owned pixels are first counting-sorted by list length, longest first (k_ppll_bin_*: histogram, scan, scatter; empty
+// pixels get the clear colour right there).  k_ppll_resolve_binned then gives every warp 32 pixels with (nearly) EQUAL
+// list length: the 32 lists live interleaved in shared memory (element i of lane l at [i*32 + l]: all lanes touch the same
+// row at the same time, no bank conflicts), every lane chases its own list, sorts it (insertion sort while the next node
+// is in flight up to 32 keys, Shell sort with Ciura's gaps beyond) and blends it.  One instantiation per length class
+// 1..32 / 33..64 / 65..128 / 129..256 so that short lists keep high occupancy; lists longer than 256 (possible only with
+// max_frags > 256) take the cooperative kernel above, restricted to those pixels.
+// n_sorted[k] = number of pixels whose list is longer than kBinBounds[k]; the order array is sorted by descending length,
+// so class k owns the slots [n_sorted[k-1], n_sorted[k]).
+constexpr int kBinClasses = 5;
+__device__ __constant__ int kBinBounds[kBinClasses] = {256, 128, 64, 32, 0};
+
+__global__ void k_ppll_bin_count(const __grid_constant__ FrameParams P, const uint32_t* counts, uint32_t max_frags, unsigned int* hist) {
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    const uint32_t c = valid ? min(counts[addr_gen(P, x, y)], max_frags) : 0u;
+    if (c) {   // empty pixels are not binned (they would all hammer one address); equal lengths in a warp share one atomic
+        const unsigned m = __match_any_sync(__activemask(), c);
+        if ((threadIdx.x & 31) == uint32_t(__ffs(m) - 1)) atomicAdd(hist + c, (unsigned)__popc(m));
+    }
+}
+__global__ void k_ppll_bin_scan(uint32_t max_frags, const unsigned int* hist, unsigned int* offsets, unsigned int* n_sorted) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned acc = 0;
+        int k = 0;
+        for (int len = int(max_frags); len >= 1; len--) {
+            while (k < kBinClasses && len <= kBinBounds[k]) n_sorted[k++] = acc;
+            offsets[len] = acc;
+            acc += hist[len];
+        }
+        while (k < kBinClasses) n_sorted[k++] = acc;
+    }
+}
+__global__ void k_ppll_bin_scatter(const __grid_constant__ FrameParams P, const uint32_t* counts, uint32_t max_frags, unsigned int* offsets,
+                                   uint32_t* order, float4* image) {
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    if (!valid) return;
+    const uint32_t c = min(counts[addr_gen(P, x, y)], max_frags);
+    if (c == 0) { image[size_t(y) * P.W + x] = make_float4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]); return; }   // discard -> clear colour
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned m = __match_any_sync(__activemask(), c);
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (int(lane) == leader) base = atomicAdd(offsets + c, (unsigned)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    order[base + __popc(m & ((1u << lane) - 1u))] = y * P.W + x;
+}
+
+// CLASS k serves the slots [n_sorted[k-1], n_sorted[k]) (k >= 1), lists of at most MAXN = kBinBounds[k-1] keys.
+template <int MAXN, int WARPS, int CLASS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_ppll_resolve_binned(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
+                      const uint32_t* order, const unsigned int* n_sorted, uint32_t max_frags, int early_out, float4* image, Counters* C) {
+    extern __shared__ unsigned long long s_dyn[];                 // WARPS * MAXN * 32 keys, then 256 floats
+    float* s_unorm = reinterpret_cast<float*>(s_dyn + size_t(WARPS) * MAXN * 32);
+    for (uint32_t i = threadIdx.x; i < 256u; i += WARPS * 32) s_unorm[i] = float(i) / 255.0f;
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long* mine = s_dyn + size_t(warp) * MAXN * 32 + lane;   // element i at mine[i * 32]
+    const uint32_t first = n_sorted[CLASS - 1], last = n_sorted[CLASS];
+    uint32_t sorted = 0, trunc = 0, mx = 0;
+    for (uint32_t base = first + (blockIdx.x * WARPS + warp) * 32u; base < last; base += gridDim.x * WARPS * 32u) {
+        const uint32_t slot = base + lane;
+        if (slot < last) {
+            const uint32_t pixel = order[slot];
+            const uint32_t x = pixel % P.W, y = pixel / P.W;
+            const uint32_t a = addr_gen(P, x, y);
+            const uint32_t total = counts[a], c = min(total, max_frags);
+            sorted += c; trunc += total - c; mx = max(mx, total);
+            lv_ppll_node nd = nodes[heads[a]];
+            if (MAXN <= 32) {
+                for (uint32_t i = 0; i < c; i++) {
+                    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
+                    if (i + 1 < c) nd = nodes[nd.next];
+                    uint32_t j = i;
+                    while (j > 0 && mine[(j - 1) * 32] > key) { mine[j * 32] = mine[(j - 1) * 32]; j--; }
+                    mine[j * 32] = key;
+                }
+            } else {
+                for (uint32_t i = 0; i < c; i++) {
+                    mine[i * 32] = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
+                    if (i + 1 < c) nd = nodes[nd.next];
+                }
+                const uint32_t gaps[6] = {132u, 57u, 23u, 10u, 4u, 1u};   // Ciura
+#pragma unroll
+                for (int gi = 0; gi < 6; gi++) {
+                    const uint32_t gap = gaps[gi];
+                    if (gap >= uint32_t(MAXN)) continue;
+                    for (uint32_t i = gap; i < c; i++) {
+                        const unsigned long long key = mine[i * 32];
+                        uint32_t j = i;
+                        while (j >= gap && mine[(j - gap) * 32] > key) { mine[j * 32] = mine[(j - gap) * 32]; j -= gap; }
+                        mine[j * 32] = key;
+                    }
+                }
+            }
+            float r = 0.0f, g = 0.0f, b = 0.0f, al = 0.0f;
+            for (uint32_t i = 0; i < c; i++) {
+                if (early_out && !(al < 0.99f)) break;
+                const uint32_t col = uint32_t(mine[i * 32] & 0xffffffffull);
+                const float sr = s_unorm[col & 0xffu], sg = s_unorm[(col >> 8) & 0xffu];
+                const float sb = s_unorm[(col >> 16) & 0xffu], sa = s_unorm[col >> 24];
+                r = r + (1.0f - al) * sa * sr;
+                g = g + (1.0f - al) * sa * sg;
+                b = b + (1.0f - al) * sa * sb;
+                al = al + (1.0f - al) * sa;
+            }
+            r = r / al; g = g / al; b = b / al;
+            image[size_t(y) * P.W + x] = make_float4(r * al + P.bg[0] * (1.0f - al), g * al + P.bg[1] * (1.0f - al),
+                                                      b * al + P.bg[2] * (1.0f - al), al + P.bg[3] * (1.0f - al));
+        }
+        __syncwarp();
+    }
+    flush_counter(&C->frags_sorted, sorted);
+    flush_counter(&C->frags_truncated, trunc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0 && mx) atomicMax(&C->max_depth_complexity, mx);
