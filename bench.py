@@ -98,6 +98,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/traffic.json);
+    only valid for the workload the capture was taken on (config5 for k_rtao_rays)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if workload != "config5" or not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+
+
 def ray_bytes(T, I, rays_primary, rays_ao):
     """B_ray = 64 T + 32 I + 16 [primary] + 4 per ray."""
     return 64 * T + 32 * I + 16 * rays_primary + 4 * (rays_primary + rays_ao)
@@ -375,7 +384,8 @@ def main():
                        "parallelism": "tile-sharded x%d (64x64 tiles, Morton round-robin, 1 NCCL all_gather/frame)" % world if world > 1 else "single GPU",
                        "rays_per_step": tot_rays, "rays_primary": tot_rp, "rays_ao": tot_ra, "T_per_ray": tot_T / tot_rays, "I_per_ray": tot_I / tot_rays,
                        "scene_upload_and_bvh_build_s": upload_build_s, "bvh_build_ms": info["build_ms"]},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": ncu_traffic("k_rtao_rays", args.workload) if world == 1 else None, "algorithmic_bytes_per_launch": my_ao_bytes,
                          "kernel": "k_rtao_rays", "kernel_ms": k_ms, "peak_source": peak_src,
                          "bytes": "64 B x T + 32 B x I + 4 B per AO ray (SURVEY 8d); T/ray %.2f, I/ray %.2f over %d AO rays (rank 0)"
                                   % (st["ao_traversal_steps"] / max(st["rays_ao"], 1), st["ao_intersections"] / max(st["rays_ao"], 1), st["rays_ao"])},

@@ -142,7 +142,8 @@ inline bool slab(const Node& n, const Ray& r, float tmax, float& tnear) {
 struct Hit { float t; uint32_t prim; int kind; };
 
 // closest hit with hitT in [tmin, tmax]; ties -> lowest primitive index
-inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStats& st) {
+inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStats& st, bool tieSafe = true) {
+    const float margin = tieSafe ? sc.lineWidth : 0.0f;   // AO rays only need the distance: no tie rule, no margin
     st.rays++;
     best.t = r.tmax; best.prim = 0xFFFFFFFFu; best.kind = 0;
     bool found = false;
@@ -156,7 +157,7 @@ inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStat
         const Node& n = sc.nodes[ni];
         float tn;
         // cull against best.t + one tube diameter so that tying candidates are always seen (closest-hit rule)
-        if (!slab(n, r, best.t + sc.lineWidth, tn)) continue;
+        if (!slab(n, r, best.t + margin, tn)) continue;
         if (n.count) {
             st.isect += n.count;
             for (uint32_t i = 0; i < n.count; i++) {
@@ -170,7 +171,7 @@ inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStat
         } else {
             st.steps++;
             float t0, t1;
-            bool h0 = slab(sc.nodes[n.left], r, best.t + sc.lineWidth, t0), h1 = slab(sc.nodes[n.left + 1], r, best.t + sc.lineWidth, t1);
+            bool h0 = slab(sc.nodes[n.left], r, best.t + margin, t0), h1 = slab(sc.nodes[n.left + 1], r, best.t + margin, t1);
             if (h0 && h1) {
                 if (t0 <= t1) { stack[sp++] = n.left + 1; stack[sp++] = n.left; } else { stack[sp++] = n.left; stack[sp++] = n.left + 1; }
             } else if (h0) stack[sp++] = n.left;

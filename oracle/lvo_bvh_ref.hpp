@@ -57,10 +57,9 @@ struct TubePrimitive {
     }
     // acceptance rule of lvo_shaders.hpp (own-AABB slab test on the ORIGINAL interval + IntersectionTube + range check);
     // ray.tmax has meanwhile been shortened to the best hit by the traverser, which only removes non-improving candidates
-    std::optional<Intersection> intersect(const BRay& ray, float otmin, float otmax) const {
+    std::optional<Intersection> intersect(const BRay& ray, const RayInv& ri, float otmin, float otmax) const {
         float t; int kind;
         vec3 ro = V3(ray.origin[0], ray.origin[1], ray.origin[2]), rd = V3(ray.direction[0], ray.direction[1], ray.direction[2]);
-        RayInv ri = makeRayInv(ro, rd);
         if (acceptCandidate(ro, rd, ri, p0, p1, radius, capped, otmin, otmax, t, kind))
             return std::make_optional(Intersection{t, kind});
         return std::nullopt;
@@ -107,16 +106,16 @@ struct TieBreakClosestIntersector {
         BScalar distance() const { return intersection.distance() + margin; }
     };
     static constexpr bool any_hit = false;
-    const Scene& sc; bool capped; float otmin, otmax;
+    const Scene& sc; bool capped; float otmin, otmax, margin; RayInv ri;
     bool have = false; float bestT = 0; size_t bestPrim = 0;
-    TieBreakClosestIntersector(const Scene& s, bool c, float a, float b) : sc(s), capped(c), otmin(a), otmax(b) {}
+    TieBreakClosestIntersector(const Scene& s, bool c, float a, float b, float m, const RayInv& r) : sc(s), capped(c), otmin(a), otmax(b), margin(m), ri(r) {}
     std::optional<Result> intersect(size_t index, const BRay& ray) {
         size_t p = sc.bvh.primitive_indices[index];
         TubePrimitive prim = sc.prims[p]; prim.capped = capped;
-        if (auto hit = prim.intersect(ray, otmin, otmax)) {
+        if (auto hit = prim.intersect(ray, ri, otmin, otmax)) {
             if (!have || hit->t < bestT || (hit->t == bestT && p < bestPrim)) {
                 have = true; bestT = hit->t; bestPrim = p;
-                return std::make_optional(Result{p, *hit, sc.lineWidth});
+                return std::make_optional(Result{p, *hit, margin});
             }
         }
         return std::nullopt;
@@ -126,11 +125,11 @@ struct TieBreakClosestIntersector {
 struct AnyIntersector {
     struct Result { BScalar t; BScalar distance() const { return t; } };
     static constexpr bool any_hit = true;
-    const Scene& sc; bool capped; float otmin, otmax;
-    AnyIntersector(const Scene& s, bool c, float a, float b) : sc(s), capped(c), otmin(a), otmax(b) {}
+    const Scene& sc; bool capped; float otmin, otmax; RayInv ri;
+    AnyIntersector(const Scene& s, bool c, float a, float b, const RayInv& r) : sc(s), capped(c), otmin(a), otmax(b), ri(r) {}
     std::optional<Result> intersect(size_t index, const BRay& ray) {
         TubePrimitive prim = sc.prims[sc.bvh.primitive_indices[index]]; prim.capped = capped;
-        if (auto hit = prim.intersect(ray, otmin, otmax)) return std::make_optional(Result{hit->t});
+        if (auto hit = prim.intersect(ray, ri, otmin, otmax)) return std::make_optional(Result{hit->t});
         return std::nullopt;
     }
 };
@@ -139,12 +138,12 @@ template <class F>
 struct AllIntersector {
     struct Result { BScalar t; BScalar distance() const { return t; } };
     static constexpr bool any_hit = false;
-    const Scene& sc; bool capped; float otmin, otmax; F& f;
-    AllIntersector(const Scene& s, bool c, float a, float b, F& fn) : sc(s), capped(c), otmin(a), otmax(b), f(fn) {}
+    const Scene& sc; bool capped; float otmin, otmax; RayInv ri; F& f;
+    AllIntersector(const Scene& s, bool c, float a, float b, const RayInv& r, F& fn) : sc(s), capped(c), otmin(a), otmax(b), ri(r), f(fn) {}
     std::optional<Result> intersect(size_t index, const BRay& ray) {
         size_t p = sc.bvh.primitive_indices[index];
         TubePrimitive prim = sc.prims[p]; prim.capped = capped;
-        if (auto hit = prim.intersect(ray, otmin, otmax)) f(uint32_t(p), hit->t, hit->kind);
+        if (auto hit = prim.intersect(ray, ri, otmin, otmax)) f(uint32_t(p), hit->t, hit->kind);
         return std::nullopt;  // never shrink the interval: every candidate must be visited
     }
 };
@@ -153,12 +152,12 @@ struct AllIntersector {
 // must not reject a box whose segment the canonical acceptance rule admits.
 using Traverser = bvh::SingleRayTraverser<BBvh, 64, bvh::RobustNodeIntersector<BBvh>>;
 
-inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStats& st) {
+inline bool traceClosest(const Scene& sc, Ray r, bool capped, Hit& best, RayStats& st, bool tieSafe = true) {
     st.rays++;
     best.t = r.tmax; best.prim = 0xFFFFFFFFu; best.kind = 0;
     if (sc.segs.empty()) return false;
     BRay ray(BVec3(r.o.x, r.o.y, r.o.z), BVec3(r.d.x, r.d.y, r.d.z), r.tmin, r.tmax);
-    TieBreakClosestIntersector isect(sc, capped, r.tmin, r.tmax);
+    TieBreakClosestIntersector isect(sc, capped, r.tmin, r.tmax, tieSafe ? sc.lineWidth : 0.0f, makeRayInv(r.o, r.d));
     Traverser trav(sc.bvh);
     Traverser::Statistics s;
     auto hit = trav.traverse(ray, isect, s);
@@ -172,7 +171,7 @@ inline bool traceAny(const Scene& sc, Ray r, bool capped, RayStats& st) {
     st.rays++;
     if (sc.segs.empty()) return false;
     BRay ray(BVec3(r.o.x, r.o.y, r.o.z), BVec3(r.d.x, r.d.y, r.d.z), r.tmin, r.tmax);
-    AnyIntersector isect(sc, capped, r.tmin, r.tmax);
+    AnyIntersector isect(sc, capped, r.tmin, r.tmax, makeRayInv(r.o, r.d));
     Traverser trav(sc.bvh);
     Traverser::Statistics s;
     auto hit = trav.traverse(ray, isect, s);
@@ -185,7 +184,7 @@ inline void traceAll(const Scene& sc, Ray r, bool capped, RayStats& st, F&& f) {
     st.rays++;
     if (sc.segs.empty()) return;
     BRay ray(BVec3(r.o.x, r.o.y, r.o.z), BVec3(r.d.x, r.d.y, r.d.z), r.tmin, r.tmax);
-    AllIntersector<F> isect(sc, capped, r.tmin, r.tmax, f);
+    AllIntersector<F> isect(sc, capped, r.tmin, r.tmax, makeRayInv(r.o, r.d), f);
     Traverser trav(sc.bvh);
     Traverser::Statistics s;
     trav.traverse(ray, isect, s);

@@ -278,7 +278,7 @@ void lvo_render_rtao(void* h, const lv_camera* cam, const lvo_options* o, uint32
                     vec3 dir = normalize((surfaceTangent * hs.x + surfaceBitangent * hs.y) + surfaceNormal * hs.z);
                     Ray ar; ar.o = vertexPositionWorld + dir * offsetFactor; ar.d = dir; ar.tmin = 0.0f; ar.tmax = o->ao_radius;
                     float occ = 1.0f;                                                   // traceAoRay :158-175
-                    if (o->ao_use_distance) { Hit ah; if (traceClosest(sc, ar, u.useCappedTubes, ah, sa)) occ = ah.t / o->ao_radius; }
+                    if (o->ao_use_distance) { Hit ah; if (traceClosest(sc, ar, u.useCappedTubes, ah, sa, false)) occ = ah.t / o->ao_radius; }
                     else { if (traceAny(sc, ar, u.useCappedTubes, sa)) occ = 0.0f; }
                     aoFactor += occ;
                 }
