@@ -138,14 +138,36 @@ struct __align__(16) AoHit {
     float4 tng;       // surface tangent (segment direction), unused
 };
 
+__device__ __forceinline__ void apron_mark_owned(const FrameParams& P, uint32_t x, uint32_t y, unsigned int stamp) {
+    P.apron_marks[size_t(y) * P.W + x] = stamp;
+}
+
 __global__ void __launch_bounds__(kBlockThreads)
 k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* ao, AoHit* hit_list,
-               unsigned int* hit_count, Counters* C) {
+               unsigned int* hit_count, Counters* C, unsigned int* apron_mark, unsigned int apron_stamp) {
     uint32_t x, y;
-    const bool valid = thread_pixel(P, x, y);
+    bool valid;
+    if (apron_mark) {
+        // apron launch (tile-sharded + jittered tube rays only): the one-pixel ring around every owned tile, because the
+        // tube pass looks the AO image up bilinearly at a jittered position.  A ring pixel shared by several owned tiles, or
+        // owned itself, is claimed once through the stamp array.
+        const uint32_t ts = P.tile_size, ring = 4 * ts + 4, per_tile = (ring + kBlockThreads - 1) / kBlockThreads;
+        const uint32_t tile = blockIdx.x / per_tile, t = (blockIdx.x - tile * per_tile) * kBlockThreads + threadIdx.x;
+        const uint2 tl = P.tiles[tile];
+        int lx, ly;
+        if (t < ts + 2) { lx = int(t) - 1; ly = -1; }
+        else if (t < 2 * ts + 4) { lx = int(t - (ts + 2)) - 1; ly = int(ts); }
+        else if (t < 3 * ts + 4) { lx = -1; ly = int(t - (2 * ts + 4)); }
+        else { lx = int(ts); ly = int(t - (3 * ts + 4)); }
+        const long long gx = (long long)tl.x * ts + lx, gy = (long long)tl.y * ts + ly;
+        valid = t < ring && gx >= 0 && gy >= 0 && gx < (long long)P.W && gy < (long long)P.H;
+        x = uint32_t(gx); y = uint32_t(gy);
+        if (valid) valid = atomicExch(apron_mark + size_t(y) * P.W + x, apron_stamp) != apron_stamp;
+    } else valid = thread_pixel(P, x, y);
     uint32_t steps = 0, isect = 0;
     bool hit = false;
     AoHit rec;
+    if (valid && !apron_mark && apron_stamp) apron_mark_owned(P, x, y, apron_stamp);
     if (valid) {
         uint32_t seed = tea(x + y * P.W, P.frame_number);
         float xix = 0.5f, xiy = 0.5f;

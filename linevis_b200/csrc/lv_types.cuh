@@ -64,6 +64,7 @@ struct FrameParams {
     // owned image tiles (Morton order); tile_size x tile_size pixels each
     const uint2* tiles;
     uint32_t n_tiles, tile_size;
+    unsigned int* apron_marks;   // W*H stamps, only in tile-sharded + jittered mode (see k_rtao_primary)
     // PPLL addressing (reference Data/Shaders/Utils/TiledAddress.glsl)
     uint32_t padded_w, padded_h, addr_tw, addr_th;
 };

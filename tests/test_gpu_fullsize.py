@@ -107,17 +107,21 @@ def test_config4_like_fragment_count_is_bvh_independent(random1m):
         ctx.set_option("b200_bvh_leaf_size", leaf)
         sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
         img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="priority_queue")
-        counts.append((st["frags_generated"], st["frags_sorted"], st["max_depth_complexity"], float(img.sum())))
+        counts.append((st["frags_generated"], st["frags_sorted"], st["max_depth_complexity"], int(np.isnan(img).sum()), float(np.nansum(img))))
         sc.close(); ctx.close()
     assert counts[0] == counts[1]
 
 
-def test_sharded_union_equals_full_frame_at_1080p(helix100k):
+@pytest.mark.parametrize("tube_jitter", [False, True])
+def test_sharded_union_equals_full_frame_at_1080p(helix100k, tube_jitter):
+    """8 ranks emulated on one GPU.  Without tube jitter the AO lookup sits on the pixel centre and neighbouring texels only
+    enter with weights ~1e-4 (float error of the re-projection), so unowned neighbours (left at 1.0) may move a border pixel
+    by <= 2e-4; with jittered tube rays the library renders a one-pixel AO ring around its tiles and the union is exact."""
     pos, attr, seg = helix100k
     cam = lv.make_camera(1920, 1080)
     tf = scenes.standard_transfer_function(opacity=(0.3, 1.0))
     settings = {"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 4, "num_samples_per_frame": 1,
-                "num_accumulated_frames": 1, "use_jittered_primary_rays": True}
+                "num_accumulated_frames": 2 if tube_jitter else 1, "use_jittered_primary_rays": True}
     ctx = lv.Context(0)
     ctx.set_transfer_function(tf); ctx.set_new_settings(settings)
     sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
@@ -135,5 +139,10 @@ def test_sharded_union_equals_full_frame_at_1080p(helix100k):
         acc[m] = out[m]
         rays += st["rays_primary"] + st["rays_ao"]
         s.close(); c.close()
-    assert not np.isnan(acc).any() and np.abs(acc - full).max() <= 1e-5
-    assert rays == st_full["rays_primary"] + st_full["rays_ao"], "work is partitioned, not duplicated"
+    assert not np.isnan(acc).any()
+    if tube_jitter:
+        assert np.array_equal(acc, full)
+        assert rays >= st_full["rays_primary"] + st_full["rays_ao"]           # the AO ring is extra work
+    else:
+        assert np.abs(acc - full).max() <= 2e-4
+        assert rays == st_full["rays_primary"] + st_full["rays_ao"], "work is partitioned, not duplicated"
