@@ -69,7 +69,7 @@ struct lv_ctx {
     // sharding
     uint32_t rank = 0, world = 1, tile_size = 64;
     std::vector<uint2> tiles_host; DevBuf<uint2> tiles_dev; uint32_t tiles_w = 0, tiles_h = 0;
-    DevBuf<uint2> tiles_tmp;
+    DevBuf<uint2> tiles_tmp; std::vector<uint32_t> peer_off; uint32_t peer_w = 0, peer_h = 0, peer_world = 0, peer_tile = 0;
     // frame buffers
     DevBuf<unsigned int> apron_marks; unsigned int apron_stamp = 0;
     DevBuf<float4> image; DevBuf<float> ao, occ; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
@@ -485,16 +485,28 @@ int lv_pack_owned_tiles(lv_ctx* c, const float* image, uint32_t W, uint32_t H, f
 int lv_unpack_tiles(lv_ctx* c, const float* packed, uint32_t src_rank, uint32_t world, uint32_t W, uint32_t H, float* image) {
     if (!c || !image || !packed || world == 0 || src_rank >= world) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_unpack_tiles: bad argument");
     LV_CUDA(c, cudaSetDevice(c->device));
-    std::vector<uint2> t;
-    enumerate_tiles(W, H, c->tile_size, src_rank, world, t);
-    if (t.empty()) return LV_OK;
-    LV_CUDA(c, c->tiles_tmp.ensure(t.size()));
-    LV_CUDA(c, cudaMemcpyAsync(c->tiles_tmp.p, t.data(), t.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    // device copies of every rank's tile list are cached per (W, H, world, tile size): no host work / sync per frame
+    if (c->peer_w != W || c->peer_h != H || c->peer_world != world || c->peer_tile != c->tile_size) {
+        std::vector<uint2> all;
+        c->peer_off.assign(world + 1, 0);
+        for (uint32_t r = 0; r < world; r++) {
+            std::vector<uint2> t;
+            enumerate_tiles(W, H, c->tile_size, r, world, t);
+            all.insert(all.end(), t.begin(), t.end());
+            c->peer_off[r + 1] = uint32_t(all.size());
+        }
+        LV_CUDA(c, c->tiles_tmp.ensure(std::max<size_t>(1, all.size())));
+        LV_CUDA(c, cudaMemcpyAsync(c->tiles_tmp.p, all.data(), all.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->peer_w = W; c->peer_h = H; c->peer_world = world; c->peer_tile = c->tile_size;
+    }
+    const uint32_t n = c->peer_off[src_rank + 1] - c->peer_off[src_rank];
+    if (n == 0) return LV_OK;
     const uint32_t tt = c->tile_size * c->tile_size;
-    dim3 grid((tt + 255) / 256, uint32_t(t.size()));
-    k_unpack_tiles<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(packed), W, H, c->tiles_tmp.p, c->tile_size, reinterpret_cast<float4*>(image));
+    dim3 grid((tt + 255) / 256, n);
+    k_unpack_tiles<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(packed), W, H, c->tiles_tmp.p + c->peer_off[src_rank], c->tile_size,
+                                                reinterpret_cast<float4*>(image));
     LV_CUDA(c, cudaGetLastError());
-    LV_CUDA(c, cudaStreamSynchronize(c->stream));  // `t` (host staging) must outlive the copy
     return LV_OK;
 }
 

@@ -48,17 +48,17 @@ __device__ __forceinline__ void camera_ray(const FrameParams& P, uint32_t px, ui
 // closest-hit only (parity / debugging entry point lv_trace_primary)
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, lv_hit* hits, Counters* C) {
+    __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
     uint32_t x, y;
     const bool valid = thread_pixel(P, x, y);
     uint32_t steps = 0, isect = 0, nhit = 0;
+    Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
+    if (valid) camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
+    HitRec h;
+    const bool hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_stack[threadIdx.x >> 5], steps, isect);
     if (valid) {
-        Vec3 ro, rd;
-        camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
-        HitRec h;
         lv_hit out; out.t = 0.0f; out.prim = kNone; out.kind = 0; out.pad = 0;
-        if (bvh_trace<0>(S, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, steps, isect)) {
-            out.t = h.t; out.prim = h.prim; out.kind = h.kind; nhit = 1;
-        }
+        if (hit) { out.t = h.t; out.prim = h.prim; out.kind = h.kind; nhit = 1; }
         hits[size_t(y) * P.W + x] = out;
     }
     flush_counter(&C->rays_primary, valid ? 1 : 0);
@@ -72,44 +72,52 @@ k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDe
 // (reference TubeRayTracing.glsl:61-82,198-274).  `image` is the accumulation image (float RGBA).
 __global__ void __launch_bounds__(kBlockThreads)
 k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C) {
+    __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
+    uint32_t* stack = s_stack[threadIdx.x >> 5];
     uint32_t x, y;
     const bool valid = thread_pixel(P, x, y);
     uint32_t steps = 0, isect = 0, rays = 0, nhit = 0;
-    if (valid) {
-        float fr = 0.0f, fg = 0.0f, fb = 0.0f, fa = 0.0f;
-        const uint32_t nspp = P.use_jitter ? P.spp : 1u;
-        for (uint32_t si = 0; si < nspp; si++) {
-            float xix = 0.5f, xiy = 0.5f;
-            if (P.use_jitter) {
-                uint32_t seed = P.det_sampling ? tea(19u, P.frame_number * P.spp + si)
-                                               : tea(x + y * P.W, P.frame_number * P.spp + si);
-                xix = rnd(seed); xiy = rnd(seed);
-            }
-            Vec3 ro, rd;
-            camera_ray(P, x, y, xix, xiy, ro, rd);
-            float cr = 0.0f, cg = 0.0f, cb = 0.0f, ca = 0.0f;
-            float tmin = 0.0001f;
-            for (uint32_t hi = 0; hi < P.max_depth; hi++) {
-                HitRec h;
+    float fr = 0.0f, fg = 0.0f, fb = 0.0f, fa = 0.0f;
+    const uint32_t nspp = P.use_jitter ? P.spp : 1u;
+    for (uint32_t si = 0; si < nspp; si++) {
+        float xix = 0.5f, xiy = 0.5f;
+        if (P.use_jitter) {
+            uint32_t seed = P.det_sampling ? tea(19u, P.frame_number * P.spp + si)
+                                           : tea(x + y * P.W, P.frame_number * P.spp + si);
+            xix = rnd(seed); xiy = rnd(seed);
+        }
+        Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
+        if (valid) camera_ray(P, x, y, xix, xiy, ro, rd);
+        float cr = 0.0f, cg = 0.0f, cb = 0.0f, ca = 0.0f;
+        float tmin = 0.0001f;
+        bool live = valid;
+        // traceRayTransparent (:61-82): the warp's rays are traced as a packet; lanes drop out at a miss or alpha > 0.99
+        for (uint32_t hi = 0; hi < P.max_depth; hi++) {
+            if (__ballot_sync(0xffffffffu, live) == 0u) break;
+            HitRec h;
+            const bool hit = bvh_trace_packet(S, live, ro, rd, tmin, 1000.0f, P.use_capped != 0, h, stack, steps, isect);
+            if (live) {
                 rays++;
-                Vec4 hc; float hit_t; bool has;
-                if (bvh_trace<0>(S, ro, rd, tmin, 1000.0f, P.use_capped != 0, h, steps, isect)) {
-                    SegRec s = load_seg(S.segs + h.idx);
-                    Shaded sh = shade_hit(P, ro, rd, h.t, h.kind, s);
-                    hc = sh.color; hit_t = sh.hit_t; has = true;
+                Vec4 hc; float hit_t;
+                if (hit) {
+                    const SegRec s = load_seg(S.segs + h.idx);
+                    const Shaded sh = shade_hit(P, ro, rd, h.t, h.kind, s);
+                    hc = sh.color; hit_t = sh.hit_t;
                     if (hi == 0 && si == 0) nhit = 1;
                 } else {  // Miss (TubeRayTracing.glsl:290-298)
-                    hc = v4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]); hit_t = 0.0f; has = false;
+                    hc = v4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]); hit_t = 0.0f;
                 }
                 tmin = hit_t + maxf_(hit_t * 1e-5f, 1e-7f);
                 cr = cr + (1.0f - ca) * hc.w * hc.x;
                 cg = cg + (1.0f - ca) * hc.w * hc.y;
                 cb = cb + (1.0f - ca) * hc.w * hc.z;
                 ca = ca + (1.0f - ca) * hc.w;
-                if (!has || ca > 0.99f) break;
+                if (!hit || ca > 0.99f) live = false;
             }
-            fr += cr; fg += cg; fb += cb; fa += ca;
         }
+        fr += cr; fg += cg; fb += cb; fa += ca;
+    }
+    if (valid) {
         if (P.use_jitter) { float dn = float(P.spp); fr /= dn; fg /= dn; fb /= dn; fa /= dn; }
         float4* px = image + size_t(y) * P.W + x;
         if (P.frame_number != 0) {
@@ -168,14 +176,17 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
     bool hit = false;
     AoHit rec;
     if (valid && !apron_mark && apron_stamp) apron_mark_owned(P, x, y, apron_stamp);
+    __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
+    Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
     if (valid) {
         uint32_t seed = tea(x + y * P.W, P.frame_number);
         float xix = 0.5f, xiy = 0.5f;
         if (P.ao_jitter) { xix = rnd(seed); xiy = rnd(seed); }
-        Vec3 ro, rd;
         camera_ray(P, x, y, xix, xiy, ro, rd);
-        HitRec h;
-        hit = bvh_trace<0>(S, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, steps, isect);
+    }
+    HitRec h;
+    hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_stack[threadIdx.x >> 5], steps, isect);
+    if (valid) {
         if (hit) {
             // analytic stand-in for the barycentric vertex fetch of the triangle-mesh path (:222-276)
             const SegRec s = load_seg(S.segs + h.idx);

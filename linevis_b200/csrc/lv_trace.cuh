@@ -141,6 +141,74 @@ __device__ __forceinline__ bool bvh_trace(const SceneDev& S, Vec3 o, Vec3 d, flo
     return found;
 }
 
+// Closest hit for a WARP PACKET of coherent rays (the 8x4 pixel patch of camera rays a warp owns).  The warp walks the
+// BVH together with one shared stack: a child is visited if any lane's box test (against that lane's own best hit plus the
+// tie margin) passes, near child first by majority vote, and every node / record is fetched once per warp.  Each lane keeps
+// its own closest hit under the same rules as bvh_trace<0> (acceptance rule, ties -> lowest segment index), so the result is
+// identical; only the order in which candidates are met differs, and the result does not depend on that order.
+// Must be called by all 32 lanes; `active` = this lane has a ray.  `stack` = kStackSize words of shared memory per warp.
+__device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active, Vec3 o, Vec3 d, float tmin, float tmax, bool capped,
+                                                 HitRec& best, uint32_t* stack, uint32_t& steps, uint32_t& isect) {
+    best.t = tmax; best.idx = 0; best.prim = 0xFFFFFFFFu; best.kind = 0;
+    bool found = false;
+    if (S.n_seg == 0 || __ballot_sync(0xffffffffu, active) == 0u) return false;
+    const uint32_t lane = threadIdx.x & 31;
+    const RayQ rq = make_rayq(o, d);
+    const RayBox rb = make_raybox(o, d);
+    uint32_t node = 0;
+    int sp = 0;
+    while (true) {
+        const Node64 nd = load_node(S.nodes + node);
+        steps += (lane == 0);
+        const float tcull = best.t + S.line_width;
+        float tl, tr;
+        const bool hl = active && box_hit(rb, nd.l0, nd.l1, tmin, tcull, tl);
+        const bool hr = active && box_hit(rb, nd.r0, nd.r1, tmin, tcull, tr);
+        const unsigned ml = __ballot_sync(0xffffffffu, hl), mr = __ballot_sync(0xffffffffu, hr);
+        const uint32_t cw[2] = {__float_as_uint(nd.l0.w), __float_as_uint(nd.r0.w)};
+        const unsigned mk[2] = {ml, mr};
+        uint32_t inner[2]; int n_inner = 0; int inner_side[2];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            if (!mk[side]) continue;
+            const uint32_t w = cw[side];
+            if (w & kLeafBit) {
+                const uint32_t ref = w & kRefMask, cnt = ((w >> 27) & 15u) + 1u;
+                isect += (lane == 0) ? cnt : 0u;
+                const bool mine = side ? hr : hl;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const SegRec s = load_seg(S.segs + ref + i);
+                    float t; uint32_t kind;
+                    if (mine && seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
+                        if (!found || t <= best.t) {
+                            const uint32_t prim = __ldg(S.prim_ids + ref + i);
+                            if (!found || t < best.t || prim < best.prim) { best.t = t; best.idx = ref + i; best.prim = prim; best.kind = kind; found = true; }
+                        }
+                    }
+                }
+            } else { inner_side[n_inner] = side; inner[n_inner++] = w; }
+        }
+        if (n_inner == 2) {
+            // near child first: majority of the lanes that hit both (or either)
+            const unsigned right_near = __ballot_sync(0xffffffffu, hr && (!hl || tr < tl));
+            const unsigned left_near = __ballot_sync(0xffffffffu, hl && (!hr || tl <= tr));
+            const bool rf = __popc(right_near) > __popc(left_near);
+            if (lane == 0) stack[sp] = rf ? inner[0] : inner[1];
+            sp++;
+            node = rf ? inner[1] : inner[0];
+        } else if (n_inner == 1) node = inner[0];
+        else {
+            if (sp == 0) break;
+            --sp;
+            __syncwarp();
+            node = stack[sp];
+        }
+        (void)inner_side;
+        __syncwarp();
+    }
+    return found;
+}
+
 // All candidates with hitT in [tmin, tmax]; f(record_index, t, kind, SegRec) per accepted candidate.
 template <class F>
 __device__ __forceinline__ void bvh_trace_all(const SceneDev& S, Vec3 o, Vec3 d, float tmin, float tmax, bool capped,
