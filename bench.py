@@ -107,11 +107,6 @@ def ncu_traffic(kernel, workload):
     return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
 
 
-def ray_bytes(T, I, rays_primary, rays_ao):
-    """B_ray = 64 T + 32 I + 16 [primary] + 4 per ray."""
-    return 64 * T + 32 * I + 16 * rays_primary + 4 * (rays_primary + rays_ao)
-
-
 # ------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, wl, ppll_wl):
     """The reference's own CPU path for this workload, on the host cores (rank 0 only)."""

@@ -79,7 +79,7 @@ struct lv_ctx {
     DevBuf<uint32_t> heads, counts, bin_order; DevBuf<unsigned int> bin_hist; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
     unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
     cudaEvent_t ev[8] = {};
-    bool rtao_rays_timed = false;
+    bool rtao_rays_timed = false, binned_attr_set = false;
 };
 
 struct lv_scene {
@@ -525,7 +525,6 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     if (n == 0) { *out = s; return LV_OK; }
     const float r = line_width * 0.5f;
     cudaStream_t st = c->stream;
-    BuildTmp T{};
     DevBuf<float> bounds, boxes; DevBuf<unsigned long long> keys, keys2; DevBuf<uint32_t> vals;
     DevBuf<int2> children, ranges; DevBuf<int> parent; DevBuf<unsigned int> flags; DevBuf<char> cubtmp;
     auto cleanup = [&]() { bounds.release(); boxes.release(); keys.release(); keys2.release(); vals.release(); children.release(); ranges.release(); parent.release(); flags.release(); cubtmp.release(); };
@@ -794,10 +793,9 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
             k_ppll_resolve<<<uint32_t((n_own + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
                 P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, c->bin_order.p, nsort);
         auto smem = [](int maxn, int warps) { return size_t(warps) * maxn * 32 * 8 + 256 * 4; };
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!c->binned_attr_set) {
             LV_CUDA(c, cudaFuncSetAttribute(k_ppll_resolve_binned<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem(256, 1))));
-            attr_set = true;
+            c->binned_attr_set = true;
         }
         const uint32_t pg = uint32_t(c->num_sms) * 6u;
         if (max_frags > 128u) k_ppll_resolve_binned<256, 1, 1><<<pg, 32, smem(256, 1), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);

@@ -12,18 +12,6 @@
 
 namespace lv {
 
-struct BuildTmp {
-    float* bounds;             // 6 floats: scene min xyz, max xyz
-    unsigned long long *keys, *keys_sorted;
-    uint32_t *vals, *vals_sorted;
-    int2* children;            // per inner node: child index, bit31 set = leaf (record index)
-    int2* ranges;              // per inner node: [first, last]
-    int* parent;               // [2N-1]: inner nodes 0..N-2, leaves N-1..2N-2
-    float* boxes;              // [2N-1][6]
-    unsigned int* flags;       // per inner node arrival counter
-    void* cub_tmp; size_t cub_bytes;
-};
-
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
     if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
     else atomicMax(reinterpret_cast<unsigned int*>(a), __float_as_uint(v));

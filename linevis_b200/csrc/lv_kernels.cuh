@@ -236,10 +236,10 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
 //     intersect their leaves together;
 //   - popped entries carry their box entry distance and are skipped when the closest hit found meanwhile is nearer.
 // Tried and dropped (measured, no gain): sorting the rays of 128 neighbouring hit pixels into 64 direction bins,
-// warp-private chunks of consecutive ray numbers, a second compaction pass over box-test survivors inside the leaf phase.
+// warp-private chunks of consecutive ray numbers, a second compaction pass over box-test survivors inside the leaf phase,
+// precomputing the ray directions in a separate full-utilisation kernel (the refill is not where the time goes).
 // The per-ray result (4 B) goes to occ[r]; sample-ordered summation happens in k_rtao_reduce.
 constexpr uint32_t kDone = 0x7FFFFFFFu;
-constexpr int kRefillBelow = 24;
 constexpr int kAoStack = 72;
 
 __global__ void __launch_bounds__(kBlockThreads)

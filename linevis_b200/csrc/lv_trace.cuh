@@ -1,4 +1,5 @@
-// lv_trace.cuh -- per-thread BVH traversal over 64-byte child-pair nodes (closest / any / all hits).
+// lv_trace.cuh -- BVH traversal building blocks over 64-byte child-pair nodes: canonical slab test, loads, the warp-packet
+// closest-hit traversal.  (The AO ray stream and the PPLL all-hits packet live in lv_kernels.cuh.)
 //
 // Replaces traceRayEXT / rayQueryEXT against the driver's acceleration structure
 // (reference TubeRayTracing.glsl:56,68; VulkanRayTracedAmbientOcclusion.glsl:164-165,201-204).
@@ -79,73 +80,11 @@ struct HitRec {
     uint32_t kind;
 };
 
-// MODE 0: closest hit, MODE 1: any hit (terminate on first accepted candidate).
-template <int MODE>
-__device__ __forceinline__ bool bvh_trace(const SceneDev& S, Vec3 o, Vec3 d, float tmin, float tmax, bool capped,
-                                          HitRec& best, uint32_t& steps, uint32_t& isect) {
-    best.t = tmax; best.idx = 0; best.prim = 0xFFFFFFFFu; best.kind = 0;
-    if (S.n_seg == 0) return false;
-    const RayQ rq = make_rayq(o, d);
-    const RayBox rb = make_raybox(o, d);
-    uint32_t stack[kStackSize];
-    int sp = 0;
-    uint32_t node = 0;
-    bool found = false;
-    while (true) {
-        const Node64 nd = load_node(S.nodes + node);
-        steps++;
-        float tl, tr;
-        // Boxes are culled against best.t + one tube diameter, not best.t: the reference's float32 quadratic reports hitT
-        // with an error of up to a few % of r, so a candidate that TIES the current best (adjacent capsules share an end
-        // sphere) may have a box entry slightly beyond it; the tie rule must still see it, whatever the BVH looks like.
-        const float tcull = MODE == 0 ? best.t + S.line_width : best.t;
-        bool hl = box_hit(rb, nd.l0, nd.l1, tmin, tcull, tl);
-        bool hr = box_hit(rb, nd.r0, nd.r1, tmin, tcull, tr);
-        const uint32_t lw = __float_as_uint(nd.l0.w), rw = __float_as_uint(nd.r0.w);   // absent children have a box that never hits
-        const uint32_t lref = lw & kRefMask, rref = rw & kRefMask;
-        const uint32_t lcnt = (lw & kLeafBit) ? ((lw >> 27) & 15u) + 1u : 0u, rcnt = (rw & kLeafBit) ? ((rw >> 27) & 15u) + 1u : 0u;
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            bool h = side ? hr : hl;
-            uint32_t cnt = side ? rcnt : lcnt, ref = side ? rref : lref;
-            if (h && cnt) {
-                isect += cnt;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    SegRec s = load_seg(S.segs + ref + i);
-                    float t; uint32_t kind;
-                    if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
-                        if (MODE == 1) { best.t = t; best.idx = ref + i; best.kind = kind; return true; }
-                        if (!found || t <= best.t) {
-                            uint32_t prim = __ldg(S.prim_ids + ref + i);
-                            if (!found || t < best.t || prim < best.prim) {
-                                best.t = t; best.idx = ref + i; best.prim = prim; best.kind = kind; found = true;
-                            }
-                        }
-                    }
-                }
-                if (side) hr = false; else hl = false;
-            }
-        }
-        if (hl && hr) {
-            uint32_t nearn = lref, farn = rref;
-            if (tr < tl) { nearn = rref; farn = lref; }
-            if (sp < kStackSize) stack[sp++] = farn;
-            node = nearn;
-        } else if (hl) node = lref;
-        else if (hr) node = rref;
-        else {
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
-    }
-    return found;
-}
-
 // Closest hit for a WARP PACKET of coherent rays (the 8x4 pixel patch of camera rays a warp owns).  The warp walks the
 // BVH together with one shared stack: a child is visited if any lane's box test (against that lane's own best hit plus the
 // tie margin) passes, near child first by majority vote, and every node / record is fetched once per warp.  Each lane keeps
-// its own closest hit under the same rules as bvh_trace<0> (acceptance rule, ties -> lowest segment index), so the result is
-// identical; only the order in which candidates are met differs, and the result does not depend on that order.
+// its own closest hit (acceptance rule above, ties -> lowest segment index); the order in which candidates are met does not
+// influence the result.
 // Must be called by all 32 lanes; `active` = this lane has a ray.  `stack` = kStackSize words of shared memory per warp.
 __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active, Vec3 o, Vec3 d, float tmin, float tmax, bool capped,
                                                  HitRec& best, uint32_t* stack, uint32_t& steps, uint32_t& isect) {
@@ -167,7 +106,7 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
         const unsigned ml = __ballot_sync(0xffffffffu, hl), mr = __ballot_sync(0xffffffffu, hr);
         const uint32_t cw[2] = {__float_as_uint(nd.l0.w), __float_as_uint(nd.r0.w)};
         const unsigned mk[2] = {ml, mr};
-        uint32_t inner[2]; int n_inner = 0; int inner_side[2];
+        uint32_t inner[2]; int n_inner = 0;
 #pragma unroll
         for (int side = 0; side < 2; side++) {
             if (!mk[side]) continue;
@@ -186,7 +125,7 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
                         }
                     }
                 }
-            } else { inner_side[n_inner] = side; inner[n_inner++] = w; }
+            } else inner[n_inner++] = w;
         }
         if (n_inner == 2) {
             // near child first: majority of the lanes that hit both (or either)
@@ -203,53 +142,9 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
             __syncwarp();
             node = stack[sp];
         }
-        (void)inner_side;
         __syncwarp();
     }
     return found;
-}
-
-// All candidates with hitT in [tmin, tmax]; f(record_index, t, kind, SegRec) per accepted candidate.
-template <class F>
-__device__ __forceinline__ void bvh_trace_all(const SceneDev& S, Vec3 o, Vec3 d, float tmin, float tmax, bool capped,
-                                              uint32_t& steps, uint32_t& isect, F&& f) {
-    if (S.n_seg == 0) return;
-    const RayQ rq = make_rayq(o, d);
-    const RayBox rb = make_raybox(o, d);
-    uint32_t stack[kStackSize];
-    int sp = 0;
-    uint32_t node = 0;
-    while (true) {
-        const Node64 nd = load_node(S.nodes + node);
-        steps++;
-        float tl, tr;
-        bool hl = box_hit(rb, nd.l0, nd.l1, tmin, tmax, tl);
-        bool hr = box_hit(rb, nd.r0, nd.r1, tmin, tmax, tr);
-        const uint32_t lw = __float_as_uint(nd.l0.w), rw = __float_as_uint(nd.r0.w);   // absent children have a box that never hits
-        const uint32_t lref = lw & kRefMask, rref = rw & kRefMask;
-        const uint32_t lcnt = (lw & kLeafBit) ? ((lw >> 27) & 15u) + 1u : 0u, rcnt = (rw & kLeafBit) ? ((rw >> 27) & 15u) + 1u : 0u;
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            bool h = side ? hr : hl;
-            uint32_t cnt = side ? rcnt : lcnt, ref = side ? rref : lref;
-            if (h && cnt) {
-                isect += cnt;
-                for (uint32_t i = 0; i < cnt; i++) {
-                    SegRec s = load_seg(S.segs + ref + i);
-                    float t; uint32_t kind;
-                    if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) f(ref + i, t, kind, s);
-                }
-                if (side) hr = false; else hl = false;
-            }
-        }
-        if (hl && hr) { if (sp < kStackSize) stack[sp++] = rref; node = lref; }
-        else if (hl) node = lref;
-        else if (hr) node = rref;
-        else {
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
-    }
 }
 
 }  // namespace lv
