@@ -37,6 +37,7 @@ struct Options {
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
     uint32_t ao_refill_below = 24;
+    uint32_t ao_min_blocks = 10;      // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 10 / 12)
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
@@ -277,13 +278,21 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
         // one float per (hit pixel, sample); worst case every owned pixel (and ring pixel) is hit
         const size_t max_hits = size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + (apron ? ring : 0));
         LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
-        int per_sm = 0;
-        LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rtao_rays, kBlockThreads, 0));
-        const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
-        LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-        k_rtao_rays<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, c->occ.p, c->ao_hits.p, c->small.p,
-                                                            reinterpret_cast<unsigned long long*>(c->small.p + 2), c->counters.p);
-        LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        auto launch = [&](auto kern) -> int {
+            int per_sm = 0;
+            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
+            const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
+            LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+            kern<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, c->occ.p, c->ao_hits.p, c->small.p,
+                                                         reinterpret_cast<unsigned long long*>(c->small.p + 2), c->counters.p);
+            LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+            return LV_OK;
+        };
+        int lrc;
+        if (c->opt.ao_min_blocks >= 12) lrc = launch(k_rtao_rays<12>);
+        else if (c->opt.ao_min_blocks >= 10) lrc = launch(k_rtao_rays<10>);
+        else lrc = launch(k_rtao_rays<8>);
+        if (lrc) return lrc;
         c->rtao_rays_timed = true;
         k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, c->ao.p);
     }
@@ -395,6 +404,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
+    else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
     else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
     else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
@@ -435,6 +445,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
+    else if (k == "b200_ao_min_blocks") v = std::to_string(o.ao_min_blocks);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());

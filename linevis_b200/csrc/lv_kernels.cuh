@@ -242,7 +242,8 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
 constexpr uint32_t kDone = 0x7FFFFFFFu;
 constexpr int kAoStack = 72;
 
-__global__ void __launch_bounds__(kBlockThreads)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
             const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
     const uint32_t lane = threadIdx.x & 31;

@@ -62,14 +62,22 @@ __device__ __forceinline__ bool seg_box_hit(const RayBox& rb, const SegRec& s, f
                    fmaxf(s.a.x, s.b.x) + r, fmaxf(s.a.y, s.b.y) + r, fmaxf(s.a.z, s.b.z) + r, tmin, tmax, tn);
 }
 
+// 256-bit read-only loads (LDG.E.256, new on sm_100): a 64-byte node is 2 load instructions instead of 4, a 32-byte
+// segment record 1 instead of 2.  With every lane on a different node the L1 handles one wavefront per lane PER LOAD
+// INSTRUCTION, and that wavefront rate -- not DRAM, not issue -- was what bound k_rtao_rays (profiles/r1e: L1 76 %).
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 __device__ __forceinline__ Node64 load_node(const Node64* p) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-    Node64 n; n.l0 = __ldg(q); n.l1 = __ldg(q + 1); n.r0 = __ldg(q + 2); n.r1 = __ldg(q + 3);
+    Node64 n;
+    ldg256(p, n.l0, n.l1);
+    ldg256(reinterpret_cast<const char*>(p) + 32, n.r0, n.r1);
     return n;
 }
 __device__ __forceinline__ SegRec load_seg(const SegRec* p) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-    SegRec s; s.a = __ldg(q); s.b = __ldg(q + 1);
+    SegRec s;
+    ldg256(p, s.a, s.b);
     return s;
 }
 

@@ -8,7 +8,7 @@ namespace lv {
 
 // 32-byte packed segment record, stored in BVH (Morton) order.  Replaces two dependent 48-byte
 // LinePointDataUnified gathers (reference src/LineData/LineRenderData.hpp:99-106) by one 32-byte load.
-struct __align__(16) SegRec {
+struct __align__(32) SegRec {
     float4 a;  // p0.xyz, attr0
     float4 b;  // p1.xyz, attr1
 };
@@ -17,7 +17,7 @@ struct __align__(16) SegRec {
 // child word: leaf  = bit31 | (count-1) << 27 | first record (BVH order), 1 <= count <= 16, record index < 2^27;
 //             inner = node index.  `count` is repeated in the max.w lane (0 for inner).  An absent child is the point
 //             box (+inf, +inf, +inf), which the canonical slab test can never hit.
-struct __align__(16) Node64 {
+struct __align__(64) Node64 {
     float4 l0;  // lmin.xyz, as_float(left child word)
     float4 l1;  // lmax.xyz, as_float(lcount)
     float4 r0;  // rmin.xyz, as_float(right child word)

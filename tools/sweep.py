@@ -11,6 +11,7 @@ ap.add_argument("--leaf", type=int, nargs="+", default=[1, 2, 4, 8])
 ap.add_argument("--refill", type=int, nargs="+", default=[16, 24, 28, 32])
 ap.add_argument("--ppll-workload", default="none")
 ap.add_argument("--vote", type=int, nargs="+", default=[12])
+ap.add_argument("--minb", type=int, nargs="+", default=[8])
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 wl = bench.WORKLOADS[args.workload]
@@ -23,7 +24,8 @@ for leaf in args.leaf:
     ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": wl["ao_spp"], "ambient_occlusion_iterations": 1,
                           "num_samples_per_frame": 1, "num_accumulated_frames": 1, "b200_bvh_leaf_size": leaf})
     sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
-    for refill, vote in itertools.product(args.refill, args.vote):
+    for refill, vote, minb in itertools.product(args.refill, args.vote, args.minb):
+        ctx.set_option("b200_ao_min_blocks", minb)
         ctx.set_option("b200_ao_refill_below", refill)
         ctx.set_option("b200_ao_leaf_vote", vote)
         ts = []
@@ -33,8 +35,8 @@ for leaf in args.leaf:
         k, t = np.min([a for a, _ in ts[1:]]), np.min([b for _, b in ts[1:]])
         rays = st["rays_primary"] + st["rays_ao"]
         by = 64 * st["ao_traversal_steps"] + 32 * st["ao_intersections"] + 4 * st["rays_ao"]
-        print("leaf %d refill %2d vote %2d: k_rtao_rays %.2f ms  frame %.2f ms  %.0f Mrays/s  T/ray %.1f I/ray %.1f  algGB/s %.0f  build %.1f ms" %
-              (leaf, refill, vote, k, t, rays / t / 1e3, st["ao_traversal_steps"] / st["rays_ao"], st["ao_intersections"] / st["rays_ao"], by / k / 1e6, sc.info()["build_ms"]), flush=True)
+        print("leaf %d refill %2d vote %2d minb %2d: k_rtao_rays %.2f ms  frame %.2f ms  %.0f Mrays/s  T/ray %.1f I/ray %.1f  algGB/s %.0f  build %.1f ms" %
+              (leaf, refill, vote, minb, k, t, rays / t / 1e3, st["ao_traversal_steps"] / st["rays_ao"], st["ao_intersections"] / st["rays_ao"], by / k / 1e6, sc.info()["build_ms"]), flush=True)
     sc.close(); ctx.close()
 if args.ppll_workload != "none":
     pw = bench.PPLL_WORKLOADS[args.ppll_workload]
