@@ -57,6 +57,7 @@ typedef struct lv_camera {
     float fov_y;                /* fieldOfViewY, radians */
     float background[4];        /* backgroundColor; foregroundColor = 1 - background (LineData.cpp:1284-1285) */
     uint32_t width, height;     /* viewportSize */
+    float near_dist, far_dist;  /* camera near / far clip distance (depth cues: DepthCues/ComputeDepthValues.glsl:39-40) */
 } lv_camera;
 
 /*

@@ -21,6 +21,8 @@ class LvCamera(ctypes.Structure):
         ("background", ctypes.c_float * 4),
         ("width", ctypes.c_uint32),
         ("height", ctypes.c_uint32),
+        ("near_dist", ctypes.c_float),
+        ("far_dist", ctypes.c_float),
     ]
 
 
@@ -68,4 +70,5 @@ def make_camera(width, height, eye=(0.0, 0.0, 0.8), center=(0.0, 0.0, 0.0), up=(
     cam.fov_y = fov_y
     cam.background[:] = np.asarray(background, np.float32)
     cam.width, cam.height = int(width), int(height)
+    cam.near_dist, cam.far_dist = near, far
     return cam

@@ -73,7 +73,7 @@ struct lv_ctx {
     DevBuf<uint2> tiles_tmp; std::vector<uint32_t> peer_off; uint32_t peer_w = 0, peer_h = 0, peer_world = 0, peer_tile = 0;
     // frame buffers
     DevBuf<unsigned int> apron_marks; unsigned int apron_stamp = 0;
-    DevBuf<float4> image; DevBuf<float> ao, occ; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
+    DevBuf<float4> image; DevBuf<float> ao, occ, depth_mm; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
     uint32_t ao_w = 0, ao_h = 0;
     DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[2..3] = 64-bit ao work counter
     // PPLL
@@ -168,6 +168,8 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.line_width = sc ? sc->line_width : c->opt.line_width;
     const Options& o = c->opt;
     P.use_capped = o.use_capped_tubes; P.use_halos = o.use_halos; P.use_ao = 0;
+    P.use_depth_cues = 0; P.depth_cue_strength = o.depth_cue_strength; P.depth_min_max = nullptr;
+    P.near_dist = cam->near_dist; P.far_dist = cam->far_dist;
     P.ao_strength = o.ao_strength; P.ao_gamma = o.ao_gamma; P.ao_radius = o.ao_radius;
     P.ao_spp = o.ao_spp; P.ao_use_distance = o.ao_use_distance; P.ao_jitter = o.ao_jitter_primary;
     P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
@@ -238,6 +240,8 @@ int deliver(lv_ctx* c, const void* src, void* dst, uint32_t W, uint32_t H, size_
     return LV_OK;
 }
 
+bool cam_ok(const FrameParams& P) { return P.far_dist > P.near_dist; }
+
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 // ---- RTAO pass (S5) into ctx->ao --------------------------------------------------------------
@@ -300,6 +304,19 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     return LV_OK;
 }
 
+// LineRenderer::computeDepthRange (reference src/Renderers/LineRenderer.cpp:410-431), once per frame when depth cues are on
+int run_depth_range(lv_ctx* c, const lv_scene* sc, FrameParams& P) {
+    if (!(c->opt.depth_cue_strength > 0.0f) || sc->n_seg == 0) return LV_OK;
+    if (!(cam_ok(P))) return fail(c, LV_ERR_INVALID_ARGUMENT, "depth cues need lv_camera.near_dist < far_dist");
+    LV_CUDA(c, c->depth_mm.ensure(2));
+    const float init[2] = {P.far_dist, P.near_dist};
+    LV_CUDA(c, cudaMemcpyAsync(c->depth_mm.p, init, 8, cudaMemcpyHostToDevice, c->stream));
+    k_depth_range<<<c->num_sms * 8, 256, 0, c->stream>>>(P, sc->segs.p, uint32_t(sc->n_seg), c->depth_mm.p);
+    LV_CUDA(c, cudaGetLastError());
+    P.use_depth_cues = 1; P.depth_min_max = c->depth_mm.p;
+    return LV_OK;
+}
+
 int ppll_prepare(lv_ctx* c, const lv_scene* sc, const FrameParams& P, uint64_t linked_list_size) {
     const size_t npad = size_t(P.padded_w) * P.padded_h;
     if (linked_list_size == 0) {
@@ -348,7 +365,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (!c) return LV_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->hits.release(); c->ao_hits.release();
+    c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -369,10 +386,8 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     auto u = [&]() { return uint32_t(strtoul(value, nullptr, 10)); };
     if (k == "line_width") o.line_width = f();
     else if (k == "band_width") o.band_width = f();
-    else if (k == "depth_cue_strength") {
-        if (f() > 0.0f) return fail(c, LV_ERR_INVALID_ARGUMENT, "depth cues are not implemented on this path (SURVEY 8a note); use depth_cue_strength = 0");
-        o.depth_cue_strength = 0.0f;
-    } else if (k == "ambient_occlusion_mode") {
+    else if (k == "depth_cue_strength") o.depth_cue_strength = f() > 0.0f ? f() : 0.0f;   // <= 0 switches USE_DEPTH_CUES off (LineRenderer.cpp:449-460)
+    else if (k == "ambient_occlusion_mode") {
         if (strcmp(value, "RTAO")) return fail(c, LV_ERR_INVALID_ARGUMENT, "only ambient_occlusion_mode = RTAO is implemented");
         o.ao_mode = value;
     } else if (k == "ambient_occlusion_strength") o.ao_strength = f();
@@ -704,6 +719,7 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
             if ((rc = run_rtao(c, sc, P, frame_number))) return rc;
         P.use_ao = 1; P.ao_tex = c->ao.p;
     }
+    if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (P.n_tiles) k_tubes<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
     LV_CUDA(c, cudaGetLastError());
@@ -747,6 +763,7 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
     if (rc) return rc;
     if (P.padded_w != c->padded_w || P.padded_h != c->padded_h) return fail(c, LV_ERR_STATE, "lv_ppll_gather: resolution changed since lv_ppll_clear");
     if ((rc = reset_counters(c))) return rc;
+    if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (P.n_tiles)
         k_ppll_gather<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);

@@ -45,6 +45,40 @@ __device__ __forceinline__ void camera_ray(const FrameParams& P, uint32_t px, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// Depth cues: min / max view depth over the line vertices inside the frustum (+- 1e-2), reference
+// Data/Shaders/DepthCues/ComputeDepthValues.glsl:60-98 + MinMaxDepthReduction (LineRenderer.cpp:410-431).  min/max are exact
+// and order independent, so one pass with warp shuffles + integer atomics on the (positive) float bit patterns replaces
+// the reference's multi-pass tree reduction.  out = {min, max}, initialised to {farDist, nearDist} by the host.
+__global__ void k_depth_range(const __grid_constant__ FrameParams P, const SegRec* segs, uint32_t n_seg, float* out) {
+    float dmin = P.far_dist, dmax = P.near_dist;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_seg; i += gridDim.x * blockDim.x) {
+        const SegRec s = segs[i];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float4 p = e ? s.b : s.a;
+            const Vec4 sp = mat_mul(P.view, v4(p.x, p.y, p.z, 1.0f));
+            const Vec4 ndc = mat_mul(P.proj, sp);
+            const float nx = ndc.x / ndc.w, ny = ndc.y / ndc.w, nz = ndc.z / ndc.w;
+            if (nx >= -1.0f && ny >= -1.0f && nz >= -1.0f && nx <= 1.0f && ny <= 1.0f && nz <= 1.0f) {
+                const float depth = clampf_(-sp.z, P.near_dist, P.far_dist);
+                dmin = minf_(dmin, depth - 1e-2f);
+                dmax = maxf_(dmax, depth + 1e-2f);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = minf_(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = maxf_(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // near > 1e-2 is not guaranteed, so the values may be negative: use the sign-aware float atomics of the BVH builder
+        atomic_min_f(out, dmin);
+        atomic_max_f(out + 1, dmax);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // closest-hit only (parity / debugging entry point lv_trace_primary)
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, lv_hit* hits, Counters* C) {

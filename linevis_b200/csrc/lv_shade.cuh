@@ -165,9 +165,13 @@ __device__ __forceinline__ Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 
     }
     // blinnPhongShadingTube (Lighting.glsl:100-191)
     float aof = 1.0f, kA = 0.1f, kD = 0.9f;
+    float view_z = 0.0f;
+    if (P.use_ao || P.use_depth_cues) {
+        Vec4 vp = mat_mul(P.view, v4(pos.x, pos.y, pos.z, 1.0f));   // screenSpacePosition, RayHitCommon.glsl:389-391
+        view_z = vp.z;
+        if (P.use_ao) aof = ao_factor(P, v3(vp.x, vp.y, vp.z));
+    }
     if (P.use_ao) {
-        Vec4 vp = mat_mul(P.view, v4(pos.x, pos.y, pos.z, 1.0f));   // RayHitCommon.glsl:389-391
-        aof = ao_factor(P, v3(vp.x, vp.y, vp.z));
         kA = 0.2f + (1.0f - aof) * 0.5f;
         kD = 0.9f * aof;
     }
@@ -184,6 +188,12 @@ __device__ __forceinline__ Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 
     float spec = 0.3f * det_pow(clampf_(fabsf(dot3(n2, h)), 0.0f, 1.0f), 30.0f);
     Vec3 col = v3((kA * base.x + kdc * base.x) + spec, (kA * base.y + kdc * base.y) + spec, (kA * base.z + kdc * base.z) + spec);
     if (P.use_ao) col = col * aof;
+    if (P.use_depth_cues) {                                      // Utils/Lighting.glsl:183-187
+        const float dmin = __ldg(P.depth_min_max), dmax = __ldg(P.depth_min_max + 1);
+        float f = clampf_((-view_z - dmin) / (dmax - dmin), 0.0f, 1.0f);
+        f = f * f * P.depth_cue_strength;
+        col = v3(mixf_(col.x, 0.5f, f), mixf_(col.y, 0.5f, f), mixf_(col.z, 0.5f, f));
+    }
     // halo / outline (RayHitCommon.glsl:437-506)
     float abs_c = P.use_halos ? fabsf(ribbon) : 0.0f;
     float depth = length3(pos - cam);

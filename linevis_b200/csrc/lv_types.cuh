@@ -46,6 +46,10 @@ struct FrameParams {
     // shader defines / settings
     int use_capped, use_halos, use_ao;
     float ao_strength, ao_gamma, ao_radius;
+    int use_depth_cues;            // USE_DEPTH_CUES (depth_cue_strength > 0)
+    float depth_cue_strength;
+    const float* depth_min_max;    // device: {minDepth, maxDepth} of this frame (k_depth_range)
+    float near_dist, far_dist;
     uint32_t ao_spp;
     int ao_use_distance, ao_jitter;
     float subdiv_corr;        // cos(pi / tubeNumSubdivisions)

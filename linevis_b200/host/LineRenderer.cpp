@@ -112,6 +112,8 @@ void LineRenderer::fillCamera(lv_camera& cam) const {
     std::memcpy(cam.background, sceneData->clearColor, 16);
     cam.width = sceneData->viewportWidth;
     cam.height = sceneData->viewportHeight;
+    cam.near_dist = sceneData->nearClip;
+    cam.far_dist = sceneData->farClip;
 }
 
 // ---------------------------------------------------------------------------------------------- B200RayTracer

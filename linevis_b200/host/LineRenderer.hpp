@@ -24,6 +24,7 @@ struct SceneData {
     float viewMatrix[16], projectionMatrix[16];
     float cameraPosition[3];
     float fovY = 1.0f;
+    float nearClip = 0.01f, farClip = 100.0f;   // sgl::Camera::getNearClipDistance / getFarClipDistance (depth cues)
     float clearColor[4] = {1, 1, 1, 1};
     uint32_t viewportWidth = 0, viewportHeight = 0;
     std::vector<float> sceneTexture;  // viewportWidth * viewportHeight * 4

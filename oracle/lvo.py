@@ -24,13 +24,14 @@ class LvoOptions(ctypes.Structure):
         ("tube_num_subdivisions", ctypes.c_uint32), ("num_samples_per_frame", ctypes.c_uint32),
         ("use_jittered_rays", ctypes.c_int32), ("use_deterministic_sampling", ctypes.c_int32),
         ("max_depth_complexity", ctypes.c_uint32), ("tile_w", ctypes.c_uint32), ("tile_h", ctypes.c_uint32),
+        ("depth_cue_strength", ctypes.c_float),
     ]
 
 
 def default_options(**kw):
     """Reference defaults (LineData.hpp:377-378, VulkanRayTracedAmbientOcclusion.hpp:150-153, LineData.cpp:52,
     VulkanRayTracer.hpp:137-142, LineRenderer.cpp:739-740); AO off until ao_strength > 0."""
-    o = LvoOptions(1, 1, 0.0, 1.0, 0.1, 4, 1, 1, 6, 1, 0, 0, 1024, 2, 8)
+    o = LvoOptions(1, 1, 0.0, 1.0, 0.1, 4, 1, 1, 6, 1, 0, 0, 1024, 2, 8, 0.0)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise KeyError(k)
@@ -167,6 +168,11 @@ class OracleScene:
 
     def num_nodes(self):
         return int(self.lib.lvo_scene_num_nodes(ctypes.c_void_p(self.h)))
+
+    def depth_range(self, cam):
+        out = np.zeros(2, np.float32)
+        self.lib.lvo_depth_range(ctypes.c_void_p(self.h), ctypes.byref(cam), _p(out, ctypes.c_float))
+        return float(out[0]), float(out[1])
 
     def trace_primary(self, cam, opts=None, bruteforce=False):
         opts = opts or default_options()

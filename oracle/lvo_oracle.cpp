@@ -53,6 +53,7 @@ typedef struct lvo_options {
     int32_t use_deterministic_sampling; // DETERMINISTIC_SAMPLING
     uint32_t max_depth_complexity;      // maxDepthComplexity (VulkanRayTracer.hpp:139)
     uint32_t tile_w, tile_h;            // LineRenderer::tileWidth/tileHeight (LineRenderer.cpp:739-740)
+    float depth_cue_strength;           // depth_cue_strength (LineRenderer.cpp:449-460); 0 = USE_DEPTH_CUES off
 } lvo_options;
 
 }  // extern "C"
@@ -78,6 +79,18 @@ Uniforms makeUniforms(const Scene& sc, const lv_camera& cam, const lvo_options& 
     u.useCappedTubes = o.use_capped_tubes != 0; u.useHalos = o.use_halos != 0;
     u.useAmbientOcclusion = (o.ao_strength > 0.0f) && aoTex != nullptr;
     u.aoTexture = aoTex;
+    u.useDepthCues = o.depth_cue_strength > 0.0f;
+    u.depthCueStrength = o.depth_cue_strength;
+    u.minDepth = 0.0f; u.maxDepth = 1.0f;                                              // LineRenderer.hpp:222-223
+    if (u.useDepthCues) {
+        // LineRenderer::computeDepthRange (LineRenderer.cpp:410-431) over the line vertices = the end points of all segments
+        float dmin = cam.far_dist, dmax = cam.near_dist;
+        for (const auto& s : sc.segs) {
+            depthRangeOfVertex(cam.view, cam.proj, cam.near_dist, cam.far_dist, s.p0, dmin, dmax);
+            depthRangeOfVertex(cam.view, cam.proj, cam.near_dist, cam.far_dist, s.p1, dmin, dmax);
+        }
+        u.minDepth = dmin; u.maxDepth = dmax;
+    }
     return u;
 }
 
@@ -445,6 +458,13 @@ void lvo_ppll_resolve(const lv_camera* cam, const lvo_options* o, const uint32_t
         }
     }
     if (stats) { stats[0] = sorted; stats[1] = trunc; stats[2] = maxdc; }
+}
+
+void lvo_depth_range(void* h, const lv_camera* cam, float* out2) {
+    Scene& sc = *static_cast<Scene*>(h);
+    lvo_options o{}; o.depth_cue_strength = 1.0f;
+    Uniforms u = makeUniforms(sc, *cam, o, nullptr, 0, 0, 1, nullptr);
+    out2[0] = u.minDepth; out2[1] = u.maxDepth;
 }
 
 int lvo_num_threads(void) {

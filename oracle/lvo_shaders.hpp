@@ -286,6 +286,8 @@ struct Uniforms {
     vec4 backgroundColor, foregroundColor;
     float lineWidth;
     float ambientOcclusionStrength, ambientOcclusionGamma;
+    float depthCueStrength, minDepth, maxDepth;   // USE_DEPTH_CUES; DepthMinMaxBuffer (Utils/Lighting.glsl:28-33)
+    bool useDepthCues;
     uint32_t viewportW, viewportH;
     // transfer function (sgl TransferFunctionWindow; LUT by specification)
     const float* tfLut; uint32_t tfK; float minAttributeValue, maxAttributeValue;
@@ -370,6 +372,11 @@ static inline vec4 blinnPhongShadingTube(const Uniforms& u, vec4 baseColor, vec3
     float isv = kS * det_pow(clamp(fabsf(dot(n, h)), 0.0f, 1.0f), s);
     vec3 phongColor = (Ia + Id) + V3(isv, isv, isv);
     if (u.useAmbientOcclusion) phongColor = phongColor * ambientOcclusionFactor;
+    if (u.useDepthCues) {                                                              // Utils/Lighting.glsl:183-187
+        float depthCueFactor = clamp((-screenSpacePosition.z - u.minDepth) / (u.maxDepth - u.minDepth), 0.0f, 1.0f);
+        depthCueFactor = depthCueFactor * depthCueFactor * u.depthCueStrength;
+        phongColor = V3(mix(phongColor.x, 0.5f, depthCueFactor), mix(phongColor.y, 0.5f, depthCueFactor), mix(phongColor.z, 0.5f, depthCueFactor));
+    }
     return vec4{phongColor.x, phongColor.y, phongColor.z, baseColor.w};
 }
 
@@ -404,7 +411,7 @@ static inline HitColor computeFragmentColor(const Uniforms& u, vec3 fragmentPosi
         }
     }
     vec3 screenSpacePosition = V3(0, 0, 0);
-    if (u.useAmbientOcclusion) {                                                       // :389-391
+    if (u.useAmbientOcclusion || u.useDepthCues) {                                     // :389-391
         vec4 sp = mul(u.viewMatrix, vec4{fragmentPositionWorld.x, fragmentPositionWorld.y, fragmentPositionWorld.z, 1.0f});
         screenSpacePosition = V3(sp.x, sp.y, sp.z);
     }
@@ -445,6 +452,20 @@ static inline HitColor closestHitTubeAnalytic(const Uniforms& u, vec3 ro, vec3 r
     vec3 fragmentNormal = normalize(fragmentPositionWorld - linePointInterpolated);    // :545
     bool isCap = hitKind != 0;                                                         // :548
     return computeFragmentColor(u, fragmentPositionWorld, fragmentNormal, fragmentTangent, isCap, fragmentAttribute);
+}
+
+// Depth range of one line vertex -- Data/Shaders/DepthCues/ComputeDepthValues.glsl:60-76 (min / max are folded by the caller,
+// starting from (farDist, nearDist); the tree reduction of the shader is order independent)
+static inline void depthRangeOfVertex(const float* viewMatrix, const float* projectionMatrix, float nearDist, float farDist,
+                                      vec3 p, float& dmin, float& dmax) {
+    vec4 sp = mul(viewMatrix, vec4{p.x, p.y, p.z, 1.0f});
+    vec4 ndc = mul(projectionMatrix, sp);
+    float nx = ndc.x / ndc.w, ny = ndc.y / ndc.w, nz = ndc.z / ndc.w;
+    if (nx >= -1.0f && ny >= -1.0f && nz >= -1.0f && nx <= 1.0f && ny <= 1.0f && nz <= 1.0f) {
+        float depth = clamp(-sp.z, nearDist, farDist);
+        dmin = fmin_(dmin, depth - 1e-2f);
+        dmax = fmax_(dmax, depth + 1e-2f);
+    }
 }
 
 // Miss main -- TubeRayTracing.glsl:290-298

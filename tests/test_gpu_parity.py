@@ -281,3 +281,33 @@ def test_tile_sharding_reassembles_full_frame(ctx, oracle):
         s.close(); c.close()
     assert not np.isnan(acc).any()
     assert np.abs(acc - full).max() <= 2e-4 and np.array_equal(accp, fullp)   # see test_gpu_fullsize: AO texels of unowned neighbours
+
+
+@pytest.mark.parametrize("ao", [False, True])
+def test_depth_cues_parity(ctx, oracle, ao):
+    """USE_DEPTH_CUES: min/max view depth of the line vertices (DepthCues/ComputeDepthValues.glsl) + the mix towards grey in
+    blinnPhongShadingTube (Utils/Lighting.glsl:183-187), for the tube pass and for the PPLL fragments."""
+    data, width = DATASETS["helix"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(150, 90, eye=(0.1, 0.15, 0.7))
+    tf = scenes.standard_transfer_function(opacity=(0.4, 1.0))
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"depth_cue_strength": 0.8, "ambient_occlusion_strength": 1.0 if ao else 0.0, "ambient_occlusion_samples_per_frame": 4,
+                          "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    try:
+        opts = lvo.default_options(depth_cue_strength=0.8, ao_strength=1.0 if ao else 0.0, ao_spp=4)
+        img, _ = ctx.render_tubes(sc, cam, 0)
+        ao_ref = osc.render_rtao(cam, opts, 0)[0] if ao else None
+        ref, _ = osc.render_tubes(cam, opts, tf, ao_tex=ao_ref)
+        assert np.abs(img - ref).max() <= TOL and np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+        plain, _ = osc.render_tubes(cam, lvo.default_options(ao_strength=1.0 if ao else 0.0, ao_spp=4), tf, ao_tex=ao_ref)
+        assert np.abs(plain - ref).max() > 0.02, "depth cues must change the image"
+        ctx.set_option("ambient_occlusion_strength", 0.0)
+        ctx.ppll_clear(cam, 0)
+        ctx.ppll_gather(sc, cam)
+        got = ctx.ppll_read()
+        refg = osc.ppll_gather(cam, lvo.default_options(depth_cue_strength=0.8), tf)
+        assert got["counter"] == refg["counter"]
+        assert _lists(got["heads"], got["nodes"], cam, oracle) == _lists(refg["heads"], refg["nodes"], cam, oracle)
+    finally:
+        ctx.set_new_settings({"depth_cue_strength": 0.0, "ambient_occlusion_strength": 0.0})

@@ -280,3 +280,15 @@ def test_segments_from_polylines_matches_python_host_mirror(oracle):
     assert np.allclose(np.linalg.norm(to, axis=1), 1.0, atol=1e-5)
     assert np.allclose(np.einsum("ij,ij->i", to, no), 0.0, atol=1e-4)       # Gram-Schmidt normals
     assert so.max() < len(po) and (so[:, 1] == so[:, 0] + 1).all()
+
+
+def test_depth_cue_range_known_answer(oracle):
+    """DepthCues/ComputeDepthValues.glsl:60-76: view depth of the vertices inside the frustum, +- 1e-2, clamped to [near, far]."""
+    pos = np.array([[-0.1, 0.0, 0.0], [0.1, 0.0, 0.2], [5.0, 0.0, 0.0], [5.1, 0.0, 0.0]], np.float32)   # last segment is off screen
+    sc = oracle.scene(pos, np.zeros(4, np.float32), np.array([[0, 1], [2, 3]], np.uint32), 0.01)
+    cam = lv.make_camera(64, 64)                      # camera at z = 0.8 looking down -z
+    dmin, dmax = sc.depth_range(cam)
+    assert abs(dmin - (0.6 - 0.01)) < 1e-6 and abs(dmax - (0.8 + 0.01)) < 1e-6
+    # nothing in the frustum: the neutral element (far, near) of the reduction survives
+    sc2 = oracle.scene(pos[2:], np.zeros(2, np.float32), np.array([[0, 1]], np.uint32), 0.01)
+    assert sc2.depth_range(cam) == (100.0, np.float32(0.01))
