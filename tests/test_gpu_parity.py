@@ -293,6 +293,7 @@ def test_depth_cues_parity(ctx, oracle, ao):
     tf = scenes.standard_transfer_function(opacity=(0.4, 1.0))
     ctx.set_transfer_function(tf)
     ctx.set_new_settings({"depth_cue_strength": 0.8, "ambient_occlusion_strength": 1.0 if ao else 0.0, "ambient_occlusion_samples_per_frame": 4,
+                          "use_jittered_primary_rays": True, "ambient_occlusion_distance_based": True, "ambient_occlusion_radius": 0.1,
                           "num_samples_per_frame": 1, "num_accumulated_frames": 1})
     try:
         opts = lvo.default_options(depth_cue_strength=0.8, ao_strength=1.0 if ao else 0.0, ao_spp=4)
