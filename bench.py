@@ -14,6 +14,7 @@ helix, 1920x1080, PPLL OIT") is measured beside it and reported under "ppll" in 
 madmann91/bvh library (oracle/_ref, built from /root/reference) or, if that is absent, the oracle port.
 """
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -384,8 +385,8 @@ def main():
                          "kernel": "k_rtao_rays", "kernel_ms": k_ms, "peak_source": peak_src,
                          "bytes": "64 B x T + 32 B x I + 4 B per AO ray (SURVEY 8d); T/ray %.2f, I/ray %.2f over %d AO rays (rank 0)"
                                   % (st["ao_traversal_steps"] / max(st["rays_ao"], 1), st["ao_intersections"] / max(st["rays_ao"], 1), st["rays_ao"])},
-            "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 316, "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera (316 B) in, RGBA32F frame out"},
+            "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera struct in (the scene is resident, like the reference's cached render data), RGBA32F frame out"},
             "gpu_launches": (4 + (2 + (world - 1) if world > 1 else 0)) * args.steps,   # k_rtao_primary, k_rtao_rays, k_rtao_reduce, k_tubes (+ tile pack / unpack)
             "clocks": clocks,
         }
