@@ -171,6 +171,42 @@ int lv_scene_info(const lv_scene* scene, uint64_t* n_seg, uint64_t* n_nodes, flo
                   float* aabb_min_max /* 6 floats */);
 int lv_scene_copy_bvh(const lv_scene* scene, void* nodes_out, size_t cap_bytes);
 
+/* ------------------------------------------------------------------ line frames + AO prebaker */
+
+/* Attaches the per-point line frames and the polyline structure to a scene.  Replaces the lineTangent / lineNormal members of
+ * the linePointDataBuffer (LinePointDataUnified, src/LineData/LineRenderData.hpp:99-106, filled at
+ * src/LineData/LineDataFlow.cpp:2140-2236) and `lines = lineData->getFilteredLines()` of the AO baker
+ * (src/Renderers/AmbientOcclusion/VulkanAmbientOcclusionBaker.cpp:476-497).  Needed only for ambient_occlusion_mode =
+ * "RTAO (Prebaker)".  pos_xyz / tangent_xyz / normal_xyz: n_pt*3 floats (pos_xyz = the array given to lv_scene_create);
+ * line_offsets: n_lines+1 point offsets, polyline l = points [line_offsets[l], line_offsets[l+1]), each >= 2 points,
+ * together covering all n_pt points in order.  Host pointers; copied.  Resets the baked factors. */
+int lv_scene_set_lines(lv_scene* scene, const float* pos_xyz, const float* tangent_xyz, const float* normal_xyz, uint64_t n_pt,
+                       const uint64_t* line_offsets, uint64_t n_lines);
+
+/* Host-only (no GPU needed).  Replaces AmbientOcclusionComputeRenderPass::generateBlendingWeightParametrization +
+ * recomputeStaticParametrization (VulkanAmbientOcclusionBaker.cpp:513-655): blending_weights[n_pt] (line point ->
+ * parametrization coordinate; may be NULL), sampling_locations[cap] (parametrization vertex -> line point coordinate; may be
+ * NULL), *n_param_vertices = numParametrizationVertices (may exceed cap). */
+int lv_ao_parametrize(const float* pos_xyz, const uint64_t* line_offsets, uint64_t n_lines, float expected_param_segment_length,
+                      float* blending_weights, float* sampling_locations, uint64_t cap, uint64_t* n_param_vertices);
+
+/* Object-space RTAO prebaker: runs baking iterations (one dispatch of Data/Shaders/AO/RTAO/VulkanAmbientOcclusionBaker.glsl:190-282
+ * each, frameNumber = iterations done so far) until b200_prebaker_iterations are reached; n_iterations = 0 runs all that are
+ * left (BakingMode::IMMEDIATE, VulkanAmbientOcclusionBaker::startAmbientOcclusionBaking :161-192), n_iterations = 1 is one
+ * VulkanAmbientOcclusionBaker::updateIterative step (:340-351).  Render calls in "RTAO (Prebaker)" mode run one iteration per
+ * frame themselves while iterations are left (LineRenderer::renderBase, src/Renderers/LineRenderer.cpp:257-264).
+ * Settings (GUI-only in the reference, VulkanAmbientOcclusionBaker.hpp:108,163-168): b200_prebaker_iterations (128),
+ * b200_prebaker_samples_per_frame (4), b200_prebaker_subdivisions (8), b200_prebaker_param_segment_length (0.001),
+ * b200_prebaker_radius (0.1), b200_prebaker_distance_based (true).  stats: rays_ao / ao_traversal_steps / ao_intersections. */
+int lv_ao_bake(lv_ctx* ctx, lv_scene* scene, uint32_t n_iterations, lv_stats* stats);
+/* Restart baking from iteration 0 (startAmbientOcclusionBaking: numIterations = 0). */
+int lv_ao_bake_reset(lv_scene* scene);
+/* Host copies of the baker's buffers: ambientOcclusionFactors[n_param * n_subdiv] (index subdivision + n_subdiv * vertex),
+ * blending weights [n_pt], sampling locations [n_param].  Any pointer may be NULL; caps in elements. */
+int lv_ao_read(lv_scene* scene, float* factors, size_t factors_cap, float* blending_weights, size_t weights_cap,
+               float* sampling_locations, size_t sampling_cap, uint32_t* n_param_vertices, uint32_t* n_subdivisions,
+               uint32_t* iterations_done);
+
 /* ------------------------------------------------------------------ frames ------------------- */
 
 /* Replaces VulkanRayTracer::render() (src/Renderers/RayTracing/VulkanRayTracer.cpp:131-154):

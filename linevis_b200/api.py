@@ -84,6 +84,21 @@ class Context:
     def create_scene(self, pos, attr, seg_idx, line_width=0.002):
         return Scene(self, pos, attr, seg_idx, line_width)
 
+    @staticmethod
+    def ao_parametrize(pos, line_offsets, expected_param_segment_length=0.001):
+        """lv_ao_parametrize (host only): (blending weights [n_pt], sampling locations [n_param])."""
+        lib = capi.load_library()
+        pos = np.ascontiguousarray(pos, np.float32)
+        off = np.ascontiguousarray(line_offsets, np.uint64)
+        w = np.zeros(pos.shape[0], np.float32)
+        n = ctypes.c_uint64()
+        rc = lib.lv_ao_parametrize(_ptr(pos), _ptr(off), len(off) - 1, expected_param_segment_length, _ptr(w), None, 0, ctypes.byref(n))
+        if rc != capi.LV_OK:
+            raise LineVisError(rc, "lv_ao_parametrize")
+        sl = np.zeros(max(n.value, 1), np.float32)
+        lib.lv_ao_parametrize(_ptr(pos), _ptr(off), len(off) - 1, expected_param_segment_length, _ptr(w), _ptr(sl), sl.size, ctypes.byref(n))
+        return w, sl[:n.value]
+
     # -- frames
     def trace_primary(self, scene, cam, out=None):
         if out is None:
@@ -160,6 +175,7 @@ class Scene:
         ctx._check(rc)
         self.h = h
         self.n_seg = n_seg
+        self._n_pt = n_pt
 
     def info(self):
         ns, nn, ms = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_float()
@@ -172,6 +188,33 @@ class Scene:
         nodes = np.zeros(max(n, 1), BVH_NODE_DTYPE)
         self.ctx._check(self.ctx.lib.lv_scene_copy_bvh(self.h, _ptr(nodes), nodes.nbytes))
         return nodes[:n]
+
+    # -- line frames + object-space AO prebaker ("RTAO (Prebaker)")
+    def set_lines(self, pos, tangent, normal, line_offsets):
+        """lv_scene_set_lines: per-point tangents / normals and the polyline structure (host arrays)."""
+        pos, tangent, normal = (np.ascontiguousarray(a, np.float32) for a in (pos, tangent, normal))
+        off = np.ascontiguousarray(line_offsets, np.uint64)
+        self.ctx._check(self.ctx.lib.lv_scene_set_lines(self.h, _ptr(pos), _ptr(tangent), _ptr(normal), pos.shape[0], _ptr(off), len(off) - 1))
+
+    def ao_bake(self, n_iterations=0, stats=True):
+        st = LvStats()
+        self.ctx._check(self.ctx.lib.lv_ao_bake(self.ctx.h, self.h, n_iterations, ctypes.byref(st) if stats else None))
+        return st.as_dict()
+
+    def ao_bake_reset(self):
+        self.ctx._check(self.ctx.lib.lv_ao_bake_reset(self.h))
+
+    def ao_read(self):
+        npar, nsub, done = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        lib = self.ctx.lib
+        self.ctx._check(lib.lv_ao_read(self.h, None, 0, None, 0, None, 0, ctypes.byref(npar), ctypes.byref(nsub), ctypes.byref(done)))
+        n_pt = self._n_pt
+        f = np.zeros(max(npar.value * nsub.value, 1), np.float32)
+        w = np.zeros(max(n_pt, 1), np.float32)
+        sl = np.zeros(max(npar.value, 1), np.float32)
+        self.ctx._check(lib.lv_ao_read(self.h, _ptr(f), f.size, _ptr(w), w.size, _ptr(sl), sl.size, None, None, None))
+        return dict(factors=f[:npar.value * nsub.value].reshape(npar.value, nsub.value), blending_weights=w[:n_pt],
+                    sampling_locations=sl[:npar.value], n_param=npar.value, n_subdiv=nsub.value, iterations_done=done.value)
 
     def close(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):

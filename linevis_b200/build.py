@@ -11,6 +11,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # strict float32: no FMA contraction, IEEE div/sqrt, no flush-to-zero (parity with the CPU oracle)
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    # host code too (the AO prebaker's arc-length parametrization runs on the host and must match the oracle bit for bit)
+    "-Xcompiler", "-ffp-contract=off",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
 ]
 

@@ -13,6 +13,7 @@
 #include "../../include/linevis_b200.h"
 #include "lv_bvh.cuh"
 #include "lv_kernels.cuh"
+#include "lv_bake.cuh"
 
 using namespace lv;
 
@@ -41,7 +42,12 @@ struct Options {
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
-    std::string ao_mode = "RTAO", denoiser = "None", geometry_mode = "AABBs (analytic)";
+    std::string ao_mode = "RTAO (Screen Space)", denoiser = "None", geometry_mode = "AABBs (analytic)";
+    // object-space AO prebaker (reference VulkanAmbientOcclusionBaker.hpp:108,163-168; GUI-only there, b200_prebaker_* keys here)
+    bool ao_prebaker = false;
+    uint32_t bake_iterations = 128, bake_spp = 4, bake_subdiv = 8;
+    float bake_param_len = 0.001f, bake_radius = 0.1f;
+    bool bake_use_distance = true;
 };
 
 template <class T> struct DevBuf {
@@ -86,12 +92,22 @@ struct lv_ctx {
 struct lv_scene {
     lv_ctx* ctx = nullptr;
     DevBuf<SegRec> segs; DevBuf<uint32_t> prim_ids; DevBuf<Node64> nodes;
-    uint64_t n_seg = 0, n_nodes = 0;
+    uint64_t n_seg = 0, n_nodes = 0, n_pt = 0;
     float line_width = 0.0f, build_ms = 0.0f;
     uint32_t depth = 0;
     float bounds[6] = {0, 0, 0, 0, 0, 0};
+    // line-point frames + object-space AO prebaker state (lv_scene_set_lines / lv_ao_bake)
+    DevBuf<uint2> seg_idx;                         // caller's point index pairs, caller order
+    DevBuf<float4> pt_pos, pt_tan, pt_nrm;         // per line point
+    DevBuf<SegAux> seg_aux;                        // per record, BVH order
+    std::vector<float> host_pos; std::vector<uint64_t> line_offsets;   // polylines for the (host-side) parametrization
+    DevBuf<float> sampling, weights, factors;      // samplingLocations, blending weights, ambientOcclusionFactors
+    uint32_t n_param = 0, param_subdiv = 0, bake_done = 0;
+    float param_len = 0.0f;
+    bool has_lines = false;
     SceneDev dev() const {
         SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
+        s.seg_aux = has_lines ? seg_aux.p : nullptr;
         s.n_nodes = uint32_t(n_nodes); s.radius = line_width * 0.5f; s.line_width = line_width;
         return s;
     }
@@ -183,6 +199,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.frame_number = frame_number;
     P.tf = c->tf.p; P.tfK = c->tfK; P.amin = c->amin; P.amax = c->amax;
     P.ao_tex = nullptr;
+    P.use_static_ao = 0; P.sao_factors = nullptr; P.sao_weights = nullptr;
     P.tiles = c->tiles_dev.p; P.n_tiles = uint32_t(c->tiles_host.size()); P.tile_size = c->tile_size;
     padded_size(c, P.W, P.H, P.padded_w, P.padded_h);
     P.addr_tw = o.tiling_w; P.addr_th = o.tiling_h;
@@ -244,6 +261,25 @@ bool cam_ok(const FrameParams& P) { return P.far_dist > P.near_dist; }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// persistent AO ray-stream kernel over the records in ctx->ao_hits (count in small[0], work counter in small[2..3]) into ctx->occ;
+// timed with ev[4] / ev[5].  BAKE selects the prebaker's random stream / ray origin (lv_bake.cuh).
+template <bool BAKE>
+int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S) {
+    auto launch = [&](auto kern) -> int {
+        int per_sm = 0;
+        LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
+        const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
+        LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        kern<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, c->occ.p, c->ao_hits.p, c->small.p,
+                                                     reinterpret_cast<unsigned long long*>(c->small.p + 2), c->counters.p);
+        LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        return LV_OK;
+    };
+    if (c->opt.ao_min_blocks >= 12) return launch(k_rtao_rays<12, BAKE>);
+    if (c->opt.ao_min_blocks >= 10) return launch(k_rtao_rays<10, BAKE>);
+    return launch(k_rtao_rays<8, BAKE>);
+}
+
 // ---- RTAO pass (S5) into ctx->ao --------------------------------------------------------------
 int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number) {
     const size_t npx = size_t(P.W) * P.H;
@@ -282,20 +318,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
         // one float per (hit pixel, sample); worst case every owned pixel (and ring pixel) is hit
         const size_t max_hits = size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + (apron ? ring : 0));
         LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
-        auto launch = [&](auto kern) -> int {
-            int per_sm = 0;
-            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
-            const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
-            LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-            kern<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, c->occ.p, c->ao_hits.p, c->small.p,
-                                                         reinterpret_cast<unsigned long long*>(c->small.p + 2), c->counters.p);
-            LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
-            return LV_OK;
-        };
-        int lrc;
-        if (c->opt.ao_min_blocks >= 12) lrc = launch(k_rtao_rays<12>);
-        else if (c->opt.ao_min_blocks >= 10) lrc = launch(k_rtao_rays<10>);
-        else lrc = launch(k_rtao_rays<8>);
+        int lrc = launch_ao_rays<false>(c, P, S);
         if (lrc) return lrc;
         c->rtao_rays_timed = true;
         k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, c->ao.p);
@@ -314,6 +337,127 @@ int run_depth_range(lv_ctx* c, const lv_scene* sc, FrameParams& P) {
     k_depth_range<<<c->num_sms * 8, 256, 0, c->stream>>>(P, sc->segs.p, uint32_t(sc->n_seg), c->depth_mm.p);
     LV_CUDA(c, cudaGetLastError());
     P.use_depth_cues = 1; P.depth_min_max = c->depth_mm.p;
+    return LV_OK;
+}
+
+// ---- object-space AO prebaker (S6) -------------------------------------------------------------
+// Arc-length parametrization of the polylines, on the host like the reference
+// (AmbientOcclusionComputeRenderPass::generateBlendingWeightParametrization + recomputeStaticParametrization,
+// src/Renderers/AmbientOcclusion/VulkanAmbientOcclusionBaker.cpp:513-655): every polyline is cut into
+// ceil(length / expected) equal pieces; `weights` maps a line point to its (fractional) parametrization vertex,
+// `sampling` maps a parametrization vertex to its (fractional) line point.
+float seg_length(const float* pos, uint64_t a, uint64_t b) {
+    const float dx = pos[3 * b] - pos[3 * a], dy = pos[3 * b + 1] - pos[3 * a + 1], dz = pos[3 * b + 2] - pos[3 * a + 2];
+    return std::sqrt((dx * dx + dy * dy) + dz * dz);
+}
+void ao_parametrize_host(const float* pos, const uint64_t* offsets, uint64_t n_lines, float expected, std::vector<float>& weights,
+                         std::vector<float>& sampling) {
+    const float eps = 1e-5f;
+    weights.assign(size_t(offsets[n_lines]), 0.0f);
+    sampling.clear();
+    size_t param_base = 0;
+    for (uint64_t li = 0; li < n_lines; li++) {
+        const uint64_t first = offsets[li], n = offsets[li + 1] - first;
+        if (n == 0) continue;
+        float total = 0.0f;
+        for (uint64_t i = 1; i < n; i++) total += seg_length(pos, first + i - 1, first + i);
+        const uint32_t pieces = std::max(1u, uint32_t(std::ceil(total / expected)));
+        const float piece_len = total / float(pieces);
+        // line point -> parametrization coordinate
+        weights[first] = float(param_base);
+        float walked = 0.0f;
+        for (uint64_t i = 1; i < n; i++) {
+            walked += seg_length(pos, first + i - 1, first + i);
+            const float w = walked / piece_len;
+            weights[first + i] = float(param_base) + std::min(std::max(w, 0.0f), float(pieces) - eps);
+        }
+        // parametrization vertex -> line point coordinate
+        sampling.push_back(float(uint32_t(first)));
+        if (n >= 2) {
+            float seg_begin = 0.0f, seg_end = seg_length(pos, first, first + 1);
+            uint64_t cur = 1;
+            for (uint32_t k = 1; k <= pieces; k++) {
+                uint32_t reached = uint32_t(seg_end / piece_len);
+                while (k > reached && cur < n - 1) {
+                    seg_begin = seg_end;
+                    seg_end += seg_length(pos, first + cur, first + cur + 1);
+                    reached = uint32_t(seg_end / piece_len);
+                    cur++;
+                }
+                float loc = float(cur - 1) + (float(k) * piece_len - seg_begin) / (seg_end - seg_begin);
+                loc = float(uint32_t(first)) + std::min(loc, float(uint32_t(n) - 1u) - eps);
+                sampling.push_back(loc);
+            }
+        } else {
+            for (uint32_t k = 1; k <= pieces; k++) sampling.push_back(float(uint32_t(first)));
+        }
+        param_base += size_t(pieces) + 1;
+    }
+}
+
+int ensure_parametrization(lv_ctx* c, lv_scene* sc) {
+    const Options& o = c->opt;
+    if (sc->n_param && sc->param_len == o.bake_param_len && sc->param_subdiv == o.bake_subdiv) return LV_OK;
+    std::vector<float> weights, sampling;
+    ao_parametrize_host(sc->host_pos.data(), sc->line_offsets.data(), sc->line_offsets.size() - 1, o.bake_param_len, weights, sampling);
+    if (sampling.empty()) return fail(c, LV_ERR_STATE, "AO prebaker: the scene has no line points");
+    if (uint64_t(sampling.size()) * o.bake_subdiv >= 0xFFFFFFFFull) return fail(c, LV_ERR_INVALID_ARGUMENT, "AO prebaker: too many parametrization vertices x subdivisions");
+    LV_CUDA(c, sc->sampling.ensure(sampling.size()));
+    LV_CUDA(c, sc->weights.ensure(weights.size()));
+    LV_CUDA(c, sc->factors.ensure(sampling.size() * o.bake_subdiv));
+    LV_CUDA(c, cudaMemcpyAsync(sc->sampling.p, sampling.data(), sampling.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    LV_CUDA(c, cudaMemcpyAsync(sc->weights.p, weights.data(), weights.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    LV_CUDA(c, cudaMemsetAsync(sc->factors.p, 0, sampling.size() * o.bake_subdiv * 4, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    sc->n_param = uint32_t(sampling.size()); sc->param_len = o.bake_param_len; sc->param_subdiv = o.bake_subdiv; sc->bake_done = 0;
+    return LV_OK;
+}
+
+// One dispatch of the baker compute shader with frameNumber = sc->bake_done (VulkanAmbientOcclusionBaker::updateIterative,
+// VulkanAmbientOcclusionBaker.cpp:340-351).  Counters accumulate into ctx->counters (rays_ao, ao_steps, ao_isect).
+int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
+    if (!sc->has_lines) return fail(c, LV_ERR_STATE, "AO prebaker: no line frames attached (lv_scene_set_lines)");
+    if (sc->n_seg == 0) return fail(c, LV_ERR_STATE, "AO prebaker: the scene has no segments");
+    int rc = ensure_parametrization(c, sc);
+    if (rc) return rc;
+    const Options& o = c->opt;
+    const size_t n_rec = size_t(sc->n_param) * o.bake_subdiv;
+    LV_CUDA(c, c->ao_hits.ensure(n_rec));
+    LV_CUDA(c, c->occ.ensure(n_rec * o.bake_spp));
+    LV_CUDA(c, c->small.ensure(4));
+    const unsigned int init[4] = {unsigned(n_rec), 0u, 0u, 0u};
+    LV_CUDA(c, cudaMemcpyAsync(c->small.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    BakeParams B;
+    B.pt_pos = sc->pt_pos.p; B.pt_tan = sc->pt_tan.p; B.pt_nrm = sc->pt_nrm.p; B.sampling = sc->sampling.p;
+    B.n_line_pts = uint32_t(sc->n_pt); B.n_param = sc->n_param; B.n_subdiv = o.bake_subdiv; B.spp = o.bake_spp;
+    B.frame_number = sc->bake_done; B.line_radius = sc->line_width * 0.5f;
+    FrameParams P;
+    memset(&P, 0, sizeof(P));
+    P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
+    P.ao_refill_below = int(o.ao_refill_below); P.ao_leaf_vote = int(o.ao_leaf_vote); P.frame_number = sc->bake_done;
+    k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
+    c->rtao_rays_timed = false;
+    if ((rc = launch_ao_rays<true>(c, P, sc->dev()))) return rc;
+    c->rtao_rays_timed = true;
+    k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, sc->factors.p);
+    LV_CUDA(c, cudaGetLastError());
+    sc->bake_done++;
+    return LV_OK;
+}
+
+// "RTAO (Prebaker)" as the active AO mode of a frame: LineRenderer::renderBase runs one baking iteration per rendered frame
+// while the baker is still collecting samples (BakingMode::ITERATIVE_UPDATE, reference LineRenderer.cpp:257-264), the hit
+// shader then looks the factors up by (line vertex id, phi).  The scene is the baker's state holder, hence the const_cast.
+int prepare_static_ao(lv_ctx* c, const lv_scene* sc_const, FrameParams& P) {
+    if (!c->opt.ao_prebaker || !(c->opt.ao_strength > 0.0f)) return LV_OK;
+    lv_scene* sc = const_cast<lv_scene*>(sc_const);
+    if (!sc->has_lines) return fail(c, LV_ERR_STATE, "ambient_occlusion_mode 'RTAO (Prebaker)' needs line frames (lv_scene_set_lines)");
+    int rc = ensure_parametrization(c, sc);
+    if (rc) return rc;
+    if (sc->bake_done < c->opt.bake_iterations && (rc = run_bake_iteration(c, sc))) return rc;
+    P.use_ao = 1; P.use_static_ao = 1; P.ao_tex = nullptr;
+    P.sao_factors = sc->factors.p; P.sao_weights = sc->weights.p;
+    P.n_ao_subdiv = sc->param_subdiv; P.n_line_vertices = uint32_t(sc->n_pt); P.n_param_vertices = sc->n_param;
     return LV_OK;
 }
 
@@ -388,8 +532,10 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "band_width") o.band_width = f();
     else if (k == "depth_cue_strength") o.depth_cue_strength = f() > 0.0f ? f() : 0.0f;   // <= 0 switches USE_DEPTH_CUES off (LineRenderer.cpp:449-460)
     else if (k == "ambient_occlusion_mode") {
-        if (strcmp(value, "RTAO")) return fail(c, LV_ERR_INVALID_ARGUMENT, "only ambient_occlusion_mode = RTAO is implemented");
-        o.ao_mode = value;
+        // AMBIENT_OCCLUSION_BAKER_TYPE_NAMES (reference AmbientOcclusionBaker.hpp:78-95); "RTAO" is kept as an alias of the screen-space mode
+        if (!strcmp(value, "RTAO (Screen Space)") || !strcmp(value, "RTAO")) { o.ao_prebaker = false; o.ao_mode = "RTAO (Screen Space)"; }
+        else if (!strcmp(value, "RTAO (Prebaker)")) { o.ao_prebaker = true; o.ao_mode = value; }
+        else return fail(c, LV_ERR_INVALID_ARGUMENT, "ambient_occlusion_mode must be 'RTAO (Screen Space)' or 'RTAO (Prebaker)' (SSAO / GTAO are out of scope)");
     } else if (k == "ambient_occlusion_strength") o.ao_strength = f();
     else if (k == "ambient_occlusion_gamma") o.ao_gamma = f();
     else if (k == "ambient_occlusion_iterations") o.ao_iterations = u();
@@ -411,6 +557,12 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "use_capped_tubes") o.use_capped_tubes = parse_bool(value);
     else if (k == "use_halos") o.use_halos = parse_bool(value);
     else if (k == "tube_num_subdivisions") { if (u() < 3) return fail(c, LV_ERR_INVALID_ARGUMENT, "tube_num_subdivisions must be >= 3"); o.tube_num_subdivisions = u(); }
+    else if (k == "b200_prebaker_iterations") { if (u() == 0 || u() > 4096) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_prebaker_iterations must be in [1, 4096]"); o.bake_iterations = u(); }
+    else if (k == "b200_prebaker_samples_per_frame") { if (u() == 0 || u() > 4096) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_prebaker_samples_per_frame must be in [1, 4096]"); o.bake_spp = u(); }
+    else if (k == "b200_prebaker_subdivisions") { if (u() < 3 || u() > 64) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_prebaker_subdivisions must be in [3, 64]"); o.bake_subdiv = u(); }
+    else if (k == "b200_prebaker_param_segment_length") { if (!(f() > 0.0f)) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_prebaker_param_segment_length must be > 0"); o.bake_param_len = f(); }
+    else if (k == "b200_prebaker_radius") { if (!(f() > 0.0f)) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_prebaker_radius must be > 0"); o.bake_radius = f(); }
+    else if (k == "b200_prebaker_distance_based") o.bake_use_distance = parse_bool(value);
     else if (k == "b200_max_depth_complexity") o.max_depth_complexity = u();
     else if (k == "b200_tiling_width" || k == "b200_tiling_height") {
         uint32_t v = u();
@@ -453,6 +605,12 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "use_capped_tubes") v = b(o.use_capped_tubes);
     else if (k == "use_halos") v = b(o.use_halos);
     else if (k == "tube_num_subdivisions") v = std::to_string(o.tube_num_subdivisions);
+    else if (k == "b200_prebaker_iterations") v = std::to_string(o.bake_iterations);
+    else if (k == "b200_prebaker_samples_per_frame") v = std::to_string(o.bake_spp);
+    else if (k == "b200_prebaker_subdivisions") v = std::to_string(o.bake_subdiv);
+    else if (k == "b200_prebaker_param_segment_length") v = std::to_string(o.bake_param_len);
+    else if (k == "b200_prebaker_radius") v = std::to_string(o.bake_radius);
+    else if (k == "b200_prebaker_distance_based") v = b(o.bake_use_distance);
     else if (k == "b200_max_depth_complexity") v = std::to_string(o.max_depth_complexity);
     else if (k == "b200_tiling_width") v = std::to_string(o.tiling_w);
     else if (k == "b200_tiling_height") v = std::to_string(o.tiling_h);
@@ -546,7 +704,7 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     if (line_width <= 0.0f) line_width = c->opt.line_width;
     LV_CUDA(c, cudaSetDevice(c->device));
     lv_scene* s = new lv_scene();
-    s->ctx = c; s->n_seg = n_seg; s->line_width = line_width;
+    s->ctx = c; s->n_seg = n_seg; s->n_pt = n_pt; s->line_width = line_width;
     const int n = int(n_seg);
     if (n == 0) { *out = s; return LV_OK; }
     const float r = line_width * 0.5f;
@@ -558,6 +716,8 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     LV_BUILD(cudaEventRecord(c->ev[0], st));
     LV_BUILD(bounds.ensure(6)); LV_BUILD(keys.ensure(n)); LV_BUILD(keys2.ensure(n)); LV_BUILD(vals.ensure(n));
     LV_BUILD(s->prim_ids.ensure(n)); LV_BUILD(s->segs.ensure(n));
+    LV_BUILD(s->seg_idx.ensure(n));   // caller's index pairs, kept for lv_scene_set_lines (8 B / segment)
+    LV_BUILD(cudaMemcpyAsync(s->seg_idx.p, d_idx, size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
     k_init_bounds<<<1, 32, 0, st>>>(bounds.p);
     k_scene_bounds<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p);
     k_morton<<<(n + 255) / 256, 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p, keys.p, vals.p);
@@ -583,7 +743,7 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     LV_BUILD(cudaStreamSynchronize(st));
     if (s->depth + 1 > uint32_t(kStackSize) || s->depth + 1 > uint32_t(kAoStack)) {
         const uint32_t depth = s->depth;
-        cleanup(); s->segs.release(); s->prim_ids.release(); s->nodes.release(); delete s;
+        cleanup(); s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release(); delete s;
         return fail(c, LV_ERR_STATE, "BVH depth " + std::to_string(depth) + " exceeds the traversal stack (" + std::to_string(kAoStack) + ")");
     }
     s->build_ms = elapsed(c->ev[0], c->ev[1]);
@@ -623,8 +783,107 @@ int lv_scene_create(lv_ctx* c, lv_scene** out, const float* pos, const float* at
 int lv_scene_destroy(lv_scene* s) {
     if (!s) return LV_OK;
     if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
-    s->segs.release(); s->prim_ids.release(); s->nodes.release();
+    s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release();
+    s->pt_pos.release(); s->pt_tan.release(); s->pt_nrm.release(); s->seg_aux.release();
+    s->sampling.release(); s->weights.release(); s->factors.release();
     delete s;
+    return LV_OK;
+}
+
+// ---- line frames + object-space AO prebaker
+int lv_scene_set_lines(lv_scene* s, const float* pos_xyz, const float* tangent_xyz, const float* normal_xyz, uint64_t n_pt,
+                       const uint64_t* line_offsets, uint64_t n_lines) {
+    if (!s || !s->ctx) return LV_ERR_INVALID_ARGUMENT;
+    lv_ctx* c = s->ctx;
+    if (!pos_xyz || !tangent_xyz || !normal_xyz || !line_offsets || n_lines == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_set_lines: NULL argument");
+    if (n_pt != s->n_pt || n_pt == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_set_lines: n_pt differs from the scene's point count");
+    if (line_offsets[0] != 0 || line_offsets[n_lines] != n_pt) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_set_lines: line_offsets must run from 0 to n_pt");
+    for (uint64_t i = 0; i < n_lines; i++)
+        if (line_offsets[i + 1] < line_offsets[i] + 2) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_scene_set_lines: every polyline needs >= 2 points");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    s->has_lines = false;
+    s->host_pos.assign(pos_xyz, pos_xyz + 3 * n_pt);
+    s->line_offsets.assign(line_offsets, line_offsets + n_lines + 1);
+    DevBuf<float> tmp;
+    LV_CUDA(c, tmp.ensure(3 * n_pt));
+    LV_CUDA(c, s->pt_pos.ensure(n_pt)); LV_CUDA(c, s->pt_tan.ensure(n_pt)); LV_CUDA(c, s->pt_nrm.ensure(n_pt));
+    const float* src[3] = {pos_xyz, tangent_xyz, normal_xyz};
+    float4* dst[3] = {s->pt_pos.p, s->pt_tan.p, s->pt_nrm.p};
+    const uint32_t grid = uint32_t(std::min<uint64_t>((n_pt + 255) / 256, 65535));
+    for (int k = 0; k < 3; k++) {
+        LV_CUDA(c, cudaMemcpyAsync(tmp.p, src[k], 12 * n_pt, cudaMemcpyHostToDevice, c->stream));
+        k_expand_xyz<<<grid, 256, 0, c->stream>>>(tmp.p, uint32_t(n_pt), dst[k]);
+    }
+    if (s->n_seg) {
+        LV_CUDA(c, s->seg_aux.ensure(s->n_seg));
+        k_seg_aux<<<uint32_t(std::min<uint64_t>((s->n_seg + 255) / 256, 65535)), 256, 0, c->stream>>>(s->prim_ids.p, s->seg_idx.p, s->pt_nrm.p, uint32_t(s->n_seg), s->seg_aux.p);
+    }
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    tmp.release();
+    s->has_lines = true;
+    s->n_param = 0; s->bake_done = 0;   // new frames invalidate parametrization and baked factors
+    return LV_OK;
+}
+
+int lv_ao_parametrize(const float* pos_xyz, const uint64_t* line_offsets, uint64_t n_lines, float expected_param_segment_length,
+                      float* blending_weights, float* sampling_locations, uint64_t cap, uint64_t* n_param_vertices) {
+    if (!pos_xyz || !line_offsets || n_lines == 0 || !(expected_param_segment_length > 0.0f) || !n_param_vertices) return LV_ERR_INVALID_ARGUMENT;
+    std::vector<float> w, sl;
+    ao_parametrize_host(pos_xyz, line_offsets, n_lines, expected_param_segment_length, w, sl);
+    if (blending_weights) memcpy(blending_weights, w.data(), w.size() * 4);
+    if (sampling_locations) memcpy(sampling_locations, sl.data(), std::min<uint64_t>(cap, sl.size()) * 4);
+    *n_param_vertices = sl.size();
+    return LV_OK;
+}
+
+int lv_ao_bake(lv_ctx* c, lv_scene* s, uint32_t n_iterations, lv_stats* stats) {
+    if (!c || !s) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_ao_bake: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    int rc = reset_counters(c);
+    if (rc) return rc;
+    if (!s->has_lines) return fail(c, LV_ERR_STATE, "lv_ao_bake: no line frames attached (lv_scene_set_lines)");
+    if ((rc = ensure_parametrization(c, s))) return rc;
+    const uint32_t left = s->bake_done < c->opt.bake_iterations ? c->opt.bake_iterations - s->bake_done : 0u;
+    const uint32_t todo = n_iterations ? std::min(n_iterations, left) : left;
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    float ms_rays = 0.0f;
+    for (uint32_t i = 0; i < todo; i++) {
+        if ((rc = run_bake_iteration(c, s))) return rc;
+        if (stats) { LV_CUDA(c, cudaEventSynchronize(c->ev[5])); ms_rays += elapsed(c->ev[4], c->ev[5]); }
+    }
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
+        stats->ms_rtao_rays = ms_rays;
+        stats->ms_total = stats->ms_rtao;
+    }
+    return LV_OK;
+}
+
+int lv_ao_bake_reset(lv_scene* s) {
+    if (!s) return LV_ERR_INVALID_ARGUMENT;
+    s->bake_done = 0;
+    return LV_OK;
+}
+
+int lv_ao_read(lv_scene* s, float* factors, size_t factors_cap, float* blending_weights, size_t weights_cap,
+               float* sampling_locations, size_t sampling_cap, uint32_t* n_param_vertices, uint32_t* n_subdivisions,
+               uint32_t* iterations_done) {
+    if (!s || !s->ctx) return LV_ERR_INVALID_ARGUMENT;
+    lv_ctx* c = s->ctx;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_param_vertices) *n_param_vertices = s->n_param;
+    if (n_subdivisions) *n_subdivisions = s->param_subdiv;
+    if (iterations_done) *iterations_done = s->bake_done;
+    if (factors && s->n_param) LV_CUDA(c, cudaMemcpy(factors, s->factors.p, std::min(factors_cap, size_t(s->n_param) * s->param_subdiv) * 4, cudaMemcpyDeviceToHost));
+    if (blending_weights && s->n_param) LV_CUDA(c, cudaMemcpy(blending_weights, s->weights.p, std::min(weights_cap, size_t(s->n_pt)) * 4, cudaMemcpyDeviceToHost));
+    if (sampling_locations && s->n_param) LV_CUDA(c, cudaMemcpy(sampling_locations, s->sampling.p, std::min(sampling_cap, size_t(s->n_param)) * 4, cudaMemcpyDeviceToHost));
     return LV_OK;
 }
 
@@ -711,7 +970,8 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
     if (!dev) { LV_CUDA(c, c->image.ensure(npx)); img = c->image.p; }
     else if (reinterpret_cast<uintptr_t>(rgba_out) & 15) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 16-byte aligned");
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    const bool use_ao = c->opt.ao_strength > 0.0f;
+    const bool use_ao = c->opt.ao_strength > 0.0f && !c->opt.ao_prebaker;
+    if ((rc = prepare_static_ao(c, sc, P))) return rc;
     if (use_ao) {
         // LineRenderer::renderBase -> ambientOcclusionBaker->updateIterative (reference LineRenderer.cpp:259-265): one RTAO
         // iteration per rendered frame until maxNumAccumulatedFrames (VulkanRayTracedAmbientOcclusion.cpp:89-107).
@@ -721,7 +981,10 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
     }
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    if (P.n_tiles) k_tubes<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
+    if (P.n_tiles) {
+        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
+        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
+    }
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     if (!dev && (rc = deliver(c, img, rgba_out, P.W, P.H, 16))) return rc;
@@ -763,10 +1026,15 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
     if (rc) return rc;
     if (P.padded_w != c->padded_w || P.padded_h != c->padded_h) return fail(c, LV_ERR_STATE, "lv_ppll_gather: resolution changed since lv_ppll_clear");
     if ((rc = reset_counters(c))) return rc;
+    if ((rc = prepare_static_ao(c, sc, P))) return rc;
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (P.n_tiles)
-        k_ppll_gather<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);
+    if (P.n_tiles) {
+        if (P.use_static_ao)
+            k_ppll_gather<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);
+        else
+            k_ppll_gather<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);
+    }
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (stats) {

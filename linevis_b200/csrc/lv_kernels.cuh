@@ -5,6 +5,7 @@
 // its primary rays are coherent and its framebuffer / list-head accesses fall into full 32-byte sectors.
 #pragma once
 #include "lv_trace.cuh"
+#include "lv_bake.cuh"
 
 namespace lv {
 
@@ -104,6 +105,7 @@ k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDe
 // ------------------------------------------------------------------------------------------------
 // S1 ray-gen with the traceRayTransparent loop, S3/S4 shading and the running mean over frames
 // (reference TubeRayTracing.glsl:61-82,198-274).  `image` is the accumulation image (float RGBA).
+template <bool SAO>
 __global__ void __launch_bounds__(kBlockThreads)
 k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C) {
     __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
@@ -135,7 +137,7 @@ k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev 
                 Vec4 hc; float hit_t;
                 if (hit) {
                     const SegRec s = load_seg(S.segs + h.idx);
-                    const Shaded sh = shade_hit(P, ro, rd, h.t, h.kind, s);
+                    const Shaded sh = shade_hit<SAO>(P, ro, rd, h.t, h.kind, s, SAO && S.seg_aux ? S.seg_aux + h.idx : nullptr);
                     hc = sh.color; hit_t = sh.hit_t;
                     if (hi == 0 && si == 0) nhit = 1;
                 } else {  // Miss (TubeRayTracing.glsl:290-298)
@@ -174,12 +176,6 @@ k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev 
 //   k_rtao_rays     persistent ray-stream kernel over (hit pixel, sample) pairs, see below;
 //   k_rtao_reduce   sums the per-sample occlusion values of each hit pixel IN SAMPLE ORDER (exactly the shader's
 //                   loop, :283-306) and folds the mean into the accumulation image (:313-317).
-struct __align__(16) AoHit {
-    float4 pos_off;   // hit position (vertexPositionWorld), AO ray origin offset |linePos - pos| / cos(pi/N)
-    float4 nrm_px;    // surface normal, as_float(pixel index y*W + x)
-    float4 tng;       // surface tangent (segment direction), unused
-};
-
 __device__ __forceinline__ void apron_mark_owned(const FrameParams& P, uint32_t x, uint32_t y, unsigned int stamp) {
     P.apron_marks[size_t(y) * P.W + x] = stamp;
 }
@@ -276,7 +272,9 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
 constexpr uint32_t kDone = 0x7FFFFFFFu;
 constexpr int kAoStack = 72;
 
-template <int MIN_BLOCKS>
+// BAKE = object-space prebaker (lv_bake.cuh): records are (parametrization vertex, tube subdivision) frames, the ray origin is the
+// record's position itself and the random numbers come from the vertex's LCG stream instead of a per-sample TEA seed.
+template <int MIN_BLOCKS, bool BAKE>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
             const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
@@ -313,19 +311,8 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                 if (ray_id >= total) exhausted = true;
                 else {
                     const uint32_t slot = uint32_t(ray_id / spp), sample = uint32_t(ray_id - (unsigned long long)slot * spp);
-                    const float4* hp = reinterpret_cast<const float4*>(hit_list + slot);
-                    const float4 a = __ldg(hp), b = __ldg(hp + 1), c = __ldg(hp + 2);
-                    const Vec3 pos = v3(a.x, a.y, a.z), nrm = v3(b.x, b.y, b.z), tng = v3(c.x, c.y, c.z);
-                    const Vec3 btg = cross3(nrm, tng);                               // :257
-                    const uint32_t pixel = __float_as_uint(b.w);
-                    uint32_t seed = tea(pixel, P.frame_number * spp + sample);       // :289-292
-                    const float xa = rnd(seed), xb = rnd(seed);
-                    float cs, sn;
-                    det_sincos2pi(xb, cs, sn);
-                    const float rr = sqrtf(1.0f - xa * xa);
-                    const Vec3 hs = v3(cs * rr, sn * rr, xa);                        // sampleHemisphere :151-156
-                    const Vec3 dir = normalize3((tng * hs.x + btg * hs.y) + nrm * hs.z);
-                    const Vec3 org = pos + dir * a.w;                                // :299
+                    Vec3 org, dir;
+                    ao_ray_from_record<BAKE>(hit_list + slot, sample, spp, P.frame_number, org, dir);
                     rq = make_rayq(org, dir);
                     rb = make_raybox(org, dir);
                     best = P.ao_radius; found = false;
@@ -443,6 +430,7 @@ struct GatherState { uint32_t head, stored, gen; };
 // Shade the queued hits of all lanes in lockstep rounds, then allocate the surviving fragments of the whole warp with ONE
 // atomicAdd (warp scan of the per-lane counts) so that each pixel's new nodes are CONTIGUOUS in the fragment buffer: the
 // resolve pass then walks runs of up to kGatherQueue adjacent 12-byte nodes instead of one 32-byte sector per node.
+template <bool SAO>
 __device__ __forceinline__ void gather_flush(const FrameParams& P, const SceneDev& S, Vec3 ro, Vec3 rd, uint32_t lane,
                                              uint2 (*q)[kBlockThreads], uint32_t& qn, GatherState& g, lv_ppll_node* nodes,
                                              unsigned long long* frag_counter, unsigned long long list_size) {
@@ -451,7 +439,7 @@ __device__ __forceinline__ void gather_flush(const FrameParams& P, const SceneDe
         if (i < qn) {
             const uint2 e = q[i][threadIdx.x];
             const SegRec s = load_seg(S.segs + (e.x & kRefMask));
-            const Shaded sh = shade_hit(P, ro, rd, __uint_as_float(e.y), e.x >> 28, s);
+            const Shaded sh = shade_hit<SAO>(P, ro, rd, __uint_as_float(e.y), e.x >> 28, s, SAO && S.seg_aux ? S.seg_aux + (e.x & kRefMask) : nullptr);
             if (!(sh.color.w < 0.001f)) {                                       // LinkedListGather.glsl:38
                 q[kept][threadIdx.x] = make_uint2(pack_unorm4x8(sh.color), __float_as_uint(sh.hit_t));   // kept <= i: slot is free
                 kept++;
@@ -480,6 +468,7 @@ __device__ __forceinline__ void gather_flush(const FrameParams& P, const SceneDe
     }
 }
 
+template <bool SAO>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
               lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C) {
@@ -518,7 +507,7 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                     const uint32_t ref = w & kRefMask, cnt = ((w >> 27) & 15u) + 1u;
                     isect += (lane == 0) ? cnt : 0u;
                     if (__ballot_sync(0xffffffffu, qn + cnt > uint32_t(kGatherQueue)))
-                        gather_flush(P, S, ro, rd, lane, s_queue, qn, g, nodes, frag_counter, list_size);
+                        gather_flush<SAO>(P, S, ro, rd, lane, s_queue, qn, g, nodes, frag_counter, list_size);
                     const bool mine = side ? hr : hl;
                     for (uint32_t i = 0; i < cnt; i++) {
                         const SegRec s = load_seg(S.segs + ref + i);
@@ -540,7 +529,7 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
             }
             __syncwarp();
         }
-        gather_flush(P, S, ro, rd, lane, s_queue, qn, g, nodes, frag_counter, list_size);
+        gather_flush<SAO>(P, S, ro, rd, lane, s_queue, qn, g, nodes, frag_counter, list_size);
     }
     if (valid) {
         const uint32_t a = addr_gen(P, x, y);

@@ -8,34 +8,53 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Per-thread device functions are declared LV_DEV.  In the product build that is __device__ __forceinline__.  With
+// -DLV_HOST_EMU (tests/emu only, plain g++) the same source is compiled for the host, so that per-thread device code can be
+// checked against the oracle in the CPU test suite; the handful of device intrinsics it uses get host shims below.
+#ifdef LV_HOST_EMU
+#include <cmath>
+#include <cstring>
+#define LV_DEV inline
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+template <class T> inline T __ldg(const T* p) { return *p; }
+namespace lv {
+inline int max(int a, int b) { return a < b ? b : a; }
+inline int min(int a, int b) { return b < a ? b : a; }
+}
+#else
+#define LV_DEV __device__ __forceinline__
+#endif
+
 namespace lv {
 
 struct Vec3 { float x, y, z; };
 struct Vec4 { float x, y, z, w; };
 
-__device__ __forceinline__ Vec3 v3(float x, float y, float z) { Vec3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ Vec4 v4(float x, float y, float z, float w) { Vec4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
-__device__ __forceinline__ Vec3 operator+(Vec3 a, Vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ Vec3 operator-(Vec3 a, Vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ Vec3 operator*(Vec3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ Vec3 operator*(float s, Vec3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-__device__ __forceinline__ float dot3(Vec3 a, Vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-__device__ __forceinline__ Vec3 cross3(Vec3 a, Vec3 b) {
+LV_DEV Vec3 v3(float x, float y, float z) { Vec3 r; r.x = x; r.y = y; r.z = z; return r; }
+LV_DEV Vec4 v4(float x, float y, float z, float w) { Vec4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+LV_DEV Vec3 operator+(Vec3 a, Vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+LV_DEV Vec3 operator-(Vec3 a, Vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+LV_DEV Vec3 operator*(Vec3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+LV_DEV Vec3 operator*(float s, Vec3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+LV_DEV float dot3(Vec3 a, Vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+LV_DEV Vec3 cross3(Vec3 a, Vec3 b) {
     return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
 }
-__device__ __forceinline__ float length3(Vec3 a) { return sqrtf(dot3(a, a)); }
-__device__ __forceinline__ Vec3 normalize3(Vec3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return a * inv; }
+LV_DEV float length3(Vec3 a) { return sqrtf(dot3(a, a)); }
+LV_DEV Vec3 normalize3(Vec3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return a * inv; }
 // comparison-based min/max/clamp (GLSL leaves NaN handling open; fixed here)
-__device__ __forceinline__ float minf_(float a, float b) { return (b < a) ? b : a; }
-__device__ __forceinline__ float maxf_(float a, float b) { return (a < b) ? b : a; }
-__device__ __forceinline__ float clampf_(float x, float lo, float hi) { return minf_(maxf_(x, lo), hi); }
-__device__ __forceinline__ float mixf_(float a, float b, float t) { return a * (1.0f - t) + b * t; }
-__device__ __forceinline__ float smoothstepf_(float e0, float e1, float x) {
+LV_DEV float minf_(float a, float b) { return (b < a) ? b : a; }
+LV_DEV float maxf_(float a, float b) { return (a < b) ? b : a; }
+LV_DEV float clampf_(float x, float lo, float hi) { return minf_(maxf_(x, lo), hi); }
+LV_DEV float mixf_(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+LV_DEV float smoothstepf_(float e0, float e1, float x) {
     float t = clampf_((x - e0) / (e1 - e0), 0.0f, 1.0f);
     return t * t * (3.0f - 2.0f * t);
 }
 // column-major mat4 * vec4, summed left to right over the columns
-__device__ __forceinline__ Vec4 mat_mul(const float* m, Vec4 v) {
+LV_DEV Vec4 mat_mul(const float* m, Vec4 v) {
     Vec4 r;
     r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
     r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
@@ -45,7 +64,7 @@ __device__ __forceinline__ Vec4 mat_mul(const float* m, Vec4 v) {
 }
 
 // ---- deterministic log2 / exp2 / pow / sincos (basic ops only; spec in DESIGN.md) ----
-__device__ __forceinline__ float det_log2(float x) {
+LV_DEV float det_log2(float x) {
     int eadj = 0;
     if (x < 1.17549435e-38f) { x = x * 8388608.0f; eadj = -23; }
     uint32_t b = __float_as_uint(x);
@@ -63,7 +82,7 @@ __device__ __forceinline__ float det_log2(float x) {
     float lnm = (2.0f * s) * p;
     return float(e) + lnm * 1.44269504f;
 }
-__device__ __forceinline__ float det_exp2(float z) {
+LV_DEV float det_exp2(float z) {
     if (!(z >= -126.0f)) return 0.0f;
     if (z > 127.0f) z = 127.0f;
     float n = floorf(z + 0.5f);
@@ -80,11 +99,11 @@ __device__ __forceinline__ float det_exp2(float z) {
     float scale = __uint_as_float(uint32_t(int(n) + 127) << 23);
     return p * scale;
 }
-__device__ __forceinline__ float det_pow(float x, float y) {
+LV_DEV float det_pow(float x, float y) {
     if (!(x > 0.0f)) return 0.0f;
     return det_exp2(y * det_log2(x));
 }
-__device__ __forceinline__ void det_sincos2pi(float xi, float& c, float& s) {
+LV_DEV void det_sincos2pi(float xi, float& c, float& s) {
     float a = 4.0f * xi;
     float q = floorf(a + 0.5f);
     float r = (a - q) * 1.57079633f;
@@ -108,8 +127,30 @@ __device__ __forceinline__ void det_sincos2pi(float xi, float& c, float& s) {
     else { c = sr; s = -pc; }
 }
 
+// acos for the tube angle phi (reference TubeRayTracing.glsl:554).  GLSL leaves acos undefined for |x| > 1 (the dot product of
+// two normalised vectors can exceed 1 by an ulp): the argument is clamped.  |x| <= 0.5: pi/2 - asin(x); otherwise
+// 2 asin(sqrt((1 - |x|) / 2)), mirrored for x < 0; asin(s) = s + s z P(z), z = s^2 (abs error 3e-7 vs libm).
+LV_DEV float det_acos(float x) {
+    x = clampf_(x, -1.0f, 1.0f);
+    const float ax = fabsf(x);
+    const bool small = ax <= 0.5f;
+    float z, s;
+    if (small) { z = x * x; s = x; }
+    else { z = (1.0f - ax) * 0.5f; s = sqrtf(z); }
+    float p = 3.380591050e-02f;
+    p = p * z + 1.707774773e-02f;
+    p = p * z + 3.111618385e-02f;
+    p = p * z + 4.459802806e-02f;
+    p = p * z + 7.500098646e-02f;
+    p = p * z + 1.666666567e-01f;
+    const float r = s + (s * z) * p;
+    if (small) return 1.57079633f - r;
+    if (x > 0.0f) return 2.0f * r;
+    return 3.14159265f - 2.0f * r;
+}
+
 // ---- RNG: tea / lcg / rnd (reference Data/Shaders/Renderers/RayTracing/RayTracingUtilities.glsl:134-181) ----
-__device__ __forceinline__ uint32_t tea(uint32_t val0, uint32_t val1) {
+LV_DEV uint32_t tea(uint32_t val0, uint32_t val1) {
     uint32_t v0 = val0, v1 = val1, s0 = 0;
 #pragma unroll
     for (int n = 0; n < 16; n++) {
@@ -119,10 +160,23 @@ __device__ __forceinline__ uint32_t tea(uint32_t val0, uint32_t val1) {
     }
     return v0;
 }
-__device__ __forceinline__ uint32_t lcg(uint32_t& prev) {
+LV_DEV uint32_t lcg(uint32_t& prev) {
     prev = 1664525u * prev + 1013904223u;
     return prev & 0x00FFFFFFu;
 }
-__device__ __forceinline__ float rnd(uint32_t& seed) { return float(lcg(seed)) / float(0x01000000); }
+LV_DEV float rnd(uint32_t& seed) { return float(lcg(seed)) / float(0x01000000); }
+// state after n calls of lcg(): the affine map x -> a x + c composed n times by square-and-multiply (mod 2^32).  The AO
+// prebaker draws all random numbers of a vertex from ONE stream (VulkanAmbientOcclusionBaker.glsl:196,267); a ray in
+// the middle of that stream jumps to its position instead of replaying it.
+LV_DEV uint32_t lcg_skip(uint32_t state, uint32_t n) {
+    uint32_t a = 1664525u, c = 1013904223u, acc_a = 1u, acc_c = 0u;
+    while (n) {
+        if (n & 1u) { acc_a = acc_a * a; acc_c = acc_c * a + c; }
+        c = (a + 1u) * c;
+        a = a * a;
+        n >>= 1;
+    }
+    return acc_a * state + acc_c;
+}
 
 }  // namespace lv

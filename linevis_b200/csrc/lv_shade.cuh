@@ -18,13 +18,13 @@ struct RayQ {
     float dd;  // (d.x^2 + d.y^2) + d.z^2 -- the quadratic's A for both end spheres
 };
 
-__device__ __forceinline__ RayQ make_rayq(Vec3 o, Vec3 d) {
+LV_DEV RayQ make_rayq(Vec3 o, Vec3 d) {
     RayQ r; r.o = o; r.d = d; r.dd = (d.x * d.x + d.y * d.y) + d.z * d.z; return r;
 }
 
 // ray vs sphere of radius `rad` centred at c, first root >= 0 (RayIntersectionTestsVulkan.glsl:39-72).
 // `oc` = rayOrigin - sphereCenter.
-__device__ __forceinline__ bool sphere_hit(const RayQ& r, Vec3 oc, float rad, float& t) {
+LV_DEV bool sphere_hit(const RayQ& r, Vec3 oc, float rad, float& t) {
     float A = r.dd;
     float B = 2.0f * ((r.d.x * oc.x + r.d.y * oc.y) + r.d.z * oc.z);
     float C = ((oc.x * oc.x + oc.y * oc.y) + oc.z * oc.z) - rad * rad;
@@ -40,7 +40,7 @@ __device__ __forceinline__ bool sphere_hit(const RayQ& r, Vec3 oc, float rad, fl
 }
 
 // ray vs open finite cylinder (RayIntersectionTestsVulkan.glsl:78-119)
-__device__ __forceinline__ bool cylinder_hit(const RayQ& r, Vec3 p0, Vec3 p1, Vec3 op0, float rad, float& t) {
+LV_DEV bool cylinder_hit(const RayQ& r, Vec3 p0, Vec3 p1, Vec3 op0, float rad, float& t) {
     Vec3 axis = normalize3(p1 - p0);
     Vec3 dperp = r.d - dot3(r.d, axis) * axis;
     Vec3 pperp = op0 - dot3(op0, axis) * axis;
@@ -65,7 +65,7 @@ __device__ __forceinline__ bool cylinder_hit(const RayQ& r, Vec3 p0, Vec3 p1, Ve
 }
 
 // IntersectionTube main (TubeRayTracing.glsl:452-494): min over body / sphere(p0) / sphere(p1).
-__device__ __forceinline__ bool capsule_hit(const RayQ& r, const SegRec& s, float rad, bool capped, float& t, uint32_t& kind) {
+LV_DEV bool capsule_hit(const RayQ& r, const SegRec& s, float rad, bool capped, float& t, uint32_t& kind) {
     Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
     Vec3 op0 = r.o - p0;
     bool has = false;
@@ -82,7 +82,7 @@ __device__ __forceinline__ bool capsule_hit(const RayQ& r, const SegRec& s, floa
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ Vec4 tf_lookup(const FrameParams& P, float attr) {  // TransferFunction.glsl:66-71
+LV_DEV Vec4 tf_lookup(const FrameParams& P, float attr) {  // TransferFunction.glsl:66-71
     float pos = clampf_((attr - P.amin) / (P.amax - P.amin), 0.0f, 1.0f);
     float x = pos * float(P.tfK) - 0.5f;
     float fl = floorf(x);
@@ -93,7 +93,7 @@ __device__ __forceinline__ Vec4 tf_lookup(const FrameParams& P, float attr) {  /
     return v4(mixf_(a.x, b.x, w), mixf_(a.y, b.y, w), mixf_(a.z, b.z, w), mixf_(a.w, b.w, w));
 }
 
-__device__ __forceinline__ float ao_tex_bilinear(const FrameParams& P, float u, float v) {
+LV_DEV float ao_tex_bilinear(const FrameParams& P, float u, float v) {
     float x = u * float(P.W) - 0.5f, y = v * float(P.H) - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float wx = x - fx, wy = y - fy;
@@ -107,7 +107,7 @@ __device__ __forceinline__ float ao_tex_bilinear(const FrameParams& P, float u, 
     return mixf_(a, b, wy);
 }
 
-__device__ __forceinline__ float ao_factor(const FrameParams& P, Vec3 view_pos) {  // AmbientOcclusion.glsl:84-99
+LV_DEV float ao_factor(const FrameParams& P, Vec3 view_pos) {  // AmbientOcclusion.glsl:84-99
     Vec4 ndc = mat_mul(P.proj, v4(view_pos.x, view_pos.y, view_pos.z, 1.0f));
     float nx = ndc.x / ndc.w, ny = ndc.y / ndc.w;
     float ao = ao_tex_bilinear(P, nx * 0.5f + 0.5f, ny * 0.5f + 0.5f);
@@ -115,25 +115,51 @@ __device__ __forceinline__ float ao_factor(const FrameParams& P, Vec3 view_pos) 
     return maxf_(0.0f, 1.0f - P.ao_strength + P.ao_strength * ao);
 }
 
+// getAoFactor(interpolatedVertexId, phi), STATIC_AMBIENT_OCCLUSION_PREBAKING variant (reference Utils/AmbientOcclusion.glsl:49-75):
+// blending weight of the two neighbouring line points -> position on the baked parametrization; phi -> position on the
+// circle of n_ao_subdiv baked directions; bilinear mix of the four factors.
+LV_DEV float ao_factor_static(const FrameParams& P, float vertex_id, float phi) {
+    const uint32_t last_pt = uint32_t(vertex_id);
+    const uint32_t next_pt = last_pt + 1u < P.n_line_vertices - 1u ? last_pt + 1u : P.n_line_vertices - 1u;
+    const float f_pt = vertex_id - floorf(vertex_id);
+    const float w = mixf_(__ldg(P.sao_weights + last_pt), __ldg(P.sao_weights + next_pt), f_pt);
+    const uint32_t last_v = uint32_t(w);
+    const uint32_t next_v = last_v + 1u < P.n_param_vertices - 1u ? last_v + 1u : P.n_param_vertices - 1u;
+    const float f_line = w - floorf(w);
+    const uint32_t N = P.n_ao_subdiv;
+    const float circle = clampf_(phi / 6.28318531f * float(N), 0.0f, float(N));
+    const uint32_t c_last = (uint32_t(floorf(circle)) + N) % N;
+    const uint32_t c_next = (c_last + 1u) % N;
+    const float f_circle = circle - floorf(circle);
+    const float a00 = __ldg(P.sao_factors + c_last + size_t(N) * last_v), a01 = __ldg(P.sao_factors + c_last + size_t(N) * next_v);
+    const float a10 = __ldg(P.sao_factors + c_next + size_t(N) * last_v), a11 = __ldg(P.sao_factors + c_next + size_t(N) * next_v);
+    float ao = mixf_(mixf_(a00, a01, f_line), mixf_(a10, a11, f_line), f_circle);
+    ao = det_pow(ao, P.ao_gamma);
+    return maxf_(0.0f, 1.0f - P.ao_strength + P.ao_strength * ao);
+}
+
 struct Shaded { Vec4 color; float hit_t; };
 
-__device__ __forceinline__ float aa_factor(const FrameParams& P, float distance) {  // Utils/Antialiasing.glsl:1-3
+LV_DEV float aa_factor(const FrameParams& P, float distance) {  // Utils/Antialiasing.glsl:1-3
     return distance / float(P.H) * P.fov_y;
 }
 
 // ClosestHitTubeAnalytic + computeFragmentColor + blinnPhongShadingTube for one accepted hit.
-__device__ __forceinline__ Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s) {
+// SAO = prebaked object-space AO ("RTAO (Prebaker)") instead of the screen-space AO texture; a template parameter so that the
+// default instantiation carries none of its registers.  `aux`: the record's line-point data, read only with SAO.
+template <bool SAO>
+LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegAux* aux) {
     const Vec3 cam = v3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
     Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
     Vec3 pos = ro + rd * t_hit;                                  // TubeRayTracing.glsl:517
     Vec3 seg = p1 - p0;
-    Vec3 centre; float attr;
+    Vec3 centre; float attr, u;
     if (kind == 0) {                                             // :524-530
-        float u = dot3(seg, pos - p0) / dot3(seg, seg);
+        u = dot3(seg, pos - p0) / dot3(seg, seg);
         centre = p0 + u * seg;
         attr = (1.0f - u) * s.a.w + u * s.b.w;
-    } else if (kind == 1) { centre = p0; attr = s.a.w; }
-    else { centre = p1; attr = s.b.w; }
+    } else if (kind == 1) { centre = p0; attr = s.a.w; u = 0.0f; }
+    else { centre = p1; attr = s.b.w; u = 1.0f; }
     // fragmentTangent / fragmentNormal are normalised at :544-545 and again inside computeFragmentColor (:141,:144)
     // and blinnPhongShadingTube (Lighting.glsl:138-139); the repeated normalisations are kept, they are not idempotent in float.
     Vec3 tan0 = normalize3(seg);
@@ -166,10 +192,21 @@ __device__ __forceinline__ Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 
     // blinnPhongShadingTube (Lighting.glsl:100-191)
     float aof = 1.0f, kA = 0.1f, kD = 0.9f;
     float view_z = 0.0f;
-    if (P.use_ao || P.use_depth_cues) {
+    if ((P.use_ao && !SAO) || P.use_depth_cues) {
         Vec4 vp = mat_mul(P.view, v4(pos.x, pos.y, pos.z, 1.0f));   // screenSpacePosition, RayHitCommon.glsl:389-391
         view_z = vp.z;
-        if (P.use_ao) aof = ao_factor(P, v3(vp.x, vp.y, vp.z));
+        if (P.use_ao && !SAO) aof = ao_factor(P, v3(vp.x, vp.y, vp.z));
+    }
+    if (SAO && P.use_ao) {                                       // TubeRayTracing.glsl:550-562, Lighting.glsl:118-119
+        float phi = 0.0f, vertex_id = 0.0f;
+        if (aux) {
+            const float4 a0 = __ldg(&aux->n0), a1 = __ldg(&aux->n1);
+            const Vec3 line_n = (1.0f - u) * v3(a0.x, a0.y, a0.z) + u * v3(a1.x, a1.y, a1.z);
+            phi = det_acos(dot3(nrm0, line_n));
+            if (dot3(line_n, cross3(nrm0, tan0)) < 0.0f) phi = 6.28318531f - phi;
+            vertex_id = (1.0f - u) * float(__float_as_uint(a0.w)) + u * float(__float_as_uint(a1.w));
+        }
+        aof = ao_factor_static(P, vertex_id, phi);
     }
     if (P.use_ao) {
         kA = 0.2f + (1.0f - aof) * 0.5f;

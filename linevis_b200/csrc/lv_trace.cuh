@@ -30,18 +30,18 @@ struct RayBox {
     float cx, cy, cz;     // -(o * inv)
 };
 
-__device__ __forceinline__ float safe_inv(float d) {
+LV_DEV float safe_inv(float d) {
     const float tiny = 1e-30f;
     if (fabsf(d) < tiny) d = (__float_as_uint(d) >> 31) ? -tiny : tiny;
     return 1.0f / d;
 }
-__device__ __forceinline__ RayBox make_raybox(Vec3 o, Vec3 d) {
+LV_DEV RayBox make_raybox(Vec3 o, Vec3 d) {
     RayBox b;
     b.ix = safe_inv(d.x); b.iy = safe_inv(d.y); b.iz = safe_inv(d.z);
     b.cx = -(o.x * b.ix); b.cy = -(o.y * b.iy); b.cz = -(o.z * b.iz);
     return b;
 }
-__device__ __forceinline__ bool box_hit(const RayBox& rb, float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
+LV_DEV bool box_hit(const RayBox& rb, float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
                                         float tmin, float tmax, float& tn) {
     float ax = __fmaf_rn(mnx, rb.ix, rb.cx), bx = __fmaf_rn(mxx, rb.ix, rb.cx);
     float ay = __fmaf_rn(mny, rb.iy, rb.cy), by = __fmaf_rn(mxy, rb.iy, rb.cy);
@@ -51,12 +51,12 @@ __device__ __forceinline__ bool box_hit(const RayBox& rb, float mnx, float mny, 
     tn = lo;
     return lo <= hi;
 }
-__device__ __forceinline__ bool box_hit(const RayBox& rb, float4 mn, float4 mx, float tmin, float tmax, float& tn) {
+LV_DEV bool box_hit(const RayBox& rb, float4 mn, float4 mx, float tmin, float tmax, float& tn) {
     return box_hit(rb, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, tmin, tmax, tn);
 }
 // the segment's own AABB (min/max(p0,p1) -+ r, reference src/LineData/LineDataFlow.cpp:2230-2233) against the ray's
 // ORIGINAL interval: part of the acceptance rule, and a cheap reject in front of the three quadratics
-__device__ __forceinline__ bool seg_box_hit(const RayBox& rb, const SegRec& s, float r, float tmin, float tmax) {
+LV_DEV bool seg_box_hit(const RayBox& rb, const SegRec& s, float r, float tmin, float tmax) {
     float tn;
     return box_hit(rb, fminf(s.a.x, s.b.x) - r, fminf(s.a.y, s.b.y) - r, fminf(s.a.z, s.b.z) - r,
                    fmaxf(s.a.x, s.b.x) + r, fmaxf(s.a.y, s.b.y) + r, fmaxf(s.a.z, s.b.z) + r, tmin, tmax, tn);
@@ -65,17 +65,21 @@ __device__ __forceinline__ bool seg_box_hit(const RayBox& rb, const SegRec& s, f
 // 256-bit read-only loads (LDG.E.256, new on sm_100): a 64-byte node is 2 load instructions instead of 4, a 32-byte
 // segment record 1 instead of 2.  With every lane on a different node the L1 handles one wavefront per lane PER LOAD
 // INSTRUCTION, and that wavefront rate -- not DRAM, not issue -- was what bound k_rtao_rays (profiles/r1e: L1 76 %).
-__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+#ifdef LV_HOST_EMU
+LV_DEV void ldg256(const void* p, float4& a, float4& b) { a = static_cast<const float4*>(p)[0]; b = static_cast<const float4*>(p)[1]; }
+#else
+LV_DEV void ldg256(const void* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
-__device__ __forceinline__ Node64 load_node(const Node64* p) {
+#endif
+LV_DEV Node64 load_node(const Node64* p) {
     Node64 n;
     ldg256(p, n.l0, n.l1);
     ldg256(reinterpret_cast<const char*>(p) + 32, n.r0, n.r1);
     return n;
 }
-__device__ __forceinline__ SegRec load_seg(const SegRec* p) {
+LV_DEV SegRec load_seg(const SegRec* p) {
     SegRec s;
     ldg256(p, s.a, s.b);
     return s;
@@ -88,6 +92,7 @@ struct HitRec {
     uint32_t kind;
 };
 
+#ifndef LV_HOST_EMU   // warp-collective code: GPU only (covered by the -m gpu parity tests, not by the host emulation)
 // Closest hit for a WARP PACKET of coherent rays (the 8x4 pixel patch of camera rays a warp owns).  The warp walks the
 // BVH together with one shared stack: a child is visited if any lane's box test (against that lane's own best hit plus the
 // tie margin) passes, near child first by majority vote, and every node / record is fetched once per warp.  Each lane keeps
@@ -154,5 +159,6 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
     }
     return found;
 }
+#endif  // !LV_HOST_EMU
 
 }  // namespace lv

@@ -24,10 +24,27 @@ struct __align__(64) Node64 {
     float4 r1;  // rmax.xyz, as_float(rcount)
 };
 
+// Line-point data a hit needs besides position / attribute when the prebaked (object-space) AO is looked up: the two
+// line-point indices (linePointIndices, reference TubeRayTracing.glsl:513) and the line normals at both points (:551).
+// One 32-byte record per segment, BVH order like SegRec; only fetched while shading in "RTAO (Prebaker)" mode.
+struct __align__(32) SegAux {
+    float4 n0;  // lineNormal(point 0).xyz, as_float(point index 0)
+    float4 n1;  // lineNormal(point 1).xyz, as_float(point index 1)
+};
+
+// Start frame of a batch of AO rays: what the screen-space RTAO pass keeps per hit pixel and the prebaker per
+// (parametrization vertex, tube subdivision).  k_rtao_rays turns (record, sample) into a ray.
+struct __align__(16) AoHit {
+    float4 pos_off;   // position; RTAO: AO ray origin offset |linePos - pos| / cos(pi/N) (baker: origin is the position itself)
+    float4 nrm_px;    // surface normal, as_float(output index: pixel y*W + x, or subdivision + N * vertex)
+    float4 tng;       // surface tangent; baker: as_float(LCG state of this record's first random number)
+};
+
 struct SceneDev {
     const SegRec* segs;        // [n_seg] BVH order
     const uint32_t* prim_ids;  // [n_seg] BVH order -> caller's segment index
     const Node64* nodes;       // [n_nodes], root = 0
+    const SegAux* seg_aux;     // [n_seg] BVH order, or nullptr (no line frames attached)
     uint32_t n_seg;
     uint32_t n_nodes;
     float radius;              // lineWidth * 0.5
@@ -65,6 +82,11 @@ struct FrameParams {
     float amin, amax;
     // AO texture (W*H floats) or nullptr
     const float* ao_tex;
+    // prebaked object-space AO (STATIC_AMBIENT_OCCLUSION_PREBAKING, reference Utils/AmbientOcclusion.glsl:30-75)
+    int use_static_ao;
+    const float* sao_factors;          // [n_param_vertices * n_ao_subdiv]
+    const float* sao_weights;          // [n_line_vertices] blending weight parametrization
+    uint32_t n_ao_subdiv, n_line_vertices, n_param_vertices;
     // owned image tiles (Morton order); tile_size x tile_size pixels each
     const uint2* tiles;
     uint32_t n_tiles, tile_size;

@@ -56,6 +56,7 @@ const TubeAabbRenderData& LineData::getLinePassTubeAabbRenderData(float lineWidt
         }
         if (numValidLinePoints == 1) out.linePointDataBuffer.pop_back();
         if (numValidLinePoints <= 1) continue;
+        out.lineOffsets.push_back(lineSegmentIndexCounter);
         for (uint32_t pointIdx = 1; pointIdx < numValidLinePoints; pointIdx++) {
             out.indexBuffer.push_back(lineSegmentIndexCounter + pointIdx - 1);
             out.indexBuffer.push_back(lineSegmentIndexCounter + pointIdx);
@@ -68,6 +69,7 @@ const TubeAabbRenderData& LineData::getLinePassTubeAabbRenderData(float lineWidt
         }
         lineSegmentIndexCounter += numValidLinePoints;
     }
+    out.lineOffsets.push_back(lineSegmentIndexCounter);
     cachedValid = true;
     cachedLineWidth = lineWidth;
     return out;

@@ -33,6 +33,9 @@ struct TubeAabbRenderData {
     std::vector<uint32_t> indexBuffer;                  // 2 point indices per segment
     std::vector<AABB3> aabbBuffer;                      // one per segment
     std::vector<LinePointDataUnified> linePointDataBuffer;
+    // first point of every surviving polyline + one-past-the-end (what getFilteredLines() gives the AO prebaker as separate
+    // polylines, VulkanAmbientOcclusionBaker.cpp:482); host-side addition, not part of the reference struct
+    std::vector<uint64_t> lineOffsets;
 };
 
 class LineData {

@@ -70,6 +70,18 @@ void LineRenderer::setLineData(LineDataPtr& data, bool isNewData) {
     check(lv_set_option(ctx, "tube_num_subdivisions", std::to_string(lineData->tubeNumSubdivisions).c_str()), "tube_num_subdivisions");
     check(lv_scene_create(ctx, &scene, pos.data(), attr.data(), rd.indexBuffer.data(), attr.size(), rd.indexBuffer.size() / 2, lineWidth),
           "lv_scene_create");
+    if (rd.lineOffsets.size() >= 2) {
+        // line frames for ambient_occlusion_mode = "RTAO (Prebaker)" (AmbientOcclusionComputeRenderPass::setLineData,
+        // VulkanAmbientOcclusionBaker.cpp:476-497): cheap, so always attached
+        std::vector<float> tangent(pos.size()), normal(pos.size());
+        for (size_t i = 0; i < rd.linePointDataBuffer.size(); i++) {
+            const LinePointDataUnified& p = rd.linePointDataBuffer[i];
+            tangent[3 * i] = p.lineTangent.x; tangent[3 * i + 1] = p.lineTangent.y; tangent[3 * i + 2] = p.lineTangent.z;
+            normal[3 * i] = p.lineNormal.x; normal[3 * i + 1] = p.lineNormal.y; normal[3 * i + 2] = p.lineNormal.z;
+        }
+        check(lv_scene_set_lines(scene, pos.data(), tangent.data(), normal.data(), attr.size(), rd.lineOffsets.data(), rd.lineOffsets.size() - 1),
+              "lv_scene_set_lines");
+    }
     (void)isNewData;
     lineData->resetDirty();
     dirty = false;

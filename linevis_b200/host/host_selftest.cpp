@@ -77,6 +77,15 @@ int main() {
         std::printf("ray tracer: %llu rays, %zu non-background pixels, mean R %.4f\n",
                     (unsigned long long)(rt.getLastStats().rays_primary + rt.getLastStats().rays_ao), nonbg, sum / (sd.sceneTexture.size() / 4));
         if (nonbg == 0 || rt.getLastStats().rays_ao == 0) { std::printf("FAIL: empty frame\n"); return 1; }
+        // object-space AO prebaker: the first frames each run one baking iteration, then only look the factors up
+        SettingsMap pre; pre.addKeyValue("ambient_occlusion_mode", std::string("RTAO (Prebaker)")); pre.addKeyValue("b200_prebaker_iterations", 2);
+        pre.addKeyValue("b200_prebaker_param_segment_length", 0.01f);
+        rt.setNewSettings(pre);
+        unsigned long long bakeRays[3];
+        for (int i = 0; i < 3; i++) { rt.render(); bakeRays[i] = rt.getLastStats().rays_ao; }
+        std::printf("prebaker: AO rays per frame %llu %llu %llu\n", bakeRays[0], bakeRays[1], bakeRays[2]);
+        if (bakeRays[0] == 0 || bakeRays[1] != bakeRays[0] || bakeRays[2] != 0) { std::printf("FAIL: prebaker iteration schedule\n"); return 1; }
+        for (size_t i = 0; i < sd.sceneTexture.size(); i++) if (!(sd.sceneTexture[i] >= 0.0f && sd.sceneTexture[i] <= 1.0001f)) { std::printf("FAIL: prebaker frame\n"); return 1; }
         B200PerPixelLinkedListLineRenderer pp(&sd, tf);
         pp.onResolutionChanged();
         pp.setLineData(d, true);

@@ -55,6 +55,80 @@ def segments_from_polylines(pos, attr, line_offsets, min_tangent_length=1e-4):
     return pos[keep], attr[keep], seg
 
 
+def polyline_frames(pos, line_offsets):
+    """Per-point tangent / normal of polylines exactly like LineDataFlow::getLinePassTubeAabbRenderData
+    (src/LineData/LineDataFlow.cpp:2150-2181): central-difference tangent (one-sided at the ends), normalised; normal =
+    Gram-Schmidt of the previous point's normal (first point: (1,0,0); fallbacks (0,1,0), (0,0,1) when nearly parallel)
+    against the tangent.  The polylines must be free of degenerate points (see segments_from_polylines).  Vectorised
+    over the lines, sequential along them.  Returns (tangent [n,3], normal [n,3]) float32."""
+    pos = np.asarray(pos, np.float32)
+    off = np.asarray(line_offsets, np.int64)
+    n = pos.shape[0]
+    tangent = np.zeros((n, 3), np.float32)
+    normal = np.zeros((n, 3), np.float32)
+    lens = np.diff(off)
+    f32 = np.float32
+
+    def dot(a, b):
+        return (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
+
+    def normalize(a):
+        return a * (f32(1.0) / np.sqrt(dot(a, a)))[:, None]
+
+    def cross(a, b):
+        return np.stack([a[:, 1] * b[:, 2] - b[:, 1] * a[:, 2], a[:, 2] * b[:, 0] - b[:, 2] * a[:, 0],
+                         a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]], axis=1)
+
+    last = np.tile(np.array([1, 0, 0], f32), (len(lens), 1))
+    for j in range(int(lens.max()) if len(lens) else 0):
+        act = np.nonzero(lens > j)[0]
+        i = off[act] + j
+        nxt = np.where(j + 1 < lens[act], i + 1, i)
+        prv = np.where(j > 0, i - 1, i)
+        t = normalize(pos[nxt] - pos[prv])
+        helper = last[act].copy()
+        bad = np.sqrt(dot(cross(helper, t), cross(helper, t))) < f32(0.01)
+        helper[bad] = np.array([0, 1, 0], f32)
+        bad2 = bad & (np.sqrt(dot(cross(helper, t), cross(helper, t))) < f32(0.01))
+        helper[bad2] = np.array([0, 0, 1], f32)
+        nrm = normalize(helper - dot(helper, t)[:, None] * t)
+        tangent[i], normal[i] = t, nrm
+        last[act] = nrm
+    return tangent, normal
+
+
+def polylines_with_frames(pos, attr, line_offsets):
+    """Segment soup + what the object-space AO prebaker needs: drops degenerate points like segments_from_polylines, then
+    returns dict(pos, attr, seg, tangent, normal, line_offsets) for the surviving polylines."""
+    pos = np.asarray(pos, np.float32)
+    line_offsets = np.asarray(line_offsets, np.int64)
+    p2, a2, seg = segments_from_polylines(pos, attr, line_offsets)
+    # surviving polylines = maximal runs of consecutive segments (i, i + 1)
+    if len(seg) == 0:
+        raise ValueError("no segments")
+    brk = np.nonzero(seg[1:, 0] != seg[:-1, 1])[0] + 1
+    starts = np.concatenate([[0], brk])
+    first_pt = seg[starts, 0].astype(np.int64)
+    off = np.concatenate([first_pt, [p2.shape[0]]])
+    assert first_pt[0] == 0 and np.all(np.diff(off) >= 2)
+    tangent, normal = polyline_frames(p2, off)
+    return dict(pos=p2, attr=a2, seg=seg, tangent=tangent, normal=normal, line_offsets=off.astype(np.uint64))
+
+
+def helix_polylines(n_lines=400, n_points=251, seed=1001):
+    """The helix set of helix_lines() as polylines with frames (polylines_with_frames)."""
+    rng = np.random.default_rng(seed)
+    u = rng.random(n_lines)
+    k = np.arange(n_lines)[:, None]
+    j = np.arange(n_points)[None, :]
+    rho = 0.02 + 0.23 * k / max(n_lines - 1, 1)
+    ang = 2.0 * math.pi * 6.0 / 250.0 * j + 2.0 * math.pi * u[:, None]
+    y = -0.25 + (0.5 / 250.0) * j + 0.0 * k
+    pos = np.stack([rho * np.cos(ang), y, rho * np.sin(ang)], axis=-1).reshape(-1, 3)
+    attr = ((y + 0.25) / 0.5).reshape(-1)
+    return polylines_with_frames(normalize_positions(pos), attr.astype(np.float32), np.arange(n_lines + 1) * n_points)
+
+
 def helix_lines(n_lines=400, n_points=251, seed=1001):
     """Config 2: 100 k-segment synthetic helix (Tornado-like).  Line k: radius 0.02 + 0.23 k/(n-1), pitch 0.5/250 per
     step in y, angular step 2 pi 6/250, phase 2 pi u_k, u_k ~ U(0,1); attribute = normalised y."""

@@ -24,14 +24,20 @@ class LvoOptions(ctypes.Structure):
         ("tube_num_subdivisions", ctypes.c_uint32), ("num_samples_per_frame", ctypes.c_uint32),
         ("use_jittered_rays", ctypes.c_int32), ("use_deterministic_sampling", ctypes.c_int32),
         ("max_depth_complexity", ctypes.c_uint32), ("tile_w", ctypes.c_uint32), ("tile_h", ctypes.c_uint32),
-        ("depth_cue_strength", ctypes.c_float),
+        ("depth_cue_strength", ctypes.c_float), ("use_static_ao", ctypes.c_int32),
     ]
+
+
+class LvoBakeOptions(ctypes.Structure):
+    """AmbientOcclusionComputeRenderPass settings (VulkanAmbientOcclusionBaker.hpp:163-168)."""
+    _fields_ = [("ao_radius", ctypes.c_float), ("num_tube_subdivisions", ctypes.c_uint32),
+                ("samples_per_frame", ctypes.c_uint32), ("use_distance", ctypes.c_int32)]
 
 
 def default_options(**kw):
     """Reference defaults (LineData.hpp:377-378, VulkanRayTracedAmbientOcclusion.hpp:150-153, LineData.cpp:52,
     VulkanRayTracer.hpp:137-142, LineRenderer.cpp:739-740); AO off until ao_strength > 0."""
-    o = LvoOptions(1, 1, 0.0, 1.0, 0.1, 4, 1, 1, 6, 1, 0, 0, 1024, 2, 8, 0.0)
+    o = LvoOptions(1, 1, 0.0, 1.0, 0.1, 4, 1, 1, 6, 1, 0, 0, 1024, 2, 8, 0.0, 0)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise KeyError(k)
@@ -83,6 +89,11 @@ class Oracle:
         L.lvo_backend_name.restype = ctypes.c_char_p
         L.lvo_ppll_gather.restype = ctypes.c_uint64
         L.lvo_num_threads.restype = ctypes.c_int
+        L.lvo_det_acos.restype = ctypes.c_float
+        L.lvo_det_acos.argtypes = [ctypes.c_float]
+        L.lvo_ao_parametrize.restype = ctypes.c_uint64
+        L.lvo_static_ao_factor.restype = ctypes.c_float
+        L.lvo_static_ao_factor.argtypes = [ctypes.c_void_p] + [ctypes.c_float] * 4
 
     # ---- unit helpers
     def tea(self, a, b):
@@ -146,6 +157,21 @@ class Oracle:
     def num_threads(self):
         return int(self.lib.lvo_num_threads())
 
+    def det_acos(self, x):
+        return float(self.lib.lvo_det_acos(x))
+
+    def ao_parametrize(self, pos, line_offsets, expected_param_segment_length):
+        """recomputeStaticParametrization: (blending weights [n_pt], sampling locations [n_param])."""
+        pos = _f32(pos)
+        off = np.ascontiguousarray(line_offsets, np.uint64)
+        bw = np.zeros(pos.shape[0], np.float32)
+        args = (_p(pos, ctypes.c_float), _p(off, ctypes.c_uint64), ctypes.c_uint64(len(off) - 1), ctypes.c_float(expected_param_segment_length),
+                _p(bw, ctypes.c_float))
+        n = int(self.lib.lvo_ao_parametrize(*args, None, ctypes.c_uint64(0)))
+        sl = np.zeros(max(n, 1), np.float32)
+        self.lib.lvo_ao_parametrize(*args, _p(sl, ctypes.c_float), ctypes.c_uint64(n))
+        return bw, sl[:n]
+
     def scene(self, pos, attr, seg_idx, line_width):
         return OracleScene(self, pos, attr, seg_idx, line_width)
 
@@ -168,6 +194,45 @@ class OracleScene:
 
     def num_nodes(self):
         return int(self.lib.lvo_scene_num_nodes(ctypes.c_void_p(self.h)))
+
+    # ---- object-space AO prebaker (S6)
+    def set_lines(self, tangent, normal):
+        tangent, normal = _f32(tangent), _f32(normal)
+        self.lib.lvo_scene_set_lines(ctypes.c_void_p(self.h), _p(tangent, ctypes.c_float), _p(normal, ctypes.c_float), ctypes.c_uint64(tangent.shape[0]))
+
+    def ao_bake_iteration(self, sampling_locations, frame_number, factors=None, radius=0.1, n_subdiv=8, spp=4, use_distance=True, capped=True,
+                          return_rays=False):
+        sl = _f32(sampling_locations)
+        if factors is None:
+            factors = np.zeros(sl.shape[0] * n_subdiv, np.float32)
+        factors = _f32(factors)
+        bo = LvoBakeOptions(radius, n_subdiv, spp, int(use_distance))
+        stats = np.zeros(3, np.uint64)
+        rays = np.zeros((sl.shape[0] * n_subdiv * spp, 6), np.float32) if return_rays else None
+        self.lib.lvo_ao_bake_iteration(ctypes.c_void_p(self.h), ctypes.byref(bo), ctypes.c_int(int(capped)), _p(sl, ctypes.c_float),
+                                       ctypes.c_uint64(sl.shape[0]), ctypes.c_uint32(frame_number), _p(factors, ctypes.c_float), _p(stats, ctypes.c_uint64),
+                                       _p(rays, ctypes.c_float) if return_rays else None)
+        st = dict(T=int(stats[0]), I=int(stats[1]), rays=int(stats[2]))
+        return (factors, st, rays) if return_rays else (factors, st)
+
+    def shade_hits(self, cam, opts, tf, ro, rd, t, kind, prim, amin=0.0, amax=1.0, ao_tex=None):
+        """closestHitTubeAnalytic for given hits -> [n, 5] (rgba, hitT)."""
+        tf, ro, rd, t = _f32(tf), _f32(ro), _f32(rd), _f32(t)
+        kind, prim = np.ascontiguousarray(kind, np.uint32), np.ascontiguousarray(prim, np.uint32)
+        out = np.zeros((t.shape[0], 5), np.float32)
+        aop = _p(_f32(ao_tex), ctypes.c_float) if ao_tex is not None else None
+        self.lib.lvo_shade_hits(ctypes.c_void_p(self.h), ctypes.byref(cam), ctypes.byref(opts), _p(tf, ctypes.c_float), ctypes.c_uint32(tf.shape[0]),
+                                ctypes.c_float(amin), ctypes.c_float(amax), aop, ctypes.c_uint64(t.shape[0]), _p(ro, ctypes.c_float),
+                                _p(rd, ctypes.c_float), _p(t, ctypes.c_float), _p(kind, ctypes.c_uint32), _p(prim, ctypes.c_uint32), _p(out, ctypes.c_float))
+        return out
+
+    def set_static_ao(self, factors, n_subdiv, blending_weights):
+        f, bw = _f32(factors), _f32(blending_weights)
+        self.lib.lvo_scene_set_static_ao(ctypes.c_void_p(self.h), _p(f, ctypes.c_float), ctypes.c_uint64(f.size // n_subdiv), ctypes.c_uint32(n_subdiv),
+                                         _p(bw, ctypes.c_float), ctypes.c_uint64(bw.shape[0]))
+
+    def static_ao_factor(self, vertex_id, phi, strength=1.0, gamma=1.0):
+        return float(self.lib.lvo_static_ao_factor(ctypes.c_void_p(self.h), strength, gamma, vertex_id, phi))
 
     def depth_range(self, cam):
         out = np.zeros(2, np.float32)

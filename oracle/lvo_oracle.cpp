@@ -54,13 +54,32 @@ typedef struct lvo_options {
     uint32_t max_depth_complexity;      // maxDepthComplexity (VulkanRayTracer.hpp:139)
     uint32_t tile_w, tile_h;            // LineRenderer::tileWidth/tileHeight (LineRenderer.cpp:739-740)
     float depth_cue_strength;           // depth_cue_strength (LineRenderer.cpp:449-460); 0 = USE_DEPTH_CUES off
+    int32_t use_static_ao;              // ambient_occlusion_mode == "RTAO (Prebaker)": STATIC_AMBIENT_OCCLUSION_PREBAKING
 } lvo_options;
+
+// AmbientOcclusionComputeRenderPass settings (VulkanAmbientOcclusionBaker.hpp:163-168)
+typedef struct lvo_bake_options {
+    float ao_radius;                    // ambientOcclusionRadius
+    uint32_t num_tube_subdivisions;     // numTubeSubdivisions
+    uint32_t samples_per_frame;         // numAmbientOcclusionSamplesPerFrame
+    int32_t use_distance;               // useDistance
+} lvo_bake_options;
 
 }  // extern "C"
 
 namespace {
 
 // BVH backend (Scene, buildScene, traceClosest/traceAny/traceAll) comes from the included header.
+
+// Scene + the line-point data of the object-space AO prebaker (LinePointDataUnified: position / tangent / normal per point,
+// src/LineData/LineRenderData.hpp:99-106) and its results (ambientOcclusionFactors / blending weights).
+struct SceneX : Scene {
+    std::vector<vec3> ptPos, ptTan, ptNrm;
+    std::vector<SegmentLineData> segLine;          // per segment: point indices + line normals
+    std::vector<float> aoFactors, aoBlendingWeights;
+    uint32_t numParametrizationVertices = 0, numAoTubeSubdivisions = 0;
+};
+SceneX& sx(void* h) { return *static_cast<SceneX*>(static_cast<Scene*>(h)); }
 
 Uniforms makeUniforms(const Scene& sc, const lv_camera& cam, const lvo_options& o, const float* tf, uint32_t K,
                       float amin, float amax, const float* aoTex) {
@@ -81,6 +100,15 @@ Uniforms makeUniforms(const Scene& sc, const lv_camera& cam, const lvo_options& 
     u.aoTexture = aoTex;
     u.useDepthCues = o.depth_cue_strength > 0.0f;
     u.depthCueStrength = o.depth_cue_strength;
+    u.staticAmbientOcclusionPrebaking = false;
+    if (o.use_static_ao) {
+        const SceneX& x = static_cast<const SceneX&>(sc);
+        u.useAmbientOcclusion = (o.ao_strength > 0.0f) && !x.aoFactors.empty();
+        u.staticAmbientOcclusionPrebaking = u.useAmbientOcclusion;
+        u.ambientOcclusionFactors = x.aoFactors.data(); u.ambientOcclusionBlendingWeights = x.aoBlendingWeights.data();
+        u.numAoTubeSubdivisions = x.numAoTubeSubdivisions; u.numLineVertices = uint32_t(x.aoBlendingWeights.size());
+        u.numParametrizationVertices = x.numParametrizationVertices;
+    }
     u.minDepth = 0.0f; u.maxDepth = 1.0f;                                              // LineRenderer.hpp:222-223
     if (u.useDepthCues) {
         // LineRenderer::computeDepthRange (LineRenderer.cpp:410-431) over the line vertices = the end points of all segments
@@ -194,7 +222,7 @@ void lvo_segments_from_polylines(const float* pos, const float* attr, const uint
 // ------------------------------------------------------------------------------------------ scene
 void* lvo_scene_create(const float* pos, const float* attr, const uint32_t* seg_idx, uint64_t n_pt, uint64_t n_seg, float line_width) {
     (void)n_pt;
-    Scene* sc = new Scene();
+    SceneX* sc = new SceneX();
     sc->lineWidth = line_width;
     sc->segs.resize(n_seg);
     for (uint64_t i = 0; i < n_seg; i++) {
@@ -202,9 +230,13 @@ void* lvo_scene_create(const float* pos, const float* attr, const uint32_t* seg_
         sc->segs[i] = Segment{V3(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2]), attr[a], V3(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2]), attr[b]};
     }
     buildScene(*sc);
-    return sc;
+    sc->segLine.resize(n_seg);
+    for (uint64_t i = 0; i < n_seg; i++) sc->segLine[i] = SegmentLineData{seg_idx[2 * i], seg_idx[2 * i + 1], V3(0, 0, 0), V3(0, 0, 0)};
+    sc->ptPos.resize(n_pt);
+    for (uint64_t i = 0; i < n_pt; i++) sc->ptPos[i] = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    return static_cast<Scene*>(sc);
 }
-void lvo_scene_destroy(void* h) { delete static_cast<Scene*>(h); }
+void lvo_scene_destroy(void* h) { delete &sx(h); }
 uint64_t lvo_scene_num_nodes(void* h) { return numNodes(*static_cast<Scene*>(h)); }
 const char* lvo_backend_name(void) { return backendName(); }
 
@@ -339,7 +371,7 @@ void lvo_render_tubes(void* h, const lv_camera* cam, const lvo_options* o, const
                     Hit hit; HitColor pl;
                     if (traceClosest(sc, r, u.useCappedTubes, hit, st)) {
                         const Segment& s = sc.segs[hit.prim];
-                        pl = closestHitTubeAnalytic(u, ro, rd, hit.t, hit.kind, s.p0, s.a0, s.p1, s.a1);
+                        pl = closestHitTubeAnalytic(u, ro, rd, hit.t, hit.kind, s.p0, s.a0, s.p1, s.a1, &static_cast<const SceneX&>(sc).segLine[hit.prim]);
                     } else pl = missShader(u);
                     tMin = pl.hitT + fmax_(pl.hitT * 1e-5f, 1e-7f);
                     fc.x = fc.x + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.x;
@@ -397,7 +429,7 @@ uint64_t lvo_ppll_gather(void* h, const lv_camera* cam, const lvo_options* o, co
                 Ray r; r.o = ro; r.d = rd; r.tmin = 0.0001f; r.tmax = 1000.0f;
                 traceAll(sc, r, u.useCappedTubes, st, [&](uint32_t p, float t, int kind) {
                     const Segment& s = sc.segs[p];
-                    HitColor pl = closestHitTubeAnalytic(u, ro, rd, t, kind, s.p0, s.a0, s.p1, s.a1);
+                    HitColor pl = closestHitTubeAnalytic(u, ro, rd, t, kind, s.p0, s.a0, s.p1, s.a1, &static_cast<const SceneX&>(sc).segLine[p]);
                     if (pl.hitColor.w < 0.001f) return;                                 // LinkedListGather.glsl:38
                     // frag.depth = length(fragmentPositionWorld - cameraPosition) (:52) == payload.hitT
                     rowFrags[x].push_back(Frag{packUnorm4x8(pl.hitColor), pl.hitT});
@@ -465,6 +497,173 @@ void lvo_depth_range(void* h, const lv_camera* cam, float* out2) {
     lvo_options o{}; o.depth_cue_strength = 1.0f;
     Uniforms u = makeUniforms(sc, *cam, o, nullptr, 0, 0, 1, nullptr);
     out2[0] = u.minDepth; out2[1] = u.maxDepth;
+}
+
+// ------------------------------------------------------------------------------------------ object-space AO prebaker (S6)
+float lvo_det_acos(float x) { return det_acos(x); }
+
+// Line-point frames (tangent / normal per point) for the prebaker and its lookup.
+void lvo_scene_set_lines(void* h, const float* tangent, const float* normal, uint64_t n_pt) {
+    SceneX& sc = sx(h);
+    sc.ptTan.resize(n_pt); sc.ptNrm.resize(n_pt);
+    for (uint64_t i = 0; i < n_pt; i++) {
+        sc.ptTan[i] = V3(tangent[3 * i], tangent[3 * i + 1], tangent[3 * i + 2]);
+        sc.ptNrm[i] = V3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+    }
+    for (auto& l : sc.segLine) { l.n0 = sc.ptNrm[l.idx0]; l.n1 = sc.ptNrm[l.idx1]; }
+}
+
+// AmbientOcclusionComputeRenderPass::generateBlendingWeightParametrization + recomputeStaticParametrization
+// (src/Renderers/AmbientOcclusion/VulkanAmbientOcclusionBaker.cpp:513-655).  Polylines = (pos, line_offsets[n_lines + 1]).
+// blending_weights: one float per line point; sampling_locations: capacity `cap`.  Returns numParametrizationVertices
+// (which may exceed cap; then only the first cap entries were written).
+uint64_t lvo_ao_parametrize(const float* pos, const uint64_t* line_offsets, uint64_t n_lines, float expectedParamSegmentLength,
+                            float* blendingWeightParametrizationData, float* samplingLocations, uint64_t cap) {
+    const float EPSILON = 1e-5f;
+    uint64_t numSamplingLocations = 0;
+    auto push = [&](float v) { if (numSamplingLocations < cap) samplingLocations[numSamplingLocations] = v; numSamplingLocations++; };
+    size_t segmentVertexIdOffset = 0;
+    size_t vertexIdx = 0;
+    for (uint64_t lineIdx = 0; lineIdx < n_lines; lineIdx++) {
+        const uint64_t b = line_offsets[lineIdx];
+        const size_t n = size_t(line_offsets[lineIdx + 1] - b);
+        auto line = [&](size_t i) { return V3(pos[3 * (b + i)], pos[3 * (b + i) + 1], pos[3 * (b + i) + 2]); };
+        float polylineLength = 0.0f;                                                    // :540-544
+        for (size_t i = 1; i < n; i++) polylineLength += length(line(i) - line(i - 1));
+
+        uint32_t numLineSubdivs = std::max(1u, uint32_t(std::ceil(polylineLength / expectedParamSegmentLength)));  // :574
+        float lineSubdivLength = polylineLength / float(numLineSubdivs);
+        uint32_t numSubdivVertices = numLineSubdivs + 1;
+
+        uint32_t startVertexIdx = uint32_t(vertexIdx);                                  // :580-582
+        blendingWeightParametrizationData[vertexIdx] = float(segmentVertexIdOffset);
+        vertexIdx++;
+
+        float currentLength = 0.0f;                                                     // :585-592
+        for (size_t i = 1; i < n; i++) {
+            currentLength += length(line(i) - line(i - 1));
+            float w = currentLength / lineSubdivLength;
+            blendingWeightParametrizationData[vertexIdx] = float(segmentVertexIdOffset) + clamp(w, 0.0f, float(numLineSubdivs) - EPSILON);
+            vertexIdx++;
+        }
+
+        float lastLength = 0.0f;                                                        // :594-612
+        currentLength = length(line(1) - line(0));
+        size_t currVertexIdx = 1;
+        push(float(startVertexIdx));
+        for (uint32_t i = 1; i < numSubdivVertices; i++) {
+            uint32_t parametrizationIdx = uint32_t(currentLength / lineSubdivLength);
+            while (i > parametrizationIdx && currVertexIdx < n - 1) {
+                float segLength = length(line(currVertexIdx + 1) - line(currVertexIdx));
+                lastLength = currentLength;
+                currentLength += segLength;
+                parametrizationIdx = uint32_t(currentLength / lineSubdivLength);
+                currVertexIdx++;
+            }
+            float samplingLocation = float(currVertexIdx - 1) + (float(i) * lineSubdivLength - lastLength) / (currentLength - lastLength);
+            samplingLocation = float(startVertexIdx) + std::min(samplingLocation, float(uint32_t(n) - 1u) - EPSILON);
+            push(samplingLocation);
+        }
+        segmentVertexIdOffset += numSubdivVertices;
+    }
+    return numSamplingLocations;
+}
+
+// One dispatch of the baker compute shader (Data/Shaders/AO/RTAO/VulkanAmbientOcclusionBaker.glsl:190-282): for every
+// parametrization vertex and tube subdivision, numAmbientOcclusionSamples hemisphere rays; running mean over frame_number.
+// The reference traces against the triangulated tubes; like the screen-space RTAO pass this oracle traces the analytic
+// capsules (DESIGN.md rule 5).  factors_inout: n_param * numTubeSubdivisions floats.  stats = {T, I, rays}
+// rays_out (optional, tests): 6 floats (origin, direction) per ray, index (vertex * N + subdivision) * spp + ray.
+void lvo_ao_bake_iteration(void* h, const lvo_bake_options* bo, int capped, const float* samplingLocations, uint64_t n_param,
+                           uint32_t frameNumber, float* ambientOcclusionFactors, uint64_t* stats, float* rays_out) {
+    SceneX& sc = sx(h);
+    const uint32_t numLinePoints = uint32_t(sc.ptPos.size());
+    const uint32_t numTubeSubdivisions = bo->num_tube_subdivisions;
+    const uint32_t numAmbientOcclusionSamples = bo->samples_per_frame;
+    const float lineRadius = sc.lineWidth * 0.5f;                                       // VulkanAmbientOcclusionBaker.cpp:697
+    const float ambientOcclusionRadius = bo->ao_radius;
+    uint64_t T = 0, I = 0, R = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : T, I, R)
+    for (int64_t gid = 0; gid < int64_t(n_param); gid++) {
+        RayStats st;
+        const uint32_t lineSamplingIdx = uint32_t(gid);
+        uint32_t seed = tea(lineSamplingIdx, frameNumber);                              // :196
+        // getInterpolatedLinePoint :104-124
+        const float samplingLocation = samplingLocations[lineSamplingIdx];
+        const uint32_t lowerIdx = uint32_t(samplingLocation);
+        const uint32_t upperIdx = std::min(lowerIdx + 1u, numLinePoints - 1u);
+        const float interpolationFactor = samplingLocation - floorf(samplingLocation);
+        const vec3 tl = sc.ptTan[lowerIdx], tu = sc.ptTan[upperIdx], nl = sc.ptNrm[lowerIdx], nu = sc.ptNrm[upperIdx];
+        const vec3 binormalLower = cross(tl, nl), binormalUpper = cross(tu, nu);
+        auto mix3 = [&](vec3 a, vec3 b) { return V3(mix(a.x, b.x, interpolationFactor), mix(a.y, b.y, interpolationFactor), mix(a.z, b.z, interpolationFactor)); };
+        const vec3 position = mix3(sc.ptPos[lowerIdx], sc.ptPos[upperIdx]);
+        const vec3 tangent = normalize(mix3(tl, tu));
+        const vec3 normal = normalize(mix3(nl, nu));
+        const vec3 binormal = normalize(mix3(binormalLower, binormalUpper));
+        for (uint32_t tubeSudivIdx = 0; tubeSudivIdx < numTubeSubdivisions; tubeSudivIdx++) {   // :238
+            float cosAngle, sinAngle;
+            det_sincos2pi(float(tubeSudivIdx) / float(numTubeSubdivisions), cosAngle, sinAngle);   // angle = idx / N * 2 pi
+            const vec3 surfaceNormal = cosAngle * normal + sinAngle * binormal;          // :258
+            const vec3 rayOrigin = position + (lineRadius + 1e-6f) * surfaceNormal;      // :259
+            const vec3 surfaceBitangent = cross(surfaceNormal, tangent);                 // :262
+            float occlusionFactorAccumulated = 0.0f;
+            for (uint32_t rayIdx = 0; rayIdx < numAmbientOcclusionSamples; rayIdx++) {   // :266-273
+                const float xix = rnd(seed), xiy = rnd(seed);
+                const vec3 hs = sampleHemisphere(xix, xiy);
+                const vec3 rayDirection = normalize((tangent * hs.x + surfaceBitangent * hs.y) + surfaceNormal * hs.z);   // frame * hs
+                Ray ar; ar.o = rayOrigin; ar.d = rayDirection; ar.tmin = 0.0f; ar.tmax = ambientOcclusionRadius;
+                if (rays_out) {
+                    float* ro = rays_out + 6 * ((size_t(lineSamplingIdx) * numTubeSubdivisions + tubeSudivIdx) * numAmbientOcclusionSamples + rayIdx);
+                    ro[0] = rayOrigin.x; ro[1] = rayOrigin.y; ro[2] = rayOrigin.z; ro[3] = rayDirection.x; ro[4] = rayDirection.y; ro[5] = rayDirection.z;
+                }
+                float occlusionFactor = 1.0f;                                            // traceAoRay :167-186
+                if (bo->use_distance) { Hit ah; if (traceClosest(sc, ar, capped != 0, ah, st, false)) occlusionFactor = ah.t / ambientOcclusionRadius; }
+                else { if (traceAny(sc, ar, capped != 0, st)) occlusionFactor = 0.0f; }
+                occlusionFactorAccumulated += occlusionFactor;
+            }
+            occlusionFactorAccumulated /= float(numAmbientOcclusionSamples);
+            float* dst = ambientOcclusionFactors + (tubeSudivIdx + size_t(numTubeSubdivisions) * lineSamplingIdx);
+            if (frameNumber != 0) occlusionFactorAccumulated = mix(*dst, occlusionFactorAccumulated, 1.0f / float(frameNumber + 1));  // :276-279
+            *dst = occlusionFactorAccumulated;
+        }
+        T += st.steps; I += st.isect; R += st.rays;
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = R; }
+}
+
+// Hands the baked factors + blending weights to the shading path (STATIC_AMBIENT_OCCLUSION_PREBAKING bindings,
+// LineRenderer::setRenderDataBindings / Utils/AmbientOcclusion.glsl:30-37).
+void lvo_scene_set_static_ao(void* h, const float* factors, uint64_t n_param, uint32_t n_subdiv, const float* blending_weights, uint64_t n_pt) {
+    SceneX& sc = sx(h);
+    sc.aoFactors.assign(factors, factors + n_param * n_subdiv);
+    sc.aoBlendingWeights.assign(blending_weights, blending_weights + n_pt);
+    sc.numParametrizationVertices = uint32_t(n_param); sc.numAoTubeSubdivisions = n_subdiv;
+}
+
+// ClosestHitTubeAnalytic for a list of given hits (tests: function-level parity of the device shading code).
+// ro / rd: n*3; t: n; kind: n; prim: n (segment index).  out: n*5 floats (hitColor rgba, hitT)
+void lvo_shade_hits(void* h, const lv_camera* cam, const lvo_options* o, const float* tf, uint32_t K, float amin, float amax,
+                    const float* ao_tex, uint64_t n, const float* ro, const float* rd, const float* t, const uint32_t* kind,
+                    const uint32_t* prim, float* out) {
+    SceneX& sc = sx(h);
+    Uniforms u = makeUniforms(sc, *cam, *o, tf, K, amin, amax, ao_tex);
+    for (uint64_t i = 0; i < n; i++) {
+        const Segment& s = sc.segs[prim[i]];
+        HitColor pl = closestHitTubeAnalytic(u, V3(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), V3(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]), t[i],
+                                             int(kind[i]), s.p0, s.a0, s.p1, s.a1, &sc.segLine[prim[i]]);
+        out[5 * i] = pl.hitColor.x; out[5 * i + 1] = pl.hitColor.y; out[5 * i + 2] = pl.hitColor.z; out[5 * i + 3] = pl.hitColor.w; out[5 * i + 4] = pl.hitT;
+    }
+}
+
+// getAoFactor(fragmentVertexId, phi) alone, for unit tests
+float lvo_static_ao_factor(void* h, float strength, float gamma, float fragmentVertexId, float phi) {
+    SceneX& sc = sx(h);
+    Uniforms u{};
+    u.ambientOcclusionStrength = strength; u.ambientOcclusionGamma = gamma;
+    u.ambientOcclusionFactors = sc.aoFactors.data(); u.ambientOcclusionBlendingWeights = sc.aoBlendingWeights.data();
+    u.numAoTubeSubdivisions = sc.numAoTubeSubdivisions; u.numLineVertices = uint32_t(sc.aoBlendingWeights.size());
+    u.numParametrizationVertices = sc.numParametrizationVertices;
+    return getAoFactorStatic(u, fragmentVertexId, phi);
 }
 
 int lvo_num_threads(void) {

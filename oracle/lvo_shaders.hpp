@@ -133,6 +133,28 @@ static inline void det_sincos2pi(float xi, float& c, float& s) {
     else { c = sr; s = -cr; }
 }
 
+// acos(x) for the tube angle phi (TubeRayTracing.glsl:554).  GLSL leaves acos undefined for |x| > 1 (a dot product of two
+// normalised vectors can exceed 1 by an ulp), so the argument is clamped.  |x| <= 0.5: pi/2 - asin(x);
+// else 2 asin(sqrt((1-|x|)/2)) mirrored; asin(s) = s + s z P(z), z = s^2, P fitted on [0, 0.25] (abs error 3e-7 vs libm).
+static inline float det_acos(float x) {
+    x = clamp(x, -1.0f, 1.0f);
+    const float ax = fabsf(x);
+    const bool small = ax <= 0.5f;
+    float z, s;
+    if (small) { z = x * x; s = x; }
+    else { z = (1.0f - ax) * 0.5f; s = sqrtf(z); }
+    float p = 3.380591050e-02f;
+    p = p * z + 1.707774773e-02f;
+    p = p * z + 3.111618385e-02f;
+    p = p * z + 4.459802806e-02f;
+    p = p * z + 7.500098646e-02f;
+    p = p * z + 1.666666567e-01f;
+    const float r = s + (s * z) * p;
+    if (small) return 1.57079633f - r;
+    if (x > 0.0f) return 2.0f * r;
+    return 3.14159265f - 2.0f * r;
+}
+
 // ----------------------------------------------------------------------------------------------
 // RNG -- Data/Shaders/Renderers/RayTracing/RayTracingUtilities.glsl:134-181 (integer exact)
 // ----------------------------------------------------------------------------------------------
@@ -295,6 +317,11 @@ struct Uniforms {
     bool useCappedTubes, useHalos, useAmbientOcclusion;
     // AO texture (result of the RTAO pass), W*H floats
     const float* aoTexture;
+    // STATIC_AMBIENT_OCCLUSION_PREBAKING (Utils/AmbientOcclusion.glsl:30-37; uniforms LineData.hpp:452-458)
+    bool staticAmbientOcclusionPrebaking;
+    const float* ambientOcclusionFactors;            // [numParametrizationVertices * numAoTubeSubdivisions]
+    const float* ambientOcclusionBlendingWeights;    // [numLineVertices]
+    uint32_t numAoTubeSubdivisions, numLineVertices, numParametrizationVertices;
 };
 
 // Utils/TransferFunction.glsl:66-71 -- texture(sampler1D, posFloat), linear filter, clamp to edge
@@ -335,6 +362,33 @@ static inline float getAoFactor(const Uniforms& u, vec3 screenSpacePosition) {
     return fmax_(0.0f, 1.0f - u.ambientOcclusionStrength + u.ambientOcclusionStrength * aoFactor);
 }
 
+// Utils/AmbientOcclusion.glsl:49-75 (STATIC_AMBIENT_OCCLUSION_PREBAKING variant)
+static inline float getAoFactorStatic(const Uniforms& u, float interpolatedVertexId, float phi) {
+    uint32_t lastLinePointIdx = uint32_t(interpolatedVertexId);
+    uint32_t nextLinePointIdx = lastLinePointIdx + 1u < u.numLineVertices - 1u ? lastLinePointIdx + 1u : u.numLineVertices - 1u;
+    float interpolationFactor = interpolatedVertexId - floorf(interpolatedVertexId);                    // fract
+    float blendingWeightLast = u.ambientOcclusionBlendingWeights[lastLinePointIdx];
+    float blendingWeightNext = u.ambientOcclusionBlendingWeights[nextLinePointIdx];
+    float blendingWeight = mix(blendingWeightLast, blendingWeightNext, interpolationFactor);
+    uint32_t lastVertexIdx = uint32_t(blendingWeight);
+    uint32_t nextVertexIdx = lastVertexIdx + 1u < u.numParametrizationVertices - 1u ? lastVertexIdx + 1u : u.numParametrizationVertices - 1u;
+    float interpolationFactorLine = blendingWeight - floorf(blendingWeight);
+    const uint32_t N = u.numAoTubeSubdivisions;
+    float circleIdxFlt = clamp(phi / 6.28318531f * float(N), 0.0f, float(N));                            // phi / (2.0 * M_PI) * N
+    uint32_t circleIdxLast = (uint32_t(floorf(circleIdxFlt)) + N) % N;
+    uint32_t circleIdxNext = (circleIdxLast + 1u) % N;
+    float interpolationFactorCircle = circleIdxFlt - floorf(circleIdxFlt);
+    float aoFactor00 = u.ambientOcclusionFactors[circleIdxLast + N * lastVertexIdx];
+    float aoFactor01 = u.ambientOcclusionFactors[circleIdxLast + N * nextVertexIdx];
+    float aoFactor10 = u.ambientOcclusionFactors[circleIdxNext + N * lastVertexIdx];
+    float aoFactor11 = u.ambientOcclusionFactors[circleIdxNext + N * nextVertexIdx];
+    float aoFactor0 = mix(aoFactor00, aoFactor01, interpolationFactorLine);
+    float aoFactor1 = mix(aoFactor10, aoFactor11, interpolationFactorLine);
+    float aoFactor = mix(aoFactor0, aoFactor1, interpolationFactorCircle);
+    aoFactor = det_pow(aoFactor, u.ambientOcclusionGamma);
+    return fmax_(0.0f, 1.0f - u.ambientOcclusionStrength + u.ambientOcclusionStrength * aoFactor);
+}
+
 // Utils/Antialiasing.glsl:1-3
 static inline float getAntialiasingFactor(const Uniforms& u, float distance) {
     return distance / float(u.viewportH) * u.fieldOfViewY;
@@ -342,14 +396,16 @@ static inline float getAntialiasingFactor(const Uniforms& u, float distance) {
 
 // Utils/Lighting.glsl:100-191 (no bands, no depth cues; AO branch when USE_AMBIENT_OCCLUSION && GEOMETRY_PASS_TUBE)
 static inline vec4 blinnPhongShadingTube(const Uniforms& u, vec4 baseColor, vec3 fragmentPositionWorld,
-                                         vec3 screenSpacePosition, vec3 fragmentNormal, vec3 fragmentTangent) {
+                                         vec3 screenSpacePosition, float fragmentVertexId, float phi,
+                                         vec3 fragmentNormal, vec3 fragmentTangent) {
     const vec3 ambientColor = V3(baseColor.x, baseColor.y, baseColor.z);
     const vec3 diffuseColor = ambientColor;
     float ambientOcclusionFactor = 1.0f;
     float kA, kD;
     const float kS = 0.3f, s = 30.0f;
     if (u.useAmbientOcclusion) {
-        ambientOcclusionFactor = getAoFactor(u, screenSpacePosition);
+        ambientOcclusionFactor = u.staticAmbientOcclusionPrebaking ? getAoFactorStatic(u, fragmentVertexId, phi)   // :118-125
+                                                                   : getAoFactor(u, screenSpacePosition);
         kA = 0.2f + (1.0f - ambientOcclusionFactor) * 0.5f;
         kD = 0.9f * ambientOcclusionFactor;
     } else {
@@ -385,7 +441,8 @@ struct HitColor { vec4 hitColor; float hitT; bool hasHit; };
 // computeFragmentColor -- Data/Shaders/Renderers/RayTracing/RayHitCommon.glsl:74-543
 // (variant: USE_CAPPED_TUBES, USE_HALOS, ANALYTIC_TUBE_INTERSECTIONS; no bands/multivar/stress/MLAT)
 static inline HitColor computeFragmentColor(const Uniforms& u, vec3 fragmentPositionWorld, vec3 fragmentNormal,
-                                            vec3 fragmentTangent, bool isCap, float fragmentAttribute) {
+                                            vec3 fragmentTangent, bool isCap, float phi, float fragmentVertexId,
+                                            float fragmentAttribute) {
     vec4 fragmentColor = transferFunction(u, fragmentAttribute);                       // :127
     const vec3 n = normalize(fragmentNormal);                                          // :141
     const vec3 v = normalize(u.cameraPosition - fragmentPositionWorld);                // :142
@@ -411,11 +468,11 @@ static inline HitColor computeFragmentColor(const Uniforms& u, vec3 fragmentPosi
         }
     }
     vec3 screenSpacePosition = V3(0, 0, 0);
-    if (u.useAmbientOcclusion || u.useDepthCues) {                                     // :389-391
+    if ((u.useAmbientOcclusion && !u.staticAmbientOcclusionPrebaking) || u.useDepthCues) {   // :389-391
         vec4 sp = mul(u.viewMatrix, vec4{fragmentPositionWorld.x, fragmentPositionWorld.y, fragmentPositionWorld.z, 1.0f});
         screenSpacePosition = V3(sp.x, sp.y, sp.z);
     }
-    fragmentColor = blinnPhongShadingTube(u, fragmentColor, fragmentPositionWorld, screenSpacePosition, n, t); // :415-426
+    fragmentColor = blinnPhongShadingTube(u, fragmentColor, fragmentPositionWorld, screenSpacePosition, fragmentVertexId, phi, n, t); // :415-426
     float absCoords = u.useHalos ? fabsf(ribbonPosition) : 0.0f;                       // :437-441
     float fragmentDepth = length(fragmentPositionWorld - u.cameraPosition);            // :443
     float EPSILON_OUTLINE = clamp(getAntialiasingFactor(u, fragmentDepth / u.lineWidth * 0.05f), 0.0f, 0.49f); // :451
@@ -431,27 +488,40 @@ static inline HitColor computeFragmentColor(const Uniforms& u, vec3 fragmentPosi
     return out;
 }
 
+// Per-segment line-point data the closest-hit shader reads besides position / attribute when USE_AMBIENT_OCCLUSION is on
+// (linePointIndices :513, lineNormal :551): used by the static prebaked AO lookup only.
+struct SegmentLineData { uint32_t idx0, idx1; vec3 n0, n1; };
+
 // ClosestHitTubeAnalytic main -- Data/Shaders/Renderers/RayTracing/TubeRayTracing.glsl:512-613
 static inline HitColor closestHitTubeAnalytic(const Uniforms& u, vec3 ro, vec3 rd, float hitT, int hitKind,
-                                              vec3 p0, float a0, vec3 p1, float a1) {
+                                              vec3 p0, float a0, vec3 p1, float a1, const SegmentLineData* ld = nullptr) {
     vec3 fragmentPositionWorld = ro + rd * hitT;                                       // :517
     vec3 linePointInterpolated;
     float fragmentAttribute;
+    float t;
     vec3 v = p1 - p0;                                                                  // :523
     if (hitKind == 0) {
         vec3 uu = fragmentPositionWorld - p0;
-        float t = dot(v, uu) / dot(v, v);
+        t = dot(v, uu) / dot(v, v);
         linePointInterpolated = p0 + t * v;
         fragmentAttribute = (1.0f - t) * a0 + t * a1;
     } else if (hitKind == 1) {
-        linePointInterpolated = p0; fragmentAttribute = a0;
+        linePointInterpolated = p0; fragmentAttribute = a0; t = 0.0f;
     } else {
-        linePointInterpolated = p1; fragmentAttribute = a1;
+        linePointInterpolated = p1; fragmentAttribute = a1; t = 1.0f;
     }
     vec3 fragmentTangent = normalize(v);                                               // :544
     vec3 fragmentNormal = normalize(fragmentPositionWorld - linePointInterpolated);    // :545
     bool isCap = hitKind != 0;                                                         // :548
-    return computeFragmentColor(u, fragmentPositionWorld, fragmentNormal, fragmentTangent, isCap, fragmentAttribute);
+    float phi = 0.0f, fragmentVertexId = 0.0f;
+    if (u.useAmbientOcclusion && u.staticAmbientOcclusionPrebaking && ld) {            // :550-562
+        vec3 lineNormal = (1.0f - t) * ld->n0 + t * ld->n1;
+        phi = det_acos(dot(fragmentNormal, lineNormal));
+        float val = dot(lineNormal, cross(fragmentNormal, fragmentTangent));
+        if (val < 0.0f) phi = 6.28318531f - phi;                                       // 2.0 * float(M_PI) - phi
+        fragmentVertexId = (1.0f - t) * float(ld->idx0) + t * float(ld->idx1);
+    }
+    return computeFragmentColor(u, fragmentPositionWorld, fragmentNormal, fragmentTangent, isCap, phi, fragmentVertexId, fragmentAttribute);
 }
 
 // Depth range of one line vertex -- Data/Shaders/DepthCues/ComputeDepthValues.glsl:60-76 (min / max are folded by the caller,
