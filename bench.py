@@ -40,8 +40,10 @@ WORKLOADS = {
 PPLL_WORKLOADS = {
     "config2": dict(desc="100 k-segment synthetic helix (seed 1001), 1920x1080, PPLL OIT, MAX_NUM_FRAGS 100",
                     gen=("helix", dict()), W=1920, H=1080, max_frags=100),
-    "config4": dict(desc="1 M random segments (seed 2002), 3840x2160, PPLL OIT, MAX_NUM_FRAGS 256",
-                    gen=("random", dict(n_seg=1_000_000, seed=2002)), W=3840, H=2160, max_frags=256),
+    # fragment budget: expectedAvgDepthComplexity 24 instead of the reference's 20 for <= 1 M segments (this frame holds 19.2 fragments
+    # per pixel on average; a tile shard's share varies by a few per cent and nothing may be dropped inside the timed region)
+    "config4": dict(desc="1 M random segments (seed 2002), 3840x2160, PPLL OIT, MAX_NUM_FRAGS 256, fragment budget 24 x pixels",
+                    gen=("random", dict(n_seg=1_000_000, seed=2002)), W=3840, H=2160, max_frags=256, avg_depth=24),
 }
 
 
@@ -210,13 +212,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config5", choices=list(WORKLOADS))
-    ap.add_argument("--ppll-workload", default="config2", choices=list(PPLL_WORKLOADS) + ["none"])
+    ap.add_argument("--ppll-workload", default="config2,config4",
+                    help="comma-separated PPLL workloads measured beside the tube path (%s) or 'none'; the first is reported under "
+                         "\"ppll\", further ones under \"ppll_<name>\"" % ", ".join(PPLL_WORKLOADS))
     ap.add_argument("--ref-sample", type=int, nargs=2, default=[320, 180])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
-    pw = PPLL_WORKLOADS.get(args.ppll_workload)
+    ppll_names = [n for n in args.ppll_workload.split(",") if n and n != "none"]
+    for n in ppll_names:
+        if n not in PPLL_WORKLOADS:
+            ap.error("unknown PPLL workload %r" % n)
+    pw = PPLL_WORKLOADS[ppll_names[0]] if ppll_names else None
 
     if args.impl == "reference":
         run_reference(args, wl, pw)
@@ -335,12 +343,13 @@ def main():
     d2h = (n_own * tile * tile if world > 1 else W * H) * 16
 
     # ---- PPLL path (second half of the metric), rank-local, whole frame on one GPU unless sharded
-    ppll = None
-    if pw is not None:
+    def measure_ppll(pw, with_cpu):
         ppos, pattr, pseg = generate(pw["gen"]) if pw["gen"] != wl["gen"] else (pos, attr, seg)
         pctx = lv.Context(local, stream)
         pctx.set_transfer_function(lv.scenes.standard_transfer_function(opacity=(0.1, 0.6)))
         pctx.set_option("ambient_occlusion_strength", 0.0)
+        if "avg_depth" in pw:
+            pctx.set_option("b200_expected_avg_depth_complexity", pw["avg_depth"])
         if world > 1:
             pctx.set_tile_shard(rank, world, tile)
         pscene = pctx.create_scene(ppos, pattr, pseg, lv.scenes.LINE_WIDTH)
@@ -351,22 +360,53 @@ def main():
             pst = pctx.render_ppll(pscene, pcam, pw["max_frags"], "priority_queue", 0, out=pframe, stats=True)[1]
             if i >= args.warmup:
                 res.append(pst["ms_resolve"]); gat.append(pst["ms_gather"])
-        pc = torch.tensor([pst["frags_sorted"], float(np.mean(res)), float(np.mean(gat)), pst["frags_generated"]], dtype=torch.float64, device=dev)
+        n_own_p = len(pctx.owned_tiles(pw["W"], pw["H"]))
+        pc = torch.tensor([pst["frags_sorted"], float(np.mean(res)), float(np.mean(gat)), pst["frags_generated"], pst["frags_dropped"]],
+                          dtype=torch.float64, device=dev)
         if world > 1:
-            fs = pc[[0, 3]].clone(); dist.all_reduce(fs)
+            fs = pc[[0, 3, 4]].clone(); dist.all_reduce(fs)
             tm = pc[[1, 2]].clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            pc = torch.stack([fs[0], tm[0], tm[1], fs[1]])
-        frags, res_ms, gat_ms, gen = [float(x) for x in pc.tolist()]
+            pc = torch.stack([fs[0], tm[0], tm[1], fs[1], fs[2]])
+        frags, res_ms, gat_ms, gen, dropped = [float(x) for x in pc.tolist()]
         npx = pw["W"] * pw["H"]
-        pbytes = 12 * pst["frags_sorted"] + 20 * (n_own * tile * tile if world > 1 else npx)
-        ppll = {"workload": pw["desc"], "metric": "Mfrags/s sorted (PPLL resolve)", "value": frags / (res_ms * 1e-3) / 1e6,
-                "unit": "Mfrags/s", "frags_sorted": frags, "ms_resolve": res_ms, "ms_gather": gat_ms,
-                "gather_Mfrags_per_s": gen / (gat_ms * 1e-3) / 1e6, "max_depth_complexity": pst["max_depth_complexity"],
-                "roofline": {"bound": "hbm", "achieved": pbytes / (float(np.mean(res)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": pbytes / (float(np.mean(res)) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                             "kernel": "k_ppll_resolve", "bytes": "12 B/fragment + 20 B/pixel (SURVEY 8d)"}}
-        if rank == 0 and not args.no_cpu_baseline and world == 1:
-            ppll["cpu_baseline"] = cpu_baseline_ppll(pw, ppos, pattr, pseg, (480, 270))
+        pbytes = 12 * pst["frags_sorted"] + 20 * (n_own_p * tile * tile if world > 1 else npx)
+        out = {"workload": pw["desc"], "metric": "Mfrags/s sorted (PPLL resolve)", "value": frags / (res_ms * 1e-3) / 1e6,
+               "unit": "Mfrags/s", "frags_sorted": frags, "frags_dropped": dropped, "ms_resolve": res_ms, "ms_gather": gat_ms,
+               "gather_Mfrags_per_s": gen / (gat_ms * 1e-3) / 1e6, "max_depth_complexity": pst["max_depth_complexity"],
+               "roofline": {"bound": "hbm", "achieved": pbytes / (float(np.mean(res)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": pbytes / (float(np.mean(res)) * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "kernel": "k_ppll_resolve", "bytes": "12 B/fragment + 20 B/pixel (SURVEY 8d), rank 0's share"}}
+        if with_cpu and rank == 0 and not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline_ppll(pw, ppos, pattr, pseg, (480, 270))
+        pscene.close(); pctx.close()
+        del pframe
+        torch.cuda.empty_cache()
+        return out
+
+    ppll_results = {}
+    for i, name in enumerate(ppll_names):
+        ppll_results["ppll" if i == 0 else "ppll_" + name] = measure_ppll(PPLL_WORKLOADS[name], with_cpu=(i == 0))
+
+    # ---- the collective alone (N > 1): pack + all_gather + unpack on rank 0, CUDA events, max over ranks
+    gather_ms = None
+    if fg is not None:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        g0.record()
+        for _ in range(max(3, args.steps)):
+            fg.gather(frame, assemble_on=(0,))
+        g1.record(); torch.cuda.synchronize()
+        gm = torch.tensor([g0.elapsed_time(g1) / max(3, args.steps)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        gather_ms = float(gm.item())
+    # per-rank time of the dominant kernel (load balance of the tile shards)
+    krank = torch.tensor([k_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        kall = [torch.zeros_like(krank) for _ in range(world)]
+        dist.all_gather(kall, krank)
+        k_ms_ranks = [float(t.item()) for t in kall]
+    else:
+        k_ms_ranks = [k_ms]
 
     if rank == 0:
         value = tot_rays / (ms * 1e-3) / 1e6
@@ -390,8 +430,10 @@ def main():
             "gpu_launches": (4 + (2 + (world - 1) if world > 1 else 0)) * args.steps,   # k_rtao_primary, k_rtao_rays, k_rtao_reduce, k_tubes (+ tile pack / unpack)
             "clocks": clocks,
         }
-        if ppll:
-            line["ppll"] = ppll
+        line.update(ppll_results)
+        if gather_ms is not None:
+            line["config"]["gather_ms"] = gather_ms            # pack + NCCL all_gather + unpack alone, max over ranks
+        line["config"]["k_rtao_rays_ms_per_rank"] = k_ms_ranks  # tile-shard load balance of the dominant kernel
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, pos, attr, seg, tuple(args.ref_sample))
         print(json.dumps(line))
