@@ -38,7 +38,8 @@ struct Options {
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
     uint32_t ao_refill_below = 24;
-    uint32_t ao_min_blocks = 10;      // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 10 / 12)
+    uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
+    uint32_t ao_min_blocks = 9;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10)
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
@@ -275,9 +276,19 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S) {
         LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
         return LV_OK;
     };
-    if (c->opt.ao_min_blocks >= 12) return launch(k_rtao_rays<12, BAKE>);
-    if (c->opt.ao_min_blocks >= 10) return launch(k_rtao_rays<10, BAKE>);
-    return launch(k_rtao_rays<8, BAKE>);
+    const uint32_t stack = c->opt.ao_stack, mb = c->opt.ao_min_blocks;
+#define LV_AO_STACKS(MB)                                                  \
+    switch (stack) {                                                      \
+        case 0: return launch(k_rtao_rays<MB, BAKE, 0>);                  \
+        case 1: return launch(k_rtao_rays<MB, BAKE, 1>);                  \
+        case 8: return launch(k_rtao_rays<MB, BAKE, 8>);                  \
+        case 16: return launch(k_rtao_rays<MB, BAKE, 16>);                \
+        default: return launch(k_rtao_rays<MB, BAKE, 12>);                \
+    }
+    if (mb >= 10) { LV_AO_STACKS(10) }
+    if (mb >= 9) { LV_AO_STACKS(9) }
+    LV_AO_STACKS(8)
+#undef LV_AO_STACKS
 }
 
 // ---- RTAO pass (S5) into ctx->ao --------------------------------------------------------------
@@ -572,6 +583,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
+    else if (k == "b200_ao_stack") { if (u() != 0 && u() != 1 && u() != 8 && u() != 12 && u() != 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_stack must be 0, 1, 8, 12 or 16"); o.ao_stack = u(); }
     else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
     else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
     else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
@@ -619,6 +631,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
     else if (k == "b200_ao_min_blocks") v = std::to_string(o.ao_min_blocks);
+    else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());

@@ -274,7 +274,52 @@ constexpr int kAoStack = 72;
 
 // BAKE = object-space prebaker (lv_bake.cuh): records are (parametrization vertex, tube subdivision) frames, the ray origin is the
 // record's position itself and the random numbers come from the vertex's LCG stream instead of a per-sample TEA seed.
-template <int MIN_BLOCKS, bool BAKE>
+// STACK = layout of the per-lane traversal stack (b200_ao_stack):
+//   0  two local-memory arrays (node word, entry distance) -- the measured default;
+//   1  one local-memory array of packed 64-bit entries (one LDL/STL.64 per pop / push instead of two 32-bit ones);
+//   K >= 2  the first K packed entries in SHARED memory, laid out [entry][thread] so that a warp's accesses never
+//      conflict whatever the lanes' stack depths are (local memory is interleaved per 32-bit word: lanes at different
+//      depths touch different 128-byte lines, one L1 wavefront each), deeper entries spill to a local array.
+//      K x 8 B x 128 threads = K KiB of shared memory per block.
+
+template <int K> struct AoStack {
+    static constexpr int kAoSmemStack = K;
+    unsigned long long e[kAoStack - kAoSmemStack];
+    uint32_t sm;   // shared-window address of this thread's column: entry i at sm + i * kBlockThreads * 8
+    __device__ __forceinline__ void init() {
+        __shared__ unsigned long long s_stack[kAoSmemStack][kBlockThreads];
+        sm = uint32_t(__cvta_generic_to_shared(&s_stack[0][threadIdx.x]));
+    }
+    __device__ __forceinline__ void put(int i, uint32_t node, float t) {
+        const unsigned long long v = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | node;
+        if (i < kAoSmemStack) asm volatile("st.shared.u64 [%0], %1;" ::"r"(sm + uint32_t(i) * (kBlockThreads * 8u)), "l"(v) : "memory");
+        else e[i - kAoSmemStack] = v;
+    }
+    __device__ __forceinline__ unsigned long long get(int i) const {
+        unsigned long long v;
+        if (i < kAoSmemStack) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sm + uint32_t(i) * (kBlockThreads * 8u)) : "memory");
+        else v = e[i - kAoSmemStack];
+        return v;
+    }
+};
+template <> struct AoStack<1> {
+    unsigned long long e[kAoStack];
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void put(int i, uint32_t node, float t) { e[i] = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | node; }
+    __device__ __forceinline__ unsigned long long get(int i) const { return e[i]; }
+};
+// pop until an entry whose box entry distance is still within reach; returns kDone if the stack runs empty
+template <int STACK>
+__device__ __forceinline__ uint32_t ao_stack_pop(const AoStack<STACK>& st, int& sp, float best) {
+    while (sp > 0) {
+        --sp;
+        const unsigned long long v = st.get(sp);
+        if (__uint_as_float(uint32_t(v >> 32)) <= best) return uint32_t(v);
+    }
+    return 0x7FFFFFFFu;   // kDone
+}
+
+template <int MIN_BLOCKS, bool BAKE, int STACK>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
             const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
@@ -286,8 +331,10 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
     const float radius = S.radius;
     uint32_t steps = 0, isect = 0, rays = 0;
 
-    uint32_t stk_node[kAoStack];
-    float stk_t[kAoStack];
+    uint32_t stk_node[STACK == 0 ? kAoStack : 1];
+    float stk_t[STACK == 0 ? kAoStack : 1];
+    AoStack<STACK == 0 ? 1 : STACK> pst;   // unused (and eliminated) with STACK == 0
+    if (STACK != 0) pst.init();
     int sp = 0;
     uint32_t cur = kDone;
     bool exhausted = false;          // no more rays to fetch
@@ -336,13 +383,15 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                 const uint32_t cl = __float_as_uint(nd.l0.w), cr = __float_as_uint(nd.r0.w);
                 if (hl && hr) {
                     const bool swap = tr < tl;
-                    if (sp < kAoStack) { stk_node[sp] = swap ? cl : cr; stk_t[sp] = swap ? tl : tr; sp++; }
+                    if (STACK == 0) { if (sp < kAoStack) { stk_node[sp] = swap ? cl : cr; stk_t[sp] = swap ? tl : tr; sp++; } }
+                    else if (sp < kAoStack) { pst.put(sp, swap ? cl : cr, swap ? tl : tr); sp++; }
                     cur = swap ? cr : cl;
                 } else if (hl) cur = cl;
                 else if (hr) cur = cr;
                 else {
                     cur = kDone;
-                    while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } }
+                    if (STACK == 0) { while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } } }
+                    else cur = ao_stack_pop(pst, sp, best);
                 }
             }
             // B: postponed leaves are intersected once enough lanes hold one (vote), or when nobody can step any more
@@ -363,8 +412,9 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                     }
                 }
                 cur = kDone;
-                if (!stop) while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } }
-                else sp = 0;
+                if (stop) sp = 0;
+                else if (STACK == 0) { while (sp > 0) { --sp; if (stk_t[sp] <= best) { cur = stk_node[sp]; break; } } }
+                else cur = ao_stack_pop(pst, sp, best);
             }
             if (cur == kDone && !exhausted && ray_id < total) {
                 // ray finished: traceAoRay result (:158-175)

@@ -111,6 +111,26 @@ def test_rtao_parity(ctx, oracle, jitter, use_distance, spp):
     assert np.array_equal(ao2.view(np.uint32), ref2.view(np.uint32))
 
 
+@pytest.mark.parametrize("stack", [0, 1, 8, 16])
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_stack_layouts_bit_exact(ctx, oracle, stack, use_distance):
+    """b200_ao_stack: packed-local (1) and shared-memory (2) traversal stacks of the AO ray kernel give the same AO image
+    as the oracle (and hence as the default layout); a deep scene makes the shared stack spill to its local part."""
+    data, width = DATASETS["random"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(120, 80)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 8, "ambient_occlusion_distance_based": use_distance,
+                          "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.3, "b200_ao_stack": stack})
+    try:
+        ao, st = ctx.render_rtao(sc, cam, 0)
+    finally:
+        ctx.set_new_settings({"b200_ao_stack": 12, "ambient_occlusion_radius": 0.1})
+    opts = lvo.default_options(ao_strength=1.0, ao_spp=8, ao_use_distance=int(use_distance), ao_jitter_primary=1, ao_radius=0.3)
+    ref, ost = osc.render_rtao(cam, opts, 0)
+    assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+    assert st["rays_ao"] == ost["rays_ao"] > 0
+
+
 @pytest.mark.parametrize("name,ao", [("helix", False), ("helix", True), ("random", True), ("single", False)])
 def test_tubes_parity(ctx, oracle, name, ao):
     data, width = DATASETS[name]()

@@ -50,7 +50,7 @@ def test_baked_factors_bit_exact_every_iteration(bake_ctx, oracle, distance_base
         assert np.array_equal(got["sampling_locations"], sl) and np.array_equal(got["blending_weights"], bw)
         assert st["rays_ao"] == ost["rays"] == len(sl) * 8 * 4
         assert np.array_equal(got["factors"].reshape(-1).view(np.uint32), ref.view(np.uint32)), "iteration %d" % it
-    assert 0.0 < ref.min() < 0.9 and ref.max() <= 1.0       # the helix does occlude itself
+    assert ref.min() < 0.9 and ref.max() <= 1.0 and 0.2 < ref.mean() < 0.999   # the helix does occlude itself
     assert sc.ao_bake(0)["rays_ao"] == 0                     # all b200_prebaker_iterations done: nothing left to bake
     sc.ao_bake_reset()
     assert sc.ao_bake(0)["rays_ao"] == 3 * len(sl) * 8 * 4   # immediate mode: all iterations in one call
@@ -107,7 +107,9 @@ def test_ppll_with_prebaked_ao_bit_exact(bake_ctx, oracle):
     b = lvo.per_pixel_lists(g["heads"], g["nodes"], cam, opts, oracle)
     assert a == b
     refp, _ = lvo.ppll_resolve(oracle, cam, opts, g["heads"], g["nodes"], 64, 0, canonical=True)
-    assert np.array_equal(img.view(np.uint32), refp.view(np.uint32))
+    nan = np.isnan(refp)                                     # all-alpha-0 lists resolve to 0/0 in the reference and here alike
+    assert np.array_equal(np.isnan(img), nan)
+    assert np.array_equal(img[~nan].view(np.uint32), refp[~nan].view(np.uint32))
 
 
 def test_prebaker_errors(bake_ctx):

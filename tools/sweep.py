@@ -11,7 +11,9 @@ ap.add_argument("--leaf", type=int, nargs="+", default=[1, 2, 4, 8])
 ap.add_argument("--refill", type=int, nargs="+", default=[16, 24, 28, 32])
 ap.add_argument("--ppll-workload", default="none")
 ap.add_argument("--vote", type=int, nargs="+", default=[12])
-ap.add_argument("--minb", type=int, nargs="+", default=[8])
+ap.add_argument("--minb", type=int, nargs="+", default=[10])
+ap.add_argument("--stack", type=int, nargs="+", default=[0])
+ap.add_argument("--combo", type=str, nargs="*", default=[], help="explicit minb:stack:refill:vote combinations instead of the product")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 wl = bench.WORKLOADS[args.workload]
@@ -24,8 +26,11 @@ for leaf in args.leaf:
     ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": wl["ao_spp"], "ambient_occlusion_iterations": 1,
                           "num_samples_per_frame": 1, "num_accumulated_frames": 1, "b200_bvh_leaf_size": leaf})
     sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
-    for refill, vote, minb in itertools.product(args.refill, args.vote, args.minb):
+    combos = [tuple(int(v) for v in (c.split(":")[2], c.split(":")[3], c.split(":")[0], c.split(":")[1])) for c in args.combo] \
+        or list(itertools.product(args.refill, args.vote, args.minb, args.stack))
+    for refill, vote, minb, stack in combos:
         ctx.set_option("b200_ao_min_blocks", minb)
+        ctx.set_option("b200_ao_stack", stack)
         ctx.set_option("b200_ao_refill_below", refill)
         ctx.set_option("b200_ao_leaf_vote", vote)
         ts = []
@@ -35,8 +40,8 @@ for leaf in args.leaf:
         k, t = np.min([a for a, _ in ts[1:]]), np.min([b for _, b in ts[1:]])
         rays = st["rays_primary"] + st["rays_ao"]
         by = 64 * st["ao_traversal_steps"] + 32 * st["ao_intersections"] + 4 * st["rays_ao"]
-        print("leaf %d refill %2d vote %2d minb %2d: k_rtao_rays %.2f ms  frame %.2f ms  %.0f Mrays/s  T/ray %.1f I/ray %.1f  algGB/s %.0f  build %.1f ms" %
-              (leaf, refill, vote, minb, k, t, rays / t / 1e3, st["ao_traversal_steps"] / st["rays_ao"], st["ao_intersections"] / st["rays_ao"], by / k / 1e6, sc.info()["build_ms"]), flush=True)
+        print("leaf %d refill %2d vote %2d minb %2d stack %d: k_rtao_rays %.2f ms  frame %.2f ms  %.0f Mrays/s  T/ray %.1f I/ray %.1f  algGB/s %.0f  build %.1f ms" %
+              (leaf, refill, vote, minb, stack, k, t, rays / t / 1e3, st["ao_traversal_steps"] / st["rays_ao"], st["ao_intersections"] / st["rays_ao"], by / k / 1e6, sc.info()["build_ms"]), flush=True)
     sc.close(); ctx.close()
 if args.ppll_workload != "none":
     pw = bench.PPLL_WORKLOADS[args.ppll_workload]
