@@ -39,7 +39,8 @@ struct Options {
     uint32_t bvh_leaf_size = 1;
     uint32_t ao_refill_below = 24;
     uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
-    uint32_t ao_min_blocks = 9;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10)
+    bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
+    uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
@@ -95,7 +96,7 @@ struct lv_scene {
     DevBuf<SegRec> segs; DevBuf<uint32_t> prim_ids; DevBuf<Node64> nodes;
     uint64_t n_seg = 0, n_nodes = 0, n_pt = 0;
     float line_width = 0.0f, build_ms = 0.0f;
-    uint32_t depth = 0;
+    uint32_t depth = 0, leaf_size = 1;
     float bounds[6] = {0, 0, 0, 0, 0, 0};
     // line-point frames + object-space AO prebaker state (lv_scene_set_lines / lv_ao_bake)
     DevBuf<uint2> seg_idx;                         // caller's point index pairs, caller order
@@ -265,7 +266,7 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedT
 // persistent AO ray-stream kernel over the records in ctx->ao_hits (count in small[0], work counter in small[2..3]) into ctx->occ;
 // timed with ev[4] / ev[5].  BAKE selects the prebaker's random stream / ray origin (lv_bake.cuh).
 template <bool BAKE>
-int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S) {
+int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves) {
     auto launch = [&](auto kern) -> int {
         int per_sm = 0;
         LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
@@ -276,7 +277,13 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S) {
         LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
         return LV_OK;
     };
-    const uint32_t stack = c->opt.ao_stack, mb = c->opt.ao_min_blocks;
+    const uint32_t stack = c->opt.ao_stack;
+    const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
+    const uint32_t mb = c->opt.ao_min_blocks ? c->opt.ao_min_blocks : (queue ? 8u : 9u);   // 0 = measured optimum of the variant
+    if (queue) {
+        if (mb >= 9) return stack == 8 ? launch(k_rtao_rays_q<9, BAKE, 8>) : stack == 1 ? launch(k_rtao_rays_q<9, BAKE, 1>) : launch(k_rtao_rays_q<9, BAKE, 12>);
+        return stack == 8 ? launch(k_rtao_rays_q<8, BAKE, 8>) : stack == 1 ? launch(k_rtao_rays_q<8, BAKE, 1>) : launch(k_rtao_rays_q<8, BAKE, 12>);
+    }
 #define LV_AO_STACKS(MB)                                                  \
     switch (stack) {                                                      \
         case 0: return launch(k_rtao_rays<MB, BAKE, 0>);                  \
@@ -329,7 +336,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
         // one float per (hit pixel, sample); worst case every owned pixel (and ring pixel) is hit
         const size_t max_hits = size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + (apron ? ring : 0));
         LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
-        int lrc = launch_ao_rays<false>(c, P, S);
+        int lrc = launch_ao_rays<false>(c, P, S, sc->leaf_size == 1);
         if (lrc) return lrc;
         c->rtao_rays_timed = true;
         k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, c->ao.p);
@@ -448,7 +455,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     P.ao_refill_below = int(o.ao_refill_below); P.ao_leaf_vote = int(o.ao_leaf_vote); P.frame_number = sc->bake_done;
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
-    if ((rc = launch_ao_rays<true>(c, P, sc->dev()))) return rc;
+    if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1))) return rc;
     c->rtao_rays_timed = true;
     k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, sc->factors.p);
     LV_CUDA(c, cudaGetLastError());
@@ -583,6 +590,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
+    else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
     else if (k == "b200_ao_stack") { if (u() != 0 && u() != 1 && u() != 8 && u() != 12 && u() != 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_stack must be 0, 1, 8, 12 or 16"); o.ao_stack = u(); }
     else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
     else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
@@ -631,6 +639,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
     else if (k == "b200_ao_min_blocks") v = std::to_string(o.ao_min_blocks);
+    else if (k == "b200_ao_queue") v = b(o.ao_queue);
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else return LV_ERR_UNKNOWN_OPTION;
@@ -717,7 +726,7 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     if (line_width <= 0.0f) line_width = c->opt.line_width;
     LV_CUDA(c, cudaSetDevice(c->device));
     lv_scene* s = new lv_scene();
-    s->ctx = c; s->n_seg = n_seg; s->n_pt = n_pt; s->line_width = line_width;
+    s->ctx = c; s->n_seg = n_seg; s->n_pt = n_pt; s->line_width = line_width; s->leaf_size = c->opt.bvh_leaf_size;
     const int n = int(n_seg);
     if (n == 0) { *out = s; return LV_OK; }
     const float r = line_width * 0.5f;

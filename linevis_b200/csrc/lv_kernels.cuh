@@ -429,6 +429,154 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
     flush_counter(&C->ao_isect, isect);
 }
 
+// ------------------------------------------------------------------------------------------------
+// AO ray stream with a warp-level LEAF QUEUE (b200_ao_queue, scenes built with one-record leaves).
+//
+// In k_rtao_rays a lane that reaches a leaf waits until ao_leaf_vote lanes hold one; ncu (profiles/r1g) shows what that costs
+// once the stack traffic is out of the way: the box-step block runs with 18 of 32 lanes, the capsule test with 9, and issue
+// slots are the limiter (78 % issue-active).  Here a lane does not wait: it appends (lane, record) to a 64-entry ring in
+// shared memory, pops its stack and keeps traversing with the hit distance it knows so far.  As soon as 32 entries are queued,
+// ALL lanes run one capsule test each -- entry i on lane i, the owner's ray fetched with 7 shuffles -- and hand the result
+// back through two shared-memory words per lane (atomicMin on the hit distance bits, a pending-entry counter).  The owner
+// folds the result into its `best` after the batch; until then it may walk a few nodes a tighter `best` would have culled
+// (the result does not depend on that: a closest hit is a minimum over accepted candidates, any-hit is an OR).  A ray is
+// finished when its stack is empty and none of its entries is pending.  A partial batch is flushed when fewer than
+// ao_leaf_vote lanes can still step, so that rays waiting for their last leaves do not starve.
+constexpr int kLeafQueue = 64;
+constexpr uint32_t kNoHitBits = 0x7F800000u;   // +inf
+
+template <int MIN_BLOCKS, bool BAKE, int STACK>
+__global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
+k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
+              const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
+    __shared__ uint32_t s_queue[kBlockThreads / 32][kLeafQueue];   // record index | owner lane << 27
+    __shared__ uint32_t s_hit[kBlockThreads / 32][32];             // nearest accepted hit (float bits) delivered to a lane by the current batch
+    __shared__ int s_pend[kBlockThreads / 32][32];                 // queue entries of a lane that are not processed yet
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* queue = s_queue[warp];
+    uint32_t* whit = s_hit[warp];
+    int* wpend = s_pend[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t spp = P.ao_spp;
+    const unsigned long long total = (unsigned long long)(*hit_count) * spp;
+    const bool capped = P.use_capped != 0;
+    const bool any_mode = P.ao_use_distance == 0;
+    const float radius = S.radius;
+    uint32_t steps = 0, isect = 0, rays = 0;
+
+    AoStack<STACK> pst;
+    pst.init();
+    int sp = 0;
+    uint32_t cur = kDone;
+    bool exhausted = false, has_ray = false;
+    unsigned long long ray_id = 0;
+    RayQ rq; RayBox rb;
+    float best = 0.0f;
+    bool found = false;
+    rq.o = v3(0, 0, 0); rq.d = v3(0, 0, 1); rq.dd = 1.0f; rb = make_raybox(rq.o, rq.d);
+    uint32_t q_head = 0, q_count = 0;   // uniform over the warp
+    wpend[lane] = 0;
+    __syncwarp();
+
+    while (true) {
+        // ---- refill lanes without a ray
+        const bool idle = !has_ray && !exhausted;
+        const unsigned need = __ballot_sync(0xffffffffu, idle);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if (int(lane) == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (idle) {
+                ray_id = base + __popc(need & lt_mask);
+                if (ray_id >= total) exhausted = true;
+                else {
+                    const uint32_t slot = uint32_t(ray_id / spp), sample = uint32_t(ray_id - (unsigned long long)slot * spp);
+                    Vec3 org, dir;
+                    ao_ray_from_record<BAKE>(hit_list + slot, sample, spp, P.frame_number, org, dir);
+                    rq = make_rayq(org, dir);
+                    rb = make_raybox(org, dir);
+                    best = P.ao_radius; found = false;
+                    sp = 0; cur = 0;                                                 // root
+                    has_ray = true;
+                    rays++;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
+
+        while (true) {
+            // A: one inner-node step for every lane that holds an inner node
+            if (cur != kDone && !(cur & kLeafBit)) {
+                const Node64 nd = load_node(S.nodes + cur);
+                steps++;
+                float tl, tr;
+                bool hl = box_hit(rb, nd.l0, nd.l1, 0.0f, best, tl);
+                bool hr = box_hit(rb, nd.r0, nd.r1, 0.0f, best, tr);
+                const uint32_t cl = __float_as_uint(nd.l0.w), cr = __float_as_uint(nd.r0.w);
+                if (hl && hr) {
+                    const bool swap = tr < tl;
+                    if (sp < kAoStack) { pst.put(sp, swap ? cl : cr, swap ? tl : tr); sp++; }
+                    cur = swap ? cr : cl;
+                } else if (hl) cur = cl;
+                else if (hr) cur = cr;
+                else cur = ao_stack_pop(pst, sp, best);
+            }
+            // E: lanes that hold a leaf queue its record and go on with their stack
+            const bool at_leaf = (cur & kLeafBit) != 0u;   // kDone has bit 31 clear
+            const unsigned leaf_mask = __ballot_sync(0xffffffffu, at_leaf);
+            if (leaf_mask) {
+                if (at_leaf) {
+                    queue[(q_head + q_count + __popc(leaf_mask & lt_mask)) & (kLeafQueue - 1)] = (cur & kRefMask) | (lane << 27);
+                    wpend[lane] += 1;
+                    cur = ao_stack_pop(pst, sp, best);
+                }
+                q_count += __popc(leaf_mask);
+                __syncwarp();
+            }
+            // B: a full batch of 32 capsule tests, or a partial one when too few lanes can still step
+            const unsigned movable = __ballot_sync(0xffffffffu, cur != kDone);
+            if (q_count >= 32u || (q_count != 0u && __popc(movable) < P.ao_leaf_vote)) {
+                const uint32_t n = q_count < 32u ? q_count : 32u;
+                whit[lane] = kNoHitBits;
+                __syncwarp();
+                const uint32_t e = queue[(q_head + (lane < n ? lane : 0u)) & (kLeafQueue - 1)];
+                const uint32_t owner = e >> 27;
+                RayQ r2;
+                r2.o.x = __shfl_sync(0xffffffffu, rq.o.x, owner); r2.o.y = __shfl_sync(0xffffffffu, rq.o.y, owner); r2.o.z = __shfl_sync(0xffffffffu, rq.o.z, owner);
+                r2.d.x = __shfl_sync(0xffffffffu, rq.d.x, owner); r2.d.y = __shfl_sync(0xffffffffu, rq.d.y, owner); r2.d.z = __shfl_sync(0xffffffffu, rq.d.z, owner);
+                r2.dd = __shfl_sync(0xffffffffu, rq.dd, owner);
+                if (lane < n) {
+                    const SegRec s = load_seg(S.segs + (e & kRefMask));
+                    isect++;
+                    float t; uint32_t kind;
+                    // the record's own AABB was the child box tested in its parent (one-record leaves): the acceptance rule's slab test is done
+                    if (capsule_hit(r2, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) atomicMin(&whit[owner], __float_as_uint(t));
+                    atomicSub(&wpend[owner], 1);
+                }
+                __syncwarp();
+                const uint32_t hb = whit[lane];
+                if (hb != kNoHitBits) {
+                    const float t = __uint_as_float(hb);
+                    if (!found || t < best) { best = t; found = true; }
+                    if (any_mode) { sp = 0; cur = kDone; }
+                }
+                q_head = (q_head + n) & (kLeafQueue - 1);
+                q_count -= n;
+            }
+            // a ray is finished when its stack is empty and none of its queue entries is pending: traceAoRay result (:158-175)
+            if (has_ray && cur == kDone && wpend[lane] == 0) {
+                occ[ray_id] = found ? (any_mode ? 0.0f : best / P.ao_radius) : 1.0f;
+                has_ray = false;
+            }
+            if (__popc(__ballot_sync(0xffffffffu, has_ray)) < P.ao_refill_below) break;
+        }
+    }
+    flush_counter(&C->rays_ao, rays);
+    flush_counter(&C->ao_steps, steps);
+    flush_counter(&C->ao_isect, isect);
+}
+
 __global__ void k_rtao_reduce(const __grid_constant__ FrameParams P, const float* occ, const AoHit* hit_list,
                               const unsigned int* hit_count, float* ao) {
     const uint32_t n_hit = *hit_count;

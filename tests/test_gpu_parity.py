@@ -55,7 +55,7 @@ def test_bvh_leaf_sizes_same_hits(ctx, oracle, leaf):
     try:
         sc, osc = _scene_pair(ctx, oracle, data, width)
     finally:
-        ctx.set_option("b200_bvh_leaf_size", 4)
+        ctx.set_option("b200_bvh_leaf_size", 1)
     cam = lv.make_camera(160, 96)
     hits, _ = ctx.trace_primary(sc, cam)
     ref, _ = osc.trace_primary(cam)
@@ -111,24 +111,42 @@ def test_rtao_parity(ctx, oracle, jitter, use_distance, spp):
     assert np.array_equal(ao2.view(np.uint32), ref2.view(np.uint32))
 
 
-@pytest.mark.parametrize("stack", [0, 1, 8, 16])
+@pytest.mark.parametrize("queue,stack,minb", [(False, 0, 10), (False, 1, 9), (False, 8, 8), (False, 12, 0), (False, 16, 9),
+                                              (True, 1, 9), (True, 8, 8), (True, 12, 9)])
 @pytest.mark.parametrize("use_distance", [True, False])
-def test_rtao_stack_layouts_bit_exact(ctx, oracle, stack, use_distance):
-    """b200_ao_stack: packed-local (1) and shared-memory (2) traversal stacks of the AO ray kernel give the same AO image
-    as the oracle (and hence as the default layout); a deep scene makes the shared stack spill to its local part."""
+def test_rtao_kernel_variants_bit_exact(ctx, oracle, queue, stack, minb, use_distance):
+    """Every variant of the AO ray kernel -- leaf-vote (k_rtao_rays) or leaf-queue (k_rtao_rays_q), local / packed / shared-memory
+    traversal stack, register budget -- gives the oracle's AO image bit for bit (the default, queue + 12 shared entries, is what
+    all other tests run).  A long AO radius makes the stacks deep enough to spill out of their shared part."""
     data, width = DATASETS["random"]()
     sc, osc = _scene_pair(ctx, oracle, data, width)
     cam = lv.make_camera(120, 80)
     ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 8, "ambient_occlusion_distance_based": use_distance,
-                          "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.3, "b200_ao_stack": stack})
+                          "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.3,
+                          "b200_ao_stack": stack, "b200_ao_queue": queue, "b200_ao_min_blocks": minb})
     try:
         ao, st = ctx.render_rtao(sc, cam, 0)
     finally:
-        ctx.set_new_settings({"b200_ao_stack": 12, "ambient_occlusion_radius": 0.1})
+        ctx.set_new_settings({"b200_ao_stack": 12, "b200_ao_queue": True, "b200_ao_min_blocks": 0, "ambient_occlusion_radius": 0.1})
     opts = lvo.default_options(ao_strength=1.0, ao_spp=8, ao_use_distance=int(use_distance), ao_jitter_primary=1, ao_radius=0.3)
     ref, ost = osc.render_rtao(cam, opts, 0)
     assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
     assert st["rays_ao"] == ost["rays_ao"] > 0
+
+
+def test_rtao_queue_falls_back_for_multi_record_leaves(ctx, oracle):
+    """The leaf-queue kernel relies on one-record leaves; a scene built with larger leaves takes the leaf-vote kernel."""
+    data, width = DATASETS["random"]()
+    ctx.set_option("b200_bvh_leaf_size", 4)
+    try:
+        sc, osc = _scene_pair(ctx, oracle, data, width)
+    finally:
+        ctx.set_option("b200_bvh_leaf_size", 1)
+    cam = lv.make_camera(120, 80)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": True})
+    ao, _ = ctx.render_rtao(sc, cam, 0)
+    ref, _ = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=4), 0)
+    assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
 @pytest.mark.parametrize("name,ao", [("helix", False), ("helix", True), ("random", True), ("single", False)])

@@ -24,15 +24,19 @@ sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
 for _ in range(2):
     _, st = ctx.render_tubes(sc, cam, 0, out=frame)
 full = st["ms_total"]
-print("full frame %.2f ms" % full, flush=True)
+print("full frame %.2f ms: k_rtao_rays %.2f, rest of RTAO %.2f, tubes %.2f" % (full, st["ms_rtao_rays"], st["ms_rtao"] - st["ms_rtao_rays"], st["ms_trace"]), flush=True)
 for world in args.world:
     for tile in args.tile:
-        ts = []
+        ts, parts = [], []
         for r in range(world):
             ctx.set_tile_shard(r, world, tile)
-            for _ in range(2):
+            for _ in range(3):
                 _, st = ctx.render_tubes(sc, cam, 0, out=frame)
             ts.append(st["ms_total"])
+            parts.append((st["ms_rtao_rays"], st["ms_rtao"] - st["ms_rtao_rays"], st["ms_trace"], st["rays_ao"] / 1e6))
         ts = np.array(ts)
+        pm = np.mean(parts, axis=0)
+        print("   mean per rank: k_rtao_rays %.2f ms, rest of RTAO pass %.2f ms, tube pass %.2f ms, AO rays %.2f M (min %.2f max %.2f)" %
+              (pm[0], pm[1], pm[2], pm[3], min(p[3] for p in parts), max(p[3] for p in parts)), flush=True)
         print("world %d tile %3d: rank ms min %.2f mean %.2f max %.2f  max/mean %.3f  ideal %.2f  speed-up bound %.2fx" %
               (world, tile, ts.min(), ts.mean(), ts.max(), ts.max() / ts.mean(), full / world, full / ts.max()), flush=True)

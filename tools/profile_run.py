@@ -15,6 +15,7 @@ ap.add_argument("--ppll-workload", default="config4")
 ap.add_argument("--frames", type=int, default=2)
 ap.add_argument("--skip-tubes", action="store_true")
 ap.add_argument("--skip-ppll", action="store_true")
+ap.add_argument("--opt", type=str, nargs="*", default=[], help="extra key=value options for the tube context")
 args = ap.parse_args()
 
 import torch
@@ -26,6 +27,8 @@ if not args.skip_tubes:
     ctx.set_transfer_function(lv.scenes.standard_transfer_function())
     ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": wl["ao_spp"],
                           "ambient_occlusion_iterations": 1, "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    for kv in args.opt:
+        ctx.set_option(*kv.split("=", 1))
     sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
     cam = lv.make_camera(wl["W"], wl["H"])
     frame = torch.zeros((wl["H"], wl["W"], 4), dtype=torch.float32, device=dev)

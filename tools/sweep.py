@@ -13,6 +13,7 @@ ap.add_argument("--ppll-workload", default="none")
 ap.add_argument("--vote", type=int, nargs="+", default=[12])
 ap.add_argument("--minb", type=int, nargs="+", default=[10])
 ap.add_argument("--stack", type=int, nargs="+", default=[0])
+ap.add_argument("--opt", type=str, nargs="*", default=[], help="extra key=value options applied to every configuration")
 ap.add_argument("--combo", type=str, nargs="*", default=[], help="explicit minb:stack:refill:vote combinations instead of the product")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -25,6 +26,8 @@ for leaf in args.leaf:
     ctx.set_transfer_function(lv.scenes.standard_transfer_function())
     ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": wl["ao_spp"], "ambient_occlusion_iterations": 1,
                           "num_samples_per_frame": 1, "num_accumulated_frames": 1, "b200_bvh_leaf_size": leaf})
+    for kv in args.opt:
+        ctx.set_option(*kv.split("=", 1))
     sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
     combos = [tuple(int(v) for v in (c.split(":")[2], c.split(":")[3], c.split(":")[0], c.split(":")[1])) for c in args.combo] \
         or list(itertools.product(args.refill, args.vote, args.minb, args.stack))
