@@ -220,6 +220,10 @@ def main():
     ap.add_argument("--ref-sample", type=int, nargs=2, default=[1280, 720],
                     help="centre crop (pixels) of the frame the CPU legs render: ~64 M rays, 5-10 s per step on 16 host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--assemble", default="peer", choices=["peer", "allgather"],
+                    help="N > 1: how rank 0 gets the whole frame -- 'peer': every rank's kernels store their tiles straight into rank 0's "
+                         "frame over NVLink (lv_frame_alloc / lv_ipc_*), one 1-element all_reduce as frame fence; 'allgather': pack + NCCL "
+                         "all_gather + unpack")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -274,10 +278,17 @@ def main():
 
     frame = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     n_own = len(ctx.owned_tiles(W, H))
-    from linevis_b200.sharding import FrameGather
-    fg = FrameGather(W, H, tile, rank, world, dev, ctx=ctx) if world > 1 else None
+    from linevis_b200.sharding import FrameGather, PeerFrame
+    peer = world > 1 and args.assemble == "peer"
+    fg = FrameGather(W, H, tile, rank, world, dev, ctx=ctx) if world > 1 else None     # also the e2e leg's device-side collective
+    pf = PeerFrame(ctx, W, H, rank, world, dev) if peer else None
 
     def step(stats):
+        if pf is not None:
+            # every rank's frame kernels store their tiles straight into rank 0's frame (NVLink peer stores); the fence is the frame's only collective
+            out, st = ctx.render_tubes(scene, cam, 0, out=pf.ptr, stats=stats)
+            pf.fence()
+            return st
         out, st = ctx.render_tubes(scene, cam, 0, out=frame, stats=stats)
         if fg is not None:
             # the single collective of the frame: every rank's packed tile block -> all ranks; rank 0 assembles the frame
@@ -401,7 +412,10 @@ def main():
         dist.barrier(); torch.cuda.synchronize()
         g0.record()
         for _ in range(max(3, args.steps)):
-            fg.gather(frame, assemble_on=(0,))
+            if pf is not None:
+                pf.fence()
+            else:
+                fg.gather(frame, assemble_on=(0,))
         g1.record(); torch.cuda.synchronize()
         gm = torch.tensor([g0.elapsed_time(g1) / max(3, args.steps)], dtype=torch.float64, device=dev)
         dist.all_reduce(gm, op=dist.ReduceOp.MAX)
@@ -424,7 +438,9 @@ def main():
             "config": {"workload": wl["desc"], "frame": [W, H], "segments": int(info["n_seg"]), "bvh_nodes": int(info["n_nodes"]),
                        "scene_bytes": int(scene_bytes), "l2": "inputs larger than L2 (segments + BVH = %.2f GB)" % (scene_bytes / 1e9)
                        if scene_bytes > 200e6 else "scene fits L2; the 126 MB L2 is not flushed between frames",
-                       "parallelism": "tile-sharded x%d (64x64 tiles, Morton round-robin, 1 NCCL all_gather/frame)" % world if world > 1 else "single GPU",
+                       "parallelism": ("tile-sharded x%d (64x64 tiles, Morton round-robin); " % world +
+                                       ("frame assembled on rank 0 by NVLink peer stores from the frame kernels, 1-element all_reduce as fence"
+                                        if peer else "1 NCCL all_gather/frame + unpack on rank 0")) if world > 1 else "single GPU",
                        "rays_per_step": tot_rays, "rays_primary": tot_rp, "rays_ao": tot_ra, "T_per_ray": tot_T / tot_rays, "I_per_ray": tot_I / tot_rays,
                        "scene_upload_and_bvh_build_s": upload_build_s, "bvh_build_ms": info["build_ms"], "bvh_build_ms_first_in_process": first_build_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -434,16 +450,20 @@ def main():
                                   % (st["ao_traversal_steps"] / max(st["rays_ao"], 1), st["ao_intersections"] / max(st["rays_ao"], 1), st["rays_ao"])},
             "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera struct in (the scene is resident, like the reference's cached render data), RGBA32F frame out"},
-            "gpu_launches": (4 + (2 + (world - 1) if world > 1 else 0)) * args.steps,   # k_rtao_primary, k_rtao_rays, k_rtao_reduce, k_tubes (+ tile pack / unpack)
+            # k_rtao_primary, k_rtao_rays_q, k_rtao_reduce, k_tubes (+ tile pack / unpack kernels in all_gather mode)
+            "gpu_launches": (4 + (2 + (world - 1) if (world > 1 and not peer) else 0)) * args.steps,
             "clocks": clocks,
         }
         line.update(ppll_results)
         if gather_ms is not None:
-            line["config"]["gather_ms"] = gather_ms            # pack + NCCL all_gather + unpack alone, max over ranks
+            line["config"]["assemble_ms"] = gather_ms          # the frame fence (peer mode) or pack + all_gather + unpack alone, max over ranks
         line["config"]["k_rtao_rays_ms_per_rank"] = k_ms_ranks  # tile-shard load balance of the dominant kernel
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, pos, attr, seg, tuple(args.ref_sample))
         print(json.dumps(line))
+    if pf is not None:
+        torch.cuda.synchronize(); dist.barrier()
+        pf.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

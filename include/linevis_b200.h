@@ -153,6 +153,19 @@ int lv_pack_owned_tiles(lv_ctx* ctx, const float* image, uint32_t width, uint32_
 int lv_unpack_tiles(lv_ctx* ctx, const float* packed, uint32_t src_rank, uint32_t world,
                     uint32_t width, uint32_t height, float* image);
 
+/* Peer-memory frame assembly (new): instead of pack -> NCCL all_gather -> unpack, every rank's frame kernels store
+ * their owned tiles straight into ONE frame buffer that lives on the assembling rank's GPU (NVLink peer stores, overlapped
+ * with the kernel's own work); a single tiny collective (or any other cross-rank fence) after the render call is the frame
+ * fence.  The assembling rank allocates the frame with lv_frame_alloc and exports it; the other ranks open the handle and pass
+ * the returned pointer as `rgba_out` of lv_render_tubes / lv_render_ppll / lv_ppll_resolve.
+ * handle: LV_IPC_HANDLE_BYTES opaque bytes (a cudaIpcMemHandle_t) to be shipped to the other processes by any means. */
+#define LV_IPC_HANDLE_BYTES 64
+int lv_frame_alloc(lv_ctx* ctx, uint32_t width, uint32_t height, float** frame_out /* device, W*H*4 floats, zeroed */);
+int lv_frame_free(lv_ctx* ctx, float* frame);
+int lv_ipc_export(lv_ctx* ctx, const void* device_ptr, void* handle_out);
+int lv_ipc_open(lv_ctx* ctx, const void* handle, void** peer_ptr_out);
+int lv_ipc_close(lv_ctx* ctx, void* peer_ptr);
+
 /* ------------------------------------------------------------------ scene -------------------- */
 
 /* Replaces LineDataFlow::getLinePassTubeAabbRenderData (src/LineData/LineDataFlow.cpp:2112-2277) +

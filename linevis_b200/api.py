@@ -80,6 +80,28 @@ class Context:
     def synchronize(self):
         self._check(self.lib.lv_synchronize(self.h))
 
+    # -- peer-memory frame assembly (lv_frame_alloc / lv_ipc_*): returns raw device addresses (ints)
+    def frame_alloc(self, width, height):
+        p = ctypes.c_void_p()
+        self._check(self.lib.lv_frame_alloc(self.h, width, height, ctypes.byref(p)))
+        return p.value
+
+    def frame_free(self, ptr):
+        self._check(self.lib.lv_frame_free(self.h, ctypes.c_void_p(ptr)))
+
+    def ipc_export(self, ptr):
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.lv_ipc_export(self.h, ctypes.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        self._check(self.lib.lv_ipc_open(self.h, ctypes.create_string_buffer(handle, 64), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self.lib.lv_ipc_close(self.h, ctypes.c_void_p(ptr)))
+
     # -- scene
     def create_scene(self, pos, attr, seg_idx, line_width=0.002):
         return Scene(self, pos, attr, seg_idx, line_width)

@@ -716,6 +716,61 @@ int lv_unpack_tiles(lv_ctx* c, const float* packed, uint32_t src_rank, uint32_t 
     return LV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- peer-memory frames
+int lv_frame_alloc(lv_ctx* c, uint32_t width, uint32_t height, float** frame_out) {
+    if (!c || !frame_out || width == 0 || height == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_frame_alloc: bad argument");
+    *frame_out = nullptr;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    float* p = nullptr;
+    const size_t bytes = size_t(width) * height * 16;
+    LV_CUDA(c, cudaMalloc(&p, bytes));   // a plain cudaMalloc allocation: exportable with cudaIpcGetMemHandle at offset 0
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cudaFree(p); return fail(c, LV_ERR_CUDA, std::string("lv_frame_alloc: ") + cudaGetErrorString(e)); }
+    *frame_out = p;
+    return LV_OK;
+}
+
+int lv_frame_free(lv_ctx* c, float* frame) {
+    if (!c) return LV_ERR_INVALID_ARGUMENT;
+    if (!frame) return LV_OK;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    LV_CUDA(c, cudaFree(frame));
+    return LV_OK;
+}
+
+int lv_ipc_export(lv_ctx* c, const void* device_ptr, void* handle_out) {
+    if (!c || !device_ptr || !handle_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == LV_IPC_HANDLE_BYTES, "LV_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    LV_CUDA(c, cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+    memcpy(handle_out, &h, sizeof(h));
+    return LV_OK;
+}
+
+int lv_ipc_open(lv_ctx* c, const void* handle, void** peer_ptr_out) {
+    if (!c || !handle || !peer_ptr_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_ipc_open: NULL argument");
+    *peer_ptr_out = nullptr;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    LV_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // also enables peer access to the exporting GPU
+    *peer_ptr_out = p;
+    return LV_OK;
+}
+
+int lv_ipc_close(lv_ctx* c, void* peer_ptr) {
+    if (!c) return LV_ERR_INVALID_ARGUMENT;
+    if (!peer_ptr) return LV_OK;
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    LV_CUDA(c, cudaIpcCloseMemHandle(peer_ptr));
+    return LV_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- scene
 int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const float* d_attr, const uint32_t* d_idx,
                            uint64_t n_pt, uint64_t n_seg, float line_width) {

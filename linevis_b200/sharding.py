@@ -97,3 +97,46 @@ class FrameGather:
                 else:
                     unpack_tiles_torch(self.gathered[r], owned_tiles(self.W, self.H, self.tile, r, self.world), self.tile, frame)
         return frame
+
+
+class _RawCudaArray:
+    """Zero-copy view of a raw device address for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerFrame:
+    """Peer-memory frame assembly (lv_frame_alloc / lv_ipc_*): ONE RGBA32F frame on `root`'s GPU that every rank's frame kernels
+    store their owned tiles into directly over NVLink -- no pack / all_gather / unpack.  `fence()` is the frame fence: a
+    one-element all_reduce on the current stream; after it the root's stream sees the complete frame.
+
+    ptr: the address to pass as `out=` of Context.render_tubes / render_ppll on this rank."""
+
+    def __init__(self, ctx, width, height, rank, world, device, root=0):
+        self.ctx, self.W, self.H, self.rank, self.world, self.root = ctx, width, height, rank, world, root
+        self.local = ctx.frame_alloc(width, height) if rank == root else None
+        box = [ctx.ipc_export(self.local) if rank == root else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=root)
+        self.ptr = self.local if rank == root else ctx.ipc_open(box[0])
+        self._flag = torch.zeros(1, dtype=torch.float32, device=device)
+        self.device = device
+
+    def fence(self):
+        if self.world > 1:
+            dist.all_reduce(self._flag)
+
+    def tensor(self):
+        """[H, W, 4] float32 view of the frame (root only)."""
+        assert self.rank == self.root
+        return torch.as_tensor(_RawCudaArray(self.local, (self.H, self.W, 4)), device=self.device)
+
+    def close(self):
+        if self.ptr is None:
+            return
+        if self.rank == self.root:
+            self.ctx.frame_free(self.local)
+        else:
+            self.ctx.ipc_close(self.ptr)
+        self.ptr = self.local = None

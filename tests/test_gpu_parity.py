@@ -350,3 +350,28 @@ def test_depth_cues_parity(ctx, oracle, ao):
         assert _lists(got["heads"], got["nodes"], cam, oracle) == _lists(refg["heads"], refg["nodes"], cam, oracle)
     finally:
         ctx.set_new_settings({"depth_cue_strength": 0.0, "ambient_occlusion_strength": 0.0})
+
+
+def test_peer_frame_single_process(ctx, oracle):
+    """lv_frame_alloc / lv_ipc_export and rendering into a raw library-owned frame (the peer-memory assembly path of N > 1 runs;
+    opening the handle needs a second process and is covered by tools/p2p_check.py under torchrun)."""
+    import torch
+    from linevis_b200.sharding import PeerFrame
+    data, width = DATASETS["helix"]()
+    sc = ctx.create_scene(*data, width)
+    cam = lv.make_camera(160, 100)
+    ctx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.4, 1.0)))
+    ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 4, "num_samples_per_frame": 1,
+                          "num_accumulated_frames": 1})
+    ref, _ = ctx.render_tubes(sc, cam)
+    pf = PeerFrame(ctx, 160, 100, 0, 1, torch.device("cuda", 0))
+    try:
+        assert len(ctx.ipc_export(pf.ptr)) == 64
+        ctx.render_tubes(sc, cam, 0, out=pf.ptr, stats=False)
+        pf.fence()
+        ctx.synchronize()
+        got = pf.tensor().cpu().numpy()
+    finally:
+        pf.close()
+        ctx.set_option("ambient_occlusion_strength", 0.0)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
