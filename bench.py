@@ -103,7 +103,7 @@ class ClockSampler:
 
 def ncu_traffic(kernel, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/traffic.json);
-    only valid for the workload the capture was taken on (config5 for k_rtao_rays)."""
+    only valid for the workload the capture was taken on (config5 for k_rtao_rays_q)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if workload != "config5" or not os.path.exists(p):
         return None
@@ -217,8 +217,8 @@ def main():
     ap.add_argument("--ppll-workload", default="config2,config4",
                     help="comma-separated PPLL workloads measured beside the tube path (%s) or 'none'; the first is reported under "
                          "\"ppll\", further ones under \"ppll_<name>\"" % ", ".join(PPLL_WORKLOADS))
-    ap.add_argument("--ref-sample", type=int, nargs=2, default=[1280, 720],
-                    help="centre crop (pixels) of the frame the CPU legs render: ~64 M rays, 5-10 s per step on 16 host cores")
+    ap.add_argument("--ref-sample", type=int, nargs=2, default=[1920, 1080],
+                    help="centre crop (pixels) of the frame the CPU legs render: ~90 M rays, about 10 s per step on 16 host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--assemble", default="peer", choices=["peer", "allgather"],
                     help="N > 1: how rank 0 gets the whole frame -- 'peer': every rank's kernels store their tiles straight into rank 0's "
@@ -247,6 +247,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_src = peaks()
 
@@ -327,7 +330,7 @@ def main():
     ms = float(tms.item())
     clocks = sampler.stop() if sampler else None
 
-    # ---- dominant kernel (k_rtao_rays) live timing for the roofline: CUDA events around that kernel inside the library
+    # ---- dominant kernel (k_rtao_rays_q, the AO ray stream) live timing for the roofline: CUDA events around that kernel inside the library
     kt = []
     for _ in range(max(3, args.steps)):
         s2 = ctx.render_tubes(scene, cam, 0, out=frame, stats=True)[1]
@@ -341,6 +344,16 @@ def main():
     host_np = host_frame.numpy()
 
     def step_e2e():
+        if pf is not None:
+            # every rank renders into rank 0's frame (peer stores), fence, rank 0 reads the WHOLE frame back to its pinned host
+            # buffer; the second fence keeps the next frame's stores off the buffer until that copy is done
+            ctx.render_tubes(scene, cam, 0, out=pf.ptr, stats=False)
+            pf.fence()
+            if rank == 0:
+                host_frame.copy_(pf.tensor(), non_blocking=True)
+            pf.fence()
+            torch.cuda.current_stream().synchronize()
+            return
         ctx.render_tubes(scene, cam, 0, out=host_np, stats=False)   # D2H inside, synchronises
         if fg is not None:
             fg.gather(frame, assemble_on=())                        # the collective stays in the e2e step as well
@@ -358,7 +371,8 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_ms = float(tms.item())
-    d2h = (n_own * tile * tile if world > 1 else W * H) * 16
+    # bytes read back per step: the whole frame on rank 0 (single GPU, or peer assembly), else every rank's own tiles (rank 0's share is reported)
+    d2h = (n_own * tile * tile if (world > 1 and pf is None) else W * H) * 16
 
     # ---- PPLL path (second half of the metric), rank-local, whole frame on one GPU unless sharded
     def measure_ppll(pw, with_cpu):
@@ -444,12 +458,13 @@ def main():
                        "rays_per_step": tot_rays, "rays_primary": tot_rp, "rays_ao": tot_ra, "T_per_ray": tot_T / tot_rays, "I_per_ray": tot_I / tot_rays,
                        "scene_upload_and_bvh_build_s": upload_build_s, "bvh_build_ms": info["build_ms"], "bvh_build_ms_first_in_process": first_build_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": ncu_traffic("k_rtao_rays", args.workload) if world == 1 else None, "algorithmic_bytes_per_launch": my_ao_bytes,
-                         "kernel": "k_rtao_rays", "kernel_ms": k_ms, "peak_source": peak_src,
+                         "traffic": ncu_traffic("k_rtao_rays_q", args.workload) if world == 1 else None, "algorithmic_bytes_per_launch": my_ao_bytes,
+                         "kernel": "k_rtao_rays_q", "kernel_ms": k_ms, "peak_source": peak_src,
                          "bytes": "64 B x T + 32 B x I + 4 B per AO ray (SURVEY 8d); T/ray %.2f, I/ray %.2f over %d AO rays (rank 0)"
                                   % (st["ao_traversal_steps"] / max(st["rays_ao"], 1), st["ao_intersections"] / max(st["rays_ao"], 1), st["rays_ao"])},
             "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera struct in (the scene is resident, like the reference's cached render data), RGBA32F frame out"},
+                    "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera struct in (the scene is resident, like the reference's cached render data), RGBA32F frame out"
+                    if pf is None else "every rank: lv_render_tubes into rank 0's peer frame + fence; rank 0: whole RGBA32F frame D2H into pinned host memory; lv_camera struct in on every rank"},
             # k_rtao_primary, k_rtao_rays_q, k_rtao_reduce, k_tubes (+ tile pack / unpack kernels in all_gather mode)
             "gpu_launches": (4 + (2 + (world - 1) if (world > 1 and not peer) else 0)) * args.steps,
             "clocks": clocks,
