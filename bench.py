@@ -155,7 +155,7 @@ def run_reference(args, wl, ppll_wl):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline leg
@@ -207,7 +207,29 @@ def cpu_baseline_ppll(pw, pos, attr, seg, sample):
 
 
 # ------------------------------------------------------------------------------------------------- our arm
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner at NCCL_DEBUG=VERSION/WARN):
+    file descriptor 1 is pointed at stderr for the rest of the process and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -247,9 +269,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_src = peaks()
 
@@ -475,7 +494,7 @@ def main():
         line["config"]["k_rtao_rays_ms_per_rank"] = k_ms_ranks  # tile-shard load balance of the dominant kernel
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, pos, attr, seg, tuple(args.ref_sample))
-        print(json.dumps(line))
+        emit(line)
     if pf is not None:
         torch.cuda.synchronize(); dist.barrier()
         pf.close()
