@@ -292,6 +292,48 @@ class OracleScene:
                     T=int(stats[0]), I=int(stats[1]), rays=int(stats[2]))
 
 
+TUBE_VERTEX_DTYPE = np.dtype([("position", np.float32, 3), ("line_point", np.uint32), ("normal", np.float32, 3), ("phi", np.float32)])
+
+
+class TubeMesh:
+    """The reference's triangulated capped tubes (createCappedTriangleTubesRenderDataCPU) + a triangle BVH: the geometry the
+    reference's RTAO passes are traced against (oracle/lvo_tritubes.hpp)."""
+
+    def __init__(self, oracle, pos, line_offsets, line_width, num_subdivisions=6):
+        self.lib = oracle.lib
+        self.lib.lvo_tubemesh_create.restype = ctypes.c_void_p
+        pos = _f32(pos)
+        off = np.ascontiguousarray(line_offsets, np.uint64)
+        self.h = self.lib.lvo_tubemesh_create(_p(pos, ctypes.c_float), _p(off, ctypes.c_uint64), ctypes.c_uint64(len(off) - 1),
+                                              ctypes.c_float(0.5 * line_width), ctypes.c_int(num_subdivisions))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.lvo_tubemesh_destroy(ctypes.c_void_p(self.h))
+            self.h = None
+
+    def info(self):
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self.lib.lvo_tubemesh_info(ctypes.c_void_p(self.h), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return dict(n_vertices=a.value, n_triangles=b.value, n_line_points=c.value)
+
+    def arrays(self):
+        i = self.info()
+        v = np.zeros(i["n_vertices"], TUBE_VERTEX_DTYPE)
+        t = np.zeros((i["n_triangles"], 3), np.uint32)
+        self.lib.lvo_tubemesh_copy(ctypes.c_void_p(self.h), v.ctypes.data_as(ctypes.c_void_p), t.ctypes.data_as(ctypes.c_void_p))
+        return v, t
+
+    def render_rtao(self, cam, opts, frame_number=0, ao=None):
+        if ao is None:
+            ao = np.zeros((cam.height, cam.width), np.float32)
+        ao = _f32(ao)
+        stats = np.zeros(5, np.uint64)
+        self.lib.lvo_render_rtao_triangles(ctypes.c_void_p(self.h), ctypes.byref(cam), ctypes.byref(opts), ctypes.c_uint32(frame_number),
+                                           _p(ao, ctypes.c_float), _p(stats, ctypes.c_uint64))
+        return ao, dict(T=int(stats[0]), I=int(stats[1]), rays_primary=int(stats[2]), rays_ao=int(stats[3]), pixels_hit=int(stats[4]))
+
+
 def ppll_resolve(oracle, cam, opts, heads, nodes, max_frags, sort_mode, canonical=True):
     heads = np.ascontiguousarray(heads, np.uint32)
     nodes = np.ascontiguousarray(nodes, NODE_DTYPE)

@@ -28,6 +28,7 @@
 #include "../include/linevis_b200.h"
 #include "lvo_shaders.hpp"
 #include "lvo_sort.hpp"
+#include "lvo_tritubes.hpp"
 #ifdef LVO_USE_REFERENCE_BVH
 #include "lvo_bvh_ref.hpp"   // traversal by the reference's submodules/bvh (built into oracle/_ref only)
 #else
@@ -664,6 +665,92 @@ float lvo_static_ao_factor(void* h, float strength, float gamma, float fragmentV
     u.numAoTubeSubdivisions = sc.numAoTubeSubdivisions; u.numLineVertices = uint32_t(sc.aoBlendingWeights.size());
     u.numParametrizationVertices = sc.numParametrizationVertices;
     return getAoFactorStatic(u, fragmentVertexId, phi);
+}
+
+// ------------------------------------------------------------------------------------------ triangle-tube RTAO (reference geometry)
+struct TubeMeshScene { TubeMesh mesh; TriBvh bvh; };
+
+// createCappedTriangleTubesRenderDataCPU for polylines (pos, line_offsets[n_lines + 1]); tubeRadius = lineWidth / 2.
+void* lvo_tubemesh_create(const float* pos, const uint64_t* line_offsets, uint64_t n_lines, float tube_radius, int num_circle_subdivisions) {
+    TubeMeshScene* t = new TubeMeshScene();
+    createCappedTriangleTubes(pos, line_offsets, n_lines, tube_radius, num_circle_subdivisions, t->mesh);
+    t->bvh.build(t->mesh);
+    return t;
+}
+void lvo_tubemesh_destroy(void* h) { delete static_cast<TubeMeshScene*>(h); }
+void lvo_tubemesh_info(void* h, uint64_t* n_vertices, uint64_t* n_triangles, uint64_t* n_line_points) {
+    TubeMeshScene& t = *static_cast<TubeMeshScene*>(h);
+    *n_vertices = t.mesh.vertexDataList.size(); *n_triangles = t.mesh.triangleIndices.size() / 3; *n_line_points = t.mesh.linePositions.size();
+}
+// vertices: 8 floats each (position, as_float(vertexLinePointIndex), normal, phi); indices: 3 per triangle
+void lvo_tubemesh_copy(void* h, float* vertices, uint32_t* indices) {
+    TubeMeshScene& t = *static_cast<TubeMeshScene*>(h);
+    static_assert(sizeof(TubeTriangleVertexData) == 32, "TubeTriangleVertexData is 32 bytes");
+    if (vertices) std::memcpy(vertices, t.mesh.vertexDataList.data(), t.mesh.vertexDataList.size() * 32);
+    if (indices) std::memcpy(indices, t.mesh.triangleIndices.data(), t.mesh.triangleIndices.size() * 4);
+}
+
+// The screen-space RTAO pass exactly as the reference runs it: against the TRIANGULATED tubes, with the barycentric vertex
+// fetch (Data/Shaders/AO/RTAO/VulkanRayTracedAmbientOcclusion.glsl:178-319).  stats = {T, I, rays_primary, rays_ao, pixels_hit}
+void lvo_render_rtao_triangles(void* h, const lv_camera* cam, const lvo_options* o, uint32_t frame_number, float* ao_inout, uint64_t* stats) {
+    TubeMeshScene& ts = *static_cast<TubeMeshScene*>(h);
+    const TubeMesh& m = ts.mesh;
+    Uniforms u{};
+    std::memcpy(u.inverseViewMatrix, cam->inv_view, 64); std::memcpy(u.inverseProjectionMatrix, cam->inv_proj, 64);
+    u.viewportW = cam->width; u.viewportH = cam->height;
+    const uint32_t W = cam->width, H = cam->height;
+    const uint32_t globalFrameNumber = frame_number;
+    const float subdivisionCorrectionFactor = float(std::cos(3.14159265358979323846 / double(o->tube_num_subdivisions)));   // .cpp:588
+    uint64_t T = 0, I = 0, RP = 0, RA = 0, PH = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : T, I, RP, RA, PH)
+    for (int64_t yy = 0; yy < int64_t(H); yy++) {
+        uint64_t steps = 0, isect = 0;
+        const uint32_t y = uint32_t(yy);
+        for (uint32_t x = 0; x < W; x++) {
+            uint32_t seed = tea(x + y * W, globalFrameNumber);                          // :187
+            float xix = 0.5f, xiy = 0.5f;
+            if (o->ao_jitter_primary) { xix = rnd(seed); xiy = rnd(seed); }            // :189-194
+            vec3 ro, rd; cameraRay(u, x, y, xix, xiy, ro, rd);                          // :196-203
+            float aoFactor = 1.0f;
+            TriHit hit;
+            RP++;
+            if (traceTriangles(ts.bvh, ro, rd, 0.0001f, 1000.0f, false, hit, steps, isect)) {
+                PH++;
+                const uint32_t* tri = &m.triangleIndices[3 * size_t(hit.tri)];          // :213-221
+                const vec3 bary = V3(1.0f - hit.u - hit.v, hit.u, hit.v);
+                const TubeTriangleVertexData& v0 = m.vertexDataList[tri[0]];
+                const TubeTriangleVertexData& v1 = m.vertexDataList[tri[1]];
+                const TubeTriangleVertexData& v2 = m.vertexDataList[tri[2]];
+                const uint32_t l0 = v0.vertexLinePointIndex & 0x7FFFFFFFu, l1 = v1.vertexLinePointIndex & 0x7FFFFFFFu, l2 = v2.vertexLinePointIndex & 0x7FFFFFFFu;
+                const vec3 vertexPositionWorld = interpolateVec3(v0.vertexPosition, v1.vertexPosition, v2.vertexPosition, bary);   // :251-255
+                const vec3 surfaceNormal = normalize(interpolateVec3(v0.vertexNormal, v1.vertexNormal, v2.vertexNormal, bary));
+                const vec3 linePosition = interpolateVec3(m.linePositions[l0], m.linePositions[l1], m.linePositions[l2], bary);    // :258-262
+                const vec3 surfaceTangent = normalize(interpolateVec3(m.lineTangents[l0], m.lineTangents[l1], m.lineTangents[l2], bary));
+                const vec3 surfaceBitangent = cross(surfaceNormal, surfaceTangent);
+                const float offsetFactor = length(linePosition - vertexPositionWorld) / subdivisionCorrectionFactor;               // :276
+                aoFactor = 0.0f;
+                for (uint32_t sampleIdx = 0; sampleIdx < o->ao_spp; sampleIdx++) {     // :284-303
+                    uint32_t seed2 = tea(x + y * W, globalFrameNumber * o->ao_spp + sampleIdx);
+                    const float a = rnd(seed2), b = rnd(seed2);
+                    const vec3 hs = sampleHemisphere(a, b);
+                    const vec3 dir = normalize((surfaceTangent * hs.x + surfaceBitangent * hs.y) + surfaceNormal * hs.z);
+                    const vec3 org = vertexPositionWorld + dir * offsetFactor;
+                    TriHit ah;
+                    RA++;
+                    float occ = 1.0f;                                                   // traceAoRay :158-175
+                    if (traceTriangles(ts.bvh, org, dir, 0.0f, o->ao_radius, o->ao_use_distance == 0, ah, steps, isect))
+                        occ = o->ao_use_distance ? ah.t / o->ao_radius : 0.0f;
+                    aoFactor += occ;
+                }
+                aoFactor /= float(o->ao_spp);
+            }
+            const size_t idx = size_t(y) * W + x;
+            if (frame_number != 0) aoFactor = mix(ao_inout[idx], aoFactor, 1.0f / float(frame_number + 1));   // :313-317
+            ao_inout[idx] = aoFactor;
+        }
+        T += steps; I += isect;
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = RP; stats[3] = RA; stats[4] = PH; }
 }
 
 int lvo_num_threads(void) {
