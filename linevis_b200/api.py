@@ -15,8 +15,8 @@ from .capi import LvStats, LineVisError, HIT_DTYPE, NODE_DTYPE, BVH_NODE_DTYPE, 
 class Context:
     """One renderer context per GPU (lv_ctx_create; replaces renderer construction in MainApp::setRenderer)."""
 
-    def __init__(self, device=0, stream=None):
-        self.lib = capi.load_library()
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.lib = capi.load_library(lib_path) if lib_path else capi.load_library()
         h = ctypes.c_void_p()
         rc = self.lib.lv_ctx_create(ctypes.byref(h), int(device), ctypes.c_void_p(stream) if stream else None)
         if rc != capi.LV_OK:

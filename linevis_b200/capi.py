@@ -59,14 +59,15 @@ class LineVisError(RuntimeError):
         self.code = code
 
 
-_lib = None
+_libs = {}
 
 
 def load_library(path=LIB_PATH):
-    """Load liblinevis_b200.so and declare the prototypes.  Raises if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
+    """Load liblinevis_b200.so (or another build of the same C ABI, e.g. the host emulation the CPU tests use) and declare the
+    prototypes.  Raises if it has not been built."""
+    path = os.path.abspath(path)
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise ImportError("%s not found: build it with `python -c 'import linevis_b200.build as b; b.build()'` "
                           "(nvcc, sm_100a).  linevis_b200 has no CPU fallback." % path)
@@ -114,7 +115,7 @@ def load_library(path=LIB_PATH):
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("lv_abi_version",):
             fn.restype = ctypes.c_int
-    _lib = L
+    _libs[path] = L
     return L
 
 

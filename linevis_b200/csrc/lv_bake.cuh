@@ -80,7 +80,7 @@ LV_DEV SegAux make_seg_aux(uint2 idx, const float4* pt_nrm) {
     return x;
 }
 
-#ifndef LV_HOST_EMU
+#if !defined(LV_HOST_EMU) || defined(LV_HOST_EMU_SIMT)
 __global__ void k_bake_setup(const __grid_constant__ BakeParams B, AoHit* records) {
     const uint32_t total = B.n_param * B.n_subdiv;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)

@@ -6,7 +6,9 @@
 // range of the sorted records, so a subtree with <= leaf_max records is referenced directly as a leaf
 // (first record, count) and never materialised.
 #pragma once
+#ifndef LV_HOST_EMU   // the host emulation (tests/emu) supplies cub::DeviceRadixSort::SortPairs itself
 #include <cub/cub.cuh>
+#endif
 #include "lv_types.cuh"
 #include "lv_math.cuh"
 

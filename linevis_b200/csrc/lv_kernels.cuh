@@ -285,6 +285,18 @@ constexpr int kAoStack = 72;
 template <int K> struct AoStack {
     static constexpr int kAoSmemStack = K;
     unsigned long long e[kAoStack - kAoSmemStack];
+#ifdef LV_HOST_EMU   // host emulation: plain indexing instead of shared-window addresses + inline PTX
+    unsigned long long* sm;
+    __device__ __forceinline__ void init() {
+        __shared__ unsigned long long s_stack[kAoSmemStack][kBlockThreads];
+        sm = &s_stack[0][threadIdx.x];
+    }
+    __device__ __forceinline__ void put(int i, uint32_t node, float t) {
+        const unsigned long long v = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | node;
+        if (i < kAoSmemStack) sm[size_t(i) * kBlockThreads] = v; else e[i - kAoSmemStack] = v;
+    }
+    __device__ __forceinline__ unsigned long long get(int i) const { return i < kAoSmemStack ? sm[size_t(i) * kBlockThreads] : e[i - kAoSmemStack]; }
+#else
     uint32_t sm;   // shared-window address of this thread's column: entry i at sm + i * kBlockThreads * 8
     __device__ __forceinline__ void init() {
         __shared__ unsigned long long s_stack[kAoSmemStack][kBlockThreads];
@@ -301,6 +313,7 @@ template <int K> struct AoStack {
         else v = e[i - kAoSmemStack];
         return v;
     }
+#endif
 };
 template <> struct AoStack<1> {
     unsigned long long e[kAoStack];

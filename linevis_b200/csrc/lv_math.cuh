@@ -19,10 +19,11 @@ inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); r
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 template <class T> inline T __ldg(const T* p) { return *p; }
-namespace lv {
+// integer min / max overloads nvcc provides in the global namespace
 inline int max(int a, int b) { return a < b ? b : a; }
 inline int min(int a, int b) { return b < a ? b : a; }
-}
+inline unsigned max(unsigned a, unsigned b) { return a < b ? b : a; }
+inline unsigned min(unsigned a, unsigned b) { return b < a ? b : a; }
 #else
 #define LV_DEV __device__ __forceinline__
 #endif

@@ -92,7 +92,7 @@ struct HitRec {
     uint32_t kind;
 };
 
-#ifndef LV_HOST_EMU   // warp-collective code: GPU only (covered by the -m gpu parity tests, not by the host emulation)
+#if !defined(LV_HOST_EMU) || defined(LV_HOST_EMU_SIMT)   // warp-collective code: needs a GPU or the SIMT emulator (tests/emu/emu_cuda.hpp)
 // Closest hit for a WARP PACKET of coherent rays (the 8x4 pixel patch of camera rays a warp owns).  The warp walks the
 // BVH together with one shared stack: a child is visited if any lane's box test (against that lane's own best hit plus the
 // tie margin) passes, near child first by majority vote, and every node / record is fetched once per warp.  Each lane keeps
@@ -159,6 +159,6 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
     }
     return found;
 }
-#endif  // !LV_HOST_EMU
+#endif  // warp-collective code
 
 }  // namespace lv

@@ -1,0 +1,237 @@
+"""The whole C ABI on the HOST: linevis_b200/csrc (lv_api.cu and every kernel, unchanged source) compiled against the SIMT emulator
+tests/emu/emu_cuda.hpp and compared with the oracle bit for bit -- the same statements the -m gpu parity tests make, at sizes a
+fiber-per-thread emulation finishes in seconds.  Covers what the per-function emulation (test_emu.py) cannot: the GPU BVH build,
+the warp-packet traversals, the persistent AO ray stream (leaf-queue and leaf-vote kernels, every stack layout), the AO
+prebaker, PPLL gather / resolve (plain and binned), depth cues, tile sharding.  A parity failure here is a logic bug in
+the kernels; what only a GPU can show (memory model, performance) stays with the -m gpu tests."""
+import os
+
+import numpy as np
+import pytest
+
+import linevis_b200 as lv
+from linevis_b200 import scenes
+from oracle import lvo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ectx():
+    if not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("CUDA headers not found")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(HERE, "emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    c = lv.Context(0, lib_path=mod.build())
+    yield c
+    c.close()
+
+
+def _helix(n_lines=10, n_pts=25):
+    return scenes.helix_lines(n_lines, n_pts), 0.012
+
+
+def _random(n=400):
+    return scenes.random_segments(n, 0.05, seed=11), 0.01
+
+
+def _pair(ectx, oracle, data, width):
+    return ectx.create_scene(*data, width), oracle.scene(*data, width)
+
+
+@pytest.mark.parametrize("leaf", [1, 4])
+@pytest.mark.parametrize("maker", [_helix, _random])
+def test_bvh_build_and_primary_hits(ectx, oracle, maker, leaf):
+    data, width = maker()
+    ectx.set_option("b200_bvh_leaf_size", leaf)
+    try:
+        sc, osc = _pair(ectx, oracle, data, width)
+    finally:
+        ectx.set_option("b200_bvh_leaf_size", 1)
+    cam = lv.make_camera(72, 48)
+    hits, st = ectx.trace_primary(sc, cam)
+    ref, _ = osc.trace_primary(cam)
+    assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+    assert np.array_equal(hits["prim"], ref["prim"]) and np.array_equal(hits["kind"], ref["kind"])
+    assert st["pixels_hit"] == int((ref["prim"] != 0xFFFFFFFF).sum()) > 20
+    # the emitted tree, walked from the root: every record is referenced by exactly one reachable leaf
+    nodes = sc.bvh_nodes()
+    seen = np.zeros(sc.info()["n_seg"], int)
+    todo = [0]
+    while todo:
+        nd = nodes[todo.pop()]
+        for ref_w, cnt, mn in ((nd["lref"], nd["lcount"], nd["lmin"]), (nd["rref"], nd["rcount"], nd["rmin"])):
+            if cnt:
+                first = int(ref_w) & 0x07FFFFFF
+                assert ((int(ref_w) >> 27) & 15) + 1 == int(cnt) <= leaf
+                seen[first:first + int(cnt)] += 1
+            elif np.isfinite(mn).all():
+                todo.append(int(ref_w))
+    assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("queue,stack,minb", [(True, 12, 0), (True, 1, 9), (True, 8, 8), (False, 0, 10), (False, 1, 9), (False, 12, 9), (False, 16, 8)])
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_every_kernel_variant(ectx, oracle, queue, stack, minb, use_distance):
+    data, width = _random()
+    sc, osc = _pair(ectx, oracle, data, width)
+    cam = lv.make_camera(56, 36)
+    ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
+                           "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.4,
+                           "b200_ao_stack": stack, "b200_ao_queue": queue, "b200_ao_min_blocks": minb})
+    try:
+        ao, st = ectx.render_rtao(sc, cam, 0)
+        ao2, _ = ectx.render_rtao(sc, cam, 1, out=ao.copy())
+    finally:
+        ectx.set_new_settings({"b200_ao_stack": 12, "b200_ao_queue": True, "b200_ao_min_blocks": 0, "ambient_occlusion_radius": 0.1})
+    opts = lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_jitter_primary=1, ao_radius=0.4)
+    ref, ost = osc.render_rtao(cam, opts, 0)
+    ref2, _ = osc.render_rtao(cam, opts, 1, ao=ref.copy())
+    assert st["rays_ao"] == ost["rays_ao"] > 500
+    assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(ao2.view(np.uint32), ref2.view(np.uint32))      # running mean over frames
+
+
+def test_rtao_deep_stack_spills_out_of_shared_memory(ectx, oracle):
+    # a long chain of collinear segments gives a deep, one-sided LBVH: the 12 shared stack entries overflow into the local part
+    n = 300
+    pos = np.zeros((n + 1, 3), np.float32)
+    pos[:, 0] = np.linspace(-0.25, 0.25, n + 1) ** 3 * 16
+    seg = np.stack([np.arange(n), np.arange(1, n + 1)], axis=1).astype(np.uint32)
+    data, width = (pos, np.linspace(0, 1, n + 1).astype(np.float32), seg), 0.05
+    sc, osc = _pair(ectx, oracle, data, width)
+    cam = lv.make_camera(64, 24)
+    ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_distance_based": True, "ambient_occlusion_radius": 1.0,
+                           "use_jittered_primary_rays": False})
+    try:
+        ao, st = ectx.render_rtao(sc, cam, 0)
+    finally:
+        ectx.set_new_settings({"ambient_occlusion_radius": 0.1, "use_jittered_primary_rays": True})
+    ref, _ = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=4, ao_radius=1.0, ao_jitter_primary=0), 0)
+    assert st["pixels_hit"] > 30 and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["plain", "ao", "transparent_jitter", "depth_cues"])
+def test_tube_frames(ectx, oracle, mode):
+    data, width = _helix()
+    sc, osc = _pair(ectx, oracle, data, width)
+    cam = lv.make_camera(72, 48)
+    opaque = mode != "transparent_jitter"
+    tf = scenes.standard_transfer_function(opacity=(1.0, 1.0) if opaque else (0.3, 0.8))
+    ectx.set_transfer_function(tf)
+    settings = {"ambient_occlusion_strength": 1.0 if mode == "ao" else 0.0, "ambient_occlusion_samples_per_frame": 4,
+                "use_jittered_primary_rays": True, "ambient_occlusion_distance_based": True, "depth_cue_strength": 0.8 if mode == "depth_cues" else 0.0,
+                "num_samples_per_frame": 2 if mode == "transparent_jitter" else 1, "num_accumulated_frames": 4 if mode == "transparent_jitter" else 1}
+    ectx.set_new_settings(settings)
+    opts = lvo.default_options(ao_strength=settings["ambient_occlusion_strength"], ao_spp=4, depth_cue_strength=settings["depth_cue_strength"],
+                               num_samples_per_frame=settings["num_samples_per_frame"], use_jittered_rays=int(mode == "transparent_jitter"))
+    try:
+        img, st = ectx.render_tubes(sc, cam, 0)
+        ao = osc.render_rtao(cam, opts, 0)[0] if mode == "ao" else None
+        ref, _ = osc.render_tubes(cam, opts, tf, ao_tex=ao)
+        assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+        if mode == "transparent_jitter":      # second accumulated frame
+            img2, _ = ectx.render_tubes(sc, cam, 1, out=img.copy())
+            ref2, _ = osc.render_tubes(cam, opts, tf, frame_number=1, rgba=ref.copy())
+            assert np.array_equal(img2.view(np.uint32), ref2.view(np.uint32))
+    finally:
+        ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "depth_cue_strength": 0.0, "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    assert st["pixels_hit"] > 50
+
+
+@pytest.mark.parametrize("binned", [False, True])
+@pytest.mark.parametrize("sort_mode", ["priority_queue", "bitonic"])
+def test_ppll(ectx, oracle, binned, sort_mode):
+    # dense enough for every list-length class of the resolve kernels (insertion <= 64, warp bitonic above; binned 32 / 64 / 128 / 256)
+    data = scenes.random_segments(5000, 0.35, seed=13)
+    sc, osc = _pair(ectx, oracle, data, 0.03)
+    cam = lv.make_camera(48, 32)
+    tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
+    ectx.set_transfer_function(tf)
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned})
+    try:
+        img, st = ectx.render_ppll(sc, cam, max_frags=200, sort_mode=sort_mode, linked_list_size=64 * 48 * 32)
+    finally:
+        ectx.set_option("b200_ppll_binned_resolve", False)
+    opts = lvo.default_options()
+    g = osc.ppll_gather(cam, opts, tf)
+    mine = ectx.ppll_read()
+    assert st["frags_generated"] == g["counter"] == mine["counter"] > 1000
+    assert lvo.per_pixel_lists(mine["heads"], mine["nodes"], cam, opts, oracle) == lvo.per_pixel_lists(g["heads"], g["nodes"], cam, opts, oracle)
+    ref, rst = lvo.ppll_resolve(oracle, cam, opts, g["heads"], g["nodes"], 200, lv.SORT_MODES[sort_mode], canonical=True)
+    assert st["frags_sorted"] == rst["frags_sorted"] and st["max_depth_complexity"] == rst["max_depth_complexity"] > 130
+    nan = np.isnan(ref)
+    assert np.array_equal(np.isnan(img), nan) and np.array_equal(img[~nan].view(np.uint32), ref[~nan].view(np.uint32))
+
+
+def test_ppll_overflow_and_truncation(ectx, oracle):
+    data, width = _random(600)
+    sc = ectx.create_scene(*data, 0.02)
+    cam = lv.make_camera(48, 32)
+    ectx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.2, 0.7)))
+    full, st_full = ectx.render_ppll(sc, cam, max_frags=64)
+    img, st = ectx.render_ppll(sc, cam, max_frags=64, linked_list_size=500)     # fragment buffer too small: dropped, counted, never fatal
+    assert st["frags_generated"] == st_full["frags_generated"] and st["frags_stored"] == 500 and st["frags_dropped"] == st["frags_generated"] - 500
+    img, st = ectx.render_ppll(sc, cam, max_frags=4)                            # lists longer than MAX_NUM_FRAGS are truncated
+    assert st["frags_truncated"] > 0 and st["frags_sorted"] + st["frags_truncated"] == st_full["frags_sorted"]
+
+
+def test_prebaker_and_static_lookup(ectx, oracle):
+    d = scenes.helix_polylines(8, 21)
+    width = 0.012
+    sc = ectx.create_scene(d["pos"], d["attr"], d["seg"], width)
+    sc.set_lines(d["pos"], d["tangent"], d["normal"], d["line_offsets"])
+    osc = oracle.scene(d["pos"], d["attr"], d["seg"], width)
+    osc.set_lines(d["tangent"], d["normal"])
+    ectx.set_new_settings({"ambient_occlusion_mode": "RTAO (Prebaker)", "b200_prebaker_iterations": 2, "b200_prebaker_samples_per_frame": 3,
+                           "b200_prebaker_subdivisions": 6, "b200_prebaker_param_segment_length": 0.03, "b200_prebaker_radius": 0.2,
+                           "ambient_occlusion_strength": 0.9, "ambient_occlusion_gamma": 1.4, "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    tf = scenes.standard_transfer_function(opacity=(0.5, 1.0))
+    ectx.set_transfer_function(tf)
+    cam = lv.make_camera(64, 40)
+    try:
+        bw, sl = oracle.ao_parametrize(d["pos"], d["line_offsets"], 0.03)
+        ref_f = None
+        for it in range(2):
+            st = sc.ao_bake(1)
+            ref_f, ost = osc.ao_bake_iteration(sl, it, factors=ref_f, radius=0.2, n_subdiv=6, spp=3)
+            got = sc.ao_read()
+            assert st["rays_ao"] == ost["rays"] == len(sl) * 6 * 3
+            assert np.array_equal(got["factors"].reshape(-1).view(np.uint32), ref_f.view(np.uint32)), it
+        assert np.array_equal(got["blending_weights"], bw) and np.array_equal(got["sampling_locations"], sl)
+        img, st = ectx.render_tubes(sc, cam)
+        assert st["rays_ao"] == 0
+        osc.set_static_ao(ref_f, 6, bw)
+        ref, _ = osc.render_tubes(cam, lvo.default_options(ao_strength=0.9, ao_gamma=1.4, use_static_ao=1), tf)
+        assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+    finally:
+        ectx.set_new_settings({"ambient_occlusion_mode": "RTAO (Screen Space)", "ambient_occlusion_strength": 0.0, "ambient_occlusion_gamma": 1.0})
+
+
+def test_tile_shards_union_is_the_frame(ectx, oracle):
+    data, width = _helix()
+    sc = ectx.create_scene(*data, width)
+    cam = lv.make_camera(96, 64)
+    tf = scenes.standard_transfer_function(opacity=(1.0, 1.0))
+    ectx.set_transfer_function(tf)
+    ectx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 2, "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    try:
+        full, _ = ectx.render_tubes(sc, cam)
+        acc = np.full_like(full, np.nan)
+        rays = 0
+        for r in range(3):
+            ectx.set_tile_shard(r, 3, 16)
+            part = np.full_like(full, np.nan)
+            _, st = ectx.render_tubes(sc, cam, out=part)
+            m = ~np.isnan(part[..., 0])
+            assert not (m & ~np.isnan(acc[..., 0])).any()        # shards are disjoint
+            acc[m] = part[m]
+            rays += st["rays_primary"] + st["rays_ao"]
+        assert not np.isnan(acc).any()
+    finally:
+        ectx.set_tile_shard(0, 1, 64)
+        ectx.set_option("ambient_occlusion_strength", 0.0)
+    # without jitter the AO lookup of a tile's border pixels may touch a neighbour shard's texel with weight ~1e-4
+    assert np.abs(acc - full).max() < 2e-3 and (acc == full).mean() > 0.98
