@@ -77,9 +77,11 @@ def build(force=False):
     main = os.path.join(GEN, "emu_main.cpp")
     with open(main, "w") as fh:
         fh.write('#include "../emu_cuda.hpp"\n#include "../emu_cudart.inc"\n#include "lv_api.cpp"\n')
-    # lv_api.cu includes "../../include/linevis_b200.h" relative to csrc: keep that path valid from _gen
+    # lv_api.cu includes "../../include/linevis_b200.h" relative to csrc: keep that path valid from _gen.
+    # -Bsymbolic: the library's own cuda* / lv_* definitions win over same-named symbols of the real library / libcudart that may
+    # already live in the process (the CPU suite also loads liblinevis_b200.so for the ABI checks)
     cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-DLV_HOST_EMU", "-I" + CUDA_INC, "-I" + os.path.join(HERE, "..", "..", "linevis_b200", "csrc"),
-           "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-fPIC", "-shared", "-Wno-attributes", "-Wno-unknown-pragmas",
+           "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-attributes", "-Wno-unknown-pragmas",
            "-o", OUT, main]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
