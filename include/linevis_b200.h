@@ -203,6 +203,16 @@ int lv_scene_set_lines(lv_scene* scene, const float* pos_xyz, const float* tange
 int lv_ao_parametrize(const float* pos_xyz, const uint64_t* line_offsets, uint64_t n_lines, float expected_param_segment_length,
                       float* blending_weights, float* sampling_locations, uint64_t cap, uint64_t* n_param_vertices);
 
+/* Host-only (no GPU needed).  The reference's triangulated capped tubes: createCappedTriangleTubesRenderDataCPU with tubeClosed == false
+ * (src/Renderers/Tubes/CappedTriangleTubesCPU.cpp:33-385, src/Renderers/Tubes/Tubes.cpp:35-86) -- the geometry the reference's
+ * RTAO passes are traced against and what `b200_rtao_geometry = triangles` makes lv_render_rtao / lv_render_tubes / lv_ao_bake
+ * trace instead of the analytic capsules (the scene then needs lv_scene_set_lines).  vertices: 8 floats each -- position,
+ * as_float(line point index | 0x80000000 on cap vertices), normal, phi (TubeTriangleVertexData, LineRenderData.hpp:171-176);
+ * indices: 3 per triangle.  Either array may be NULL; caps in vertices / triangles; the counts are always returned. */
+int lv_tube_mesh(const float* pos_xyz, const uint64_t* line_offsets, uint64_t n_lines, float tube_radius, uint32_t num_subdivisions,
+                 float* vertices, uint64_t vertices_cap, uint32_t* indices, uint64_t triangles_cap,
+                 uint64_t* n_vertices, uint64_t* n_triangles, uint64_t* n_line_points);
+
 /* Object-space RTAO prebaker: runs baking iterations (one dispatch of Data/Shaders/AO/RTAO/VulkanAmbientOcclusionBaker.glsl:190-282
  * each, frameNumber = iterations done so far) until b200_prebaker_iterations are reached; n_iterations = 0 runs all that are
  * left (BakingMode::IMMEDIATE, VulkanAmbientOcclusionBaker::startAmbientOcclusionBaking :161-192), n_iterations = 1 is one

@@ -121,6 +121,23 @@ class Context:
         lib.lv_ao_parametrize(_ptr(pos), _ptr(off), len(off) - 1, expected_param_segment_length, _ptr(w), _ptr(sl), sl.size, ctypes.byref(n))
         return w, sl[:n.value]
 
+    @staticmethod
+    def tube_mesh(pos, line_offsets, line_width, num_subdivisions=6, lib_path=None):
+        """lv_tube_mesh (host only): the reference's triangulated capped tubes -> (vertices [n, 8] float32 rows, triangles [m, 3] uint32,
+        number of line points)."""
+        lib = capi.load_library(lib_path) if lib_path else capi.load_library()
+        pos = np.ascontiguousarray(pos, np.float32)
+        off = np.ascontiguousarray(line_offsets, np.uint64)
+        nv, nt, nl = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        args = (_ptr(pos), _ptr(off), len(off) - 1, 0.5 * line_width, num_subdivisions)
+        rc = lib.lv_tube_mesh(*args, None, 0, None, 0, ctypes.byref(nv), ctypes.byref(nt), ctypes.byref(nl))
+        if rc != capi.LV_OK:
+            raise LineVisError(rc, "lv_tube_mesh")
+        v = np.zeros((max(nv.value, 1), 8), np.float32)
+        t = np.zeros((max(nt.value, 1), 3), np.uint32)
+        lib.lv_tube_mesh(*args, _ptr(v), nv.value, _ptr(t), nt.value, ctypes.byref(nv), ctypes.byref(nt), ctypes.byref(nl))
+        return v[:nv.value], t[:nt.value], nl.value
+
     # -- frames
     def trace_primary(self, scene, cam, out=None):
         if out is None:

@@ -14,6 +14,7 @@
 #include "lv_bvh.cuh"
 #include "lv_kernels.cuh"
 #include "lv_bake.cuh"
+#include "lv_tubemesh.hpp"
 
 using namespace lv;
 
@@ -39,6 +40,7 @@ struct Options {
     uint32_t bvh_leaf_size = 1;
     uint32_t ao_refill_below = 24;
     uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
+    bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
@@ -104,12 +106,17 @@ struct lv_scene {
     DevBuf<SegAux> seg_aux;                        // per record, BVH order
     std::vector<float> host_pos; std::vector<uint64_t> line_offsets;   // polylines for the (host-side) parametrization
     DevBuf<float> sampling, weights, factors;      // samplingLocations, blending weights, ambientOcclusionFactors
+    // triangle-tube mode of the AO passes (ensure_tube_mesh): the reference's tube mesh + a BVH over its triangles
+    DevBuf<TriRec> tris; DevBuf<uint32_t> tri_ids; DevBuf<Node64> tri_nodes; DevBuf<float4> tri_vattr, tri_line_pos, tri_line_tan;
+    uint64_t n_tri = 0; uint32_t mesh_subdiv = 0; float tri_build_ms = 0.0f;
     uint32_t n_param = 0, param_subdiv = 0, bake_done = 0;
     float param_len = 0.0f;
     bool has_lines = false;
     SceneDev dev() const {
         SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
         s.seg_aux = has_lines ? seg_aux.p : nullptr;
+        s.tris = tris.p; s.tri_ids = tri_ids.p; s.tri_nodes = tri_nodes.p; s.tri_vattr = tri_vattr.p;
+        s.tri_line_pos = tri_line_pos.p; s.tri_line_tan = tri_line_tan.p; s.n_tri = uint32_t(n_tri);
         s.n_nodes = uint32_t(n_nodes); s.radius = line_width * 0.5f; s.line_width = line_width;
         return s;
     }
@@ -263,10 +270,81 @@ bool cam_ok(const FrameParams& P) { return P.far_dist > P.near_dist; }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// Triangle-tube mode of the AO passes: generate the reference's tube mesh on the host (lv_tubemesh.hpp, like the reference's
+// createCappedTriangleTubesRenderDataCPU), upload it and build an LBVH over its triangles (lv_tri.cuh), one triangle per leaf.
+// Needs the polylines of lv_scene_set_lines.  Rebuilt when tube_num_subdivisions changes.
+int ensure_tube_mesh(lv_ctx* c, lv_scene* sc) {
+    if (!sc->has_lines) return fail(c, LV_ERR_STATE, "b200_rtao_geometry = triangles needs the polylines (lv_scene_set_lines)");
+    if (sc->n_tri && sc->mesh_subdiv == c->opt.tube_num_subdivisions) return LV_OK;
+    lvmesh::TubeMesh m;
+    lvmesh::build(sc->host_pos.data(), sc->line_offsets.data(), sc->line_offsets.size() - 1, sc->line_width * 0.5f, int(c->opt.tube_num_subdivisions), m);
+    const size_t nv = m.vertices.size(), nt = m.indices.size() / 3, nl = m.line_pos.size();
+    if (nt == 0) return fail(c, LV_ERR_STATE, "triangle-tube mode: the polylines produce no tube geometry");
+    if (nt >= (1ull << 27)) return fail(c, LV_ERR_INVALID_ARGUMENT, "triangle-tube mode: too many triangles (max 2^27-1)");
+    std::vector<float> vpos(3 * nv), vnrm(3 * nv); std::vector<uint32_t> vline(nv); std::vector<float4> lpos(nl), ltan(nl);
+    for (size_t i = 0; i < nv; i++) {
+        vpos[3 * i] = m.vertices[i].position.x; vpos[3 * i + 1] = m.vertices[i].position.y; vpos[3 * i + 2] = m.vertices[i].position.z;
+        vnrm[3 * i] = m.vertices[i].normal.x; vnrm[3 * i + 1] = m.vertices[i].normal.y; vnrm[3 * i + 2] = m.vertices[i].normal.z;
+        vline[i] = m.vertices[i].line_point;
+    }
+    for (size_t i = 0; i < nl; i++) { lpos[i] = make_float4(m.line_pos[i].x, m.line_pos[i].y, m.line_pos[i].z, 0.0f); ltan[i] = make_float4(m.line_tan[i].x, m.line_tan[i].y, m.line_tan[i].z, 0.0f); }
+    cudaStream_t st = c->stream;
+    const int n = int(nt);
+    DevBuf<float> d_vpos, d_vnrm, bounds, boxes; DevBuf<uint32_t> d_idx, d_vline, vals; DevBuf<unsigned long long> keys, keys2;
+    DevBuf<int2> children, ranges; DevBuf<int> parent; DevBuf<unsigned int> flags; DevBuf<char> cubtmp;
+    auto cleanup = [&]() { d_vpos.release(); d_vnrm.release(); bounds.release(); boxes.release(); d_idx.release(); d_vline.release(); vals.release(); keys.release(); keys2.release();
+                           children.release(); ranges.release(); parent.release(); flags.release(); cubtmp.release(); };
+#define LV_TRI(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); sc->n_tri = 0; return fail(c, e__ == cudaErrorMemoryAllocation ? LV_ERR_OUT_OF_MEMORY : LV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+    LV_TRI(cudaEventRecord(c->ev[6], st));
+    LV_TRI(d_vpos.ensure(3 * nv)); LV_TRI(d_vnrm.ensure(3 * nv)); LV_TRI(d_vline.ensure(nv)); LV_TRI(d_idx.ensure(3 * nt));
+    LV_TRI(cudaMemcpyAsync(d_vpos.p, vpos.data(), 12 * nv, cudaMemcpyHostToDevice, st));
+    LV_TRI(cudaMemcpyAsync(d_vnrm.p, vnrm.data(), 12 * nv, cudaMemcpyHostToDevice, st));
+    LV_TRI(cudaMemcpyAsync(d_vline.p, vline.data(), 4 * nv, cudaMemcpyHostToDevice, st));
+    LV_TRI(cudaMemcpyAsync(d_idx.p, m.indices.data(), 12 * nt, cudaMemcpyHostToDevice, st));
+    LV_TRI(sc->tri_vattr.ensure(nv)); LV_TRI(sc->tri_line_pos.ensure(nl)); LV_TRI(sc->tri_line_tan.ensure(nl));
+    LV_TRI(cudaMemcpyAsync(sc->tri_line_pos.p, lpos.data(), 16 * nl, cudaMemcpyHostToDevice, st));
+    LV_TRI(cudaMemcpyAsync(sc->tri_line_tan.p, ltan.data(), 16 * nl, cudaMemcpyHostToDevice, st));
+    k_tri_vertex_attr<<<uint32_t(std::min<size_t>((nv + 255) / 256, 65535)), 256, 0, st>>>(d_vnrm.p, d_vline.p, uint32_t(nv), sc->tri_vattr.p);
+    LV_TRI(bounds.ensure(6)); LV_TRI(keys.ensure(n)); LV_TRI(keys2.ensure(n)); LV_TRI(vals.ensure(n));
+    LV_TRI(sc->tri_ids.ensure(n)); LV_TRI(sc->tris.ensure(n));
+    k_init_bounds<<<1, 32, 0, st>>>(bounds.p);
+    k_tri_bounds<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_vpos.p, d_idx.p, uint32_t(n), bounds.p);
+    k_tri_morton<<<(n + 255) / 256, 256, 0, st>>>(d_vpos.p, d_idx.p, uint32_t(n), bounds.p, keys.p, vals.p);
+    size_t cub_bytes = 0;
+    LV_TRI(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys.p, keys2.p, vals.p, sc->tri_ids.p, n, 0, 63, st));
+    LV_TRI(cubtmp.ensure(cub_bytes + 16));
+    LV_TRI(cub::DeviceRadixSort::SortPairs(cubtmp.p, cub_bytes, keys.p, keys2.p, vals.p, sc->tri_ids.p, n, 0, 63, st));
+    k_pack_tris<<<(n + 255) / 256, 256, 0, st>>>(d_vpos.p, d_idx.p, sc->tri_ids.p, uint32_t(n), sc->tris.p);
+    const int n_inner = std::max(1, n - 1);
+    LV_TRI(children.ensure(n_inner)); LV_TRI(ranges.ensure(n_inner)); LV_TRI(parent.ensure(2 * size_t(n)));
+    LV_TRI(boxes.ensure(6 * (2 * size_t(n)))); LV_TRI(flags.ensure(n_inner));
+    LV_TRI(cudaMemsetAsync(flags.p, 0, size_t(n_inner) * 4, st));
+    if (n > 1) k_radix_tree<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys2.p, n, children.p, ranges.p, parent.p);
+    k_tri_fit<<<(n + 255) / 256, 256, 0, st>>>(sc->tris.p, n, children.p, parent.p, boxes.p, flags.p);
+    LV_TRI(sc->tri_nodes.ensure(n_inner));
+    k_emit_nodes<<<(n_inner + 255) / 256, 256, 0, st>>>(n, 1, children.p, ranges.p, boxes.p, sc->tri_nodes.p);
+    LV_TRI(cudaMemsetAsync(flags.p, 0, 4, st));
+    k_tree_depth<<<(n + 255) / 256, 256, 0, st>>>(n, parent.p, flags.p);
+    LV_TRI(cudaGetLastError());
+    LV_TRI(cudaEventRecord(c->ev[7], st));
+    uint32_t depth = 0;
+    LV_TRI(cudaMemcpyAsync(&depth, flags.p, 4, cudaMemcpyDeviceToHost, st));
+    LV_TRI(cudaStreamSynchronize(st));
+    cleanup();
+#undef LV_TRI
+    if (depth + 1 > uint32_t(kStackSize) || depth + 1 > uint32_t(kAoStack)) {
+        sc->n_tri = 0;
+        return fail(c, LV_ERR_STATE, "triangle BVH depth " + std::to_string(depth) + " exceeds the traversal stack (" + std::to_string(kAoStack) + ")");
+    }
+    sc->tri_build_ms = elapsed(c->ev[6], c->ev[7]);
+    sc->n_tri = nt; sc->mesh_subdiv = c->opt.tube_num_subdivisions;
+    return LV_OK;
+}
+
 // persistent AO ray-stream kernel over the records in ctx->ao_hits (count in small[0], work counter in small[2..3]) into ctx->occ;
 // timed with ev[4] / ev[5].  BAKE selects the prebaker's random stream / ray origin (lv_bake.cuh).
 template <bool BAKE>
-int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves) {
+int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves, bool tri = false) {
     auto launch = [&](auto kern) -> int {
         int per_sm = 0;
         LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
@@ -277,6 +355,8 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
         LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
         return LV_OK;
     };
+    if (tri)   // triangle-tube mode: the leaf-queue kernel over the triangle BVH (always one triangle per leaf)
+        return c->opt.ao_min_blocks >= 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 1>) : launch(k_rtao_rays_q<8, BAKE, 12, 1>);
     const uint32_t stack = c->opt.ao_stack;
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
     const uint32_t mb = c->opt.ao_min_blocks ? c->opt.ao_min_blocks : (queue ? 8u : 9u);   // 0 = measured optimum of the variant
@@ -314,6 +394,8 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     LV_CUDA(c, c->small.ensure(4));
     LV_CUDA(c, cudaMemsetAsync(c->small.p, 0, 4 * sizeof(unsigned int), c->stream));
     P.frame_number = frame_number;
+    const bool tri = c->opt.ao_triangles;
+    if (tri) { int trc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)); if (trc) return trc; }
     const SceneDev S = sc->dev();
     const uint32_t grid = pixel_grid(c, P);
     if (grid == 0) return LV_OK;
@@ -328,15 +410,22 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
         P.apron_marks = c->apron_marks.p;
     }
     const uint32_t ring = 4 * c->tile_size + 4;
-    k_rtao_primary<<<grid, kBlockThreads, 0, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, nullptr, stamp);
-    if (apron)
-        k_rtao_primary<<<P.n_tiles * ((ring + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
-            P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, c->apron_marks.p, stamp);
+    if (tri) {
+        k_rtao_primary<1><<<grid, kBlockThreads, 0, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, nullptr, stamp);
+        if (apron)
+            k_rtao_primary<1><<<P.n_tiles * ((ring + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
+                P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, c->apron_marks.p, stamp);
+    } else {
+        k_rtao_primary<0><<<grid, kBlockThreads, 0, c->stream>>>(P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, nullptr, stamp);
+        if (apron)
+            k_rtao_primary<0><<<P.n_tiles * ((ring + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
+                P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, c->apron_marks.p, stamp);
+    }
     {
         // one float per (hit pixel, sample); worst case every owned pixel (and ring pixel) is hit
         const size_t max_hits = size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + (apron ? ring : 0));
         LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
-        int lrc = launch_ao_rays<false>(c, P, S, sc->leaf_size == 1);
+        int lrc = launch_ao_rays<false>(c, P, S, sc->leaf_size == 1, tri);
         if (lrc) return lrc;
         c->rtao_rays_timed = true;
         k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, c->ao.p);
@@ -455,7 +544,8 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     P.ao_refill_below = int(o.ao_refill_below); P.ao_leaf_vote = int(o.ao_leaf_vote); P.frame_number = sc->bake_done;
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
-    if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1))) return rc;
+    if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;
+    if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1, o.ao_triangles))) return rc;
     c->rtao_rays_timed = true;
     k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, sc->factors.p);
     LV_CUDA(c, cudaGetLastError());
@@ -591,6 +681,11 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
+    else if (k == "b200_rtao_geometry") {
+        if (!strcmp(value, "triangles")) o.ao_triangles = true;
+        else if (!strcmp(value, "capsules")) o.ao_triangles = false;
+        else return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_rtao_geometry must be 'capsules' or 'triangles'");
+    }
     else if (k == "b200_ao_stack") { if (u() != 0 && u() != 1 && u() != 8 && u() != 12 && u() != 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_stack must be 0, 1, 8, 12 or 16"); o.ao_stack = u(); }
     else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
     else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
@@ -640,6 +735,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
     else if (k == "b200_ao_min_blocks") v = std::to_string(o.ao_min_blocks);
     else if (k == "b200_ao_queue") v = b(o.ao_queue);
+    else if (k == "b200_rtao_geometry") v = o.ao_triangles ? "triangles" : "capsules";
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else return LV_ERR_UNKNOWN_OPTION;
@@ -863,6 +959,7 @@ int lv_scene_destroy(lv_scene* s) {
     s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release();
     s->pt_pos.release(); s->pt_tan.release(); s->pt_nrm.release(); s->seg_aux.release();
     s->sampling.release(); s->weights.release(); s->factors.release();
+    s->tris.release(); s->tri_ids.release(); s->tri_nodes.release(); s->tri_vattr.release(); s->tri_line_pos.release(); s->tri_line_tan.release();
     delete s;
     return LV_OK;
 }
@@ -900,6 +997,7 @@ int lv_scene_set_lines(lv_scene* s, const float* pos_xyz, const float* tangent_x
     tmp.release();
     s->has_lines = true;
     s->n_param = 0; s->bake_done = 0;   // new frames invalidate parametrization and baked factors
+    s->n_tri = 0; s->mesh_subdiv = 0;   // ... and the tube mesh
     return LV_OK;
 }
 
@@ -911,6 +1009,21 @@ int lv_ao_parametrize(const float* pos_xyz, const uint64_t* line_offsets, uint64
     if (blending_weights) memcpy(blending_weights, w.data(), w.size() * 4);
     if (sampling_locations) memcpy(sampling_locations, sl.data(), std::min<uint64_t>(cap, sl.size()) * 4);
     *n_param_vertices = sl.size();
+    return LV_OK;
+}
+
+int lv_tube_mesh(const float* pos_xyz, const uint64_t* line_offsets, uint64_t n_lines, float tube_radius, uint32_t num_subdivisions,
+                 float* vertices, uint64_t vertices_cap, uint32_t* indices, uint64_t triangles_cap,
+                 uint64_t* n_vertices, uint64_t* n_triangles, uint64_t* n_line_points) {
+    if (!pos_xyz || !line_offsets || n_lines == 0 || !(tube_radius > 0.0f)) return LV_ERR_INVALID_ARGUMENT;
+    lvmesh::TubeMesh m;
+    lvmesh::build(pos_xyz, line_offsets, n_lines, tube_radius, int(num_subdivisions), m);
+    static_assert(sizeof(lvmesh::Vertex) == 32, "tube mesh vertex is 32 bytes");
+    if (vertices) memcpy(vertices, m.vertices.data(), std::min<uint64_t>(vertices_cap, m.vertices.size()) * 32);
+    if (indices) memcpy(indices, m.indices.data(), std::min<uint64_t>(triangles_cap, m.indices.size() / 3) * 12);
+    if (n_vertices) *n_vertices = m.vertices.size();
+    if (n_triangles) *n_triangles = m.indices.size() / 3;
+    if (n_line_points) *n_line_points = m.line_pos.size();
     return LV_OK;
 }
 

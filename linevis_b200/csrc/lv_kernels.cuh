@@ -6,6 +6,7 @@
 #pragma once
 #include "lv_trace.cuh"
 #include "lv_bake.cuh"
+#include "lv_tri.cuh"
 
 namespace lv {
 
@@ -180,6 +181,8 @@ __device__ __forceinline__ void apron_mark_owned(const FrameParams& P, uint32_t 
     P.apron_marks[size_t(y) * P.W + x] = stamp;
 }
 
+// PRIM = 0: analytic capsules (the default); PRIM = 1: the reference's triangulated tubes (lv_tri.cuh)
+template <int PRIM>
 __global__ void __launch_bounds__(kBlockThreads)
 k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* ao, AoHit* hit_list,
                unsigned int* hit_count, Counters* C, unsigned int* apron_mark, unsigned int apron_stamp) {
@@ -215,9 +218,13 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
         camera_ray(P, x, y, xix, xiy, ro, rd);
     }
     HitRec h;
-    hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_stack[threadIdx.x >> 5], steps, isect);
+    TriHitRec th;
+    if (PRIM == 1) hit = bvh_trace_packet_tri(S, valid, ro, rd, 0.0001f, 1000.0f, th, s_stack[threadIdx.x >> 5], steps, isect);
+    else hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_stack[threadIdx.x >> 5], steps, isect);
     if (valid) {
-        if (hit) {
+        if (hit && PRIM == 1) {
+            rec = tri_ao_frame(S, load_tri(S.tris + th.idx), th.u, th.v, P.subdiv_corr, y * P.W + x);   // the shader's barycentric fetch (:213-276)
+        } else if (hit) {
             // analytic stand-in for the barycentric vertex fetch of the triangle-mesh path (:222-276)
             const SegRec s = load_seg(S.segs + h.idx);
             const Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
@@ -458,7 +465,7 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
 constexpr int kLeafQueue = 64;
 constexpr uint32_t kNoHitBits = 0x7F800000u;   // +inf
 
-template <int MIN_BLOCKS, bool BAKE, int STACK>
+template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
               const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
@@ -521,7 +528,7 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
         while (true) {
             // A: one inner-node step for every lane that holds an inner node
             if (cur != kDone && !(cur & kLeafBit)) {
-                const Node64 nd = load_node(S.nodes + cur);
+                const Node64 nd = load_node((PRIM == 1 ? S.tri_nodes : S.nodes) + cur);
                 steps++;
                 float tl, tr;
                 bool hl = box_hit(rb, nd.l0, nd.l1, 0.0f, best, tl);
@@ -560,11 +567,19 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                 r2.d.x = __shfl_sync(0xffffffffu, rq.d.x, owner); r2.d.y = __shfl_sync(0xffffffffu, rq.d.y, owner); r2.d.z = __shfl_sync(0xffffffffu, rq.d.z, owner);
                 r2.dd = __shfl_sync(0xffffffffu, rq.dd, owner);
                 if (lane < n) {
-                    const SegRec s = load_seg(S.segs + (e & kRefMask));
                     isect++;
-                    float t; uint32_t kind;
+                    float t;
+                    bool accepted;
                     // the record's own AABB was the child box tested in its parent (one-record leaves): the acceptance rule's slab test is done
-                    if (capsule_hit(r2, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius) atomicMin(&whit[owner], __float_as_uint(t));
+                    if (PRIM == 1) {
+                        float u, v;
+                        accepted = tri_hit(r2.o, r2.d, load_tri(S.tris + (e & kRefMask)), 0.0f, P.ao_radius, t, u, v);
+                    } else {
+                        const SegRec s = load_seg(S.segs + (e & kRefMask));
+                        uint32_t kind;
+                        accepted = capsule_hit(r2, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius;
+                    }
+                    if (accepted) atomicMin(&whit[owner], __float_as_uint(t));
                     atomicSub(&wpend[owner], 1);
                 }
                 __syncwarp();

@@ -40,11 +40,25 @@ struct __align__(16) AoHit {
     float4 tng;       // surface tangent; baker: as_float(LCG state of this record's first random number)
 };
 
+// 48-byte triangle record of the triangle-tube mode (lv_tri.cuh): three vertex positions, the mesh's vertex indices in the w
+// lanes (as_float), stored in BVH (Morton) order.
+struct __align__(16) TriRec {
+    float4 a, b, c;
+};
+
 struct SceneDev {
     const SegRec* segs;        // [n_seg] BVH order
     const uint32_t* prim_ids;  // [n_seg] BVH order -> caller's segment index
     const Node64* nodes;       // [n_nodes], root = 0
     const SegAux* seg_aux;     // [n_seg] BVH order, or nullptr (no line frames attached)
+    // triangle-tube mode of the AO passes (lv_tri.cuh); all nullptr / 0 unless the tube mesh has been built
+    const TriRec* tris;        // [n_tri] BVH order
+    const uint32_t* tri_ids;   // [n_tri] BVH order -> triangle index of the mesh
+    const Node64* tri_nodes;   // BVH over the triangles, root = 0
+    const float4* tri_vattr;   // per mesh vertex: normal.xyz, as_float(line point index)
+    const float4* tri_line_pos;  // per line point of the mesh: linePosition
+    const float4* tri_line_tan;  // ... lineTangent
+    uint32_t n_tri;
     uint32_t n_seg;
     uint32_t n_nodes;
     float radius;              // lineWidth * 0.5

@@ -201,7 +201,7 @@ class OracleScene:
         self.lib.lvo_scene_set_lines(ctypes.c_void_p(self.h), _p(tangent, ctypes.c_float), _p(normal, ctypes.c_float), ctypes.c_uint64(tangent.shape[0]))
 
     def ao_bake_iteration(self, sampling_locations, frame_number, factors=None, radius=0.1, n_subdiv=8, spp=4, use_distance=True, capped=True,
-                          return_rays=False):
+                          return_rays=False, tube_mesh=None):
         sl = _f32(sampling_locations)
         if factors is None:
             factors = np.zeros(sl.shape[0] * n_subdiv, np.float32)
@@ -211,7 +211,8 @@ class OracleScene:
         rays = np.zeros((sl.shape[0] * n_subdiv * spp, 6), np.float32) if return_rays else None
         self.lib.lvo_ao_bake_iteration(ctypes.c_void_p(self.h), ctypes.byref(bo), ctypes.c_int(int(capped)), _p(sl, ctypes.c_float),
                                        ctypes.c_uint64(sl.shape[0]), ctypes.c_uint32(frame_number), _p(factors, ctypes.c_float), _p(stats, ctypes.c_uint64),
-                                       _p(rays, ctypes.c_float) if return_rays else None)
+                                       _p(rays, ctypes.c_float) if return_rays else None,
+                                       ctypes.c_void_p(tube_mesh.h) if tube_mesh is not None else None)
         st = dict(T=int(stats[0]), I=int(stats[1]), rays=int(stats[2]))
         return (factors, st, rays) if return_rays else (factors, st)
 

@@ -82,6 +82,9 @@ struct SceneX : Scene {
 };
 SceneX& sx(void* h) { return *static_cast<SceneX*>(static_cast<Scene*>(h)); }
 
+// the reference's triangulated tubes + a BVH over the triangles (lvo_tritubes.hpp)
+struct TubeMeshScene { TubeMesh mesh; TriBvh bvh; float lineWidth = 0.0f; };
+
 Uniforms makeUniforms(const Scene& sc, const lv_camera& cam, const lvo_options& o, const float* tf, uint32_t K,
                       float amin, float amax, const float* aoTex) {
     Uniforms u{};
@@ -576,8 +579,10 @@ uint64_t lvo_ao_parametrize(const float* pos, const uint64_t* line_offsets, uint
 // capsules (DESIGN.md rule 5).  factors_inout: n_param * numTubeSubdivisions floats.  stats = {T, I, rays}
 // rays_out (optional, tests): 6 floats (origin, direction) per ray, index (vertex * N + subdivision) * spp + ray.
 void lvo_ao_bake_iteration(void* h, const lvo_bake_options* bo, int capped, const float* samplingLocations, uint64_t n_param,
-                           uint32_t frameNumber, float* ambientOcclusionFactors, uint64_t* stats, float* rays_out) {
+                           uint32_t frameNumber, float* ambientOcclusionFactors, uint64_t* stats, float* rays_out, void* tube_mesh) {
+    // tube_mesh != NULL: trace the AO rays against the reference's triangulated tubes (lvo_tubemesh_create) instead of the capsules
     SceneX& sc = sx(h);
+    const TubeMeshScene* tms = static_cast<const TubeMeshScene*>(tube_mesh);
     const uint32_t numLinePoints = uint32_t(sc.ptPos.size());
     const uint32_t numTubeSubdivisions = bo->num_tube_subdivisions;
     const uint32_t numAmbientOcclusionSamples = bo->samples_per_frame;
@@ -618,7 +623,13 @@ void lvo_ao_bake_iteration(void* h, const lvo_bake_options* bo, int capped, cons
                     ro[0] = rayOrigin.x; ro[1] = rayOrigin.y; ro[2] = rayOrigin.z; ro[3] = rayDirection.x; ro[4] = rayDirection.y; ro[5] = rayDirection.z;
                 }
                 float occlusionFactor = 1.0f;                                            // traceAoRay :167-186
-                if (bo->use_distance) { Hit ah; if (traceClosest(sc, ar, capped != 0, ah, st, false)) occlusionFactor = ah.t / ambientOcclusionRadius; }
+                if (tms) {
+                    TriHit th; uint64_t s2 = 0, i2 = 0;
+                    st.rays++;
+                    if (traceTriangles(tms->bvh, ar.o, ar.d, 0.0f, ambientOcclusionRadius, bo->use_distance == 0, th, s2, i2))
+                        occlusionFactor = bo->use_distance ? th.t / ambientOcclusionRadius : 0.0f;
+                    st.steps += s2; st.isect += i2;
+                } else if (bo->use_distance) { Hit ah; if (traceClosest(sc, ar, capped != 0, ah, st, false)) occlusionFactor = ah.t / ambientOcclusionRadius; }
                 else { if (traceAny(sc, ar, capped != 0, st)) occlusionFactor = 0.0f; }
                 occlusionFactorAccumulated += occlusionFactor;
             }
@@ -668,11 +679,10 @@ float lvo_static_ao_factor(void* h, float strength, float gamma, float fragmentV
 }
 
 // ------------------------------------------------------------------------------------------ triangle-tube RTAO (reference geometry)
-struct TubeMeshScene { TubeMesh mesh; TriBvh bvh; };
-
 // createCappedTriangleTubesRenderDataCPU for polylines (pos, line_offsets[n_lines + 1]); tubeRadius = lineWidth / 2.
 void* lvo_tubemesh_create(const float* pos, const uint64_t* line_offsets, uint64_t n_lines, float tube_radius, int num_circle_subdivisions) {
     TubeMeshScene* t = new TubeMeshScene();
+    t->lineWidth = 2.0f * tube_radius;
     createCappedTriangleTubes(pos, line_offsets, n_lines, tube_radius, num_circle_subdivisions, t->mesh);
     t->bvh.build(t->mesh);
     return t;
@@ -714,7 +724,7 @@ void lvo_render_rtao_triangles(void* h, const lv_camera* cam, const lvo_options*
             float aoFactor = 1.0f;
             TriHit hit;
             RP++;
-            if (traceTriangles(ts.bvh, ro, rd, 0.0001f, 1000.0f, false, hit, steps, isect)) {
+            if (traceTriangles(ts.bvh, ro, rd, 0.0001f, 1000.0f, false, hit, steps, isect, ts.lineWidth)) {
                 PH++;
                 const uint32_t* tri = &m.triangleIndices[3 * size_t(hit.tri)];          // :213-221
                 const vec3 bary = V3(1.0f - hit.u - hit.v, hit.u, hit.v);

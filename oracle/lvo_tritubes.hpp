@@ -332,7 +332,11 @@ inline bool rayTriangle(vec3 o, vec3 d, vec3 p0, vec3 p1, vec3 p2, float tmin, f
     return t >= tmin && t <= tmax;
 }
 
-inline bool traceTriangles(const TriBvh& bvh, vec3 o, vec3 d, float tmin, float tmax, bool anyHit, TriHit& best, uint64_t& steps, uint64_t& isect) {
+// Acceptance (BVH independent, like the capsules'): the ray's [tmin, tmax] meets the triangle's own AABB under the canonical slab
+// test AND Moeller-Trumbore reports t in [tmin, tmax].  cullMargin: closest-hit traversals that care about WHICH triangle ties
+// (primary rays) cull boxes against best + margin so that every tying candidate is seen whatever the tree looks like.
+inline bool traceTriangles(const TriBvh& bvh, vec3 o, vec3 d, float tmin, float tmax, bool anyHit, TriHit& best, uint64_t& steps, uint64_t& isect,
+                           float cullMargin = 0.0f) {
     const RayInv ri = makeRayInv(o, d);
     bool found = false;
     best.t = tmax; best.tri = 0xFFFFFFFFu; best.u = best.v = 0.0f;
@@ -343,14 +347,16 @@ inline bool traceTriangles(const TriBvh& bvh, vec3 o, vec3 d, float tmin, float 
         const TriBvh::Node& nd = bvh.nodes[stack[--sp]];
         float tn;
         steps++;
-        if (!slabTest(ri, nd.bmin, nd.bmax, tmin, best.t, tn)) continue;
+        if (!slabTest(ri, nd.bmin, nd.bmax, tmin, best.t + cullMargin, tn)) continue;
         if (nd.count) {
             for (uint32_t i = 0; i < nd.count; i++) {
                 const uint32_t tri = bvh.order[nd.left + i];
                 const uint32_t* ix = &bvh.mesh->triangleIndices[3 * size_t(tri)];
-                float t, u, v;
+                float t, u, v, own_mn[3], own_mx[3], tn2;
                 isect++;
-                if (rayTriangle(o, d, bvh.mesh->vertexDataList[ix[0]].vertexPosition, bvh.mesh->vertexDataList[ix[1]].vertexPosition,
+                bvh.triBox(tri, own_mn, own_mx);
+                if (slabTest(ri, own_mn, own_mx, tmin, tmax, tn2) &&
+                    rayTriangle(o, d, bvh.mesh->vertexDataList[ix[0]].vertexPosition, bvh.mesh->vertexDataList[ix[1]].vertexPosition,
                                 bvh.mesh->vertexDataList[ix[2]].vertexPosition, tmin, tmax, t, u, v)) {
                     if (!found || t < best.t || (t == best.t && tri < best.tri)) { best = TriHit{t, u, v, tri}; found = true; }
                     if (anyHit) return true;

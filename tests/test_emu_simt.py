@@ -235,3 +235,84 @@ def test_tile_shards_union_is_the_frame(ectx, oracle):
         ectx.set_option("ambient_occlusion_strength", 0.0)
     # without jitter the AO lookup of a tile's border pixels may touch a neighbour shard's texel with weight ~1e-4
     assert np.abs(acc - full).max() < 2e-3 and (acc == full).mean() > 0.98
+
+
+def _tube_scene(ectx, oracle, n_lines=10, n_pts=25, width=0.03):
+    d = scenes.helix_polylines(n_lines, n_pts)
+    sc = ectx.create_scene(d["pos"], d["attr"], d["seg"], width)
+    sc.set_lines(d["pos"], d["tangent"], d["normal"], d["line_offsets"])
+    osc = oracle.scene(d["pos"], d["attr"], d["seg"], width)
+    osc.set_lines(d["tangent"], d["normal"])
+    return d, sc, osc, width
+
+
+@pytest.mark.parametrize("use_distance,jitter,n_sub", [(True, True, 6), (False, False, 6), (True, False, 8)])
+def test_triangle_tube_rtao(ectx, oracle, use_distance, jitter, n_sub):
+    """b200_rtao_geometry = triangles: the AO pass against the reference's own tube mesh (mesh generator on the host, LBVH over the
+    triangles, packet closest hit + barycentric fetch, AO ray stream with the triangle test) equals the oracle's restatement."""
+    d, sc, osc, width = _tube_scene(ectx, oracle)
+    tm = lvo.TubeMesh(oracle, d["pos"], d["line_offsets"], width, n_sub)
+    cam = lv.make_camera(72, 48)
+    ectx.set_new_settings({"b200_rtao_geometry": "triangles", "tube_num_subdivisions": n_sub, "ambient_occlusion_samples_per_frame": 5,
+                           "ambient_occlusion_distance_based": use_distance, "use_jittered_primary_rays": jitter, "ambient_occlusion_radius": 0.3})
+    try:
+        ao, st = ectx.render_rtao(sc, cam, 0)
+        ao2, _ = ectx.render_rtao(sc, cam, 1, out=ao.copy())
+    finally:
+        ectx.set_new_settings({"b200_rtao_geometry": "capsules", "tube_num_subdivisions": 6, "ambient_occlusion_radius": 0.1, "use_jittered_primary_rays": True})
+    opts = lvo.default_options(ao_strength=1.0, ao_spp=5, ao_use_distance=int(use_distance), ao_jitter_primary=int(jitter), ao_radius=0.3,
+                               tube_num_subdivisions=n_sub)
+    ref, ost = tm.render_rtao(cam, opts, 0)
+    ref2, _ = tm.render_rtao(cam, opts, 1, ao=ref.copy())
+    assert st["pixels_hit"] == ost["pixels_hit"] > 80 and st["rays_ao"] == ost["rays_ao"]
+    assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32)) and np.array_equal(ao2.view(np.uint32), ref2.view(np.uint32))
+    # ... and it is a different image than the analytic stand-in's
+    cap, _ = osc.render_rtao(cam, opts, 0)
+    assert np.abs(cap - ref).max() > 0.05
+
+
+def test_triangle_tube_frame_and_prebaker(ectx, oracle):
+    d, sc, osc, width = _tube_scene(ectx, oracle, 8, 21)
+    tm = lvo.TubeMesh(oracle, d["pos"], d["line_offsets"], width, 6)
+    cam = lv.make_camera(64, 40)
+    tf = scenes.standard_transfer_function(opacity=(1.0, 1.0))
+    ectx.set_transfer_function(tf)
+    ectx.set_new_settings({"b200_rtao_geometry": "triangles", "ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 4,
+                           "num_samples_per_frame": 1, "num_accumulated_frames": 1, "ambient_occlusion_radius": 0.2})
+    try:
+        # the tube pass itself stays analytic (as in the reference's analytic-intersection mode); only the AO texture comes from the mesh
+        img, st = ectx.render_tubes(sc, cam, 0)
+        opts = lvo.default_options(ao_strength=1.0, ao_spp=4, ao_radius=0.2)
+        ao, _ = tm.render_rtao(cam, opts, 0)
+        ref, _ = osc.render_tubes(cam, opts, tf, ao_tex=ao)
+        assert np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+        # prebaker: same start frames, rays against the mesh
+        ectx.set_new_settings({"ambient_occlusion_mode": "RTAO (Prebaker)", "b200_prebaker_iterations": 2, "b200_prebaker_samples_per_frame": 3,
+                               "b200_prebaker_subdivisions": 6, "b200_prebaker_param_segment_length": 0.03, "b200_prebaker_radius": 0.2})
+        bw, sl = oracle.ao_parametrize(d["pos"], d["line_offsets"], 0.03)
+        ref_f = None
+        for it in range(2):
+            bst = sc.ao_bake(1)
+            ref_f, ost = osc.ao_bake_iteration(sl, it, factors=ref_f, radius=0.2, n_subdiv=6, spp=3, tube_mesh=tm)
+            assert bst["rays_ao"] == ost["rays"]
+            assert np.array_equal(sc.ao_read()["factors"].reshape(-1).view(np.uint32), ref_f.view(np.uint32)), it
+        capsule_f, _ = osc.ao_bake_iteration(sl, 0, radius=0.2, n_subdiv=6, spp=3)
+        first_f, _ = osc.ao_bake_iteration(sl, 0, radius=0.2, n_subdiv=6, spp=3, tube_mesh=tm)
+        assert not np.array_equal(capsule_f, first_f)
+    finally:
+        ectx.set_new_settings({"b200_rtao_geometry": "capsules", "ambient_occlusion_mode": "RTAO (Screen Space)", "ambient_occlusion_strength": 0.0,
+                               "ambient_occlusion_radius": 0.1})
+
+
+def test_triangle_mode_needs_polylines(ectx):
+    data, width = _helix()
+    sc = ectx.create_scene(*data, width)
+    ectx.set_option("b200_rtao_geometry", "triangles")
+    try:
+        with pytest.raises(lv.LineVisError) as e:
+            ectx.render_rtao(sc, lv.make_camera(32, 24), 0)
+        assert e.value.code == -6 and "lv_scene_set_lines" in str(e.value)
+        with pytest.raises(lv.LineVisError):
+            ectx.set_option("b200_rtao_geometry", "nurbs")
+    finally:
+        ectx.set_option("b200_rtao_geometry", "capsules")

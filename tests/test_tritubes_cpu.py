@@ -79,3 +79,16 @@ def test_analytic_rtao_vs_reference_geometry(oracle):
     assert res[6][0] < 0.01 and res[32][0] < 0.01                  # no bias
     assert res[6][1] < 0.04 and res[32][1] < 0.5 * res[6][1] + 0.005   # per-pixel difference shrinks with the subdivision count
     assert res[6][2] <= res[6][3] and res[6][2] > 0.95 * res[6][3]  # the inscribed hexagon covers slightly fewer pixels than the capsule
+
+
+@pytest.mark.parametrize("n_sub", [4, 6, 9])
+def test_product_tube_mesh_equals_oracle(oracle, n_sub):
+    """lv_tube_mesh (the product's host-side generator, linevis_b200/csrc/lv_tubemesh.hpp) against the oracle's independent restatement:
+    vertices (position, line point, normal, phi) and triangle indices bit for bit, including a polyline that degenerates."""
+    d = scenes.helix_polylines(5, 17)
+    pos = np.concatenate([d["pos"], np.full((3, 3), 0.3, np.float32)])
+    off = np.concatenate([d["line_offsets"], [len(pos)]]).astype(np.uint64)
+    v, t, nl = lv.Context.tube_mesh(pos, off, 0.01, n_sub)
+    ov, ot = lvo.TubeMesh(oracle, pos, off, 0.01, n_sub).arrays()
+    assert nl == 5 * 17 and v.shape[0] == len(ov) and np.array_equal(t, ot)
+    assert np.array_equal(v.view(np.uint32), ov.view(np.uint32).reshape(-1, 8))
