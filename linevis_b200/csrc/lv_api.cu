@@ -40,6 +40,7 @@ struct Options {
     uint32_t bvh_leaf_size = 1;
     uint32_t ao_refill_below = 24;
     uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
+    bool ao_qnodes = false;           // experimental: AO ray stream over 32-byte quantised nodes (k_quantize_nodes, NodeQ); capsules + leaf queue only
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
@@ -106,6 +107,7 @@ struct lv_scene {
     DevBuf<SegAux> seg_aux;                        // per record, BVH order
     std::vector<float> host_pos; std::vector<uint64_t> line_offsets;   // polylines for the (host-side) parametrization
     DevBuf<float> sampling, weights, factors;      // samplingLocations, blending weights, ambientOcclusionFactors
+    DevBuf<NodeQ> qnodes; float q_origin[3] = {0, 0, 0}, q_scale[3] = {1, 1, 1};   // quantised copy of `nodes` (ensure_qnodes)
     // triangle-tube mode of the AO passes (ensure_tube_mesh): the reference's tube mesh + a BVH over its triangles
     DevBuf<TriRec> tris; DevBuf<uint32_t> tri_ids; DevBuf<Node64> tri_nodes; DevBuf<float4> tri_vattr, tri_line_pos, tri_line_tan;
     uint64_t n_tri = 0; uint32_t mesh_subdiv = 0; float tri_build_ms = 0.0f;
@@ -115,6 +117,8 @@ struct lv_scene {
     SceneDev dev() const {
         SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
         s.seg_aux = has_lines ? seg_aux.p : nullptr;
+        s.qnodes = qnodes.p;
+        for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; }
         s.tris = tris.p; s.tri_ids = tri_ids.p; s.tri_nodes = tri_nodes.p; s.tri_vattr = tri_vattr.p;
         s.tri_line_pos = tri_line_pos.p; s.tri_line_tan = tri_line_tan.p; s.n_tri = uint32_t(n_tri);
         s.n_nodes = uint32_t(n_nodes); s.radius = line_width * 0.5f; s.line_width = line_width;
@@ -270,6 +274,21 @@ bool cam_ok(const FrameParams& P) { return P.far_dist > P.near_dist; }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0.0f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// b200_ao_qnodes: the 16-bit quantised copy of the segment BVH's nodes, built on first use
+int ensure_qnodes(lv_ctx* c, lv_scene* sc) {
+    if (sc->qnodes.p || sc->n_nodes == 0) return LV_OK;
+    for (int k = 0; k < 3; k++) {
+        const float ext = sc->bounds[3 + k] - sc->bounds[k];
+        sc->q_origin[k] = sc->bounds[k];
+        sc->q_scale[k] = std::max(ext / 65535.0f * 1.0001f, 1e-30f);   // a little coarser than the exact grid: 65535 steps always reach past the upper bound
+    }
+    LV_CUDA(c, sc->qnodes.ensure(sc->n_nodes));
+    k_quantize_nodes<<<uint32_t((sc->n_nodes + 255) / 256), 256, 0, c->stream>>>(sc->nodes.p, uint32_t(sc->n_nodes), sc->q_origin[0], sc->q_origin[1], sc->q_origin[2],
+                                                                              sc->q_scale[0], sc->q_scale[1], sc->q_scale[2], sc->qnodes.p);
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
 // Triangle-tube mode of the AO passes: generate the reference's tube mesh on the host (lv_tubemesh.hpp, like the reference's
 // createCappedTriangleTubesRenderDataCPU), upload it and build an LBVH over its triangles (lv_tri.cuh), one triangle per leaf.
 // Needs the polylines of lv_scene_set_lines.  Rebuilt when tube_num_subdivisions changes.
@@ -359,6 +378,8 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
         return c->opt.ao_min_blocks >= 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 1>) : launch(k_rtao_rays_q<8, BAKE, 12, 1>);
     const uint32_t stack = c->opt.ao_stack;
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
+    if (queue && c->opt.ao_qnodes && S.qnodes)   // experimental: quantised nodes (default register budget / stack only)
+        return launch(k_rtao_rays_q<8, BAKE, 12, 0, true>);
     const uint32_t mb = c->opt.ao_min_blocks ? c->opt.ao_min_blocks : (queue ? 8u : 9u);   // 0 = measured optimum of the variant
     if (queue) {
         if (mb >= 9) return stack == 8 ? launch(k_rtao_rays_q<9, BAKE, 8>) : stack == 1 ? launch(k_rtao_rays_q<9, BAKE, 1>) : launch(k_rtao_rays_q<9, BAKE, 12>);
@@ -396,6 +417,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     P.frame_number = frame_number;
     const bool tri = c->opt.ao_triangles;
     if (tri) { int trc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)); if (trc) return trc; }
+    else if (c->opt.ao_qnodes) { int qrc = ensure_qnodes(c, const_cast<lv_scene*>(sc)); if (qrc) return qrc; }
     const SceneDev S = sc->dev();
     const uint32_t grid = pixel_grid(c, P);
     if (grid == 0) return LV_OK;
@@ -545,6 +567,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
     if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;
+    if (!o.ao_triangles && o.ao_qnodes && (rc = ensure_qnodes(c, sc))) return rc;
     if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1, o.ao_triangles))) return rc;
     c->rtao_rays_timed = true;
     k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, sc->factors.p);
@@ -681,6 +704,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
+    else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
     else if (k == "b200_rtao_geometry") {
         if (!strcmp(value, "triangles")) o.ao_triangles = true;
         else if (!strcmp(value, "capsules")) o.ao_triangles = false;
@@ -735,6 +759,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
     else if (k == "b200_ao_min_blocks") v = std::to_string(o.ao_min_blocks);
     else if (k == "b200_ao_queue") v = b(o.ao_queue);
+    else if (k == "b200_ao_qnodes") v = b(o.ao_qnodes);
     else if (k == "b200_rtao_geometry") v = o.ao_triangles ? "triangles" : "capsules";
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
@@ -959,6 +984,7 @@ int lv_scene_destroy(lv_scene* s) {
     s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release();
     s->pt_pos.release(); s->pt_tan.release(); s->pt_nrm.release(); s->seg_aux.release();
     s->sampling.release(); s->weights.release(); s->factors.release();
+    s->qnodes.release();
     s->tris.release(); s->tri_ids.release(); s->tri_nodes.release(); s->tri_vattr.release(); s->tri_line_pos.release(); s->tri_line_tan.release();
     delete s;
     return LV_OK;

@@ -221,4 +221,32 @@ __global__ void k_emit_nodes(int n, int leaf_max, const int2* children, const in
     nodes[i] = nd;
 }
 
+// Node64 -> NodeQ (b200_ao_qnodes).  q_min rounds down, q_max rounds up, then both are corrected against the traversal's own
+// dequantisation fma(q, scale, origin) until the quantised box encloses the exact one.
+__device__ __forceinline__ uint32_t quantize_bound(float b, float o, float s, bool up) {
+    float g = (b - o) / s;
+    g = up ? ceilf(g) : floorf(g);
+    int q = int(fminf(fmaxf(g, 0.0f), 65535.0f));
+    if (up) { while (q < 65535 && __fmaf_rn(float(q), s, o) < b) q++; }
+    else { while (q > 0 && __fmaf_rn(float(q), s, o) > b) q--; }
+    return uint32_t(q);
+}
+__global__ void k_quantize_nodes(const Node64* nodes, uint32_t n, float ox, float oy, float oz, float sx, float sy, float sz, NodeQ* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Node64 nd = nodes[i];
+    NodeQ q;
+    const float4 mn[2] = {nd.l0, nd.r0}, mx[2] = {nd.l1, nd.r1};
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        uint32_t* w = q.w + 4 * c;
+        if (mn[c].x == INFINITY) { w[0] = w[1] = w[2] = 0u; w[3] = kAbsentChild; continue; }   // absent child (a point box at +inf in Node64)
+        const uint32_t ax = quantize_bound(mn[c].x, ox, sx, false), ay = quantize_bound(mn[c].y, oy, sy, false), az = quantize_bound(mn[c].z, oz, sz, false);
+        const uint32_t bx = quantize_bound(mx[c].x, ox, sx, true), by = quantize_bound(mx[c].y, oy, sy, true), bz = quantize_bound(mx[c].z, oz, sz, true);
+        w[0] = ax | (ay << 16); w[1] = az | (bx << 16); w[2] = by | (bz << 16);
+        w[3] = __float_as_uint(mn[c].w);
+    }
+    out[i] = q;
+}
+
 }  // namespace lv

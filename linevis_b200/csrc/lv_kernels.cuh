@@ -465,7 +465,8 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
 constexpr int kLeafQueue = 64;
 constexpr uint32_t kNoHitBits = 0x7F800000u;   // +inf
 
-template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0>
+// QN: traverse the 32-byte quantised nodes (NodeQ, lv_types.cuh) instead of Node64 -- experimental, capsules only.
+template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, bool QN = false>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
               const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
@@ -528,12 +529,29 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
         while (true) {
             // A: one inner-node step for every lane that holds an inner node
             if (cur != kDone && !(cur & kLeafBit)) {
-                const Node64 nd = load_node((PRIM == 1 ? S.tri_nodes : S.nodes) + cur);
                 steps++;
                 float tl, tr;
-                bool hl = box_hit(rb, nd.l0, nd.l1, 0.0f, best, tl);
-                bool hr = box_hit(rb, nd.r0, nd.r1, 0.0f, best, tr);
-                const uint32_t cl = __float_as_uint(nd.l0.w), cr = __float_as_uint(nd.r0.w);
+                bool hl, hr;
+                uint32_t cl, cr;
+                if (QN) {
+                    float4 qa, qb;
+                    ldg256(S.qnodes + cur, qa, qb);   // the whole node in one request
+                    const uint32_t w0 = __float_as_uint(qa.x), w1 = __float_as_uint(qa.y), w2 = __float_as_uint(qa.z);
+                    const uint32_t w4 = __float_as_uint(qb.x), w5 = __float_as_uint(qb.y), w6 = __float_as_uint(qb.z);
+                    cl = __float_as_uint(qa.w); cr = __float_as_uint(qb.w);
+                    const float ox = S.q_origin[0], oy = S.q_origin[1], oz = S.q_origin[2], sx = S.q_scale[0], sy = S.q_scale[1], sz = S.q_scale[2];
+                    hl = cl != kAbsentChild &&
+                         box_hit(rb, __fmaf_rn(float(w0 & 0xffffu), sx, ox), __fmaf_rn(float(w0 >> 16), sy, oy), __fmaf_rn(float(w1 & 0xffffu), sz, oz),
+                                 __fmaf_rn(float(w1 >> 16), sx, ox), __fmaf_rn(float(w2 & 0xffffu), sy, oy), __fmaf_rn(float(w2 >> 16), sz, oz), 0.0f, best, tl);
+                    hr = cr != kAbsentChild &&
+                         box_hit(rb, __fmaf_rn(float(w4 & 0xffffu), sx, ox), __fmaf_rn(float(w4 >> 16), sy, oy), __fmaf_rn(float(w5 & 0xffffu), sz, oz),
+                                 __fmaf_rn(float(w5 >> 16), sx, ox), __fmaf_rn(float(w6 & 0xffffu), sy, oy), __fmaf_rn(float(w6 >> 16), sz, oz), 0.0f, best, tr);
+                } else {
+                    const Node64 nd = load_node((PRIM == 1 ? S.tri_nodes : S.nodes) + cur);
+                    hl = box_hit(rb, nd.l0, nd.l1, 0.0f, best, tl);
+                    hr = box_hit(rb, nd.r0, nd.r1, 0.0f, best, tr);
+                    cl = __float_as_uint(nd.l0.w); cr = __float_as_uint(nd.r0.w);
+                }
                 if (hl && hr) {
                     const bool swap = tr < tl;
                     if (sp < kAoStack) { pst.put(sp, swap ? cl : cr, swap ? tl : tr); sp++; }
@@ -566,6 +584,11 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                 r2.o.x = __shfl_sync(0xffffffffu, rq.o.x, owner); r2.o.y = __shfl_sync(0xffffffffu, rq.o.y, owner); r2.o.z = __shfl_sync(0xffffffffu, rq.o.z, owner);
                 r2.d.x = __shfl_sync(0xffffffffu, rq.d.x, owner); r2.d.y = __shfl_sync(0xffffffffu, rq.d.y, owner); r2.d.z = __shfl_sync(0xffffffffu, rq.d.z, owner);
                 r2.dd = __shfl_sync(0xffffffffu, rq.dd, owner);
+                RayBox rb2;
+                if (QN) {   // quantised node boxes are looser than the record's own AABB: the acceptance rule's slab test is done here, with the owner's ray
+                    rb2.ix = __shfl_sync(0xffffffffu, rb.ix, owner); rb2.iy = __shfl_sync(0xffffffffu, rb.iy, owner); rb2.iz = __shfl_sync(0xffffffffu, rb.iz, owner);
+                    rb2.cx = __shfl_sync(0xffffffffu, rb.cx, owner); rb2.cy = __shfl_sync(0xffffffffu, rb.cy, owner); rb2.cz = __shfl_sync(0xffffffffu, rb.cz, owner);
+                }
                 if (lane < n) {
                     isect++;
                     float t;
@@ -577,7 +600,7 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                     } else {
                         const SegRec s = load_seg(S.segs + (e & kRefMask));
                         uint32_t kind;
-                        accepted = capsule_hit(r2, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius;
+                        accepted = (!QN || seg_box_hit(rb2, s, radius, 0.0f, P.ao_radius)) && capsule_hit(r2, s, radius, capped, t, kind) && t >= 0.0f && t <= P.ao_radius;
                     }
                     if (accepted) atomicMin(&whit[owner], __float_as_uint(t));
                     atomicSub(&wpend[owner], 1);

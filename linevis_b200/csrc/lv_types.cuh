@@ -46,11 +46,25 @@ struct __align__(16) TriRec {
     float4 a, b, c;
 };
 
+// 32-byte QUANTISED child-pair node for the AO ray stream (b200_ao_qnodes, experimental): both child boxes on a 16-bit grid over the
+// scene bounds, so that one 256-bit load brings a whole node (the stream is bound by L1 wavefronts: two scattered 32-byte
+// requests per lane-step with Node64).  w[0] = lmin.x | lmin.y << 16, w[1] = lmin.z | lmax.x << 16, w[2] = lmax.y | lmax.z << 16,
+// w[3] = left child word (kAbsentChild if there is none); w[4..7] the same for the right child.  Bounds are dequantised as
+// fma(q, scale, origin) and rounded OUTWARD at build time against exactly that expression, so a quantised box always encloses
+// the exact one: with the canonical slab test an enclosing box is never missed when the enclosed one is hit (rule 2), and the
+// accepted set -- decided by the record's own exact AABB at the leaf -- does not change.
+struct __align__(32) NodeQ {
+    uint32_t w[8];
+};
+constexpr uint32_t kAbsentChild = 0x7FFFFFFDu;
+
 struct SceneDev {
     const SegRec* segs;        // [n_seg] BVH order
     const uint32_t* prim_ids;  // [n_seg] BVH order -> caller's segment index
     const Node64* nodes;       // [n_nodes], root = 0
     const SegAux* seg_aux;     // [n_seg] BVH order, or nullptr (no line frames attached)
+    const NodeQ* qnodes;       // [n_nodes] quantised copy of `nodes` (b200_ao_qnodes), or nullptr
+    float q_origin[3], q_scale[3];
     // triangle-tube mode of the AO passes (lv_tri.cuh); all nullptr / 0 unless the tube mesh has been built
     const TriRec* tris;        // [n_tri] BVH order
     const uint32_t* tri_ids;   // [n_tri] BVH order -> triangle index of the mesh

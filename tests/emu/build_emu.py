@@ -81,11 +81,12 @@ def build(force=False):
     # -Bsymbolic: the library's own cuda* / lv_* definitions win over same-named symbols of the real library / libcudart that may
     # already live in the process (the CPU suite also loads liblinevis_b200.so for the ABI checks)
     cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-DLV_HOST_EMU", "-I" + CUDA_INC, "-I" + os.path.join(HERE, "..", "..", "linevis_b200", "csrc"),
-           "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-attributes", "-Wno-unknown-pragmas",
+           "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
            "-o", OUT, main]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("emulation build failed:\n" + r.stderr[-6000:])
+        errors = [l for l in r.stderr.splitlines() if "error" in l or "Error" in l]
+        raise RuntimeError("emulation build failed:\n" + "\n".join(errors[:40]) + "\n...\n" + r.stderr[-3000:])
     return OUT
 
 

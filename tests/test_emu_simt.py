@@ -316,3 +316,21 @@ def test_triangle_mode_needs_polylines(ectx):
             ectx.set_option("b200_rtao_geometry", "nurbs")
     finally:
         ectx.set_option("b200_rtao_geometry", "capsules")
+
+
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_quantised_nodes(ectx, oracle, use_distance):
+    """b200_ao_qnodes (experimental): the AO ray stream over 32-byte nodes with 16-bit quantised, outward-rounded child boxes gives the
+    same AO image -- the accepted set is decided by the records' exact AABBs, an enclosing box is never missed (DESIGN.md rule 2)."""
+    for data, width in (_random(), _helix(), ((np.array([[-0.2, 0, 0], [0.2, 0.05, 0]], np.float32), np.array([0.1, 0.9], np.float32),
+                                                np.array([[0, 1]], np.uint32)), 0.05)):
+        sc, osc = _pair(ectx, oracle, data, width)
+        cam = lv.make_camera(56, 36)
+        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
+                               "ambient_occlusion_radius": 0.4, "b200_ao_qnodes": True})
+        try:
+            ao, st = ectx.render_rtao(sc, cam, 0)
+        finally:
+            ectx.set_new_settings({"b200_ao_qnodes": False, "ambient_occlusion_radius": 0.1})
+        ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
+        assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))

@@ -134,6 +134,23 @@ def test_rtao_kernel_variants_bit_exact(ctx, oracle, queue, stack, minb, use_dis
     assert st["rays_ao"] == ost["rays_ao"] > 0
 
 
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_quantised_nodes_bit_exact(ctx, oracle, use_distance):
+    """b200_ao_qnodes (experimental, off by default): 32-byte nodes with 16-bit outward-rounded child boxes -- same AO image."""
+    data, width = DATASETS["random"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(120, 80)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 8, "ambient_occlusion_distance_based": use_distance,
+                          "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.3, "b200_ao_qnodes": True})
+    try:
+        ao, st = ctx.render_rtao(sc, cam, 0)
+    finally:
+        ctx.set_new_settings({"b200_ao_qnodes": False, "ambient_occlusion_radius": 0.1})
+    opts = lvo.default_options(ao_strength=1.0, ao_spp=8, ao_use_distance=int(use_distance), ao_jitter_primary=1, ao_radius=0.3)
+    ref, ost = osc.render_rtao(cam, opts, 0)
+    assert st["rays_ao"] == ost["rays_ao"] > 0 and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+
+
 def test_rtao_queue_falls_back_for_multi_record_leaves(ctx, oracle):
     """The leaf-queue kernel relies on one-record leaves; a scene built with larger leaves takes the leaf-vote kernel."""
     data, width = DATASETS["random"]()

@@ -29,6 +29,7 @@ for leaf in args.leaf:
     for kv in args.opt:
         ctx.set_option(*kv.split("=", 1))
     sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
+    # e.g. --opt b200_ao_qnodes=true (quantised nodes), b200_ao_queue=false (leaf-vote kernel), b200_rtao_geometry=triangles (needs set_lines)
     combos = [tuple(int(v) for v in (c.split(":")[2], c.split(":")[3], c.split(":")[0], c.split(":")[1])) for c in args.combo] \
         or list(itertools.product(args.refill, args.vote, args.minb, args.stack))
     for refill, vote, minb, stack in combos:
