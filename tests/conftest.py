@@ -30,7 +30,16 @@ def oracle_ref():
 
 @pytest.fixture(scope="session")
 def ctx():
+    """The context the -m gpu tests run on.  LV_EMU_CTX=1 swaps in the host emulation of the library (tests/emu): the GPU parity tests
+    themselves can then be rehearsed without a GPU (`LV_EMU_CTX=1 pytest -m gpu tests/test_gpu_parity.py`; slow, skip the full-size file)."""
     import linevis_b200 as lv
-    c = lv.Context(0)
+    lib_path = None
+    if os.environ.get("LV_EMU_CTX"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "emu", "build_emu.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        lib_path = mod.build()
+    c = lv.Context(0, lib_path=lib_path)
     yield c
     c.close()
