@@ -266,6 +266,12 @@ int lv_ppll_resolve(lv_ctx* ctx, const lv_camera* cam, uint32_t max_frags, uint3
 int lv_ppll_read(lv_ctx* ctx, uint32_t* frag_counter, uint32_t* start_offset, size_t start_offset_cap,
                  lv_ppll_node* nodes, size_t nodes_cap, uint32_t* padded_w, uint32_t* padded_h);
 
+/* The frame in the reference's own output format: sceneTexture is an RGBA8 UNORM storage image (VulkanRayTracer.cpp:677-679), written
+ * by imageStore of the float colour, i.e. packUnorm4x8 per pixel (round(clamp(c, 0, 1) * 255), x in the lowest byte).  Converts a
+ * device RGBA32F frame (W*H*4 floats, as written by lv_render_tubes / lv_render_ppll; with tile sharding only the owned tiles are
+ * converted) into rgba8_out (W*H uint32, device or host): a quarter of the float frame's read-back bytes for callers that display. */
+int lv_frame_to_rgba8(lv_ctx* ctx, const float* rgba_device, uint32_t width, uint32_t height, uint32_t* rgba8_out);
+
 /* Device synchronisation helper for FFI callers that do not link the CUDA runtime. */
 int lv_synchronize(lv_ctx* ctx);
 

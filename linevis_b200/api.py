@@ -80,6 +80,13 @@ class Context:
     def synchronize(self):
         self._check(self.lib.lv_synchronize(self.h))
 
+    def frame_to_rgba8(self, frame, width, height, out=None):
+        """lv_frame_to_rgba8: device RGBA32F frame -> RGBA8 UNORM (uint32 per pixel, the reference's sceneTexture format)."""
+        if out is None:
+            out = np.zeros((height, width), np.uint32)
+        self._check(self.lib.lv_frame_to_rgba8(self.h, _ptr(frame), width, height, _ptr(out)))
+        return out
+
     # -- peer-memory frame assembly (lv_frame_alloc / lv_ipc_*): returns raw device addresses (ints)
     def frame_alloc(self, width, height):
         p = ctypes.c_void_p()

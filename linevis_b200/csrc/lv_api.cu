@@ -84,6 +84,7 @@ struct lv_ctx {
     DevBuf<uint2> tiles_tmp; std::vector<uint32_t> peer_off; uint32_t peer_w = 0, peer_h = 0, peer_world = 0, peer_tile = 0;
     // frame buffers
     DevBuf<unsigned int> apron_marks; unsigned int apron_stamp = 0;
+    DevBuf<uint32_t> rgba8;
     DevBuf<float4> image; DevBuf<float> ao, occ, depth_mm; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
     uint32_t ao_w = 0, ao_h = 0;
     DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[2..3] = 64-bit ao work counter
@@ -640,6 +641,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (!c) return LV_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->rgba8.release();
     c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -1350,6 +1352,25 @@ int lv_render_ppll(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t
         stats->ms_clear = elapsed(c->ev[6], c->ev[7]);
         stats->ms_total = stats->ms_clear + stats->ms_gather + stats->ms_resolve;
     }
+    return LV_OK;
+}
+
+int lv_frame_to_rgba8(lv_ctx* c, const float* rgba_device, uint32_t W, uint32_t H, uint32_t* rgba8_out) {
+    if (!c || !rgba_device || !rgba8_out || W == 0 || H == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_frame_to_rgba8: bad argument");
+    if (!is_device_pointer(rgba_device) || (reinterpret_cast<uintptr_t>(rgba_device) & 15)) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_frame_to_rgba8: the float frame must be a 16-byte aligned device pointer");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    lv_camera cam;
+    memset(&cam, 0, sizeof(cam));
+    cam.width = W; cam.height = H;
+    FrameParams P;
+    int rc = make_params(c, nullptr, &cam, 0, P);
+    if (rc) return rc;
+    const bool dev = is_device_pointer(rgba8_out);
+    uint32_t* dst = rgba8_out;
+    if (!dev) { LV_CUDA(c, c->rgba8.ensure(size_t(W) * H)); dst = c->rgba8.p; }
+    if (P.n_tiles) k_frame_to_rgba8<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, reinterpret_cast<const float4*>(rgba_device), dst);
+    LV_CUDA(c, cudaGetLastError());
+    if (!dev && (rc = deliver(c, dst, rgba8_out, W, H, 4))) return rc;
     return LV_OK;
 }
 

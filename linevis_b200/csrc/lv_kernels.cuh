@@ -1034,6 +1034,14 @@ k_ppll_resolve_binned(const __grid_constant__ FrameParams P, const uint32_t* hea
     if (lane == 0 && mx) atomicMax(&C->max_depth_complexity, mx);
 }
 
+// RGBA32F frame -> RGBA8 UNORM (the reference's sceneTexture format), owned tiles only
+__global__ void k_frame_to_rgba8(const __grid_constant__ FrameParams P, const float4* image, uint32_t* out) {
+    uint32_t x, y;
+    if (!thread_pixel(P, x, y)) return;
+    const float4 c = image[size_t(y) * P.W + x];
+    out[size_t(y) * P.W + x] = pack_unorm4x8(v4(c.x, c.y, c.z, c.w));
+}
+
 // ------------------------------------------------------------------------------------------------
 // tile pack / unpack around the multi-GPU framebuffer gather
 __global__ void k_pack_tiles(const float4* image, uint32_t W, uint32_t H, const uint2* tiles, uint32_t tile_size, float4* packed) {

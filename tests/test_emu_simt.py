@@ -334,3 +334,32 @@ def test_rtao_quantised_nodes(ectx, oracle, use_distance):
             ectx.set_new_settings({"b200_ao_qnodes": False, "ambient_occlusion_radius": 0.1})
         ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+
+
+def test_frame_to_rgba8_and_library_owned_frames(ectx, oracle):
+    """lv_frame_alloc / lv_frame_to_rgba8: rendering into a library-owned device frame and reading it back in the reference's
+    RGBA8 UNORM output format (packUnorm4x8 per pixel); with a tile shard only the owned tiles are converted."""
+    data, width = _helix()
+    sc = ectx.create_scene(*data, width)
+    cam = lv.make_camera(80, 48)
+    ectx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.4, 1.0)))
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+    img, _ = ectx.render_tubes(sc, cam)
+    frame = ectx.frame_alloc(80, 48)
+    try:
+        ectx.render_tubes(sc, cam, 0, out=frame, stats=False)
+        got = ectx.frame_to_rgba8(frame, 80, 48)
+        q = np.floor(np.clip(img, np.float32(0), np.float32(1)) * np.float32(255) + np.float32(0.5)).astype(np.uint32)
+        want = q[..., 0] | (q[..., 1] << 8) | (q[..., 2] << 16) | (q[..., 3] << 24)
+        assert np.array_equal(got, want) and len(np.unique(got)) > 20
+        ectx.set_tile_shard(1, 2, 16)
+        part = ectx.frame_to_rgba8(frame, 80, 48, out=np.zeros((48, 80), np.uint32))
+        owned = np.zeros((48, 80), bool)
+        for tx, ty in ectx.owned_tiles(80, 48):
+            owned[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16] = True
+        assert np.array_equal(part[owned], want[owned]) and (part[~owned] == 0).all()
+        with pytest.raises(lv.LineVisError):
+            ectx.frame_to_rgba8(img, 80, 48)          # a host float frame is refused
+    finally:
+        ectx.set_tile_shard(0, 1, 64)
+        ectx.frame_free(frame)
