@@ -292,3 +292,25 @@ def test_depth_cue_range_known_answer(oracle):
     # nothing in the frustum: the neutral element (far, near) of the reduction survives
     sc2 = oracle.scene(pos[2:], np.zeros(2, np.float32), np.array([[0, 1]], np.uint32), 0.01)
     assert sc2.depth_range(cam) == (100.0, np.float32(0.01))
+
+
+def test_oracle_matches_committed_regression_vectors():
+    """tests/golden/oracle_vectors.npz (written by tests/golden/make_oracle_vectors.py): the oracle recomputes every frozen output bit
+    for bit -- intersections, polyline frames / parametrization, the tube mesh, closest hits, both AO images, shaded frames (screen-space
+    and prebaked AO), baked factors, PPLL counts and the resolved frame."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(here, "golden", "make_oracle_vectors.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    frozen = np.load(os.path.join(here, "golden", "oracle_vectors.npz"))
+    assert set(frozen.files) == set(now)
+    for k in frozen.files:
+        a, b = np.ascontiguousarray(now[k]), np.ascontiguousarray(frozen[k])
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        if a.dtype.kind == "f":     # bit-exact, NaN (0/0 of an all-transparent PPLL list) matched by position
+            nan = np.isnan(a)
+            assert np.array_equal(nan, np.isnan(b)) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32)), k
+        else:
+            assert np.array_equal(a, b), k

@@ -92,3 +92,37 @@ def test_product_tube_mesh_equals_oracle(oracle, n_sub):
     ov, ot = lvo.TubeMesh(oracle, pos, off, 0.01, n_sub).arrays()
     assert nl == 5 * 17 and v.shape[0] == len(ov) and np.array_equal(t, ot)
     assert np.array_equal(v.view(np.uint32), ov.view(np.uint32).reshape(-1, 8))
+
+
+def test_tube_mesh_known_answer_straight_line(oracle):
+    """Hand-derived from the reference's algorithm: a straight polyline along +x.  The first normal is the Gram-Schmidt of the
+    fallback axis (0,1,0) (the start axis (1,0,0) is parallel to the tangent, Tubes.cpp:57-64), the binormal is t x n = (0,0,1), ring
+    vertex k sits at centre + r (cos(2 pi k/N) n + sin(2 pi k/N) b) (Tubes.cpp:35-52 rotates by tan/cos steps), the start cap's pole
+    at p0 - r t, the end cap's pole at p_last + r t (CappedTriangleTubesCPU.cpp:341-361)."""
+    n_sub, r = 8, 0.05
+    pos = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0]], np.float32)
+    for v, t in (lvo.TubeMesh(oracle, pos, [0, 3], 2 * r, n_sub).arrays(), None):
+        break
+    pv, pt, nl = lv.Context.tube_mesh(pos, [0, 3], 2 * r, n_sub)
+    assert nl == 3 and np.array_equal(pv.view(np.uint32), v.view(np.uint32).reshape(-1, 8)) and np.array_equal(pt, t)
+    n_lat = n_sub // 2
+    cap_v = n_sub * (n_lat - 1) + 1
+    ring = v[cap_v:cap_v + 3 * n_sub]
+    k = np.arange(n_sub)
+    for i in range(3):
+        want = np.stack([np.full(n_sub, float(i)), r * np.cos(2 * np.pi * k / n_sub), r * np.sin(2 * np.pi * k / n_sub)], axis=1)
+        np.testing.assert_allclose(ring["position"][i * n_sub:(i + 1) * n_sub], want, atol=2e-7)
+        assert (ring["line_point"][i * n_sub:(i + 1) * n_sub] == i).all()
+        np.testing.assert_allclose(ring["phi"][i * n_sub:(i + 1) * n_sub], 2 * np.pi * k / n_sub, atol=1e-6)
+    np.testing.assert_allclose(ring["normal"][:, 0], 0.0, atol=1e-6)
+    np.testing.assert_allclose(v["position"][0], [-r, 0, 0], atol=1e-7)                 # start cap pole
+    np.testing.assert_allclose(v["position"][-1], [2 + r, 0, 0], atol=1e-7)             # end cap pole (last vertex written)
+    assert v["line_point"][0] == 0x80000000 and v["line_point"][-1] == (2 | 0x80000000)
+    # every cap vertex lies on its end sphere, outside the tube's extent along the axis
+    start, end = v[:cap_v], v[cap_v + 3 * n_sub:]
+    np.testing.assert_allclose(np.linalg.norm(start["position"] - pos[0], axis=1), r, rtol=1e-5)
+    np.testing.assert_allclose(np.linalg.norm(end["position"] - pos[2], axis=1), r, rtol=1e-5)
+    assert (start["position"][:, 0] < 0).all() and (end["position"][:, 0] > 2).all()
+    # side quads: triangle (a, b, c) of ring i / i+1 uses vertices j, j+1 of ring i and j+1 of ring i+1
+    first_side = t[cap_v and (n_sub * (n_lat - 1) * 2 + n_sub)]
+    assert list(first_side) == [cap_v, cap_v + 1, cap_v + n_sub + 1]
