@@ -222,6 +222,13 @@ int lv_tube_mesh(const float* pos_xyz, const uint64_t* line_offsets, uint64_t n_
  * b200_prebaker_samples_per_frame (4), b200_prebaker_subdivisions (8), b200_prebaker_param_segment_length (0.001),
  * b200_prebaker_radius (0.1), b200_prebaker_distance_based (true).  stats: rays_ao / ao_traversal_steps / ao_intersections. */
 int lv_ao_bake(lv_ctx* ctx, lv_scene* scene, uint32_t n_iterations, lv_stats* stats);
+/* Multi-GPU baking (new; the reference bakes on one GPU): the parametrization vertices are independent, so rank r bakes the slice
+ * [first_vertex, first_vertex + n_vertices) (n_vertices == 0: everything from first_vertex) with the same settings and the same
+ * iteration count as the other ranks and the ranks then exchange their slices of the factor buffer (lv_ao_factors gives the
+ * device buffer, index subdivision + n_subdiv * vertex, n_floats = n_param_vertices * n_subdiv): any collective or peer copy will
+ * do, linevis_b200/sharding.py::exchange_baked_slices broadcasts each rank's slice.  The result is bit-identical to a one-GPU bake. */
+int lv_ao_set_vertex_range(lv_scene* scene, uint64_t first_vertex, uint64_t n_vertices);
+int lv_ao_factors(lv_scene* scene, float** device_factors, uint64_t* n_floats);
 /* Restart baking from iteration 0 (startAmbientOcclusionBaking: numIterations = 0). */
 int lv_ao_bake_reset(lv_scene* scene);
 /* Host copies of the baker's buffers: ambientOcclusionFactors[n_param * n_subdiv] (index subdivision + n_subdiv * vertex),

@@ -247,6 +247,16 @@ class Scene:
         self.ctx._check(self.ctx.lib.lv_ao_bake(self.ctx.h, self.h, n_iterations, ctypes.byref(st) if stats else None))
         return st.as_dict()
 
+    def ao_set_vertex_range(self, first_vertex, n_vertices=0):
+        """Multi-GPU baking: this context bakes only the parametrization vertices [first_vertex, first_vertex + n_vertices)."""
+        self.ctx._check(self.ctx.lib.lv_ao_set_vertex_range(self.h, int(first_vertex), int(n_vertices)))
+
+    def ao_factors_ptr(self):
+        """(device address, number of floats) of the baked factor buffer, for the slice exchange between ranks."""
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self.ctx._check(self.ctx.lib.lv_ao_factors(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
     def ao_bake_reset(self):
         self.ctx._check(self.ctx.lib.lv_ao_bake_reset(self.h))
 

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "lv_scene_copy_bvh", "lv_render_tubes", "lv_render_ppll", "lv_trace_primary", "lv_render_rtao", "lv_ppll_clear",
     "lv_ppll_gather", "lv_ppll_resolve", "lv_ppll_read", "lv_synchronize",
     "lv_scene_set_lines", "lv_ao_parametrize", "lv_ao_bake", "lv_ao_bake_reset", "lv_ao_read",
-    "lv_frame_alloc", "lv_frame_free", "lv_ipc_export", "lv_ipc_open", "lv_ipc_close", "lv_tube_mesh", "lv_frame_to_rgba8",
+    "lv_frame_alloc", "lv_frame_free", "lv_ipc_export", "lv_ipc_open", "lv_ipc_close", "lv_tube_mesh", "lv_frame_to_rgba8", "lv_ao_set_vertex_range", "lv_ao_factors",
 ]
 
 
@@ -101,6 +101,8 @@ def load_library(path=LIB_PATH):
     L.lv_ppll_resolve.argtypes = [vp, P(LvCamera), u32, u32, vp, P(LvStats)]
     L.lv_ppll_read.argtypes = [vp, P(u32), vp, ctypes.c_size_t, vp, ctypes.c_size_t, P(u32), P(u32)]
     L.lv_synchronize.argtypes = [vp]
+    L.lv_ao_set_vertex_range.argtypes = [vp, u64, u64]
+    L.lv_ao_factors.argtypes = [vp, P(vp), P(u64)]
     L.lv_frame_to_rgba8.argtypes = [vp, vp, u32, u32, vp]
     L.lv_tube_mesh.argtypes = [vp, vp, u64, f32, u32, vp, u64, vp, u64, P(u64), P(u64), P(u64)]
     L.lv_frame_alloc.argtypes = [vp, u32, u32, P(vp)]

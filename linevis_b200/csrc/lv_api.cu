@@ -113,6 +113,7 @@ struct lv_scene {
     DevBuf<TriRec> tris; DevBuf<uint32_t> tri_ids; DevBuf<Node64> tri_nodes; DevBuf<float4> tri_vattr, tri_line_pos, tri_line_tan;
     uint64_t n_tri = 0; uint32_t mesh_subdiv = 0; float tri_build_ms = 0.0f;
     uint32_t n_param = 0, param_subdiv = 0, bake_done = 0;
+    uint64_t bake_first = 0, bake_count = 0;       // slice of parametrization vertices baked here (count 0 = all), lv_ao_set_vertex_range
     float param_len = 0.0f;
     bool has_lines = false;
     SceneDev dev() const {
@@ -551,7 +552,10 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     int rc = ensure_parametrization(c, sc);
     if (rc) return rc;
     const Options& o = c->opt;
-    const size_t n_rec = size_t(sc->n_param) * o.bake_subdiv;
+    const uint64_t first = std::min<uint64_t>(sc->bake_first, sc->n_param);
+    const uint64_t count = sc->bake_count ? std::min<uint64_t>(sc->bake_count, sc->n_param - first) : sc->n_param - first;
+    if (count == 0) { sc->bake_done++; return LV_OK; }   // an empty slice (more ranks than vertices) still takes part in the iteration count
+    const size_t n_rec = size_t(count) * o.bake_subdiv;
     LV_CUDA(c, c->ao_hits.ensure(n_rec));
     LV_CUDA(c, c->occ.ensure(n_rec * o.bake_spp));
     LV_CUDA(c, c->small.ensure(4));
@@ -561,6 +565,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     B.pt_pos = sc->pt_pos.p; B.pt_tan = sc->pt_tan.p; B.pt_nrm = sc->pt_nrm.p; B.sampling = sc->sampling.p;
     B.n_line_pts = uint32_t(sc->n_pt); B.n_param = sc->n_param; B.n_subdiv = o.bake_subdiv; B.spp = o.bake_spp;
     B.frame_number = sc->bake_done; B.line_radius = sc->line_width * 0.5f;
+    B.first_vertex = uint32_t(first); B.n_vertices = uint32_t(count);
     FrameParams P;
     memset(&P, 0, sizeof(P));
     P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
@@ -1080,6 +1085,24 @@ int lv_ao_bake(lv_ctx* c, lv_scene* s, uint32_t n_iterations, lv_stats* stats) {
         stats->ms_rtao_rays = ms_rays;
         stats->ms_total = stats->ms_rtao;
     }
+    return LV_OK;
+}
+
+int lv_ao_set_vertex_range(lv_scene* s, uint64_t first_vertex, uint64_t n_vertices) {
+    if (!s) return LV_ERR_INVALID_ARGUMENT;
+    s->bake_first = first_vertex; s->bake_count = n_vertices;
+    return LV_OK;
+}
+
+int lv_ao_factors(lv_scene* s, float** device_factors, uint64_t* n_floats) {
+    if (!s || !s->ctx || !device_factors) return LV_ERR_INVALID_ARGUMENT;
+    lv_ctx* c = s->ctx;
+    if (!s->has_lines) return fail(c, LV_ERR_STATE, "lv_ao_factors: no line frames attached (lv_scene_set_lines)");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_parametrization(c, s);
+    if (rc) return rc;
+    *device_factors = s->factors.p;
+    if (n_floats) *n_floats = uint64_t(s->n_param) * s->param_subdiv;
     return LV_OK;
 }
 

@@ -22,6 +22,7 @@ struct BakeParams {
     const float* sampling;     // [n_param] samplingLocations (VulkanAmbientOcclusionBaker.cpp:594-612)
     uint32_t n_line_pts, n_param, n_subdiv, spp, frame_number;
     float line_radius;
+    uint32_t first_vertex, n_vertices;   // the slice of parametrization vertices this context bakes (multi-GPU: lv_ao_set_vertex_range)
 };
 
 LV_DEV Vec3 mix3_(Vec3 a, Vec3 b, float t) { return v3(mixf_(a.x, b.x, t), mixf_(a.y, b.y, t), mixf_(a.z, b.z, t)); }
@@ -82,9 +83,9 @@ LV_DEV SegAux make_seg_aux(uint2 idx, const float4* pt_nrm) {
 
 #if !defined(LV_HOST_EMU) || defined(LV_HOST_EMU_SIMT)
 __global__ void k_bake_setup(const __grid_constant__ BakeParams B, AoHit* records) {
-    const uint32_t total = B.n_param * B.n_subdiv;
+    const uint32_t total = B.n_vertices * B.n_subdiv;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-        records[i] = bake_record(B, i / B.n_subdiv, i % B.n_subdiv);
+        records[i] = bake_record(B, B.first_vertex + i / B.n_subdiv, i % B.n_subdiv);
 }
 
 __global__ void k_seg_aux(const uint32_t* prim_ids, const uint2* seg_idx, const float4* pt_nrm, uint32_t n_seg, SegAux* aux) {

@@ -140,3 +140,24 @@ class PeerFrame:
         else:
             self.ctx.ipc_close(self.ptr)
         self.ptr = self.local = None
+
+
+# ---- multi-GPU baking of the object-space AO (lv_ao_set_vertex_range / lv_ao_factors) ----------------------------------------------
+def bake_vertex_range(n_param, rank, world):
+    """Slice [first, first + count) of the parametrization vertices rank `rank` bakes: contiguous, as equal as possible."""
+    base, extra = divmod(int(n_param), int(world))
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def exchange_baked_slices(factors, n_param, n_subdiv, rank, world):
+    """factors: flat tensor [n_param * n_subdiv] (device view of lv_ao_factors, or a CPU tensor under gloo) in which this rank has baked
+    its own vertex slice.  After the call every rank holds all slices: rank r's slice is broadcast from r (the slices differ in
+    length, which rules out one all_gather_into_tensor; the payload is a few MB)."""
+    if world == 1:
+        return factors
+    for r in range(world):
+        first, count = bake_vertex_range(n_param, r, world)
+        if count:
+            dist.broadcast(factors[first * n_subdiv:(first + count) * n_subdiv], src=r)
+    return factors

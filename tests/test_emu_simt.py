@@ -363,3 +363,36 @@ def test_frame_to_rgba8_and_library_owned_frames(ectx, oracle):
     finally:
         ectx.set_tile_shard(0, 1, 64)
         ectx.frame_free(frame)
+
+
+def test_prebaker_vertex_slices_union_is_the_full_bake(ectx, oracle):
+    """Multi-GPU baking: three contexts' worth of vertex slices (lv_ao_set_vertex_range), each baked for two iterations, put together
+    equal the one-GPU bake bit for bit; slices leave the other vertices' factors untouched."""
+    from linevis_b200.sharding import bake_vertex_range
+    d = scenes.helix_polylines(6, 17)
+    width = 0.012
+    ectx.set_new_settings({"b200_prebaker_iterations": 2, "b200_prebaker_samples_per_frame": 2, "b200_prebaker_subdivisions": 6,
+                           "b200_prebaker_param_segment_length": 0.03, "b200_prebaker_radius": 0.2})
+    def make():
+        sc = ectx.create_scene(d["pos"], d["attr"], d["seg"], width)
+        sc.set_lines(d["pos"], d["tangent"], d["normal"], d["line_offsets"])
+        return sc
+    full = make()
+    full.ao_bake(0)
+    want = full.ao_read()
+    n_param = want["n_param"]
+    assert want["iterations_done"] == 2 and n_param > 20
+    merged = np.zeros_like(want["factors"])
+    rays = 0
+    for r in range(3):
+        first, count = bake_vertex_range(n_param, r, 3)
+        sc = make()
+        sc.ao_set_vertex_range(first, count)
+        rays += sc.ao_bake(0)["rays_ao"]
+        got = sc.ao_read()["factors"]
+        assert np.array_equal(got[:first], np.zeros_like(got[:first])) and np.array_equal(got[first + count:], np.zeros_like(got[first + count:]))
+        merged[first:first + count] = got[first:first + count]
+    assert rays == 2 * n_param * 6 * 2
+    assert np.array_equal(merged.view(np.uint32), want["factors"].view(np.uint32))
+    assert [bake_vertex_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
+    assert bake_vertex_range(2, 3, 4) == (2, 0)

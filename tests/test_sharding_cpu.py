@@ -94,3 +94,40 @@ def test_two_rank_frame_gather_over_gloo():
         p.join(30)
         assert p.exitcode == 0
     assert all(res)
+
+
+def _bake_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import lvo
+        o = lvo.Oracle("own")
+        d = scenes.helix_polylines(5, 15)
+        osc = o.scene(d["pos"], d["attr"], d["seg"], 0.012)
+        osc.set_lines(d["tangent"], d["normal"])
+        bw, sl = o.ao_parametrize(d["pos"], d["line_offsets"], 0.03)
+        n_param, n_sub = len(sl), 6
+        full, _ = osc.ao_bake_iteration(sl, 0, radius=0.2, n_subdiv=n_sub, spp=2)
+        # this rank "bakes" only its vertex slice (the oracle stands in for the GPU), everything else stays zero
+        first, count = sharding.bake_vertex_range(n_param, rank, world)
+        mine = torch.zeros(n_param * n_sub)
+        mine[first * n_sub:(first + count) * n_sub] = torch.from_numpy(full[first * n_sub:(first + count) * n_sub])
+        sharding.exchange_baked_slices(mine, n_param, n_sub, rank, world)
+        q.put((rank, bool(torch.equal(mine, torch.from_numpy(full)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_baked_slices_exchange_gloo_world3():
+    """Multi-GPU baking, host logic: every rank bakes a contiguous vertex slice, the slices are broadcast, all ranks end with the full
+    factor buffer (world size 3 so that the slices differ in length)."""
+    world, port = 3, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bake_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True), (2, True)]
