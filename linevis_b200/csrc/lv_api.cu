@@ -187,6 +187,10 @@ void padded_size(const lv_ctx* c, uint32_t W, uint32_t H, uint32_t& pw, uint32_t
 int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, FrameParams& P) {
     if (!cam || cam->width == 0 || cam->height == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "camera: width/height must be > 0");
     if (uint64_t(cam->width) * cam->height > 0xFFFFFFFFull) return fail(c, LV_ERR_INVALID_ARGUMENT, "frame too large");
+    // NaN / inf camera matrices would make NaN rays, and NaN passes every slab test of the traversals (also an absent child's): refuse them
+    for (int k = 0; k < 16; k++)
+        if (!std::isfinite(cam->view[k]) || !std::isfinite(cam->proj[k]) || !std::isfinite(cam->inv_view[k]) || !std::isfinite(cam->inv_proj[k]))
+            return fail(c, LV_ERR_INVALID_ARGUMENT, "camera: matrices must be finite");
     int rc = ensure_tiles(c, cam->width, cam->height);
     if (rc) return rc;
     memset(&P, 0, sizeof(P));

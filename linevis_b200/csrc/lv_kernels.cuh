@@ -277,6 +277,8 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
 // precomputing the ray directions in a separate full-utilisation kernel (the refill is not where the time goes).
 // The per-ray result (4 B) goes to occ[r]; sample-ordered summation happens in k_rtao_reduce.
 constexpr uint32_t kDone = 0x7FFFFFFFu;
+// rq.dd = |d|^2 is NaN exactly when a component of the direction is NaN (it cannot be 0 or inf for a normalised direction)
+__device__ __forceinline__ bool ao_ray_valid(const RayQ& rq) { return rq.dd == rq.dd; }
 constexpr int kAoStack = 72;
 
 // BAKE = object-space prebaker (lv_bake.cuh): records are (parametrization vertex, tube subdivision) frames, the ray origin is the
@@ -383,7 +385,9 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                     rq = make_rayq(org, dir);
                     rb = make_raybox(org, dir);
                     best = P.ao_radius; found = false;
-                    sp = 0; cur = 0;                                                 // root
+                    // a ray without a direction (NaN: the start frame of a hit on a zero-length segment has no tangent) hits nothing; it must
+                    // not enter the traversal either -- NaN passes every slab test, including the one of an absent child
+                    sp = 0; cur = ao_ray_valid(rq) ? 0u : kDone;                     // root
                     rays++;
                 }
             }
@@ -518,7 +522,7 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                     rq = make_rayq(org, dir);
                     rb = make_raybox(org, dir);
                     best = P.ao_radius; found = false;
-                    sp = 0; cur = 0;                                                 // root
+                    sp = 0; cur = ao_ray_valid(rq) ? 0u : kDone;                     // root (a NaN ray hits nothing and must not be traversed, see k_rtao_rays)
                     has_ray = true;
                     rays++;
                 }

@@ -396,3 +396,46 @@ def test_prebaker_vertex_slices_union_is_the_full_bake(ectx, oracle):
     assert np.array_equal(merged.view(np.uint32), want["factors"].view(np.uint32))
     assert [bake_vertex_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
     assert bake_vertex_range(2, 3, 4) == (2, 0)
+
+
+_HANG_SCRIPT = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import linevis_b200 as lv
+ctx = lv.Context(0, lib_path=%(lib)r)
+# a zero-length segment next to a regular one that starts in the same point; with leaf size 2 the whole scene is ONE leaf and the root's
+# right child is absent.  A hit on the zero-length segment has no tangent (0/0): its AO rays have NaN directions.
+pos = np.array([[-0.05, -0.13, -0.09], [-0.05, -0.13, -0.09], [-0.05, -0.13, -0.09], [-0.02, -0.17, -0.10]], np.float32)
+data = (pos, np.array([0.1, 0.2, 0.3, 0.4], np.float32), np.array([[0, 1], [2, 3]], np.uint32))
+cam = lv.make_camera(43, 32, eye=(0.037, 0.027, 0.8))
+for leaf, queue in ((2, True), (1, True), (1, False)):
+    ctx.set_option("b200_bvh_leaf_size", leaf)
+    sc = ctx.create_scene(*data, 0.04)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 3, "ambient_occlusion_radius": 0.05, "b200_ao_queue": queue})
+    ao, st = ctx.render_rtao(sc, cam, 0)
+    assert st["pixels_hit"] > 0 and st["rays_ao"] == 3 * st["pixels_hit"] and not np.isnan(ao).any()
+one = (pos[:2], np.array([0.1, 0.2], np.float32), np.array([[0, 1]], np.uint32))     # a scene that is nothing but one zero-length segment
+sc = ctx.create_scene(*one, 0.04)
+ao, st = ctx.render_rtao(sc, cam, 0)
+bad = lv.make_camera(16, 16)
+bad.inv_view[5] = float("nan")
+try:
+    ctx.render_rtao(sc, bad, 0)
+    raise SystemExit("NaN camera accepted")
+except lv.LineVisError as e:
+    assert e.code == -1
+print("ok")
+'''
+
+
+def test_nan_rays_cannot_hang_the_traversal(ectx):
+    """Found by tools/fuzz_emu.py: a hit on a zero-length segment has a 0/0 tangent, its AO rays have NaN directions, and NaN passes every
+    slab test -- also the one of an ABSENT child, whose word 0 points back at the root: an endless loop (on a GPU: a hung kernel) in
+    single-leaf scenes.  Such rays now never enter the traversal (they hit nothing, which is also what the oracle's arithmetic
+    gives), and NaN camera matrices are refused.  Run in a subprocess: a regression would hang, not fail."""
+    import subprocess, sys
+    root = os.path.dirname(HERE)
+    script = _HANG_SCRIPT % {"root": root, "lib": os.path.join(HERE, "emu", "liblinevis_b200_emu.so")}
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

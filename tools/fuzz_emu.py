@@ -14,6 +14,11 @@ from oracle import lvo
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=120)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--start", type=int, default=0, help="first case index (to replay one case: --start I --cases 1)")
+ap.add_argument("--cases", type=int, default=0, help="stop after this many cases (0 = until --seconds)")
+ap.add_argument("--basic", action="store_true", help="skip the accumulation / tile-shard phase")
+ap.add_argument("--case-timeout", type=int, default=120, help="seconds before a case is reported as hanging (SIGALRM, exits)")
+ap.add_argument("--verbose", action="store_true", help="print every case before it runs (a hang then shows its seed)")
 args = ap.parse_args()
 spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "emu", "build_emu.py"))
 mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
@@ -48,18 +53,30 @@ def random_scene(rng):
     return None, (pos, rng.random(2 * n).astype(np.float32), np.arange(2 * n, dtype=np.uint32).reshape(n, 2))
 
 
+import signal
+
+
+def _hang(signum, frame):
+    print("HANG: case %d (seed %d) exceeded %d s" % (it - 1, args.seed * 1000003 + it - 1, args.case_timeout), flush=True)
+    os._exit(3)
+
+
+signal.signal(signal.SIGALRM, _hang)
 t_end = time.time() + args.seconds
-it, bad = 0, 0
-while time.time() < t_end:
+it, bad = args.start, 0
+while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     seed = args.seed * 1000003 + it
     rng = np.random.default_rng(seed)
     it += 1
+    signal.alarm(args.case_timeout)
     d, data = random_scene(rng)
     width = float(rng.choice([0.002, 0.01, 0.04]))
     W, H = int(rng.integers(8, 70)), int(rng.integers(8, 50))
     eye = (float(rng.normal(0, 0.1)), float(rng.normal(0, 0.1)), float(rng.choice([0.3, 0.8, 1.5])))
     cam = lv.make_camera(W, H, eye=eye)
     leaf = int(rng.choice([1, 1, 2, 4]))
+    if args.verbose:
+        print("case %d seed %d: n_seg %d, %dx%d, width %g, eye %s" % (it - 1, seed, data[2].shape[0], W, H, width, eye), flush=True)
     ctx.set_option("b200_bvh_leaf_size", leaf)
     sc = ctx.create_scene(*data, width); osc = o.scene(*data, width)
     ctx.set_option("b200_bvh_leaf_size", 1)
@@ -75,16 +92,24 @@ while time.time() < t_end:
     opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(dist), ao_jitter_primary=int(jit), ao_radius=radius,
                                use_capped_tubes=int(capped), use_halos=int(halos))
     fails = []
+    if args.verbose:
+        print("   phase primary", flush=True)
     hits, _ = ctx.trace_primary(sc, cam); ref, _ = osc.trace_primary(cam, opts)
     if not (np.array_equal(bits(hits["t"]), bits(ref["t"])) and np.array_equal(hits["prim"], ref["prim"]) and np.array_equal(hits["kind"], ref["kind"])):
         fails.append("primary")
+    if args.verbose:
+        print("   phase rtao", flush=True)
     ao, _ = ctx.render_rtao(sc, cam, 0); rao, _ = osc.render_rtao(cam, opts, 0)
     if not same(ao, rao):
         fails.append("rtao")
+    if args.verbose:
+        print("   phase tubes", flush=True)
     img, _ = ctx.render_tubes(sc, cam, 0); rimg, _ = osc.render_tubes(cam, opts, tf, ao_tex=rao)
     if not same(img, rimg):
         fails.append("tubes")
     ctx.set_option("ambient_occlusion_strength", 0.0)
+    if args.verbose:
+        print("   phase ppll", flush=True)
     mf = int(rng.choice([4, 32, 128]))
     mode = int(rng.choice([0, 5]))
     pimg, pst = ctx.render_ppll(sc, cam, max_frags=mf, sort_mode=mode, linked_list_size=200 * W * H)
@@ -114,9 +139,48 @@ while time.time() < t_end:
         if not np.array_equal(bits(sc.ao_read()["factors"].reshape(-1)), bits(rf)):
             fails.append("prebaker")
         ctx.set_option("ambient_occlusion_mode", "RTAO (Screen Space)")
+    # accumulation over frames with jittered multi-sample rays + depth cues; then the same frame from tile shards (AO apron ring)
+    if args.basic:
+        if fails:
+            bad += 1
+            print("MISMATCH seed %d: %s" % (seed, fails), flush=True)
+        sc.close()
+        continue
+    nspf = int(rng.integers(1, 4)); dcs = float(rng.choice([0.0, 0.8]))
+    ctx.set_new_settings({"ambient_occlusion_mode": "RTAO (Screen Space)", "ambient_occlusion_strength": 1.0, "num_samples_per_frame": nspf,
+                          "num_accumulated_frames": 3, "depth_cue_strength": dcs, "b200_ao_qnodes": False})
+    o2 = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(dist), ao_jitter_primary=int(jit), ao_radius=radius,
+                             use_capped_tubes=int(capped), use_halos=int(halos), num_samples_per_frame=nspf, use_jittered_rays=1, depth_cue_strength=dcs)
+    acc = np.zeros((H, W, 4), np.float32); racc = np.zeros((H, W, 4), np.float32); rao2 = np.zeros((H, W), np.float32)
+    for f in range(2):
+        acc, _ = ctx.render_tubes(sc, cam, f, out=acc)
+        rao2, _ = osc.render_rtao(cam, o2, f, ao=rao2)
+        racc, _ = osc.render_tubes(cam, o2, tf, ao_tex=rao2, frame_number=f, rgba=racc)
+    if not same(acc, racc):
+        fails.append("accumulated jittered frame")
+    world = int(rng.integers(2, 4)); ts = int(rng.choice([16, 32]))
+    merged = np.full((H, W, 4), np.nan, np.float32)
+    for r in range(world):
+        c2 = lv.Context(0, lib_path=mod.build())
+        c2.set_transfer_function(tf)
+        c2.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": dist, "use_jittered_primary_rays": jit,
+                             "ambient_occlusion_radius": radius, "use_capped_tubes": capped, "use_halos": halos, "ambient_occlusion_strength": 1.0,
+                             "num_samples_per_frame": nspf, "num_accumulated_frames": 3, "depth_cue_strength": dcs})
+        c2.set_tile_shard(r, world, ts)
+        s2 = c2.create_scene(*data, width)
+        part = np.full((H, W, 4), np.nan, np.float32)
+        part, _ = c2.render_tubes(s2, cam, 0, out=part)
+        m = ~np.isnan(part[..., 0])
+        merged[m] = part[m]
+        s2.close(); c2.close()
+    first, _ = ctx.render_tubes(sc, cam, 0)
+    if np.isnan(merged).any() or not same(merged, first):
+        fails.append("tile shards (world %d, tile %d)" % (world, ts))
+    ctx.set_new_settings({"num_samples_per_frame": 1, "num_accumulated_frames": 1, "depth_cue_strength": 0.0})
     if fails:
         bad += 1
         print("MISMATCH seed %d: %s  (n_seg %d, %dx%d, width %g, leaf %d, spp %d dist %s jit %s radius %g queue %s stack %d qn %s capped %s)" %
               (seed, fails, data[2].shape[0], W, H, width, leaf, spp, dist, jit, radius, queue, stack, qn, capped), flush=True)
     sc.close()
-print("fuzz: %d cases, %d mismatching" % (it, bad))
+signal.alarm(0)
+print("fuzz: %d cases, %d mismatching" % (it - args.start, bad))
