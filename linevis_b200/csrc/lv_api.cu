@@ -331,7 +331,9 @@ int ensure_tube_mesh(lv_ctx* c, lv_scene* sc) {
     LV_TRI(cudaMemcpyAsync(sc->tri_line_tan.p, ltan.data(), 16 * nl, cudaMemcpyHostToDevice, st));
     k_tri_vertex_attr<<<uint32_t(std::min<size_t>((nv + 255) / 256, 65535)), 256, 0, st>>>(d_vnrm.p, d_vline.p, uint32_t(nv), sc->tri_vattr.p);
     LV_TRI(bounds.ensure(6)); LV_TRI(keys.ensure(n)); LV_TRI(keys2.ensure(n)); LV_TRI(vals.ensure(n));
-    LV_TRI(sc->tri_ids.ensure(n)); LV_TRI(sc->tris.ensure(n));
+    LV_TRI(sc->tri_ids.ensure(size_t(n) + 1)); LV_TRI(sc->tris.ensure(size_t(n) + 1));   // + the dummy record of an absent child (k_emit_nodes)
+    LV_TRI(cudaMemsetAsync(sc->tris.p + n, 0xFF, sizeof(TriRec), st));
+    LV_TRI(cudaMemsetAsync(sc->tri_ids.p + n, 0xFF, 4, st));
     k_init_bounds<<<1, 32, 0, st>>>(bounds.p);
     k_tri_bounds<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_vpos.p, d_idx.p, uint32_t(n), bounds.p);
     k_tri_morton<<<(n + 255) / 256, 256, 0, st>>>(d_vpos.p, d_idx.p, uint32_t(n), bounds.p, keys.p, vals.p);
@@ -924,7 +926,9 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
 #define LV_BUILD(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); delete s; return fail(c, e__ == cudaErrorMemoryAllocation ? LV_ERR_OUT_OF_MEMORY : LV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
     LV_BUILD(cudaEventRecord(c->ev[0], st));
     LV_BUILD(bounds.ensure(6)); LV_BUILD(keys.ensure(n)); LV_BUILD(keys2.ensure(n)); LV_BUILD(vals.ensure(n));
-    LV_BUILD(s->prim_ids.ensure(n)); LV_BUILD(s->segs.ensure(n));
+    LV_BUILD(s->prim_ids.ensure(size_t(n) + 1)); LV_BUILD(s->segs.ensure(size_t(n) + 1));   // + the dummy record an absent child refers to (k_emit_nodes)
+    LV_BUILD(cudaMemsetAsync(s->segs.p + n, 0xFF, sizeof(SegRec), st));            // all NaN: never hit
+    LV_BUILD(cudaMemsetAsync(s->prim_ids.p + n, 0xFF, 4, st));
     LV_BUILD(s->seg_idx.ensure(n));   // caller's index pairs, kept for lv_scene_set_lines (8 B / segment)
     LV_BUILD(cudaMemcpyAsync(s->seg_idx.p, d_idx, size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
     k_init_bounds<<<1, 32, 0, st>>>(bounds.p);

@@ -198,8 +198,11 @@ __global__ void k_emit_nodes(int n, int leaf_max, const int2* children, const in
             Node64 nd;
             nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0x80000000u));
             nd.l1 = make_float4(b[3], b[4], b[5], __uint_as_float(1u));
-            nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));   // absent: a point at +inf never passes the slab test
-            nd.r1 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
+            // absent child: a point box at +inf, which no finite ray's slab test passes.  A NaN ray passes EVERY min/max slab test, so the
+            // word must not be an inner-node index (0 would lead back to the root: an endless loop); it references the dummy record the
+            // scene keeps behind its last one (all NaN, never hit) as a one-record leaf.
+            nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0x80000000u | uint32_t(n)));
+            nd.r1 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(1u));
             nodes[0] = nd;
         }
         return;
@@ -210,8 +213,8 @@ __global__ void k_emit_nodes(int n, int leaf_max, const int2* children, const in
         const float* b = boxes;
         nd.l0 = make_float4(b[0], b[1], b[2], __uint_as_float(0x80000000u | ((uint32_t(n) - 1u) << 27)));
         nd.l1 = make_float4(b[3], b[4], b[5], __uint_as_float(uint32_t(n)));
-        nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
-        nd.r1 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0u));
+        nd.r0 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(0x80000000u | uint32_t(n)));   // absent child -> the dummy record (see above)
+        nd.r1 = make_float4(INFINITY, INFINITY, INFINITY, __uint_as_float(1u));
         nodes[0] = nd;
         return;
     }

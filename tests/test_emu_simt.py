@@ -63,11 +63,13 @@ def test_bvh_build_and_primary_hits(ectx, oracle, maker, leaf):
     while todo:
         nd = nodes[todo.pop()]
         for ref_w, cnt, mn in ((nd["lref"], nd["lcount"], nd["lmin"]), (nd["rref"], nd["rcount"], nd["rmin"])):
-            if cnt:
+            if not np.isfinite(mn).all():
+                assert int(ref_w) == (0x80000000 | sc.info()["n_seg"]) and cnt == 1     # absent child -> the dummy record behind the last one
+            elif cnt:
                 first = int(ref_w) & 0x07FFFFFF
                 assert ((int(ref_w) >> 27) & 15) + 1 == int(cnt) <= leaf
                 seen[first:first + int(cnt)] += 1
-            elif np.isfinite(mn).all():
+            else:
                 todo.append(int(ref_w))
     assert (seen == 1).all()
 
@@ -425,6 +427,23 @@ try:
     raise SystemExit("NaN camera accepted")
 except lv.LineVisError as e:
     assert e.code == -1
+# a finite but degenerate camera (all-zero inverse projection): every primary ray has the direction normalize(0) = NaN.  The packet
+# traversals then "hit" every box, the absent child's too -- which is a one-record leaf on an all-NaN dummy record, not a way back
+# to the root: every pass terminates and sees nothing.
+zero = lv.make_camera(24, 16)
+for k in range(16):
+    zero.inv_proj[k] = 0.0
+ctx.set_transfer_function(np.array([[1, 1, 1, 1], [0, 0, 0, 1]], np.float32))
+for leaf in (1, 2):
+    ctx.set_option("b200_bvh_leaf_size", leaf)
+    for d in (data, one):
+        sc = ctx.create_scene(*d, 0.04)
+        hits, st = ctx.trace_primary(sc, zero)
+        assert st["pixels_hit"] == 0
+        ao, st = ctx.render_rtao(sc, zero, 0)
+        img, st = ctx.render_tubes(sc, zero, 0)
+        img, st = ctx.render_ppll(sc, zero, max_frags=8)
+        assert st["frags_generated"] == 0
 print("ok")
 '''
 
