@@ -458,3 +458,13 @@ def test_nan_rays_cannot_hang_the_traversal(ectx):
     script = _HANG_SCRIPT % {"root": root, "lib": os.path.join(HERE, "emu", "liblinevis_b200_emu.so")}
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def test_fuzz_smoke(ectx):
+    """A short fixed-seed run of tools/fuzz_emu.py (random degenerate / duplicated / axis-aligned scenes, random cameras and settings,
+    every pass and kernel variant incl. accumulation and tile shards) -- in a subprocess, because what it guards against includes hangs."""
+    import subprocess, sys
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_emu.py"), "--seed", "3", "--cases", "12", "--seconds", "140"],
+                       capture_output=True, text=True, timeout=170)
+    assert r.returncode == 0 and "12 cases, 0 mismatching" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
