@@ -17,6 +17,7 @@ class Context:
 
     def __init__(self, device=0, stream=None, lib_path=None):
         self.lib = capi.load_library(lib_path) if lib_path else capi.load_library()
+        self.lib_path = lib_path
         h = ctypes.c_void_p()
         rc = self.lib.lv_ctx_create(ctypes.byref(h), int(device), ctypes.c_void_p(stream) if stream else None)
         if rc != capi.LV_OK:

@@ -392,7 +392,13 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, cur != kDone) == 0u) break;
+        if (__ballot_sync(0xffffffffu, cur != kDone) == 0u) {
+            // nobody traverses: the stream is drained, or every ray just fetched was invalid -- those are finished here (nothing hit) and the
+            // warp fetches again (leaving instead would drop their results, and the rest of the stream if this is the last warp running)
+            if (!exhausted && ray_id < total) { occ[ray_id] = 1.0f; ray_id = total; }
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
+            continue;
+        }
 
         // ---- trace until too many lanes of the warp are idle again
         while (true) {

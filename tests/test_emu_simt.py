@@ -418,8 +418,14 @@ for leaf, queue in ((2, True), (1, True), (1, False)):
     ao, st = ctx.render_rtao(sc, cam, 0)
     assert st["pixels_hit"] > 0 and st["rays_ao"] == 3 * st["pixels_hit"] and not np.isnan(ao).any()
 one = (pos[:2], np.array([0.1, 0.2], np.float32), np.array([[0, 1]], np.uint32))     # a scene that is nothing but one zero-length segment
+for queue in (False, True):   # EVERY AO ray is invalid here: each one still has to deliver its result (nothing hit), and the warps have to go on fetching
+    c1 = lv.Context(0, lib_path=%(lib)r)   # a fresh context: its per-ray result buffer holds no results of earlier frames
+    c1.set_new_settings({"ambient_occlusion_samples_per_frame": 3, "ambient_occlusion_radius": 0.05, "b200_ao_queue": queue})
+    s1 = c1.create_scene(*one, 0.04)
+    ao, st = c1.render_rtao(s1, cam, 0)
+    assert st["pixels_hit"] > 0 and st["rays_ao"] == 3 * st["pixels_hit"] and np.array_equal(ao, np.ones_like(ao)), (queue, st, ao.min())
+    s1.close(); c1.close()
 sc = ctx.create_scene(*one, 0.04)
-ao, st = ctx.render_rtao(sc, cam, 0)
 bad = lv.make_camera(16, 16)
 bad.inv_view[5] = float("nan")
 try:

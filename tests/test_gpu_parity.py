@@ -166,6 +166,45 @@ def test_rtao_queue_falls_back_for_multi_record_leaves(ctx, oracle):
     assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("queue", [True, False])
+def test_rtao_degenerate_segments(ctx, oracle, queue):
+    """Zero-length segments (spheres) have no tangent: the AO rays of a hit on one have NaN directions.  They hit nothing (AO 1, as the
+    oracle's arithmetic gives), never enter the traversal, and still deliver a result -- in a scene made of nothing else too, where every
+    ray a warp fetches is invalid.  Mixed with regular and duplicated segments the frame is the oracle's, bit for bit."""
+    cam = lv.make_camera(96, 64)
+    settings = {"ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": False,
+                "ambient_occlusion_radius": 0.1, "b200_ao_queue": queue}
+    pts = np.array([[0.0, 0.0, 0.0], [0.3, 0.2, -0.1], [-0.3, -0.2, 0.1]], np.float32)
+    pos = np.repeat(pts, 2, axis=0)
+    only = (pos, np.linspace(0, 1, 6).astype(np.float32), np.arange(6, dtype=np.uint32).reshape(3, 2))
+    fresh = lv.Context(0, lib_path=ctx.lib_path)   # a fresh per-ray result buffer (no results of earlier frames in it)
+    try:
+        fresh.set_new_settings(settings)
+        sc = fresh.create_scene(*only, 0.08)
+        ao, st = fresh.render_rtao(sc, cam, 0)
+        assert st["pixels_hit"] > 0 and st["rays_ao"] == 4 * st["pixels_hit"]
+        assert np.array_equal(ao, np.ones_like(ao))
+        sc.close()
+    finally:
+        fresh.close()
+    rng = np.random.default_rng(5)
+    n = 120
+    p0 = (rng.random((n, 3)) - 0.5) * 0.8
+    p1 = p0 + rng.standard_normal((n, 3)) * 0.1
+    p0[n // 2:] = p0[:n - n // 2]; p1[n // 2:] = p1[:n - n // 2]       # exact duplicates
+    p1[::5] = p0[::5]                                                  # zero-length
+    pos = np.empty((2 * n, 3), np.float32); pos[0::2], pos[1::2] = p0, p1
+    data = (pos, rng.random(2 * n).astype(np.float32), np.arange(2 * n, dtype=np.uint32).reshape(n, 2))
+    sc, osc = _scene_pair(ctx, oracle, data, 0.04)
+    ctx.set_new_settings(settings)
+    try:
+        ao, st = ctx.render_rtao(sc, cam, 0)
+    finally:
+        ctx.set_option("b200_ao_queue", True)
+    ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=4, ao_use_distance=1, ao_jitter_primary=0, ao_radius=0.1), 0)
+    assert st["rays_ao"] == ost["rays_ao"] > 0 and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("name,ao", [("helix", False), ("helix", True), ("random", True), ("single", False)])
 def test_tubes_parity(ctx, oracle, name, ao):
     data, width = DATASETS[name]()
