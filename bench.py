@@ -246,7 +246,10 @@ def main():
                     help="N > 1: how rank 0 gets the whole frame -- 'peer': every rank's kernels store their tiles straight into rank 0's "
                          "frame over NVLink (lv_frame_alloc / lv_ipc_*), one 1-element all_reduce as frame fence; 'allgather': pack + NCCL "
                          "all_gather + unpack")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="extra lv_set_option settings for A/B runs (e.g. b200_ao_qnodes=true, b200_ppll_reg_sort=true); recorded in config.options")
     args = ap.parse_args()
+    extra_opts = dict(o.split("=", 1) for o in args.opt)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
     ppll_names = [n for n in args.ppll_workload.split(",") if n and n != "none"]
@@ -282,6 +285,7 @@ def main():
         "ambient_occlusion_samples_per_frame": wl["ao_spp"], "ambient_occlusion_iterations": 1, "ambient_occlusion_radius": 0.1,
         "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": True,
         "num_samples_per_frame": 1, "num_accumulated_frames": 1, "use_deterministic_sampling": False})
+    ctx.set_new_settings(extra_opts)
     tile = 64
     if world > 1:
         ctx.set_tile_shard(rank, world, tile)
@@ -399,6 +403,7 @@ def main():
         pctx = lv.Context(local, stream)
         pctx.set_transfer_function(lv.scenes.standard_transfer_function(opacity=(0.1, 0.6)))
         pctx.set_option("ambient_occlusion_strength", 0.0)
+        pctx.set_new_settings(extra_opts)
         if "avg_depth" in pw:
             pctx.set_option("b200_expected_avg_depth_complexity", pw["avg_depth"])
         if world > 1:
@@ -475,7 +480,8 @@ def main():
                                        ("frame assembled on rank 0 by NVLink peer stores from the frame kernels, 1-element all_reduce as fence"
                                         if peer else "1 NCCL all_gather/frame + unpack on rank 0")) if world > 1 else "single GPU",
                        "rays_per_step": tot_rays, "rays_primary": tot_rp, "rays_ao": tot_ra, "T_per_ray": tot_T / tot_rays, "I_per_ray": tot_I / tot_rays,
-                       "scene_upload_and_bvh_build_s": upload_build_s, "bvh_build_ms": info["build_ms"], "bvh_build_ms_first_in_process": first_build_ms},
+                       "scene_upload_and_bvh_build_s": upload_build_s, "bvh_build_ms": info["build_ms"], "bvh_build_ms_first_in_process": first_build_ms,
+                       **({"options": extra_opts} if extra_opts else {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ncu_traffic("k_rtao_rays_q", args.workload) if world == 1 else None, "algorithmic_bytes_per_launch": my_ao_bytes,
                          "kernel": "k_rtao_rays_q", "kernel_ms": k_ms, "peak_source": peak_src,

@@ -44,6 +44,7 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
+    bool ppll_reg_sort = false;         // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory; untimed, see DESIGN 8
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
@@ -715,6 +716,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
+    else if (k == "b200_ppll_reg_sort") o.ppll_reg_sort = parse_bool(value);
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
     else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
@@ -776,6 +778,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_rtao_geometry") v = o.ao_triangles ? "triangles" : "capsules";
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
+    else if (k == "b200_ppll_reg_sort") v = b(o.ppll_reg_sort);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
     return LV_OK;
@@ -1319,10 +1322,14 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
     // All eight modes produce the depth-sorted order; only the priority queue stops blending at alpha >= 0.99
     // (reference LinkedListSort.glsl:217).  See DESIGN.md for the reference's bitonicSort defect.
     const int early_out = (sort_mode == LV_SORT_PRIORITY_QUEUE) ? 1 : 0;
-    if (P.n_tiles && !c->opt.ppll_binned_resolve)
-        k_ppll_resolve<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img,
-                                                                       c->counters.p, nullptr, nullptr);
-    else if (P.n_tiles) {
+    if (P.n_tiles && !c->opt.ppll_binned_resolve) {
+        if (c->opt.ppll_reg_sort)
+            k_ppll_resolve<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img,
+                                                                                 c->counters.p, nullptr, nullptr);
+        else
+            k_ppll_resolve<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img,
+                                                                                  c->counters.p, nullptr, nullptr);
+    } else if (P.n_tiles) {
         const size_t n_own = size_t(P.n_tiles) * c->tile_size * c->tile_size;
         LV_CUDA(c, c->bin_hist.ensure(2 * (size_t(kResolveCap) + 2) + 8));   // hist | offsets | n_sorted[kBinClasses]
         LV_CUDA(c, c->bin_order.ensure(n_own));
@@ -1335,7 +1342,7 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
         // lists longer than 256 keys: cooperative kernel over the head of the order array; the launch covers the worst case,
         // surplus blocks exit on n_sorted[0]
         if (max_frags > 256u)
-            k_ppll_resolve<<<uint32_t((n_own + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
+            k_ppll_resolve<false><<<uint32_t((n_own + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
                 P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, c->bin_order.p, nsort);
         auto smem = [](int maxn, int warps) { return size_t(warps) * maxn * 32 * 8 + 256 * 4; };
         if (!c->binned_attr_set) {

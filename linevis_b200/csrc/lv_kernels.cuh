@@ -836,6 +836,49 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long* s, uint32_
     }
 }
 
+// The same network with the keys in REGISTERS (KPL per lane, n <= 32 * KPL; b200_ppll_reg_sort): a compare-exchange is a pair of
+// selects (partner in the same lane) or a 64-bit shuffle plus a select (partner in another lane) instead of two shared-memory
+// round trips, runtime index arithmetic and a __syncwarp per pass.  Network position p = lane * KPL + r, so the passes with distance
+// < KPL stay inside a lane; the keys are fetched at [r * 32 + lane] (conflict-free; which key starts where is irrelevant to a sort)
+// and come back to [p] in ascending order.  Missing keys are +inf padding.
+template <int KPL>
+__device__ __forceinline__ void warp_bitonic_sort_reg(unsigned long long* s, uint32_t n, uint32_t lane) {
+    unsigned long long k[KPL];
+#pragma unroll
+    for (int r = 0; r < KPL; r++) { const uint32_t e = uint32_t(r) * 32u + lane; k[r] = e < n ? s[e] : ~0ull; }
+#pragma unroll
+    for (int kk = 2; kk <= 32 * KPL; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= KPL) {
+                const uint32_t pl = uint32_t(j / KPL);                                          // partner = lane ^ pl, same register
+                const bool up = kk >= 32 * KPL || (lane & uint32_t(kk / KPL)) == 0u;              // ascending block: (p & kk) == 0
+                const bool keep_min = ((lane & pl) == 0u) == up;
+#pragma unroll
+                for (int r = 0; r < KPL; r++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], int(pl));
+                    k[r] = ((o < k[r]) == keep_min) ? o : k[r];   // equal keys: taking the partner's copy changes nothing
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KPL; r++) {
+                    if ((r & j) == 0) {
+                        const int q = r | j;
+                        const bool up = kk < KPL ? (r & kk) == 0 : (kk >= 32 * KPL || (lane & uint32_t(kk / KPL)) == 0u);
+                        const unsigned long long a = k[r], b = k[q];
+                        const bool sw = (a > b) == up;                // equal keys may swap: no effect
+                        k[r] = sw ? b : a; k[q] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();   // every lane has fetched its keys before any is overwritten
+#pragma unroll
+    for (int r = 0; r < KPL; r++) { const uint32_t p2 = lane * uint32_t(KPL) + uint32_t(r); if (p2 < n) s[p2] = k[r]; }
+}
+
+template <bool REGSORT>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
                uint32_t max_frags, int early_out, float4* image, Counters* C, const uint32_t* order, const unsigned int* n_sorted) {
@@ -890,7 +933,9 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
         for (unsigned m = __ballot_sync(0xffffffffu, sel && c > uint32_t(kResolveInsertionMax)); m; m &= m - 1) {
             const int src = __ffs(m) - 1;
             const uint32_t n = __shfl_sync(0xffffffffu, c, src), base = __shfl_sync(0xffffffffu, excl, src);
-            warp_bitonic_sort(tile + base, n, lane);
+            if (REGSORT && n <= 128u) warp_bitonic_sort_reg<4>(tile + base, n, lane);
+            else if (REGSORT && n <= 256u) warp_bitonic_sort_reg<8>(tile + base, n, lane);
+            else warp_bitonic_sort(tile + base, n, lane);
         }
         __syncwarp();
         if (sel) {

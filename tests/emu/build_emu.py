@@ -82,11 +82,12 @@ def build(force=False):
     # already live in the process (the CPU suite also loads liblinevis_b200.so for the ABI checks)
     cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-DLV_HOST_EMU", "-I" + CUDA_INC, "-I" + os.path.join(HERE, "..", "..", "linevis_b200", "csrc"),
            "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-attributes", "-Wno-unknown-pragmas", "-Wno-subobject-linkage",
-           "-o", OUT, main]
+           "-o", OUT + ".tmp", main]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         errors = [l for l in r.stderr.splitlines() if "error" in l or "Error" in l]
         raise RuntimeError("emulation build failed:\n" + "\n".join(errors[:40]) + "\n...\n" + r.stderr[-3000:])
+    os.replace(OUT + ".tmp", OUT)   # a process that has the previous build mapped keeps its own inode
     return OUT
 
 

@@ -143,20 +143,22 @@ def test_tube_frames(ectx, oracle, mode):
     assert st["pixels_hit"] > 50
 
 
-@pytest.mark.parametrize("binned", [False, True])
+@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort"])
 @pytest.mark.parametrize("sort_mode", ["priority_queue", "bitonic"])
-def test_ppll(ectx, oracle, binned, sort_mode):
-    # dense enough for every list-length class of the resolve kernels (insertion <= 64, warp bitonic above; binned 32 / 64 / 128 / 256)
+def test_ppll(ectx, oracle, variant, sort_mode):
+    # dense enough for every list-length class of the resolve kernels (insertion <= 64, warp bitonic above -- in shared memory, or in
+    # registers with 4 / 8 keys per lane; binned 32 / 64 / 128 / 256)
+    binned = variant == "binned"
     data = scenes.random_segments(5000, 0.35, seed=13)
     sc, osc = _pair(ectx, oracle, data, 0.03)
     cam = lv.make_camera(48, 32)
     tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
     ectx.set_transfer_function(tf)
-    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned})
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned, "b200_ppll_reg_sort": variant == "reg_sort"})
     try:
         img, st = ectx.render_ppll(sc, cam, max_frags=200, sort_mode=sort_mode, linked_list_size=64 * 48 * 32)
     finally:
-        ectx.set_option("b200_ppll_binned_resolve", False)
+        ectx.set_new_settings({"b200_ppll_binned_resolve": False, "b200_ppll_reg_sort": False})
     opts = lvo.default_options()
     g = osc.ppll_gather(cam, opts, tf)
     mine = ectx.ppll_read()

@@ -286,6 +286,32 @@ def test_ppll_resolve_parity(ctx, oracle, mode):
     assert np.array_equal(img[~nan].view(np.uint32), ref_img[~nan].view(np.uint32)), "resolve expected bit-exact vs canonical oracle order"
 
 
+@pytest.mark.parametrize("variant", ["b200_ppll_reg_sort", "b200_ppll_binned_resolve"])
+def test_ppll_resolve_variants_bit_exact(ctx, oracle, variant):
+    """The optional resolve kernels -- warp bitonic sort in registers (4 / 8 keys per lane) and the count-binned one -- give the default
+    kernel's frame bit for bit, on lists deep enough for every length class (a dense scene seen through a small frame)."""
+    data = scenes.random_segments(5000, 0.35, seed=13)
+    sc, osc = _scene_pair(ctx, oracle, data, 0.03)
+    cam = lv.make_camera(96, 64)
+    tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
+    ctx.set_transfer_function(tf)
+    ctx.set_option("ambient_occlusion_strength", 0.0)
+    size = 64 * 96 * 64   # no overflow: which fragments an overflowing buffer drops is a race, in the reference too
+    want, wst = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
+    ctx.set_option(variant, True)
+    try:
+        img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
+    finally:
+        ctx.set_option(variant, False)
+    assert st["frags_dropped"] == wst["frags_dropped"] == 0
+    assert st["frags_sorted"] == wst["frags_sorted"] and st["max_depth_complexity"] == wst["max_depth_complexity"] > 130
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(img), nan) and np.array_equal(img[~nan].view(np.uint32), want[~nan].view(np.uint32))
+    g = osc.ppll_gather(cam, lvo.default_options(), tf, linked_list_size=size)
+    ref, _ = lvo.ppll_resolve(oracle, cam, lvo.default_options(), g["heads"], g["nodes"], 256, lv.SORT_MODES["bitonic"], canonical=True)
+    assert np.array_equal(np.isnan(ref), nan) and np.array_equal(img[~nan].view(np.uint32), ref[~nan].view(np.uint32))
+
+
 def test_ppll_overflow_is_counted_not_fatal(ctx, oracle):
     data, width = DATASETS["helix"]()
     sc, osc = _scene_pair(ctx, oracle, data, width)

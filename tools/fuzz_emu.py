@@ -22,7 +22,8 @@ ap.add_argument("--verbose", action="store_true", help="print every case before 
 args = ap.parse_args()
 spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "emu", "build_emu.py"))
 mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
-ctx = lv.Context(0, lib_path=mod.build())
+LIB = mod.build()   # once: the sources may change under a long run
+ctx = lv.Context(0, lib_path=LIB)
 o = lvo.Oracle("own")
 
 
@@ -112,6 +113,7 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
         print("   phase ppll", flush=True)
     mf = int(rng.choice([4, 32, 128]))
     mode = int(rng.choice([0, 5]))
+    ctx.set_new_settings({"b200_ppll_reg_sort": bool(rng.integers(0, 2)), "b200_ppll_binned_resolve": bool(rng.integers(0, 3) == 0)})
     pimg, pst = ctx.render_ppll(sc, cam, max_frags=mf, sort_mode=mode, linked_list_size=200 * W * H)
     po = lvo.default_options(use_capped_tubes=int(capped), use_halos=int(halos))
     g = osc.ppll_gather(cam, po, tf, linked_list_size=200 * W * H)
@@ -161,7 +163,7 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     world = int(rng.integers(2, 4)); ts = int(rng.choice([16, 32]))
     merged = np.full((H, W, 4), np.nan, np.float32)
     for r in range(world):
-        c2 = lv.Context(0, lib_path=mod.build())
+        c2 = lv.Context(0, lib_path=LIB)
         c2.set_transfer_function(tf)
         c2.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": dist, "use_jittered_primary_rays": jit,
                              "ambient_occlusion_radius": radius, "use_capped_tubes": capped, "use_halos": halos, "ambient_occlusion_strength": 1.0,
