@@ -394,6 +394,30 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     e2e_ms = float(tms.item())
+    # ---- the same step with the frame delivered in the reference's own sceneTexture format (RGBA8 UNORM, lv_frame_to_rgba8): a quarter
+    # of the read-back bytes.  Reported beside `e2e` (which stays the RGBA32F delivery), single GPU only; never fatal.
+    e2e8 = None
+    if world == 1:
+        try:
+            host8 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
+            host8_np = host8.numpy().view(np.uint32)
+
+            def step_e2e8():
+                ctx.render_tubes(scene, cam, 0, out=frame, stats=False)
+                ctx.frame_to_rgba8(frame, W, H, out=host8_np)       # conversion kernel + D2H inside, synchronises
+            for _ in range(2):
+                step_e2e8()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_e2e8()
+            torch.cuda.synchronize()
+            ms8 = (time.perf_counter() - t0) * 1e3 / args.steps
+            e2e8 = {"value": tot_rays / (ms8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms8, "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera),
+                    "d2h_bytes_per_step": W * H * 4, "nonzero_pixels": int(np.count_nonzero(host8_np)),
+                    "note": "lv_render_tubes into a device frame + lv_frame_to_rgba8 into pinned host memory (RGBA8 UNORM, the reference's sceneTexture format)"}
+        except Exception as e:   # noqa: BLE001 -- an optional extra measurement must not cost the bench line
+            e2e8 = {"error": "%s: %s" % (type(e).__name__, e)}
     # bytes read back per step: the whole frame on rank 0 (single GPU, or peer assembly), else every rank's own tiles (rank 0's share is reported)
     d2h = (n_own * tile * tile if (world > 1 and pf is None) else W * H) * 16
 
@@ -495,6 +519,8 @@ def main():
             "clocks": clocks,
         }
         line.update(ppll_results)
+        if e2e8 is not None:
+            line["e2e_rgba8"] = e2e8
         if gather_ms is not None:
             line["config"]["assemble_ms"] = gather_ms          # the frame fence (peer mode) or pack + all_gather + unpack alone, max over ranks
         line["config"]["k_rtao_rays_ms_per_rank"] = k_ms_ranks  # tile-shard load balance of the dominant kernel

@@ -457,3 +457,23 @@ def test_peer_frame_single_process(ctx, oracle):
         pf.close()
         ctx.set_option("ambient_occlusion_strength", 0.0)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_frame_to_rgba8(ctx, oracle):
+    """lv_frame_to_rgba8: the frame in the reference's sceneTexture format (packUnorm4x8 per pixel), from a device frame into host memory."""
+    import torch
+    data, width = DATASETS["helix"]()
+    sc = ctx.create_scene(*data, width)
+    cam = lv.make_camera(160, 100)
+    ctx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.4, 1.0)))
+    ctx.set_option("ambient_occlusion_strength", 0.0)
+    frame = torch.zeros((100, 160, 4), dtype=torch.float32, device="cuda")
+    ctx.render_tubes(sc, cam, 0, out=frame, stats=False)
+    got = ctx.frame_to_rgba8(frame, 160, 100)
+    f = frame.cpu().numpy()
+    q = np.floor(np.clip(f, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint32)   # round(clamp(c, 0, 1) * 255), halves never occur exactly off 0.5 ties
+    want = q[..., 0] | (q[..., 1] << 8) | (q[..., 2] << 16) | (q[..., 3] << 24)
+    assert (np.abs(((got[..., None] >> np.array([0, 8, 16, 24], np.uint32)) & 0xFF).astype(np.int64) - q.astype(np.int64)) <= 1).all()
+    assert (got == want).mean() > 0.999
+    with pytest.raises(lv.LineVisError):
+        ctx.frame_to_rgba8(f, 160, 100)      # a host float frame is refused
