@@ -44,6 +44,7 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
+    uint32_t ppll_resolve_tile = 1024;  // plain resolve: keys per warp in the shared tile (256 / 512 / 1024; raised to hold max_frags)
     bool ppll_reg_sort = false;         // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory; untimed, see DESIGN 8
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
@@ -717,6 +718,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ppll_reg_sort") o.ppll_reg_sort = parse_bool(value);
+    else if (k == "b200_ppll_resolve_tile") { if (u() != 256 && u() != 512 && u() != 1024) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_resolve_tile must be 256, 512 or 1024"); o.ppll_resolve_tile = u(); }
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
     else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
@@ -779,6 +781,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else if (k == "b200_ppll_reg_sort") v = b(o.ppll_reg_sort);
+    else if (k == "b200_ppll_resolve_tile") v = std::to_string(o.ppll_resolve_tile);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
     return LV_OK;
@@ -1323,12 +1326,16 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
     // (reference LinkedListSort.glsl:217).  See DESIGN.md for the reference's bitonicSort defect.
     const int early_out = (sort_mode == LV_SORT_PRIORITY_QUEUE) ? 1 : 0;
     if (P.n_tiles && !c->opt.ppll_binned_resolve) {
-        if (c->opt.ppll_reg_sort)
-            k_ppll_resolve<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img,
-                                                                                 c->counters.p, nullptr, nullptr);
-        else
-            k_ppll_resolve<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img,
-                                                                                  c->counters.p, nullptr, nullptr);
+        // shared key tile per warp: the smallest of 256 / 512 / 1024 that is >= the option and can hold the longest list
+        const uint32_t cap = std::max(c->opt.ppll_resolve_tile, max_frags) <= 256u ? 256u : (std::max(c->opt.ppll_resolve_tile, max_frags) <= 512u ? 512u : 1024u);
+        const uint32_t grid = pixel_grid(c, P);
+#define LV_RESOLVE(RS, CAPV) k_ppll_resolve<RS, CAPV><<<grid, kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, nullptr, nullptr)
+        if (c->opt.ppll_reg_sort) {
+            if (cap == 256u) LV_RESOLVE(true, 256); else if (cap == 512u) LV_RESOLVE(true, 512); else LV_RESOLVE(true, 1024);
+        } else {
+            if (cap == 256u) LV_RESOLVE(false, 256); else if (cap == 512u) LV_RESOLVE(false, 512); else LV_RESOLVE(false, 1024);
+        }
+#undef LV_RESOLVE
     } else if (P.n_tiles) {
         const size_t n_own = size_t(P.n_tiles) * c->tile_size * c->tile_size;
         LV_CUDA(c, c->bin_hist.ensure(2 * (size_t(kResolveCap) + 2) + 8));   // hist | offsets | n_sorted[kBinClasses]

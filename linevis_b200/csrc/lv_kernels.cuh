@@ -878,16 +878,18 @@ __device__ __forceinline__ void warp_bitonic_sort_reg(unsigned long long* s, uin
     for (int r = 0; r < KPL; r++) { const uint32_t p2 = lane * uint32_t(KPL) + uint32_t(r); if (p2 < n) s[p2] = k[r]; }
 }
 
-template <bool REGSORT>
+// CAP: keys per warp in the shared tile (b200_ppll_resolve_tile; must hold the longest list, max_frags <= CAP).  A smaller tile
+// lets more warps live on an SM -- the walk is a dependent pointer chase, so short-list frames are bound by warps in flight.
+template <bool REGSORT, int CAP = kResolveCap>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
                uint32_t max_frags, int early_out, float4* image, Counters* C, const uint32_t* order, const unsigned int* n_sorted) {
-    __shared__ unsigned long long s_keys[kResolveWarps * kResolveCap];
+    __shared__ unsigned long long s_keys[kResolveWarps * CAP];
     __shared__ float s_unorm[256];   // unpackUnorm4x8: float(b) / 255.0f, tabulated once (4 IEEE divisions per fragment otherwise)
     for (uint32_t i = threadIdx.x; i < 256u; i += kBlockThreads) s_unorm[i] = float(i) / 255.0f;
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long* tile = s_keys + warp * kResolveCap;
+    unsigned long long* tile = s_keys + warp * CAP;
     uint32_t x, y;
     bool valid;
     if (order) {   // binned mode: this kernel only takes the first n_sorted[0] pixels of `order` (lists longer than 256 keys)
@@ -907,7 +909,7 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (int(lane) >= o) incl += v; }
         const uint32_t excl = incl - c;
-        const bool sel = c > 0 && incl <= uint32_t(kResolveCap);
+        const bool sel = c > 0 && incl <= uint32_t(CAP);
         if (sel) {
             unsigned long long* mine = tile + excl;
             lv_ppll_node nd = nodes[head];

@@ -143,7 +143,7 @@ def test_tube_frames(ectx, oracle, mode):
     assert st["pixels_hit"] > 50
 
 
-@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort"])
+@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort", "tile256", "reg_sort+tile512"])
 @pytest.mark.parametrize("sort_mode", ["priority_queue", "bitonic"])
 def test_ppll(ectx, oracle, variant, sort_mode):
     # dense enough for every list-length class of the resolve kernels (insertion <= 64, warp bitonic above -- in shared memory, or in
@@ -154,11 +154,12 @@ def test_ppll(ectx, oracle, variant, sort_mode):
     cam = lv.make_camera(48, 32)
     tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
     ectx.set_transfer_function(tf)
-    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned, "b200_ppll_reg_sort": variant == "reg_sort"})
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned, "b200_ppll_reg_sort": "reg_sort" in variant,
+                           "b200_ppll_resolve_tile": 256 if "tile256" in variant else (512 if "tile512" in variant else 1024)})
     try:
         img, st = ectx.render_ppll(sc, cam, max_frags=200, sort_mode=sort_mode, linked_list_size=64 * 48 * 32)
     finally:
-        ectx.set_new_settings({"b200_ppll_binned_resolve": False, "b200_ppll_reg_sort": False})
+        ectx.set_new_settings({"b200_ppll_binned_resolve": False, "b200_ppll_reg_sort": False, "b200_ppll_resolve_tile": 1024})
     opts = lvo.default_options()
     g = osc.ppll_gather(cam, opts, tf)
     mine = ectx.ppll_read()

@@ -286,10 +286,11 @@ def test_ppll_resolve_parity(ctx, oracle, mode):
     assert np.array_equal(img[~nan].view(np.uint32), ref_img[~nan].view(np.uint32)), "resolve expected bit-exact vs canonical oracle order"
 
 
-@pytest.mark.parametrize("variant", ["b200_ppll_reg_sort", "b200_ppll_binned_resolve"])
+@pytest.mark.parametrize("variant", [{"b200_ppll_reg_sort": True}, {"b200_ppll_binned_resolve": True}, {"b200_ppll_resolve_tile": 256},
+                                     {"b200_ppll_reg_sort": True, "b200_ppll_resolve_tile": 512}], ids=lambda v: "+".join(v))
 def test_ppll_resolve_variants_bit_exact(ctx, oracle, variant):
-    """The optional resolve kernels -- warp bitonic sort in registers (4 / 8 keys per lane) and the count-binned one -- give the default
-    kernel's frame bit for bit, on lists deep enough for every length class (a dense scene seen through a small frame)."""
+    """The optional resolve kernels -- warp bitonic sort in registers (4 / 8 keys per lane), smaller shared key tiles, the count-binned one --
+    give the default kernel's frame bit for bit, on lists deep enough for every length class (a dense scene seen through a small frame)."""
     data = scenes.random_segments(5000, 0.35, seed=13)
     sc, osc = _scene_pair(ctx, oracle, data, 0.03)
     cam = lv.make_camera(96, 64)
@@ -298,11 +299,11 @@ def test_ppll_resolve_variants_bit_exact(ctx, oracle, variant):
     ctx.set_option("ambient_occlusion_strength", 0.0)
     size = 64 * 96 * 64   # no overflow: which fragments an overflowing buffer drops is a race, in the reference too
     want, wst = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
-    ctx.set_option(variant, True)
+    ctx.set_new_settings(variant)
     try:
         img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
     finally:
-        ctx.set_option(variant, False)
+        ctx.set_new_settings({"b200_ppll_reg_sort": False, "b200_ppll_binned_resolve": False, "b200_ppll_resolve_tile": 1024})
     assert st["frags_dropped"] == wst["frags_dropped"] == 0
     assert st["frags_sorted"] == wst["frags_sorted"] and st["max_depth_complexity"] == wst["max_depth_complexity"] > 130
     nan = np.isnan(want)
