@@ -66,6 +66,8 @@ def sources():
 
 
 def build(force=False):
+    if os.environ.get("LV_EMU_LIB"):   # a prebuilt variant, e.g. the AddressSanitizer build of tools/emu_asan.sh
+        return os.environ["LV_EMU_LIB"]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(s) <= os.path.getmtime(OUT) for s in sources()):
         return OUT
     os.makedirs(GEN, exist_ok=True)

@@ -125,6 +125,23 @@ inline bool resolve_warp(Block* b, int w) {
     return released;
 }
 
+// LV_EMU_ORDER=reverse|random: the order in which the scheduler runs the lanes of a warp (and the warps of a block) between two
+// rendez-vous points.  Results must not depend on it: a kernel that does has a race the hardware's lockstep execution may hide
+// (e.g. a missing __syncwarp between a shared-memory write and another lane's read).  Default: ascending.
+inline int order_mode() {
+    static const int m = [] { const char* e = std::getenv("LV_EMU_ORDER"); return !e ? 0 : (std::strcmp(e, "reverse") == 0 ? 1 : (std::strcmp(e, "random") == 0 ? 2 : 0)); }();
+    return m;
+}
+inline void make_order(int* perm, int n) {
+    static thread_local uint64_t rng = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < n; i++) perm[i] = order_mode() == 1 ? n - 1 - i : i;
+    if (order_mode() == 2)
+        for (int i = n - 1; i > 0; i--) {
+            rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+            std::swap(perm[i], perm[int(rng % uint64_t(i + 1))]);
+        }
+}
+
 inline void run_block(Block* b) {
     cur_block() = b;
     for (int t = 0; t < b->nthreads; t++) {
@@ -140,12 +157,18 @@ inline void run_block(Block* b) {
     const int nwarps = (b->nthreads + 31) / 32;
     while (true) {
         bool progress = false, all_done = true;
-        for (int w = 0; w < nwarps; w++) {
+        int worder[64];
+        if (nwarps <= 64) make_order(worder, nwarps);
+        for (int wk = 0; wk < nwarps; wk++) {
+            const int w = nwarps <= 64 ? worder[wk] : wk;
             bool again = true;
             while (again) {
                 again = false;
                 const int base = w * 32, n = std::min(32, b->nthreads - base);
-                for (int i = 0; i < n; i++) {
+                int lorder[32];
+                make_order(lorder, n);
+                for (int k = 0; k < n; k++) {
+                    const int i = lorder[k];
                     Lane& l = b->lanes[base + i];
                     while (l.state == RUN) { b->cur = base + i; swapcontext(&b->sched, &l.ctx); progress = true; }
                 }
