@@ -112,6 +112,49 @@ def test_config4_like_fragment_count_is_bvh_independent(random1m):
     assert counts[0] == counts[1]
 
 
+def test_config3_ao_image_is_kernel_independent(random1m):
+    """Config 3 (1 M segments, 1080p, 16 spp): every AO ray-stream kernel -- leaf queue (default), leaf vote, quantised nodes, other
+    stack layouts -- produces the same AO image bit for bit, with the same number of rays."""
+    pos, attr, seg = random1m
+    cam = lv.make_camera(1920, 1080)
+    ctx = lv.Context(0)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 16, "ambient_occlusion_iterations": 1, "ambient_occlusion_distance_based": True,
+                          "use_jittered_primary_rays": True})
+    sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
+    want, wst = ctx.render_rtao(sc, cam, 0)
+    assert wst["rays_ao"] == 16 * wst["pixels_hit"] > 0
+    for variant in ({"b200_ao_queue": False}, {"b200_ao_qnodes": True}, {"b200_ao_stack": 1}, {"b200_ao_queue": False, "b200_ao_stack": 0},
+                    {"b200_ao_stack": 16, "b200_ao_min_blocks": 9}):
+        ctx.set_new_settings(variant)
+        got, st = ctx.render_rtao(sc, cam, 0)
+        ctx.set_new_settings({"b200_ao_queue": True, "b200_ao_qnodes": False, "b200_ao_stack": 12, "b200_ao_min_blocks": 0})
+        assert st["rays_ao"] == wst["rays_ao"], variant
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), variant
+    sc.close(); ctx.close()
+
+
+def test_config4_like_resolve_is_kernel_independent(random1m):
+    """1 M segments, MAX_NUM_FRAGS 256: the resolve variants (in-register sort, smaller key tiles, count-binned) give the default kernel's
+    frame bit for bit on a frame with long lists (no fragment is dropped, so the lists are the same sets in every run)."""
+    pos, attr, seg = random1m
+    cam = lv.make_camera(1280, 720)
+    ctx = lv.Context(0)
+    ctx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.1, 0.6)))
+    ctx.set_option("b200_expected_avg_depth_complexity", 40)
+    sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
+    want, wst = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic")
+    assert wst["frags_dropped"] == 0 and wst["max_depth_complexity"] > 64
+    for variant in ({"b200_ppll_reg_sort": True}, {"b200_ppll_resolve_tile": 256}, {"b200_ppll_reg_sort": True, "b200_ppll_resolve_tile": 512},
+                    {"b200_ppll_binned_resolve": True}):
+        ctx.set_new_settings(variant)
+        got, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic")
+        ctx.set_new_settings({"b200_ppll_reg_sort": False, "b200_ppll_resolve_tile": 1024, "b200_ppll_binned_resolve": False})
+        assert st["frags_sorted"] == wst["frags_sorted"] and st["frags_dropped"] == 0, variant
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32)), variant
+    sc.close(); ctx.close()
+
+
 @pytest.mark.parametrize("tube_jitter", [False, True])
 def test_sharded_union_equals_full_frame_at_1080p(helix100k, tube_jitter):
     """8 ranks emulated on one GPU.  Without tube jitter the AO lookup sits on the pixel centre and neighbouring texels only
