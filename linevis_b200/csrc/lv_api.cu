@@ -44,6 +44,7 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
+    bool ppll_raster_gather = false;    // b200_ppll_gather_mode = raster: object-order gather (one warp per segment) instead of the ray-cast one; untimed
     uint32_t ppll_resolve_tile = 1024;  // plain resolve: keys per warp in the shared tile (256 / 512 / 1024; raised to hold max_frags)
     bool ppll_reg_sort = false;         // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory; untimed, see DESIGN 8
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
@@ -718,6 +719,10 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ppll_reg_sort") o.ppll_reg_sort = parse_bool(value);
+    else if (k == "b200_ppll_gather_mode") {
+        if (strcmp(value, "raycast") && strcmp(value, "raster")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_gather_mode must be raycast or raster");
+        o.ppll_raster_gather = !strcmp(value, "raster");
+    }
     else if (k == "b200_ppll_resolve_tile") { if (u() != 256 && u() != 512 && u() != 1024) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_resolve_tile must be 256, 512 or 1024"); o.ppll_resolve_tile = u(); }
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
@@ -781,6 +786,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else if (k == "b200_ppll_reg_sort") v = b(o.ppll_reg_sort);
+    else if (k == "b200_ppll_gather_mode") v = o.ppll_raster_gather ? "raster" : "raycast";
     else if (k == "b200_ppll_resolve_tile") v = std::to_string(o.ppll_resolve_tile);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
@@ -1284,7 +1290,21 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
     if ((rc = prepare_static_ao(c, sc, P))) return rc;
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (P.n_tiles) {
+    if (P.n_tiles && c->opt.ppll_raster_gather && c->world == 1 && sc->n_seg) {   // object order: one warp per segment (single GPU only)
+        LV_CUDA(c, c->small.ensure(4));
+        LV_CUDA(c, cudaMemsetAsync(c->small.p, 0, 4 * sizeof(unsigned int), c->stream));
+        unsigned long long* work = reinterpret_cast<unsigned long long*>(c->small.p + 2);
+        int per_sm = 0;
+        if (P.use_static_ao) {
+            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<true>, kBlockThreads, 0));
+            k_ppll_gather_raster<true><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>(
+                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work);
+        } else {
+            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<false>, kBlockThreads, 0));
+            k_ppll_gather_raster<false><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>(
+                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work);
+        }
+    } else if (P.n_tiles) {
         if (P.use_static_ao)
             k_ppll_gather<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);
         else

@@ -801,6 +801,99 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     flush_counter(&C->frags_generated, g.gen);
 }
 
+// S9 gather, OBJECT ORDER (b200_ppll_gather_mode = raster; like the reference, whose gather pass is a rasterisation of the tube
+// geometry, LinkedListGather.glsl).  One warp takes one segment: a conservative screen rectangle of the capsule (the hull of the two
+// end spheres' projected bounding boxes, padded by a pixel), whose pixels the lanes test 32 at a time with EXACTLY the predicates of
+// the ray-cast gather -- the pixel-centre camera ray, the record's own-AABB slab test, capsule_hit, t in [1e-4, 1000] -- so the set of
+// fragments per pixel is the same, bit for bit; only the (race-dependent, in the reference too) order inside a list differs.
+// Fragments are appended the reference's way: one counter bump per warp round, atomicExch on the pixel's head.  No BVH is involved;
+// the work is proportional to the screen area of the tubes instead of the traversal's visits.  Single GPU only (no tile ownership test).
+template <bool SAO>
+__global__ void __launch_bounds__(kBlockThreads)
+k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
+                     lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C,
+                     unsigned long long* work_counter) {
+    const uint32_t lane = threadIdx.x & 31;
+    const float tmin = 0.0001f, tmax = 1000.0f;
+    const bool capped = P.use_capped != 0;
+    uint32_t isect = 0, gen = 0;
+    // radius of the end spheres in view space: scaled by the largest column of the view matrix's 3x3 (1 for a rigid camera), a little generous
+    float sc2 = 0.0f;
+#pragma unroll
+    for (int cI = 0; cI < 3; cI++) sc2 = fmaxf(sc2, P.view[4 * cI] * P.view[4 * cI] + P.view[4 * cI + 1] * P.view[4 * cI + 1] + P.view[4 * cI + 2] * P.view[4 * cI + 2]);
+    const float rv = S.radius * sqrtf(sc2) * 1.001f;
+    // persistent warps fetch chunks of kRasterChunk consecutive records (Morton order: neighbours in space) from a global counter --
+    // the screen area of a segment, i.e. its cost, varies by orders of magnitude
+    constexpr uint32_t kRasterChunk = 8;
+    while (true) {
+      unsigned long long first = 0;
+      if (lane == 0) first = atomicAdd(work_counter, (unsigned long long)kRasterChunk);
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (first >= S.n_seg) break;
+      const uint32_t last = uint32_t(first + kRasterChunk < S.n_seg ? first + kRasterChunk : S.n_seg);
+      for (uint32_t seg = uint32_t(first); seg < last; seg++) {
+        const SegRec s = load_seg(S.segs + seg);          // same address in every lane: one broadcast fetch
+        // lanes 0..15: the 8 corners of the view-space bounding cube of each end sphere, projected
+        const float4 pe = ((lane >> 3) & 1u) ? s.b : s.a;
+        const Vec4 vp = mat_mul(P.view, v4(pe.x, pe.y, pe.z, 1.0f));
+        const Vec4 cl = mat_mul(P.proj, v4(vp.x + ((lane & 1u) ? rv : -rv), vp.y + ((lane & 2u) ? rv : -rv), vp.z + ((lane & 4u) ? rv : -rv), 1.0f));
+        float fx = (cl.x / cl.w * 0.5f + 0.5f) * float(P.W) - 0.5f;       // continuous pixel coordinate: pixel px has its centre at fx = px
+        float fy = (cl.y / cl.w * 0.5f + 0.5f) * float(P.H) - 0.5f;
+        const bool bad = !(cl.w > 1e-6f) || !(fx == fx) || !(fy == fy);     // at / behind the eye plane, or not a number: no bound
+        fx = fminf(fmaxf(fx, -4.0f), float(P.W) + 4.0f); fy = fminf(fmaxf(fy, -4.0f), float(P.H) + 4.0f);
+        float xmin = fx, xmax = fx, ymin = fy, ymax = fy;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        int x0 = int(floorf(xmin)) - 1, x1 = int(ceilf(xmax)) + 1, y0 = int(floorf(ymin)) - 1, y1 = int(ceilf(ymax)) + 1;
+        if (__ballot_sync(0xffffffffu, bad)) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
+        x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, int(P.W) - 1); y1 = min(y1, int(P.H) - 1);
+        if (x0 > x1 || y0 > y1) continue;                  // off screen
+        const uint32_t bw = uint32_t(x1 - x0 + 1), area = bw * uint32_t(y1 - y0 + 1);
+        for (uint32_t base = 0; base < area; base += 32u) {
+            const uint32_t i = base + lane;
+            bool keep = false;
+            uint32_t px = 0, py = 0, col = 0;
+            float depth = 0.0f;
+            if (i < area) {
+                px = uint32_t(x0) + i % bw; py = uint32_t(y0) + i / bw;
+                Vec3 ro, rd;
+                camera_ray(P, px, py, 0.5f, 0.5f, ro, rd);
+                const RayBox rb = make_raybox(ro, rd);
+                isect++;
+                float t; uint32_t kind;
+                if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(make_rayq(ro, rd), s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
+                    const Shaded sh = shade_hit<SAO>(P, ro, rd, t, kind, s, SAO && S.seg_aux ? S.seg_aux + seg : nullptr);
+                    if (!(sh.color.w < 0.001f)) { keep = true; col = pack_unorm4x8(sh.color); depth = sh.hit_t; }   // LinkedListGather.glsl:38
+                }
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (km) {
+                unsigned long long idx = 0;
+                const int leader = __ffs(km) - 1;
+                if (int(lane) == leader) idx = atomicAdd(frag_counter, (unsigned long long)__popc(km));   // fragCounter, LinkedListGather.glsl:55
+                idx = __shfl_sync(0xffffffffu, idx, leader) + __popc(km & ((1u << lane) - 1u));
+                if (keep) {
+                    gen++;
+                    if (idx < list_size) {                                                                 // :57
+                        const uint32_t a = addr_gen(P, px, py);
+                        lv_ppll_node nd; nd.color = col; nd.depth = depth;
+                        nd.next = atomicExch(heads + a, uint32_t(idx));                                    // :60
+                        nodes[idx] = nd;
+                        atomicAdd(counts + a, 1u);
+                    }
+                }
+            }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&C->rays_primary, (unsigned long long)P.W * P.H);   // the pixels the pass covers
+    flush_counter(&C->isect, isect);
+    flush_counter(&C->frags_generated, gen);
+}
+
 // S10 resolve.  Per warp: 32 pixels.  Lanes walk their own lists (32 independent pointer chases in flight) into a
 // shared-memory tile of kResolveCap 64-bit keys (depth bits << 32 | colour); lists are packed back to back, as many
 // pixels per round as fit.  Each packed list is then sorted by the whole warp with an all-ascending bitonic network

@@ -143,7 +143,7 @@ def test_tube_frames(ectx, oracle, mode):
     assert st["pixels_hit"] > 50
 
 
-@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort", "tile256", "reg_sort+tile512"])
+@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort", "tile256", "reg_sort+tile512", "raster"])
 @pytest.mark.parametrize("sort_mode", ["priority_queue", "bitonic"])
 def test_ppll(ectx, oracle, variant, sort_mode):
     # dense enough for every list-length class of the resolve kernels (insertion <= 64, warp bitonic above -- in shared memory, or in
@@ -155,11 +155,12 @@ def test_ppll(ectx, oracle, variant, sort_mode):
     tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
     ectx.set_transfer_function(tf)
     ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned, "b200_ppll_reg_sort": "reg_sort" in variant,
-                           "b200_ppll_resolve_tile": 256 if "tile256" in variant else (512 if "tile512" in variant else 1024)})
+                           "b200_ppll_resolve_tile": 256 if "tile256" in variant else (512 if "tile512" in variant else 1024),
+                           "b200_ppll_gather_mode": "raster" if variant == "raster" else "raycast"})
     try:
         img, st = ectx.render_ppll(sc, cam, max_frags=200, sort_mode=sort_mode, linked_list_size=64 * 48 * 32)
     finally:
-        ectx.set_new_settings({"b200_ppll_binned_resolve": False, "b200_ppll_reg_sort": False, "b200_ppll_resolve_tile": 1024})
+        ectx.set_new_settings({"b200_ppll_binned_resolve": False, "b200_ppll_reg_sort": False, "b200_ppll_resolve_tile": 1024, "b200_ppll_gather_mode": "raycast"})
     opts = lvo.default_options()
     g = osc.ppll_gather(cam, opts, tf)
     mine = ectx.ppll_read()
@@ -169,6 +170,35 @@ def test_ppll(ectx, oracle, variant, sort_mode):
     assert st["frags_sorted"] == rst["frags_sorted"] and st["max_depth_complexity"] == rst["max_depth_complexity"] > 130
     nan = np.isnan(ref)
     assert np.array_equal(np.isnan(img), nan) and np.array_equal(img[~nan].view(np.uint32), ref[~nan].view(np.uint32))
+
+
+@pytest.mark.parametrize("eye_z", [0.8, 0.1, 0.0])
+def test_ppll_raster_gather(ectx, oracle, eye_z):
+    """b200_ppll_gather_mode = raster: the object-order gather produces the ray-cast gather's fragments -- per pixel the same multiset of
+    (colour, depth bits) -- also with the camera inside the data (segments at and behind the eye plane get no screen bound and fall back
+    to the whole frame), and its overflow behaviour is the reference's (dropped, counted)."""
+    data = scenes.random_segments(1500, 0.35, seed=21)
+    sc, osc = _pair(ectx, oracle, data, 0.02)
+    cam = lv.make_camera(56, 40, eye=(0.03, -0.02, eye_z))
+    tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
+    ectx.set_transfer_function(tf)
+    opts = lvo.default_options(use_capped_tubes=int(eye_z != 0.1), use_halos=int(eye_z != 0.0))
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": "raster", "use_capped_tubes": eye_z != 0.1, "use_halos": eye_z != 0.0})
+    try:
+        size = 400 * 56 * 40
+        img, st = ectx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
+        mine = ectx.ppll_read()
+        small, sst = ectx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=1000)
+    finally:
+        ectx.set_new_settings({"b200_ppll_gather_mode": "raycast", "use_capped_tubes": True, "use_halos": True})
+    g = osc.ppll_gather(cam, opts, tf, linked_list_size=size)
+    assert st["frags_generated"] == g["counter"] == mine["counter"] > 1000 and st["frags_dropped"] == 0
+    assert lvo.per_pixel_lists(mine["heads"], mine["nodes"], cam, opts, oracle) == lvo.per_pixel_lists(g["heads"], g["nodes"], cam, opts, oracle)
+    if st["max_depth_complexity"] <= 256:
+        ref, _ = lvo.ppll_resolve(oracle, cam, opts, g["heads"], g["nodes"], 256, lv.SORT_MODES["bitonic"], canonical=True)
+        nan = np.isnan(ref)
+        assert np.array_equal(np.isnan(img), nan) and np.array_equal(img[~nan].view(np.uint32), ref[~nan].view(np.uint32))
+    assert sst["frags_generated"] == st["frags_generated"] and sst["frags_stored"] == 1000 and sst["frags_dropped"] == st["frags_generated"] - 1000
 
 
 def test_ppll_overflow_and_truncation(ectx, oracle):

@@ -155,6 +155,32 @@ def test_config4_like_resolve_is_kernel_independent(random1m):
     sc.close(); ctx.close()
 
 
+def test_config4_like_raster_gather_equals_raycast_gather(random1m):
+    """1 M segments: the object-order gather generates exactly the ray-cast gather's fragments (same count, same per-pixel list lengths)
+    and -- nothing dropped or truncated, so every list is the same set -- the same resolved frame, bit for bit."""
+    pos, attr, seg = random1m
+    cam = lv.make_camera(1280, 720)
+    ctx = lv.Context(0)
+    ctx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.1, 0.6)))
+    ctx.set_option("b200_expected_avg_depth_complexity", 40)
+    sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
+    out = {}
+    for mode in ("raycast", "raster"):
+        ctx.set_option("b200_ppll_gather_mode", mode)
+        img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic")
+        r = ctx.ppll_read()
+        lengths, visited = _walk_lists(r["heads"], r["nodes"])
+        assert visited == min(r["counter"], len(r["nodes"]))
+        out[mode] = (img, st, lengths)
+    (a, sa, la), (b, sb, lb) = out["raycast"], out["raster"]
+    assert sa["frags_dropped"] == sb["frags_dropped"] == 0 and sa["frags_truncated"] == sb["frags_truncated"] == 0
+    assert sa["frags_generated"] == sb["frags_generated"] and sa["max_depth_complexity"] == sb["max_depth_complexity"]
+    assert np.array_equal(la, lb)
+    nan = np.isnan(a)
+    assert np.array_equal(np.isnan(b), nan) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+    sc.close(); ctx.close()
+
+
 @pytest.mark.parametrize("tube_jitter", [False, True])
 def test_sharded_union_equals_full_frame_at_1080p(helix100k, tube_jitter):
     """8 ranks emulated on one GPU.  Without tube jitter the AO lookup sits on the pixel centre and neighbouring texels only
