@@ -84,6 +84,7 @@ struct lv_ctx {
     // sharding
     uint32_t rank = 0, world = 1, tile_size = 64;
     std::vector<uint2> tiles_host; DevBuf<uint2> tiles_dev; uint32_t tiles_w = 0, tiles_h = 0;
+    DevBuf<unsigned char> owned_map; uint32_t tiles_x = 0;   // world > 1: 1 byte per tile of the frame, 1 = owned (object-order PPLL gather)
     DevBuf<uint2> tiles_tmp; std::vector<uint32_t> peer_off; uint32_t peer_w = 0, peer_h = 0, peer_world = 0, peer_tile = 0;
     // frame buffers
     DevBuf<unsigned int> apron_marks; unsigned int apron_stamp = 0;
@@ -175,6 +176,14 @@ int ensure_tiles(lv_ctx* c, uint32_t W, uint32_t H) {
     LV_CUDA(c, c->tiles_dev.ensure(std::max<size_t>(1, c->tiles_host.size())));
     if (!c->tiles_host.empty())
         LV_CUDA(c, cudaMemcpyAsync(c->tiles_dev.p, c->tiles_host.data(), c->tiles_host.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    c->tiles_x = (W + c->tile_size - 1) / c->tile_size;
+    if (c->world > 1) {
+        const uint32_t tiles_y = (H + c->tile_size - 1) / c->tile_size;
+        std::vector<unsigned char> map(size_t(c->tiles_x) * tiles_y, 0);
+        for (const uint2& t : c->tiles_host) map[size_t(t.y) * c->tiles_x + t.x] = 1;
+        LV_CUDA(c, c->owned_map.ensure(map.size()));
+        LV_CUDA(c, cudaMemcpyAsync(c->owned_map.p, map.data(), map.size(), cudaMemcpyHostToDevice, c->stream));
+    }
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
     c->tiles_w = W; c->tiles_h = H;
     return LV_OK;
@@ -656,7 +665,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->rgba8.release();
-    c->tf.release(); c->tiles_dev.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
+    c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -1290,7 +1299,11 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
     if ((rc = prepare_static_ao(c, sc, P))) return rc;
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (P.n_tiles && c->opt.ppll_raster_gather && c->world == 1 && sc->n_seg) {   // object order: one warp per segment (single GPU only)
+    if (P.n_tiles && c->opt.ppll_raster_gather && sc->n_seg) {   // object order: one warp per segment
+        const unsigned char* owned = c->world > 1 ? c->owned_map.p : nullptr;
+        unsigned long long n_pixels = 0;
+        for (const uint2& t : c->tiles_host)
+            n_pixels += (unsigned long long)std::min(c->tile_size, P.W - t.x * c->tile_size) * std::min(c->tile_size, P.H - t.y * c->tile_size);
         LV_CUDA(c, c->small.ensure(4));
         LV_CUDA(c, cudaMemsetAsync(c->small.p, 0, 4 * sizeof(unsigned int), c->stream));
         unsigned long long* work = reinterpret_cast<unsigned long long*>(c->small.p + 2);
@@ -1298,11 +1311,11 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
         if (P.use_static_ao) {
             LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<true>, kBlockThreads, 0));
             k_ppll_gather_raster<true><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>(
-                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work);
+                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels);
         } else {
             LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<false>, kBlockThreads, 0));
             k_ppll_gather_raster<false><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>(
-                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work);
+                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels);
         }
     } else if (P.n_tiles) {
         if (P.use_static_ao)

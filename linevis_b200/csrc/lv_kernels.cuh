@@ -807,12 +807,13 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
 // the ray-cast gather -- the pixel-centre camera ray, the record's own-AABB slab test, capsule_hit, t in [1e-4, 1000] -- so the set of
 // fragments per pixel is the same, bit for bit; only the (race-dependent, in the reference too) order inside a list differs.
 // Fragments are appended the reference's way: one counter bump per warp round, atomicExch on the pixel's head.  No BVH is involved;
-// the work is proportional to the screen area of the tubes instead of the traversal's visits.  Single GPU only (no tile ownership test).
+// the work is proportional to the screen area of the tubes instead of the traversal's visits.  Tile-sharded frames: candidates outside
+// this rank's tiles are skipped (owned_tiles: one byte per tile of the frame).
 template <bool SAO>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
                      lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C,
-                     unsigned long long* work_counter) {
+                     unsigned long long* work_counter, const unsigned char* owned_tiles, uint32_t tiles_x, unsigned long long n_pixels) {
     const uint32_t lane = threadIdx.x & 31;
     const float tmin = 0.0001f, tmax = 1000.0f;
     const bool capped = P.use_capped != 0;
@@ -857,8 +858,9 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
             bool keep = false;
             uint32_t px = 0, py = 0, col = 0;
             float depth = 0.0f;
-            if (i < area) {
-                px = uint32_t(x0) + i % bw; py = uint32_t(y0) + i / bw;
+            if (i < area) { px = uint32_t(x0) + i % bw; py = uint32_t(y0) + i / bw; }
+            // tile-sharded frames: only the pixels of this rank's tiles (1 byte per tile of the frame)
+            if (i < area && (!owned_tiles || owned_tiles[(py / P.tile_size) * tiles_x + px / P.tile_size])) {
                 Vec3 ro, rd;
                 camera_ray(P, px, py, 0.5f, 0.5f, ro, rd);
                 const RayBox rb = make_raybox(ro, rd);
@@ -889,7 +891,7 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         }
       }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&C->rays_primary, (unsigned long long)P.W * P.H);   // the pixels the pass covers
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&C->rays_primary, n_pixels);   // the pixels the pass covers (what the ray-cast gather counts as rays)
     flush_counter(&C->isect, isect);
     flush_counter(&C->frags_generated, gen);
 }

@@ -272,6 +272,38 @@ def test_tile_shards_union_is_the_frame(ectx, oracle):
     assert np.abs(acc - full).max() < 2e-3 and (acc == full).mean() > 0.98
 
 
+@pytest.mark.parametrize("gather", ["raycast", "raster"])
+def test_ppll_tile_shards_union_is_the_frame(ectx, oracle, gather):
+    """PPLL with tile sharding, both gather modes: every rank gathers and resolves only its tiles; the union is the unsharded frame bit
+    for bit, and the ranks' fragment counts add up."""
+    data = scenes.random_segments(1200, 0.35, seed=5)
+    sc = ectx.create_scene(*data, 0.02)
+    cam = lv.make_camera(80, 56)
+    ectx.set_transfer_function(scenes.standard_transfer_function(opacity=(0.2, 0.7)))
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": gather})
+    size = 300 * 80 * 56
+    try:
+        full, fst = ectx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
+        acc = np.full_like(full, np.nan)
+        frags = pixels = 0
+        for r in range(3):
+            ectx.set_tile_shard(r, 3, 16)
+            part = np.full_like(full, np.nan)
+            _, st = ectx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size, out=part)
+            owned = np.zeros(full.shape[:2], bool)
+            for tx, ty in ectx.owned_tiles(80, 56):
+                owned[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16] = True
+            assert np.isnan(part[~owned]).all()                    # nothing outside the rank's tiles is written
+            acc[owned] = part[owned]
+            frags += st["frags_generated"]; pixels += st["rays_primary"]
+    finally:
+        ectx.set_tile_shard(0, 1, 64)
+        ectx.set_option("b200_ppll_gather_mode", "raycast")
+    assert frags == fst["frags_generated"] and pixels == fst["rays_primary"] == 80 * 56
+    nan = np.isnan(full)
+    assert np.array_equal(np.isnan(acc), nan) and np.array_equal(acc[~nan].view(np.uint32), full[~nan].view(np.uint32))
+
+
 def _tube_scene(ectx, oracle, n_lines=10, n_pts=25, width=0.03):
     d = scenes.helix_polylines(n_lines, n_pts)
     sc = ectx.create_scene(d["pos"], d["attr"], d["seg"], width)
