@@ -45,6 +45,7 @@ struct Options {
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
     bool ppll_raster_gather = false;    // b200_ppll_gather_mode = raster: object-order gather (one warp per segment) instead of the ray-cast one; untimed
+    bool ppll_contiguous = false;       // ... = raster_contiguous: plus count -> scan -> fill, every list one contiguous run, pointer-free resolve
     uint32_t ppll_resolve_tile = 1024;  // plain resolve: keys per warp in the shared tile (256 / 512 / 1024; raised to hold max_frags)
     bool ppll_reg_sort = false;         // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory; untimed, see DESIGN 8
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
@@ -94,6 +95,8 @@ struct lv_ctx {
     DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[2..3] = 64-bit ao work counter
     // PPLL
     DevBuf<uint32_t> heads, counts, bin_order; DevBuf<unsigned int> bin_hist; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
+    // raster_contiguous gather: staged fragments, exclusive scan of the counts, fill cursors; lists_contiguous tells the resolve pass
+    DevBuf<lv_ppll_node> stage; DevBuf<uint32_t> list_offs; DevBuf<unsigned int> fill_cursor; DevBuf<char> scan_tmp; bool lists_contiguous = false;
     unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
     cudaEvent_t ev[8] = {};
     bool rtao_rays_timed = false, binned_attr_set = false;
@@ -665,7 +668,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->rgba8.release();
-    c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
+    c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -729,8 +732,10 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
     else if (k == "b200_ppll_reg_sort") o.ppll_reg_sort = parse_bool(value);
     else if (k == "b200_ppll_gather_mode") {
-        if (strcmp(value, "raycast") && strcmp(value, "raster")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_gather_mode must be raycast or raster");
-        o.ppll_raster_gather = !strcmp(value, "raster");
+        if (strcmp(value, "raycast") && strcmp(value, "raster") && strcmp(value, "raster_contiguous"))
+            return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_gather_mode must be raycast, raster or raster_contiguous");
+        o.ppll_raster_gather = strcmp(value, "raycast") != 0;
+        o.ppll_contiguous = !strcmp(value, "raster_contiguous");
     }
     else if (k == "b200_ppll_resolve_tile") { if (u() != 256 && u() != 512 && u() != 1024) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_resolve_tile must be 256, 512 or 1024"); o.ppll_resolve_tile = u(); }
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
@@ -795,7 +800,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else if (k == "b200_ppll_reg_sort") v = b(o.ppll_reg_sort);
-    else if (k == "b200_ppll_gather_mode") v = o.ppll_raster_gather ? "raster" : "raycast";
+    else if (k == "b200_ppll_gather_mode") v = o.ppll_contiguous ? "raster_contiguous" : (o.ppll_raster_gather ? "raster" : "raycast");
     else if (k == "b200_ppll_resolve_tile") v = std::to_string(o.ppll_resolve_tile);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
@@ -1308,16 +1313,30 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
         LV_CUDA(c, cudaMemsetAsync(c->small.p, 0, 4 * sizeof(unsigned int), c->stream));
         unsigned long long* work = reinterpret_cast<unsigned long long*>(c->small.p + 2);
         int per_sm = 0;
-        if (P.use_static_ao) {
-            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<true>, kBlockThreads, 0));
-            k_ppll_gather_raster<true><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>(
-                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels);
-        } else {
-            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<false>, kBlockThreads, 0));
-            k_ppll_gather_raster<false><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>(
-                P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels);
+        const bool contig = c->opt.ppll_contiguous;
+        if (contig) LV_CUDA(c, c->stage.ensure(c->list_size));
+        lv_ppll_node* dst = contig ? c->stage.p : c->nodes.p;
+#define LV_RASTER(SAOV, STAGEV) do { \
+            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<SAOV, STAGEV>, kBlockThreads, 0)); \
+            k_ppll_gather_raster<SAOV, STAGEV><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>( \
+                P, sc->dev(), c->heads.p, c->counts.p, dst, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels); } while (0)
+        if (P.use_static_ao) { if (contig) LV_RASTER(true, true); else LV_RASTER(true, false); }
+        else { if (contig) LV_RASTER(false, true); else LV_RASTER(false, false); }
+#undef LV_RASTER
+        if (contig) {   // counts -> offsets (exclusive scan) -> every pixel's fragments into one contiguous run of the node buffer
+            const size_t npad = size_t(P.padded_w) * P.padded_h;
+            LV_CUDA(c, c->list_offs.ensure(npad)); LV_CUDA(c, c->fill_cursor.ensure(npad));
+            LV_CUDA(c, cudaMemsetAsync(c->fill_cursor.p, 0, npad * 4, c->stream));
+            size_t tmp_bytes = 0;
+            LV_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->counts.p, c->list_offs.p, int(npad), c->stream));
+            LV_CUDA(c, c->scan_tmp.ensure(tmp_bytes + 16));
+            LV_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp.p, tmp_bytes, c->counts.p, c->list_offs.p, int(npad), c->stream));
+            k_ppll_fill<<<uint32_t(c->num_sms) * 8u, 256, 0, c->stream>>>(c->stage.p, c->frag_counter.p, c->list_size, c->list_offs.p, c->fill_cursor.p,
+                                                                     c->counts.p, c->heads.p, c->nodes.p);
         }
+        c->lists_contiguous = contig;
     } else if (P.n_tiles) {
+        c->lists_contiguous = false;
         if (P.use_static_ao)
             k_ppll_gather<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), c->heads.p, c->counts.p, c->nodes.p, c->frag_counter.p, c->list_size, c->counters.p);
         else
@@ -1362,12 +1381,11 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
         // shared key tile per warp: the smallest of 256 / 512 / 1024 that is >= the option and can hold the longest list
         const uint32_t cap = std::max(c->opt.ppll_resolve_tile, max_frags) <= 256u ? 256u : (std::max(c->opt.ppll_resolve_tile, max_frags) <= 512u ? 512u : 1024u);
         const uint32_t grid = pixel_grid(c, P);
-#define LV_RESOLVE(RS, CAPV) k_ppll_resolve<RS, CAPV><<<grid, kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, nullptr, nullptr)
-        if (c->opt.ppll_reg_sort) {
-            if (cap == 256u) LV_RESOLVE(true, 256); else if (cap == 512u) LV_RESOLVE(true, 512); else LV_RESOLVE(true, 1024);
-        } else {
-            if (cap == 256u) LV_RESOLVE(false, 256); else if (cap == 512u) LV_RESOLVE(false, 512); else LV_RESOLVE(false, 1024);
-        }
+#define LV_RESOLVE(RS, CAPV, CT) k_ppll_resolve<RS, CAPV, CT><<<grid, kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, nullptr, nullptr)
+#define LV_RESOLVE_CAP(RS, CT) do { if (cap == 256u) LV_RESOLVE(RS, 256, CT); else if (cap == 512u) LV_RESOLVE(RS, 512, CT); else LV_RESOLVE(RS, 1024, CT); } while (0)
+        if (c->lists_contiguous) { if (c->opt.ppll_reg_sort) LV_RESOLVE_CAP(true, true); else LV_RESOLVE_CAP(false, true); }
+        else { if (c->opt.ppll_reg_sort) LV_RESOLVE_CAP(true, false); else LV_RESOLVE_CAP(false, false); }
+#undef LV_RESOLVE_CAP
 #undef LV_RESOLVE
     } else if (P.n_tiles) {
         const size_t n_own = size_t(P.n_tiles) * c->tile_size * c->tile_size;

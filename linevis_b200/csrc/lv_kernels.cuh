@@ -809,7 +809,11 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
 // Fragments are appended the reference's way: one counter bump per warp round, atomicExch on the pixel's head.  No BVH is involved;
 // the work is proportional to the screen area of the tubes instead of the traversal's visits.  Tile-sharded frames: candidates outside
 // this rank's tiles are skipped (owned_tiles: one byte per tile of the frame).
-template <bool SAO>
+// STAGE (b200_ppll_gather_mode = raster_contiguous): fragments go to a staging array as (colour, depth, pixel address) and only the
+// per-pixel counts are bumped; an exclusive scan of the counts and k_ppll_fill then place every pixel's fragments in ONE contiguous
+// run of the node buffer (next = previous slot, head = last slot: still the reference's linked structure), which the resolve pass
+// reads by index instead of chasing pointers (k_ppll_resolve<.., CONTIG>).
+template <bool SAO, bool STAGE = false>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
                      lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C,
@@ -882,8 +886,8 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
                     if (idx < list_size) {                                                                 // :57
                         const uint32_t a = addr_gen(P, px, py);
                         lv_ppll_node nd; nd.color = col; nd.depth = depth;
-                        nd.next = atomicExch(heads + a, uint32_t(idx));                                    // :60
-                        nodes[idx] = nd;
+                        nd.next = STAGE ? a : atomicExch(heads + a, uint32_t(idx));                        // :60
+                        nodes[idx] = nd;                                                                   // STAGE: `nodes` is the staging array
                         atomicAdd(counts + a, 1u);
                     }
                 }
@@ -894,6 +898,21 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&C->rays_primary, n_pixels);   // the pixels the pass covers (what the ray-cast gather counts as rays)
     flush_counter(&C->isect, isect);
     flush_counter(&C->frags_generated, gen);
+}
+
+// staged fragments -> contiguous per-pixel runs (offs = exclusive scan of counts; cursor zeroed).  The order inside a run is the order
+// of arrival (a race, like the reference's list order).
+__global__ void k_ppll_fill(const lv_ppll_node* stage, const unsigned long long* frag_counter, unsigned long long list_size, const uint32_t* offs,
+                            unsigned int* cursor, const uint32_t* counts, uint32_t* heads, lv_ppll_node* nodes) {
+    const unsigned long long n = *frag_counter < list_size ? *frag_counter : list_size;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        lv_ppll_node f = stage[i];
+        const uint32_t a = f.next;
+        const uint32_t k = atomicAdd(cursor + a, 1u), slot = offs[a] + k;
+        f.next = k ? slot - 1u : kNone;
+        nodes[slot] = f;
+        if (k + 1u == counts[a]) heads[a] = slot;
+    }
 }
 
 // S10 resolve.  Per warp: 32 pixels.  Lanes walk their own lists (32 independent pointer chases in flight) into a
@@ -975,7 +994,8 @@ __device__ __forceinline__ void warp_bitonic_sort_reg(unsigned long long* s, uin
 
 // CAP: keys per warp in the shared tile (b200_ppll_resolve_tile; must hold the longest list, max_frags <= CAP).  A smaller tile
 // lets more warps live on an SM -- the walk is a dependent pointer chase, so short-list frames are bound by warps in flight.
-template <bool REGSORT, int CAP = kResolveCap>
+// CONTIG: every list is a contiguous run ending at its head (k_ppll_fill): node i of the walk is nodes[head - i], no pointer chase.
+template <bool REGSORT, int CAP = kResolveCap, bool CONTIG = false>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
                uint32_t max_frags, int early_out, float4* image, Counters* C, const uint32_t* order, const unsigned int* n_sorted) {
@@ -1012,7 +1032,7 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
                 // short list: this lane insertion-sorts its own slice while the next node is in flight (32 lists in parallel)
                 for (uint32_t i = 0; i < c; i++) {
                     const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
-                    if (i + 1 < c) nd = nodes[nd.next];
+                    if (i + 1 < c) nd = nodes[CONTIG ? head - (i + 1u) : nd.next];
                     uint32_t j = i;
                     while (j > 0 && mine[j - 1] > key) { mine[j] = mine[j - 1]; j--; }
                     mine[j] = key;
@@ -1020,7 +1040,7 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
             } else {
                 for (uint32_t i = 0; i < c; i++) {
                     mine[i] = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
-                    if (i + 1 < c) nd = nodes[nd.next];
+                    if (i + 1 < c) nd = nodes[CONTIG ? head - (i + 1u) : nd.next];
                 }
             }
         }

@@ -272,7 +272,7 @@ inline unsigned atomicMax(unsigned* p, unsigned v) { return emu_atomic_minmax(p,
 
 // (integer min / max overloads: lv_math.cuh's LV_HOST_EMU block)
 
-// ---- cub::DeviceRadixSort::SortPairs (the one cub entry point the BVH builder uses): a stable sort on the selected key bits
+// ---- cub::DeviceRadixSort::SortPairs (BVH builder; a stable sort on the selected key bits) and cub::DeviceScan::ExclusiveSum (PPLL fill)
 namespace cub {
 struct DeviceRadixSort {
     template <class K, class V>
@@ -284,6 +284,15 @@ struct DeviceRadixSort {
         const K mask = (end_bit - begin_bit >= int(sizeof(K) * 8)) ? ~K(0) : (((K(1) << (end_bit - begin_bit)) - 1) << begin_bit);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (keys_in[a] & mask) < (keys_in[b] & mask); });
         for (int i = 0; i < n; i++) { keys_out[i] = keys_in[order[i]]; vals_out[i] = vals_in[order[i]]; }
+        return cudaSuccess;
+    }
+};
+struct DeviceScan {
+    template <class In, class Out>
+    static cudaError_t ExclusiveSum(void* tmp, size_t& tmp_bytes, const In* in, Out* out, int n, cudaStream_t) {
+        if (!tmp) { tmp_bytes = 16; return cudaSuccess; }
+        Out acc = 0;
+        for (int i = 0; i < n; i++) { const Out v = Out(in[i]); out[i] = acc; acc += v; }
         return cudaSuccess;
     }
 };

@@ -143,12 +143,13 @@ def test_tube_frames(ectx, oracle, mode):
     assert st["pixels_hit"] > 50
 
 
-@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort", "tile256", "reg_sort+tile512", "raster"])
+@pytest.mark.parametrize("variant", ["plain", "binned", "reg_sort", "tile256", "reg_sort+tile512", "raster", "raster_contiguous", "raster_contiguous+reg_sort",
+                                     "raster_contiguous+binned"])
 @pytest.mark.parametrize("sort_mode", ["priority_queue", "bitonic"])
 def test_ppll(ectx, oracle, variant, sort_mode):
     # dense enough for every list-length class of the resolve kernels (insertion <= 64, warp bitonic above -- in shared memory, or in
     # registers with 4 / 8 keys per lane; binned 32 / 64 / 128 / 256)
-    binned = variant == "binned"
+    binned = "binned" in variant
     data = scenes.random_segments(5000, 0.35, seed=13)
     sc, osc = _pair(ectx, oracle, data, 0.03)
     cam = lv.make_camera(48, 32)
@@ -156,7 +157,7 @@ def test_ppll(ectx, oracle, variant, sort_mode):
     ectx.set_transfer_function(tf)
     ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_binned_resolve": binned, "b200_ppll_reg_sort": "reg_sort" in variant,
                            "b200_ppll_resolve_tile": 256 if "tile256" in variant else (512 if "tile512" in variant else 1024),
-                           "b200_ppll_gather_mode": "raster" if variant == "raster" else "raycast"})
+                           "b200_ppll_gather_mode": variant.split("+")[0] if variant.startswith("raster") else "raycast"})
     try:
         img, st = ectx.render_ppll(sc, cam, max_frags=200, sort_mode=sort_mode, linked_list_size=64 * 48 * 32)
     finally:
@@ -172,8 +173,9 @@ def test_ppll(ectx, oracle, variant, sort_mode):
     assert np.array_equal(np.isnan(img), nan) and np.array_equal(img[~nan].view(np.uint32), ref[~nan].view(np.uint32))
 
 
+@pytest.mark.parametrize("mode", ["raster", "raster_contiguous"])
 @pytest.mark.parametrize("eye_z", [0.8, 0.1, 0.0])
-def test_ppll_raster_gather(ectx, oracle, eye_z):
+def test_ppll_raster_gather(ectx, oracle, eye_z, mode):
     """b200_ppll_gather_mode = raster: the object-order gather produces the ray-cast gather's fragments -- per pixel the same multiset of
     (colour, depth bits) -- also with the camera inside the data (segments at and behind the eye plane get no screen bound and fall back
     to the whole frame), and its overflow behaviour is the reference's (dropped, counted)."""
@@ -183,7 +185,7 @@ def test_ppll_raster_gather(ectx, oracle, eye_z):
     tf = scenes.standard_transfer_function(opacity=(0.2, 0.7))
     ectx.set_transfer_function(tf)
     opts = lvo.default_options(use_capped_tubes=int(eye_z != 0.1), use_halos=int(eye_z != 0.0))
-    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": "raster", "use_capped_tubes": eye_z != 0.1, "use_halos": eye_z != 0.0})
+    ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": mode, "use_capped_tubes": eye_z != 0.1, "use_halos": eye_z != 0.0})
     try:
         size = 400 * 56 * 40
         img, st = ectx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
@@ -194,6 +196,18 @@ def test_ppll_raster_gather(ectx, oracle, eye_z):
     g = osc.ppll_gather(cam, opts, tf, linked_list_size=size)
     assert st["frags_generated"] == g["counter"] == mine["counter"] > 1000 and st["frags_dropped"] == 0
     assert lvo.per_pixel_lists(mine["heads"], mine["nodes"], cam, opts, oracle) == lvo.per_pixel_lists(g["heads"], g["nodes"], cam, opts, oracle)
+    if mode == "raster_contiguous":      # every list is one run of the node buffer, ending at its head, linked slot by slot
+        heads, nxt = mine["heads"].astype(np.int64), mine["nodes"]["next"].astype(np.int64)
+        NONE = 0xFFFFFFFF
+        runs = sorted((h, ) for h in heads[heads != NONE])
+        covered = 0
+        for (h,) in runs:
+            n = 0
+            while nxt[h - n] != NONE:
+                assert nxt[h - n] == h - n - 1
+                n += 1
+            covered += n + 1
+        assert covered == mine["counter"]
     if st["max_depth_complexity"] <= 256:
         ref, _ = lvo.ppll_resolve(oracle, cam, opts, g["heads"], g["nodes"], 256, lv.SORT_MODES["bitonic"], canonical=True)
         nan = np.isnan(ref)
@@ -272,7 +286,7 @@ def test_tile_shards_union_is_the_frame(ectx, oracle):
     assert np.abs(acc - full).max() < 2e-3 and (acc == full).mean() > 0.98
 
 
-@pytest.mark.parametrize("gather", ["raycast", "raster"])
+@pytest.mark.parametrize("gather", ["raycast", "raster", "raster_contiguous"])
 def test_ppll_tile_shards_union_is_the_frame(ectx, oracle, gather):
     """PPLL with tile sharding, both gather modes: every rank gathers and resolves only its tiles; the union is the unsharded frame bit
     for bit, and the ranks' fragment counts add up."""

@@ -165,19 +165,21 @@ def test_config4_like_raster_gather_equals_raycast_gather(random1m):
     ctx.set_option("b200_expected_avg_depth_complexity", 40)
     sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
     out = {}
-    for mode in ("raycast", "raster"):
+    for mode in ("raycast", "raster", "raster_contiguous"):
         ctx.set_option("b200_ppll_gather_mode", mode)
         img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic")
         r = ctx.ppll_read()
         lengths, visited = _walk_lists(r["heads"], r["nodes"])
         assert visited == min(r["counter"], len(r["nodes"]))
         out[mode] = (img, st, lengths)
-    (a, sa, la), (b, sb, lb) = out["raycast"], out["raster"]
-    assert sa["frags_dropped"] == sb["frags_dropped"] == 0 and sa["frags_truncated"] == sb["frags_truncated"] == 0
-    assert sa["frags_generated"] == sb["frags_generated"] and sa["max_depth_complexity"] == sb["max_depth_complexity"]
-    assert np.array_equal(la, lb)
+    a, sa, la = out["raycast"]
     nan = np.isnan(a)
-    assert np.array_equal(np.isnan(b), nan) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+    for mode in ("raster", "raster_contiguous"):
+        b, sb, lb = out[mode]
+        assert sa["frags_dropped"] == sb["frags_dropped"] == 0 and sa["frags_truncated"] == sb["frags_truncated"] == 0, mode
+        assert sa["frags_generated"] == sb["frags_generated"] and sa["max_depth_complexity"] == sb["max_depth_complexity"], mode
+        assert np.array_equal(la, lb), mode
+        assert np.array_equal(np.isnan(b), nan) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32)), mode
     sc.close(); ctx.close()
 
 

@@ -313,16 +313,18 @@ def test_ppll_resolve_variants_bit_exact(ctx, oracle, variant):
     assert np.array_equal(np.isnan(ref), nan) and np.array_equal(img[~nan].view(np.uint32), ref[~nan].view(np.uint32))
 
 
+@pytest.mark.parametrize("mode", ["raster", "raster_contiguous"])
 @pytest.mark.parametrize("name,eye_z", [("random", 0.8), ("helix", 0.8), ("random", 0.05)])
-def test_ppll_raster_gather_bit_exact(ctx, oracle, name, eye_z):
-    """b200_ppll_gather_mode = raster (object-order gather, one warp per segment): per pixel the same multiset of fragments as the oracle's
-    all-hits enumeration, the same counters, the same resolved frame -- also with the camera inside the data."""
+def test_ppll_raster_gather_bit_exact(ctx, oracle, name, eye_z, mode):
+    """b200_ppll_gather_mode = raster (object-order gather, one warp per segment) and raster_contiguous (+ count / scan / fill: every list
+    one contiguous run, index-addressed resolve): per pixel the same multiset of fragments as the oracle's all-hits enumeration, the
+    same counters, the same resolved frame -- also with the camera inside the data."""
     data, width = DATASETS[name]()
     sc, osc = _scene_pair(ctx, oracle, data, width)
     cam = lv.make_camera(128, 96, eye=(0.02, -0.01, eye_z))
     tf = scenes.standard_transfer_function(opacity=(0.1, 0.6))
     ctx.set_transfer_function(tf)
-    ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": "raster"})
+    ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": mode})
     size = 300 * 128 * 96
     try:
         img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)

@@ -115,7 +115,7 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     mode = int(rng.choice([0, 5]))
     ctx.set_new_settings({"b200_ppll_reg_sort": bool(rng.integers(0, 2)), "b200_ppll_binned_resolve": bool(rng.integers(0, 3) == 0),
                           "b200_ppll_resolve_tile": int(rng.choice([256, 512, 1024])),
-                          "b200_ppll_gather_mode": str(rng.choice(["raycast", "raster"]))})
+                          "b200_ppll_gather_mode": str(rng.choice(["raycast", "raster", "raster_contiguous"]))})
     pimg, pst = ctx.render_ppll(sc, cam, max_frags=mf, sort_mode=mode, linked_list_size=200 * W * H)
     po = lvo.default_options(use_capped_tubes=int(capped), use_halos=int(halos))
     g = osc.ppll_gather(cam, po, tf, linked_list_size=200 * W * H)
