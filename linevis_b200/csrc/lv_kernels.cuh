@@ -845,15 +845,26 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         float fx = (cl.x / cl.w * 0.5f + 0.5f) * float(P.W) - 0.5f;       // continuous pixel coordinate: pixel px has its centre at fx = px
         float fy = (cl.y / cl.w * 0.5f + 0.5f) * float(P.H) - 0.5f;
         const bool bad = !(cl.w > 1e-6f) || !(fx == fx) || !(fy == fy);     // at / behind the eye plane, or not a number: no bound
+        // the projected sphere centre of this lane's end point and the distance of this lane's corner from it: the projected capsule lies
+        // within max(distance) of the projected axis (a straight 2-D segment), which culls most of a diagonal segment's rectangle below
+        const Vec4 cc = mat_mul(P.proj, vp);
+        const float ccx = (cc.x / cc.w * 0.5f + 0.5f) * float(P.W) - 0.5f, ccy = (cc.y / cc.w * 0.5f + 0.5f) * float(P.H) - 0.5f;
+        float rad = sqrtf((fx - ccx) * (fx - ccx) + (fy - ccy) * (fy - ccy));
         fx = fminf(fmaxf(fx, -4.0f), float(P.W) + 4.0f); fy = fminf(fmaxf(fy, -4.0f), float(P.H) + 4.0f);
         float xmin = fx, xmax = fx, ymin = fy, ymax = fy;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
             ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+            rad = fmaxf(rad, __shfl_xor_sync(0xffffffffu, rad, o));
         }
+        const float ax = __shfl_sync(0xffffffffu, ccx, 0), ay = __shfl_sync(0xffffffffu, ccy, 0);      // lanes 0-7: end point a, 8-15: b
+        const float ex = __shfl_sync(0xffffffffu, ccx, 8) - ax, ey = __shfl_sync(0xffffffffu, ccy, 8) - ay;
+        const float l2 = ex * ex + ey * ey, inv_l2 = l2 > 0.0f ? 1.0f / l2 : 0.0f;
+        const float lim2 = (rad + 1.5f) * (rad + 1.5f);                                                 // + a pixel and a half of slack
         int x0 = int(floorf(xmin)) - 1, x1 = int(ceilf(xmax)) + 1, y0 = int(floorf(ymin)) - 1, y1 = int(ceilf(ymax)) + 1;
-        if (__ballot_sync(0xffffffffu, bad)) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
+        const bool no_bound = __ballot_sync(0xffffffffu, bad) != 0u;
+        if (no_bound) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, int(P.W) - 1); y1 = min(y1, int(P.H) - 1);
         if (x0 > x1 || y0 > y1) continue;                  // off screen
         const uint32_t bw = uint32_t(x1 - x0 + 1), area = bw * uint32_t(y1 - y0 + 1);
@@ -864,7 +875,14 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
             float depth = 0.0f;
             if (i < area) { px = uint32_t(x0) + i % bw; py = uint32_t(y0) + i / bw; }
             // tile-sharded frames: only the pixels of this rank's tiles (1 byte per tile of the frame)
-            if (i < area && (!owned_tiles || owned_tiles[(py / P.tile_size) * tiles_x + px / P.tile_size])) {
+            bool cand = i < area && (!owned_tiles || owned_tiles[(py / P.tile_size) * tiles_x + px / P.tile_size]);
+            if (cand && !no_bound) {   // 2-D distance from the projected axis; a NaN anywhere keeps the candidate
+                const float qx = float(px) - ax, qy = float(py) - ay;
+                const float tt = fminf(fmaxf((qx * ex + qy * ey) * inv_l2, 0.0f), 1.0f);
+                const float dx = qx - tt * ex, dy = qy - tt * ey;
+                if (dx * dx + dy * dy > lim2) cand = false;
+            }
+            if (cand) {
                 Vec3 ro, rd;
                 camera_ray(P, px, py, 0.5f, 0.5f, ro, rd);
                 const RayBox rb = make_raybox(ro, rd);
