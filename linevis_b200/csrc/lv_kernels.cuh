@@ -1045,12 +1045,30 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
         const bool sel = c > 0 && incl <= uint32_t(CAP);
         if (sel) {
             unsigned long long* mine = tile + excl;
+            if (CONTIG) {
+                // the list is the run nodes[head - c + 1 .. head]: four independent node fetches in flight per lane, then their inserts
+                const bool ins = c <= uint32_t(kResolveInsertionMax);
+                for (uint32_t i = 0; i < c; i += 4u) {
+                    lv_ppll_node n4[4];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4u; u++) if (i + u < c) n4[u] = nodes[head - (i + u)];
+#pragma unroll
+                    for (uint32_t u = 0; u < 4u; u++) {
+                        if (i + u < c) {
+                            const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(n4[u].depth)) << 32) | n4[u].color;
+                            uint32_t j = i + u;
+                            if (ins) while (j > 0 && mine[j - 1] > key) { mine[j] = mine[j - 1]; j--; }
+                            mine[j] = key;
+                        }
+                    }
+                }
+            } else {
             lv_ppll_node nd = nodes[head];
             if (c <= uint32_t(kResolveInsertionMax)) {
                 // short list: this lane insertion-sorts its own slice while the next node is in flight (32 lists in parallel)
                 for (uint32_t i = 0; i < c; i++) {
                     const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
-                    if (i + 1 < c) nd = nodes[CONTIG ? head - (i + 1u) : nd.next];
+                    if (i + 1 < c) nd = nodes[nd.next];
                     uint32_t j = i;
                     while (j > 0 && mine[j - 1] > key) { mine[j] = mine[j - 1]; j--; }
                     mine[j] = key;
@@ -1058,8 +1076,9 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
             } else {
                 for (uint32_t i = 0; i < c; i++) {
                     mine[i] = (static_cast<unsigned long long>(__float_as_uint(nd.depth)) << 32) | nd.color;
-                    if (i + 1 < c) nd = nodes[CONTIG ? head - (i + 1u) : nd.next];
+                    if (i + 1 < c) nd = nodes[nd.next];
                 }
+            }
             }
         }
         __syncwarp();
