@@ -863,6 +863,8 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         const float l2 = ex * ex + ey * ey, inv_l2 = l2 > 0.0f ? 1.0f / l2 : 0.0f;
         const float lim2 = (rad + 1.5f) * (rad + 1.5f);                                                 // + a pixel and a half of slack
         int x0 = int(floorf(xmin)) - 1, x1 = int(ceilf(xmax)) + 1, y0 = int(floorf(ymin)) - 1, y1 = int(ceilf(ymax)) + 1;
+        // every corner of both bounding cubes behind the eye plane (w <= 0): no forward ray reaches the capsule
+        if (__ballot_sync(0xffffffffu, cl.w > 0.0f) == 0u) continue;
         const bool no_bound = __ballot_sync(0xffffffffu, bad) != 0u;
         if (no_bound) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, int(P.W) - 1); y1 = min(y1, int(P.H) - 1);
