@@ -827,6 +827,10 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
 #pragma unroll
     for (int cI = 0; cI < 3; cI++) sc2 = fmaxf(sc2, P.view[4 * cI] * P.view[4 * cI] + P.view[4 * cI + 1] * P.view[4 * cI + 1] + P.view[4 * cI + 2] * P.view[4 * cI + 2]);
     const float rv = S.radius * sqrtf(sc2) * 1.001f;
+    // how much the clip coordinates change over one radius (w: 1 x rv for a perspective matrix), and the clip w below which a point counts as near
+    const float dw = rv * (fabsf(P.proj[3]) + fabsf(P.proj[7]) + fabsf(P.proj[11]));
+    const float dcx = rv * (fabsf(P.proj[0]) + fabsf(P.proj[4]) + fabsf(P.proj[8])), dcy = rv * (fabsf(P.proj[1]) + fabsf(P.proj[5]) + fabsf(P.proj[9]));
+    const float thr = 4.0f * dw + 1e-6f;
     // persistent warps fetch chunks of kRasterChunk consecutive records (Morton order: neighbours in space) from a global counter --
     // the screen area of a segment, i.e. its cost, varies by orders of magnitude
     constexpr uint32_t kRasterChunk = 8;
@@ -838,9 +842,34 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
       const uint32_t last = uint32_t(first + kRasterChunk < S.n_seg ? first + kRasterChunk : S.n_seg);
       for (uint32_t seg = uint32_t(first); seg < last; seg++) {
         const SegRec s = load_seg(S.segs + seg);          // same address in every lane: one broadcast fetch
+        // view-space end points; clip coordinates are linear along the axis
+        Vec4 va = mat_mul(P.view, v4(s.a.x, s.a.y, s.a.z, 1.0f)), vb = mat_mul(P.view, v4(s.b.x, s.b.y, s.b.z, 1.0f));
+        const Vec4 ca = mat_mul(P.proj, va), cb = mat_mul(P.proj, vb);
+        if (fmaxf(ca.w, cb.w) + dw <= 0.0f) continue;       // the whole capsule is behind the eye plane: no forward ray reaches it
+        bool full_frame = false;
+        if (fminf(ca.w, cb.w) < thr) {
+            // Near the eye plane the projection has no bound.  Split the axis at clip w = thr: the FRONT part (w >= thr) projects to a
+            // bounded rectangle; the NEAR part (its reachable points have 0 < w <= thr + dw) can only be on screen -- |clip x| <= w and
+            // |clip y| <= w -- if its axis comes within that distance (+ a radius) of the view axis.  If it does: whole frame.
+            const bool a_front = ca.w >= cb.w;
+            const Vec4 vF = a_front ? va : vb, vN = a_front ? vb : va, cF = a_front ? ca : cb, cN = a_front ? cb : ca;
+            const float span = cF.w - cN.w;                                               // >= 0
+            const float ts = (cF.w > thr && span > 0.0f) ? (cF.w - thr) / span : 0.0f;     // S: where the near part starts (w = thr, or F)
+            const float te = (cN.w < -dw && span > 0.0f) ? (cF.w + dw) / span : 1.0f;      // E: where it stops being reachable (w = -dw, or N)
+            const float sx = cF.x + ts * (cN.x - cF.x), sy = cF.y + ts * (cN.y - cF.y), e_x = cF.x + te * (cN.x - cF.x), e_y = cF.y + te * (cN.y - cF.y);
+            const float lim = thr + dw;
+            const float near_x = ((sx < 0.0f) != (e_x < 0.0f)) ? 0.0f : fminf(fabsf(sx), fabsf(e_x));
+            const float near_y = ((sy < 0.0f) != (e_y < 0.0f)) ? 0.0f : fminf(fabsf(sy), fabsf(e_y));
+            const bool near_off_screen = near_x > lim + dcx || near_y > lim + dcy;        // a NaN anywhere: not provably off screen
+            if (!near_off_screen) full_frame = true;
+            else if (!(cF.w > thr)) continue;                                             // no front part, near part off screen
+            else {                                                                        // bound the front part F..S only
+                const Vec4 vS = v4(vF.x + ts * (vN.x - vF.x), vF.y + ts * (vN.y - vF.y), vF.z + ts * (vN.z - vF.z), 1.0f);
+                va = vF; vb = vS;
+            }
+        }
         // lanes 0..15: the 8 corners of the view-space bounding cube of each end sphere, projected
-        const float4 pe = ((lane >> 3) & 1u) ? s.b : s.a;
-        const Vec4 vp = mat_mul(P.view, v4(pe.x, pe.y, pe.z, 1.0f));
+        const Vec4 vp = ((lane >> 3) & 1u) ? vb : va;
         const Vec4 cl = mat_mul(P.proj, v4(vp.x + ((lane & 1u) ? rv : -rv), vp.y + ((lane & 2u) ? rv : -rv), vp.z + ((lane & 4u) ? rv : -rv), 1.0f));
         float fx = (cl.x / cl.w * 0.5f + 0.5f) * float(P.W) - 0.5f;       // continuous pixel coordinate: pixel px has its centre at fx = px
         float fy = (cl.y / cl.w * 0.5f + 0.5f) * float(P.H) - 0.5f;
@@ -863,9 +892,7 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         const float l2 = ex * ex + ey * ey, inv_l2 = l2 > 0.0f ? 1.0f / l2 : 0.0f;
         const float lim2 = (rad + 1.5f) * (rad + 1.5f);                                                 // + a pixel and a half of slack
         int x0 = int(floorf(xmin)) - 1, x1 = int(ceilf(xmax)) + 1, y0 = int(floorf(ymin)) - 1, y1 = int(ceilf(ymax)) + 1;
-        // every corner of both bounding cubes behind the eye plane (w <= 0): no forward ray reaches the capsule
-        if (__ballot_sync(0xffffffffu, cl.w > 0.0f) == 0u) continue;
-        const bool no_bound = __ballot_sync(0xffffffffu, bad) != 0u;
+        const bool no_bound = full_frame || __ballot_sync(0xffffffffu, bad) != 0u;
         if (no_bound) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, int(P.W) - 1); y1 = min(y1, int(P.H) - 1);
         if (x0 > x1 || y0 > y1) continue;                  // off screen
