@@ -1304,7 +1304,7 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
     if ((rc = prepare_static_ao(c, sc, P))) return rc;
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    if (P.n_tiles && c->opt.ppll_raster_gather && sc->n_seg) {   // object order: one warp per segment
+    if (P.n_tiles && c->opt.ppll_raster_gather && sc->n_seg && P.W < 65536u && P.H < 65536u) {   // object order: one warp per segment (candidate pixels are queued as x | y << 16)
         const unsigned char* owned = c->world > 1 ? c->owned_map.p : nullptr;
         unsigned long long n_pixels = 0;
         for (const uint2& t : c->tiles_host)

@@ -818,7 +818,9 @@ __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
                      lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C,
                      unsigned long long* work_counter, const unsigned char* owned_tiles, uint32_t tiles_x, unsigned long long n_pixels) {
+    __shared__ uint32_t s_cand[kBlockThreads / 32][64];   // per warp: queued candidate pixels (x | y << 16)
     const uint32_t lane = threadIdx.x & 31;
+    uint32_t* queue = s_cand[threadIdx.x >> 5];
     const float tmin = 0.0001f, tmax = 1000.0f;
     const bool capped = P.use_capped != 0;
     uint32_t isect = 0, gen = 0;
@@ -897,47 +899,63 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, int(P.W) - 1); y1 = min(y1, int(P.H) - 1);
         if (x0 > x1 || y0 > y1) continue;                  // off screen
         const uint32_t bw = uint32_t(x1 - x0 + 1), area = bw * uint32_t(y1 - y0 + 1);
+        // The cheap tests (ownership, 2-D cull) thin the rectangle out; their survivors are queued per warp and taken 32 at a time, so
+        // that the expensive part -- camera ray, slab test, capsule test, shading -- runs with full warps.
+        uint32_t q_count = 0;                               // uniform over the warp; <= 31 between rounds
         for (uint32_t base = 0; base < area; base += 32u) {
             const uint32_t i = base + lane;
-            bool keep = false;
-            uint32_t px = 0, py = 0, col = 0;
-            float depth = 0.0f;
-            if (i < area) { px = uint32_t(x0) + i % bw; py = uint32_t(y0) + i / bw; }
+            uint32_t cx = 0, cy = 0;
+            if (i < area) { cx = uint32_t(x0) + i % bw; cy = uint32_t(y0) + i / bw; }
             // tile-sharded frames: only the pixels of this rank's tiles (1 byte per tile of the frame)
-            bool cand = i < area && (!owned_tiles || owned_tiles[(py / P.tile_size) * tiles_x + px / P.tile_size]);
+            bool cand = i < area && (!owned_tiles || owned_tiles[(cy / P.tile_size) * tiles_x + cx / P.tile_size]);
             if (cand && !no_bound) {   // 2-D distance from the projected axis; a NaN anywhere keeps the candidate
-                const float qx = float(px) - ax, qy = float(py) - ay;
+                const float qx = float(cx) - ax, qy = float(cy) - ay;
                 const float tt = fminf(fmaxf((qx * ex + qy * ey) * inv_l2, 0.0f), 1.0f);
                 const float dx = qx - tt * ex, dy = qy - tt * ey;
                 if (dx * dx + dy * dy > lim2) cand = false;
             }
-            if (cand) {
-                Vec3 ro, rd;
-                camera_ray(P, px, py, 0.5f, 0.5f, ro, rd);
-                const RayBox rb = make_raybox(ro, rd);
-                isect++;
-                float t; uint32_t kind;
-                if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(make_rayq(ro, rd), s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
-                    const Shaded sh = shade_hit<SAO>(P, ro, rd, t, kind, s, SAO && S.seg_aux ? S.seg_aux + seg : nullptr);
-                    if (!(sh.color.w < 0.001f)) { keep = true; col = pack_unorm4x8(sh.color); depth = sh.hit_t; }   // LinkedListGather.glsl:38
-                }
-            }
-            const unsigned km = __ballot_sync(0xffffffffu, keep);
-            if (km) {
-                unsigned long long idx = 0;
-                const int leader = __ffs(km) - 1;
-                if (int(lane) == leader) idx = atomicAdd(frag_counter, (unsigned long long)__popc(km));   // fragCounter, LinkedListGather.glsl:55
-                idx = __shfl_sync(0xffffffffu, idx, leader) + __popc(km & ((1u << lane) - 1u));
-                if (keep) {
-                    gen++;
-                    if (idx < list_size) {                                                                 // :57
-                        const uint32_t a = addr_gen(P, px, py);
-                        lv_ppll_node nd; nd.color = col; nd.depth = depth;
-                        nd.next = STAGE ? a : atomicExch(heads + a, uint32_t(idx));                        // :60
-                        nodes[idx] = nd;                                                                   // STAGE: `nodes` is the staging array
-                        atomicAdd(counts + a, 1u);
+            const unsigned cm = __ballot_sync(0xffffffffu, cand);
+            if (cand) queue[q_count + __popc(cm & ((1u << lane) - 1u))] = cx | (cy << 16);
+            q_count += __popc(cm);
+            __syncwarp();
+            const bool last_round = base + 32u >= area;
+            while (q_count >= 32u || (last_round && q_count != 0u)) {
+                const uint32_t n = q_count < 32u ? q_count : 32u;
+                q_count -= n;
+                const uint32_t e = queue[q_count + (lane < n ? lane : 0u)];   // the newest n entries
+                const uint32_t px = e & 0xffffu, py = e >> 16;
+                bool keep = false;
+                uint32_t col = 0;
+                float depth = 0.0f;
+                if (lane < n) {
+                    Vec3 ro, rd;
+                    camera_ray(P, px, py, 0.5f, 0.5f, ro, rd);
+                    const RayBox rb = make_raybox(ro, rd);
+                    isect++;
+                    float t; uint32_t kind;
+                    if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(make_rayq(ro, rd), s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
+                        const Shaded sh = shade_hit<SAO>(P, ro, rd, t, kind, s, SAO && S.seg_aux ? S.seg_aux + seg : nullptr);
+                        if (!(sh.color.w < 0.001f)) { keep = true; col = pack_unorm4x8(sh.color); depth = sh.hit_t; }   // LinkedListGather.glsl:38
                     }
                 }
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                if (km) {
+                    unsigned long long idx = 0;
+                    const int leader = __ffs(km) - 1;
+                    if (int(lane) == leader) idx = atomicAdd(frag_counter, (unsigned long long)__popc(km));   // fragCounter, LinkedListGather.glsl:55
+                    idx = __shfl_sync(0xffffffffu, idx, leader) + __popc(km & ((1u << lane) - 1u));
+                    if (keep) {
+                        gen++;
+                        if (idx < list_size) {                                                                 // :57
+                            const uint32_t a = addr_gen(P, px, py);
+                            lv_ppll_node nd; nd.color = col; nd.depth = depth;
+                            nd.next = STAGE ? a : atomicExch(heads + a, uint32_t(idx));                        // :60
+                            nodes[idx] = nd;                                                                   // STAGE: `nodes` is the staging array
+                            atomicAdd(counts + a, 1u);
+                        }
+                    }
+                }
+                __syncwarp();   // the entries just read may be overwritten by the next push
             }
         }
       }
