@@ -833,6 +833,8 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
     const float dw = rv * (fabsf(P.proj[3]) + fabsf(P.proj[7]) + fabsf(P.proj[11]));
     const float dcx = rv * (fabsf(P.proj[0]) + fabsf(P.proj[4]) + fabsf(P.proj[8])), dcy = rv * (fabsf(P.proj[1]) + fabsf(P.proj[5]) + fabsf(P.proj[9]));
     const float thr = 4.0f * dw + 1e-6f;
+    const bool persp = P.proj[3] == 0.0f && P.proj[7] == 0.0f && P.proj[11] == -1.0f && P.proj[15] == 0.0f && P.proj[1] == 0.0f && P.proj[4] == 0.0f;
+    const float focal_px = fmaxf(fabsf(P.proj[0]) * 0.5f * float(P.W), fabsf(P.proj[5]) * 0.5f * float(P.H));
     // persistent warps fetch chunks of kRasterChunk consecutive records (Morton order: neighbours in space) from a global counter --
     // the screen area of a segment, i.e. its cost, varies by orders of magnitude
     constexpr uint32_t kRasterChunk = 8;
@@ -881,6 +883,12 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         const Vec4 cc = mat_mul(P.proj, vp);
         const float ccx = (cc.x / cc.w * 0.5f + 0.5f) * float(P.W) - 0.5f, ccy = (cc.y / cc.w * 0.5f + 0.5f) * float(P.H) - 0.5f;
         float rad = sqrtf((fx - ccx) * (fx - ccx) + (fy - ccy) * (fy - ccy));
+        if (persp && cc.w > rv) {
+            // a tighter bound for a perspective matrix (clip w = -z): a point c + d of the sphere, |d| <= rv, projects within
+            // F rv sqrt(1 + |c.xy|^2 / w^2) / (w - rv) pixels of the projected centre (Cauchy-Schwarz on w d.xy - c.xy d.w)
+            const float rs = focal_px * rv * sqrtf(1.0f + (vp.x * vp.x + vp.y * vp.y) / (cc.w * cc.w)) / (cc.w - rv) * 1.001f;
+            if (rs < rad) rad = rs;                                                              // NaN: keeps the corner bound
+        }
         fx = fminf(fmaxf(fx, -4.0f), float(P.W) + 4.0f); fy = fminf(fmaxf(fy, -4.0f), float(P.H) + 4.0f);
         float xmin = fx, xmax = fx, ymin = fy, ymax = fy;
 #pragma unroll
@@ -892,7 +900,7 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         const float ax = __shfl_sync(0xffffffffu, ccx, 0), ay = __shfl_sync(0xffffffffu, ccy, 0);      // lanes 0-7: end point a, 8-15: b
         const float ex = __shfl_sync(0xffffffffu, ccx, 8) - ax, ey = __shfl_sync(0xffffffffu, ccy, 8) - ay;
         const float l2 = ex * ex + ey * ey, inv_l2 = l2 > 0.0f ? 1.0f / l2 : 0.0f;
-        const float lim2 = (rad + 1.5f) * (rad + 1.5f);                                                 // + a pixel and a half of slack
+        const float lim2 = (rad + 1.0f) * (rad + 1.0f);                                                 // + a pixel of slack
         int x0 = int(floorf(xmin)) - 1, x1 = int(ceilf(xmax)) + 1, y0 = int(floorf(ymin)) - 1, y1 = int(ceilf(ymax)) + 1;
         const bool no_bound = full_frame || __ballot_sync(0xffffffffu, bad) != 0u;
         if (no_bound) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
