@@ -122,6 +122,7 @@ def run_reference(args, wl, ppll_wl):
         o = lvo.Oracle("ref"); kind = "reference"
     except (FileNotFoundError, OSError):
         o = lvo.Oracle("own"); kind = "port"
+    o.set_num_threads()          # torchrun exports OMP_NUM_THREADS=1 for nproc > 1: size the pool explicitly (all host cores)
     pos, attr, seg = generate(wl["gen"])
     t0 = time.time()
     sc = o.scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
@@ -166,6 +167,7 @@ def cpu_baseline(wl, pos, attr, seg, sample, budget_s=25.0):
         o = lvo.Oracle("ref"); kind = "reference"
     except (FileNotFoundError, OSError):
         o = lvo.Oracle("own"); kind = "port"
+    o.set_num_threads()
     t0 = time.time()
     sc = o.scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
     build_s = time.time() - t0
@@ -191,6 +193,7 @@ def cpu_baseline_ppll(pw, pos, attr, seg, sample):
         o = lvo.Oracle("ref"); kind = "reference"
     except (FileNotFoundError, OSError):
         o = lvo.Oracle("own"); kind = "port"
+    o.set_num_threads()
     sc = o.scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
     sw, sh = sample
     sub = lv.make_camera(sw, sh, fov_y=2.0 * math.atan(0.5 * sh / pw["H"]))

@@ -62,10 +62,11 @@ class LineVisError(RuntimeError):
 _libs = {}
 
 
-def load_library(path=LIB_PATH):
+def load_library(path=None):
     """Load liblinevis_b200.so (or another build of the same C ABI, e.g. the host emulation the CPU tests use) and declare the
-    prototypes.  Raises if it has not been built."""
-    path = os.path.abspath(path)
+    prototypes.  Raises if it has not been built.  LINEVIS_B200_LIB names another CUDA build of the same sources for A/B
+    measurements (e.g. the -fmad=true build of tools/build_variant.py); it is never a CPU path."""
+    path = os.path.abspath(path or os.environ.get("LINEVIS_B200_LIB") or LIB_PATH)
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

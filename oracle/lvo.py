@@ -157,6 +157,13 @@ class Oracle:
     def num_threads(self):
         return int(self.lib.lvo_num_threads())
 
+    def set_num_threads(self, n=None):
+        """Size the OpenMP pool explicitly (default: every host core this process may run on); torchrun exports OMP_NUM_THREADS=1."""
+        if n is None:
+            n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.lib.lvo_set_num_threads(ctypes.c_int(int(n)))
+        return self.num_threads()
+
     def det_acos(self, x):
         return float(self.lib.lvo_det_acos(x))
 

@@ -771,4 +771,14 @@ int lvo_num_threads(void) {
 #endif
 }
 
+// Size of the OpenMP pool of every driver above.  Launchers such as torchrun export OMP_NUM_THREADS=1 for nproc > 1; the benchmark's CPU
+// legs set the pool explicitly (the reference library's own benchmark uses all hardware threads, submodules/bvh/test/benchmark.cpp:142-144).
+void lvo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 }  // extern "C"

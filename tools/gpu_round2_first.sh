@@ -28,6 +28,15 @@ ab raster b200_ppll_gather_mode=raster
 ab raster_contig b200_ppll_gather_mode=raster_contiguous
 ab raster_contig_regsort b200_ppll_gather_mode=raster_contiguous b200_ppll_reg_sort=true
 
+# 4. FMA contraction on (build/liblinevis_b200_fmad.so, tools/build_variant.py): speed and max|delta| vs the strict build / the oracle
+LINEVIS_B200_LIB=build/liblinevis_b200_fmad.so timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/r2a_ab_fmad.json 2> $O/r2a_ab_fmad.err; echo "ab fmad rc=$?"
+timeout 300 python tools/fmad_delta.py > $O/r2a_fmad_delta.log 2>&1; cat $O/r2a_fmad_delta.log
+
+# 5. compute-sanitizer on small scenes through every default kernel and the main variants
+for tool in memcheck racecheck synccheck; do
+    timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py > $O/r2a_sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?"; tail -2 $O/r2a_sanitizer_$tool.log
+done
+
 python - <<'EOF'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2a_*.json")):
