@@ -44,10 +44,14 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
-    bool ppll_raster_gather = false;    // b200_ppll_gather_mode = raster: object-order gather (one warp per segment) instead of the ray-cast one; untimed
+    bool ao_wide = false;               // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
+    uint32_t ao_wide_top = 0;           // ... and serves the first levels (up to this many wide nodes) from shared memory (bulk-copied per block)
+    bool ppll_raster_gather = true;     // b200_ppll_gather_mode = raster (default): object-order gather (one warp per segment); raycast = the BVH packet gather
     bool ppll_contiguous = false;       // ... = raster_contiguous: plus count -> scan -> fill, every list one contiguous run, pointer-free resolve
+    float ppll_raster_slack = 0.1f;     // object-order gather: pixels added to the 2-D cull's bound on top of the float-error term (see the kernel)
+    uint32_t ppll_raster_min_blocks = 4;  // ... blocks per SM the kernel is compiled for (4 / 5 / 6: 128 / 102 / 85 registers)
     uint32_t ppll_resolve_tile = 1024;  // plain resolve: keys per warp in the shared tile (256 / 512 / 1024; raised to hold max_frags)
-    bool ppll_reg_sort = false;         // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory; untimed, see DESIGN 8
+    bool ppll_reg_sort = true;          // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory (config 4: 4.84 -> 2.87 ms)
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
     uint32_t ao_leaf_vote = 12;
     uint32_t expected_avg_depth_complexity = 0;  // 0 = reference rule (20 / 120)
@@ -96,6 +100,7 @@ struct lv_ctx {
     // PPLL
     DevBuf<uint32_t> heads, counts, bin_order; DevBuf<unsigned int> bin_hist; DevBuf<lv_ppll_node> nodes; DevBuf<unsigned long long> frag_counter;
     // raster_contiguous gather: staged fragments, exclusive scan of the counts, fill cursors; lists_contiguous tells the resolve pass
+    DevBuf<float4> pixel_rays;   // object-order gather: per-pixel camera rays of the frame (k_pixel_rays)
     DevBuf<lv_ppll_node> stage; DevBuf<uint32_t> list_offs; DevBuf<unsigned int> fill_cursor; DevBuf<char> scan_tmp; bool lists_contiguous = false;
     unsigned long long list_size = 0; uint32_t padded_w = 0, padded_h = 0;
     cudaEvent_t ev[8] = {};
@@ -116,6 +121,9 @@ struct lv_scene {
     std::vector<float> host_pos; std::vector<uint64_t> line_offsets;   // polylines for the (host-side) parametrization
     DevBuf<float> sampling, weights, factors;      // samplingLocations, blending weights, ambientOcclusionFactors
     DevBuf<NodeQ> qnodes; float q_origin[3] = {0, 0, 0}, q_scale[3] = {1, 1, 1};   // quantised copy of `nodes` (ensure_qnodes)
+    // 4-wide quantised tree (ensure_wnodes): nodes in breadth-first order, level_end[l] = number of nodes in levels 0..l
+    DevBuf<NodeW4> wnodes; float w_origin[3] = {0, 0, 0}, w_scale[3] = {1, 1, 1}; uint64_t n_wnodes = 0; uint32_t w_need = 0;
+    std::vector<uint32_t> w_level_end; float w_build_ms = 0.0f; bool w_failed = false;
     // triangle-tube mode of the AO passes (ensure_tube_mesh): the reference's tube mesh + a BVH over its triangles
     DevBuf<TriRec> tris; DevBuf<uint32_t> tri_ids; DevBuf<Node64> tri_nodes; DevBuf<float4> tri_vattr, tri_line_pos, tri_line_tan;
     uint64_t n_tri = 0; uint32_t mesh_subdiv = 0; float tri_build_ms = 0.0f;
@@ -127,7 +135,8 @@ struct lv_scene {
         SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
         s.seg_aux = has_lines ? seg_aux.p : nullptr;
         s.qnodes = qnodes.p;
-        for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; }
+        for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; s.w_origin[k] = w_origin[k]; s.w_scale[k] = w_scale[k]; }
+        s.wnodes = n_wnodes ? wnodes.p : nullptr; s.w_top = 0;
         s.tris = tris.p; s.tri_ids = tri_ids.p; s.tri_nodes = tri_nodes.p; s.tri_vattr = tri_vattr.p;
         s.tri_line_pos = tri_line_pos.p; s.tri_line_tan = tri_line_tan.p; s.n_tri = uint32_t(n_tri);
         s.n_nodes = uint32_t(n_nodes); s.radius = line_width * 0.5f; s.line_width = line_width;
@@ -237,6 +246,9 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.tiles = c->tiles_dev.p; P.n_tiles = uint32_t(c->tiles_host.size()); P.tile_size = c->tile_size;
     padded_size(c, P.W, P.H, P.padded_w, P.padded_h);
     P.addr_tw = o.tiling_w; P.addr_th = o.tiling_h;
+    for (P.addr_tw_log2 = 0; (1u << P.addr_tw_log2) < P.addr_tw; P.addr_tw_log2++) {}
+    for (P.addr_th_log2 = 0; (1u << P.addr_th_log2) < P.addr_th; P.addr_th_log2++) {}
+    P.raster_slack = o.ppll_raster_slack;
     return LV_OK;
 }
 
@@ -307,6 +319,61 @@ int ensure_qnodes(lv_ctx* c, lv_scene* sc) {
     k_quantize_nodes<<<uint32_t((sc->n_nodes + 255) / 256), 256, 0, c->stream>>>(sc->nodes.p, uint32_t(sc->n_nodes), sc->q_origin[0], sc->q_origin[1], sc->q_origin[2],
                                                                               sc->q_scale[0], sc->q_scale[1], sc->q_scale[2], sc->qnodes.p);
     LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+// b200_ao_wide: the 4-wide quantised tree, collapsed from the child-pair nodes on first use (breadth-first rounds of k_w4_round).
+// Leaves `n_wnodes` at 0 (the stream then stays on the child-pair nodes) when the scene has multi-record leaves or the tree would need
+// more traversal stack than the kernel has.
+int ensure_wnodes(lv_ctx* c, lv_scene* sc) {
+    if (sc->n_wnodes || sc->w_failed || sc->n_nodes == 0) return LV_OK;
+    if (sc->leaf_size != 1) { sc->w_failed = true; return LV_OK; }
+    W4Grid G;
+    for (int k = 0; k < 3; k++) {
+        const float ext = sc->bounds[3 + k] - sc->bounds[k];
+        float s = std::max(ext / 65535.0f * 1.0001f, 1e-30f), o = sc->bounds[k], om = 0.0f;
+        auto dq = [&](uint32_t q) { uint32_t bits = 0x4B000000u | q; float x; memcpy(&x, &bits, 4); return std::fmaf(x, s, om); };   // = w4_dequant
+        for (int it = 0; it < 64; it++) {   // the shifted origin is rounded at magnitude 2^23 * s: make sure the grid still spans the bounds
+            om = std::fmaf(-8388608.0f, s, o);
+            if (dq(0) > sc->bounds[k]) { o -= s; continue; }
+            if (dq(65535) < sc->bounds[3 + k]) { s *= 1.001f; continue; }
+            break;
+        }
+        if (dq(0) > sc->bounds[k] || dq(65535) < sc->bounds[3 + k]) { sc->w_failed = true; return LV_OK; }
+        G.o[k] = o; G.s[k] = s; G.om[k] = om;
+        sc->w_origin[k] = om; sc->w_scale[k] = s;
+    }
+    DevBuf<uint3> q0, q1; DevBuf<unsigned int> ctr;   // ctr: [0] next queue count, [1] node allocator, [2] stack need
+    auto cleanup = [&]() { q0.release(); q1.release(); ctr.release(); };
+#define LV_W4(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); sc->wnodes.release(); return fail(c, e_ == cudaErrorMemoryAllocation ? LV_ERR_OUT_OF_MEMORY : LV_ERR_CUDA, std::string("wide BVH: ") + cudaGetErrorString(e_)); } } while (0)
+    const size_t cap = size_t(sc->n_nodes);          // every wide node is rooted at a distinct inner binary node
+    LV_W4(sc->wnodes.ensure(cap)); LV_W4(q0.ensure(cap)); LV_W4(q1.ensure(cap)); LV_W4(ctr.ensure(4));
+    cudaStream_t st = c->stream;
+    LV_W4(cudaEventRecord(c->ev[6], st));
+    const uint3 root = make_uint3(0u, 0u, 0u);
+    const unsigned int init[4] = {0u, 1u, 0u, 0u};
+    LV_W4(cudaMemcpyAsync(q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+    LV_W4(cudaMemcpyAsync(ctr.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    uint32_t n_in = 1, total = 1;
+    sc->w_level_end.clear();
+    uint3 *in = q0.p, *out = q1.p;
+    while (n_in) {
+        sc->w_level_end.push_back(total);
+        LV_W4(cudaMemsetAsync(ctr.p, 0, 4, st));
+        k_w4_round<<<(n_in + 127) / 128, 128, 0, st>>>(sc->nodes.p, in, n_in, out, ctr.p, ctr.p + 1, sc->wnodes.p, ctr.p + 2, G);
+        unsigned int h[3];
+        LV_W4(cudaMemcpyAsync(h, ctr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        LV_W4(cudaStreamSynchronize(st));
+        n_in = h[0]; total = h[1]; sc->w_need = h[2];
+        std::swap(in, out);
+    }
+    LV_W4(cudaEventRecord(c->ev[7], st));
+    LV_W4(cudaStreamSynchronize(st));
+    sc->w_build_ms = elapsed(c->ev[6], c->ev[7]);
+    cleanup();
+#undef LV_W4
+    if (sc->w_need + 1 > uint32_t(kAoStackWide)) { sc->wnodes.release(); sc->w_failed = true; return LV_OK; }   // deeper than the stream's stack: stay on the child-pair nodes
+    sc->n_wnodes = total;
     return LV_OK;
 }
 
@@ -401,8 +468,11 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
         return c->opt.ao_min_blocks >= 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 1>) : launch(k_rtao_rays_q<8, BAKE, 12, 1>);
     const uint32_t stack = c->opt.ao_stack;
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
+    if (queue && c->opt.ao_wide && S.wnodes)     // 4-wide quantised tree
+        return c->opt.ao_min_blocks == 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 0, 2>) : c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_q<7, BAKE, 12, 0, 2>)
+                                                                                                                : launch(k_rtao_rays_q<8, BAKE, 12, 0, 2>);
     if (queue && c->opt.ao_qnodes && S.qnodes)   // experimental: quantised nodes (default register budget / stack only)
-        return launch(k_rtao_rays_q<8, BAKE, 12, 0, true>);
+        return launch(k_rtao_rays_q<8, BAKE, 12, 0, 1>);
     const uint32_t mb = c->opt.ao_min_blocks ? c->opt.ao_min_blocks : (queue ? 8u : 9u);   // 0 = measured optimum of the variant
     if (queue) {
         if (mb >= 9) return stack == 8 ? launch(k_rtao_rays_q<9, BAKE, 8>) : stack == 1 ? launch(k_rtao_rays_q<9, BAKE, 1>) : launch(k_rtao_rays_q<9, BAKE, 12>);
@@ -440,6 +510,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     P.frame_number = frame_number;
     const bool tri = c->opt.ao_triangles;
     if (tri) { int trc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)); if (trc) return trc; }
+    else if (c->opt.ao_wide) { int wrc = ensure_wnodes(c, const_cast<lv_scene*>(sc)); if (wrc) return wrc; }
     else if (c->opt.ao_qnodes) { int qrc = ensure_qnodes(c, const_cast<lv_scene*>(sc)); if (qrc) return qrc; }
     const SceneDev S = sc->dev();
     const uint32_t grid = pixel_grid(c, P);
@@ -594,7 +665,8 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
     if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;
-    if (!o.ao_triangles && o.ao_qnodes && (rc = ensure_qnodes(c, sc))) return rc;
+    if (!o.ao_triangles && o.ao_wide && (rc = ensure_wnodes(c, sc))) return rc;
+    if (!o.ao_triangles && !o.ao_wide && o.ao_qnodes && (rc = ensure_qnodes(c, sc))) return rc;
     if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1, o.ao_triangles))) return rc;
     c->rtao_rays_timed = true;
     k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, sc->factors.p);
@@ -667,7 +739,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (!c) return LV_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->rgba8.release();
+    c->rgba8.release(); c->pixel_rays.release();
     c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -737,10 +809,14 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         o.ppll_raster_gather = strcmp(value, "raycast") != 0;
         o.ppll_contiguous = !strcmp(value, "raster_contiguous");
     }
+    else if (k == "b200_ppll_raster_slack") { if (!(f() >= 0.0f)) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_raster_slack must be >= 0"); o.ppll_raster_slack = f(); }
+    else if (k == "b200_ppll_raster_min_blocks") { if (u() < 4 || u() > 6) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_raster_min_blocks must be 4, 5 or 6"); o.ppll_raster_min_blocks = u(); }
     else if (k == "b200_ppll_resolve_tile") { if (u() != 256 && u() != 512 && u() != 1024) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ppll_resolve_tile must be 256, 512 or 1024"); o.ppll_resolve_tile = u(); }
     else if (k == "b200_ao_min_blocks") o.ao_min_blocks = u();
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
     else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
+    else if (k == "b200_ao_wide") o.ao_wide = parse_bool(value);
+    else if (k == "b200_ao_wide_top") { if (u() > 1365) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_wide_top must be <= 1365 nodes"); o.ao_wide_top = u(); }
     else if (k == "b200_rtao_geometry") {
         if (!strcmp(value, "triangles")) o.ao_triangles = true;
         else if (!strcmp(value, "capsules")) o.ao_triangles = false;
@@ -796,12 +872,16 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_min_blocks") v = std::to_string(o.ao_min_blocks);
     else if (k == "b200_ao_queue") v = b(o.ao_queue);
     else if (k == "b200_ao_qnodes") v = b(o.ao_qnodes);
+    else if (k == "b200_ao_wide") v = b(o.ao_wide);
+    else if (k == "b200_ao_wide_top") v = std::to_string(o.ao_wide_top);
     else if (k == "b200_rtao_geometry") v = o.ao_triangles ? "triangles" : "capsules";
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
     else if (k == "b200_ppll_reg_sort") v = b(o.ppll_reg_sort);
     else if (k == "b200_ppll_gather_mode") v = o.ppll_contiguous ? "raster_contiguous" : (o.ppll_raster_gather ? "raster" : "raycast");
     else if (k == "b200_ppll_resolve_tile") v = std::to_string(o.ppll_resolve_tile);
+    else if (k == "b200_ppll_raster_slack") v = std::to_string(o.ppll_raster_slack);
+    else if (k == "b200_ppll_raster_min_blocks") v = std::to_string(o.ppll_raster_min_blocks);
     else return LV_ERR_UNKNOWN_OPTION;
     snprintf(buf, cap, "%s", v.c_str());
     return LV_OK;
@@ -1025,7 +1105,7 @@ int lv_scene_destroy(lv_scene* s) {
     s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release();
     s->pt_pos.release(); s->pt_tan.release(); s->pt_nrm.release(); s->seg_aux.release();
     s->sampling.release(); s->weights.release(); s->factors.release();
-    s->qnodes.release();
+    s->qnodes.release(); s->wnodes.release();
     s->tris.release(); s->tri_ids.release(); s->tri_nodes.release(); s->tri_vattr.release(); s->tri_line_pos.release(); s->tri_line_tan.release();
     delete s;
     return LV_OK;
@@ -1316,12 +1396,18 @@ int lv_ppll_gather(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, lv_stats
         const bool contig = c->opt.ppll_contiguous;
         if (contig) LV_CUDA(c, c->stage.ensure(c->list_size));
         lv_ppll_node* dst = contig ? c->stage.p : c->nodes.p;
-#define LV_RASTER(SAOV, STAGEV) do { \
-            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<SAOV, STAGEV>, kBlockThreads, 0)); \
-            k_ppll_gather_raster<SAOV, STAGEV><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>( \
-                P, sc->dev(), c->heads.p, c->counts.p, dst, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels); } while (0)
-        if (P.use_static_ao) { if (contig) LV_RASTER(true, true); else LV_RASTER(true, false); }
-        else { if (contig) LV_RASTER(false, true); else LV_RASTER(false, false); }
+        // the pixel-centre camera rays of this frame, once per pixel (the gather tests every pixel against many segments)
+        LV_CUDA(c, c->pixel_rays.ensure(2 * size_t(P.W) * P.H));
+        k_pixel_rays<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, c->pixel_rays.p);
+#define LV_RASTER(SAOV, STAGEV, MB) do { \
+            LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ppll_gather_raster<SAOV, STAGEV, MB>, kBlockThreads, 0)); \
+            k_ppll_gather_raster<SAOV, STAGEV, MB><<<uint32_t(std::max(1, per_sm) * c->num_sms), kBlockThreads, 0, c->stream>>>( \
+                P, sc->dev(), c->heads.p, c->counts.p, dst, c->frag_counter.p, c->list_size, c->counters.p, work, owned, c->tiles_x, n_pixels, c->pixel_rays.p); } while (0)
+        if (P.use_static_ao) { if (contig) LV_RASTER(true, true, 4); else LV_RASTER(true, false, 4); }
+        else if (contig) LV_RASTER(false, true, 4);
+        else if (c->opt.ppll_raster_min_blocks == 6) LV_RASTER(false, false, 6);
+        else if (c->opt.ppll_raster_min_blocks == 5) LV_RASTER(false, false, 5);
+        else LV_RASTER(false, false, 4);
 #undef LV_RASTER
         if (contig) {   // counts -> offsets (exclusive scan) -> every pixel's fragments into one contiguous run of the node buffer
             const size_t npad = size_t(P.padded_w) * P.padded_h;

@@ -252,4 +252,83 @@ __global__ void k_quantize_nodes(const Node64* nodes, uint32_t n, float ox, floa
     out[i] = q;
 }
 
+// ---- 4-wide quantised tree (NodeW4) -------------------------------------------------------------------------------------------
+// Dequantisation of a 16-bit grid coordinate q: 0x4B000000 | q is the float 8388608 + q (exact), so ONE logic operation + ONE fma
+// replace an integer-to-float conversion (a quarter-rate instruction; it is what made the 32-byte NodeQ kernel lose) + an fma:
+//     bound = fma(as_float(0x4B000000 | q), scale, origin_m),   origin_m = origin - 8388608 * scale (rounded once, on the host).
+// The builder rounds against exactly this expression, so its rounding errors are part of the grid, not of the bound.
+LV_DEV float w4_dequant(uint32_t q, float scale, float origin_m) { return __fmaf_rn(__uint_as_float(0x4B000000u | q), scale, origin_m); }
+
+__device__ __forceinline__ uint32_t w4_quantize(float b, float o, float s, float om, bool up) {
+    float g = (b - o) / s;
+    g = up ? ceilf(g) : floorf(g);
+    int q = int(fminf(fmaxf(g, 0.0f), 65535.0f));
+    if (up) { while (q < 65535 && w4_dequant(uint32_t(q), s, om) < b) q++; while (q > 0 && w4_dequant(uint32_t(q - 1), s, om) >= b) q--; }
+    else { while (q > 0 && w4_dequant(uint32_t(q), s, om) > b) q--; while (q < 65535 && w4_dequant(uint32_t(q + 1), s, om) <= b) q++; }
+    return uint32_t(q);
+}
+
+struct W4Grid { float o[3], s[3], om[3]; };
+
+// One breadth-first round of the collapse: every queue item (binary node, wide-node index, stack need of the path so far) becomes a
+// wide node.  Its children start as the binary node's two; while there are fewer than four, the inner child with the largest surface
+// area is replaced by its own two children (the usual greedy collapse of a binary BVH into a wide one).  Inner children get
+// consecutive wide indices from `alloc` and go to the next round's queue.  `need` = the worst-case traversal stack: a step pushes
+// every hit child but the one it descends into, so a path needs sum (children - 1) entries.
+__global__ void k_w4_round(const Node64* nodes, const uint3* in_q, uint32_t n_in, uint3* out_q, unsigned int* out_count, unsigned int* alloc,
+                           NodeW4* wnodes, unsigned int* need, const W4Grid G) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in) return;
+    const uint3 item = in_q[i];
+    float4 lo[4], hi[4];
+    int n = 0;
+    {
+        const Node64 nd = nodes[item.x];
+        if (nd.l0.x != INFINITY) { lo[n] = nd.l0; hi[n] = nd.l1; n++; }
+        if (nd.r0.x != INFINITY) { lo[n] = nd.r0; hi[n] = nd.r1; n++; }
+    }
+    while (n < 4) {
+        int pick = -1; float best = -1.0f;
+        for (int k = 0; k < n; k++) {
+            if (__float_as_uint(lo[k].w) & 0x80000000u) continue;   // a leaf
+            const float dx = hi[k].x - lo[k].x, dy = hi[k].y - lo[k].y, dz = hi[k].z - lo[k].z;
+            const float a = dx * dy + dy * dz + dz * dx;
+            if (a > best) { best = a; pick = k; }
+        }
+        if (pick < 0) break;
+        const Node64 nd = nodes[__float_as_uint(lo[pick].w)];
+        const bool hl = nd.l0.x != INFINITY, hr = nd.r0.x != INFINITY;
+        if (hl && hr) { lo[pick] = nd.l0; hi[pick] = nd.l1; lo[n] = nd.r0; hi[n] = nd.r1; n++; }
+        else if (hl) { lo[pick] = nd.l0; hi[pick] = nd.l1; }
+        else if (hr) { lo[pick] = nd.r0; hi[pick] = nd.r1; }
+        else break;
+    }
+    int n_inner = 0;
+    for (int k = 0; k < n; k++) n_inner += (__float_as_uint(lo[k].w) & 0x80000000u) ? 0 : 1;
+    uint32_t wbase = 0, qbase = 0;
+    if (n_inner) { wbase = atomicAdd(alloc, (unsigned)n_inner); qbase = atomicAdd(out_count, (unsigned)n_inner); }
+    const uint32_t path = item.z + uint32_t(n > 0 ? n - 1 : 0);
+    atomicMax(need, path);
+    NodeW4 w;
+    int inner_i = 0;
+    for (int k = 0; k < 4; k++) {
+        uint32_t* bw = w.w + 8 * (k >> 1) + 3 * (k & 1);
+        uint32_t& cw = w.w[8 * (k >> 1) + 6 + (k & 1)];
+        if (k >= n) { bw[0] = bw[1] = bw[2] = 0u; cw = kAbsentChild; continue; }
+        const uint32_t ax = w4_quantize(lo[k].x, G.o[0], G.s[0], G.om[0], false), ay = w4_quantize(lo[k].y, G.o[1], G.s[1], G.om[1], false),
+                       az = w4_quantize(lo[k].z, G.o[2], G.s[2], G.om[2], false);
+        const uint32_t bx = w4_quantize(hi[k].x, G.o[0], G.s[0], G.om[0], true), by = w4_quantize(hi[k].y, G.o[1], G.s[1], G.om[1], true),
+                       bz = w4_quantize(hi[k].z, G.o[2], G.s[2], G.om[2], true);
+        bw[0] = ax | (ay << 16); bw[1] = az | (bx << 16); bw[2] = by | (bz << 16);
+        const uint32_t word = __float_as_uint(lo[k].w);
+        if (word & 0x80000000u) cw = word;
+        else {
+            cw = wbase + uint32_t(inner_i);
+            out_q[qbase + uint32_t(inner_i)] = make_uint3(word, wbase + uint32_t(inner_i), path);
+            inner_i++;
+        }
+    }
+    wnodes[item.y] = w;
+}
+
 }  // namespace lv

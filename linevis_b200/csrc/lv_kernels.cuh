@@ -291,9 +291,10 @@ constexpr int kAoStack = 72;
 //      depths touch different 128-byte lines, one L1 wavefront each), deeper entries spill to a local array.
 //      K x 8 B x 128 threads = K KiB of shared memory per block.
 
-template <int K> struct AoStack {
+constexpr int kAoStackWide = 96;   // 4-wide tree: a step pushes up to three entries (lv_scene checks the tree's exact need against this)
+template <int K, int CAP = kAoStack> struct AoStack {
     static constexpr int kAoSmemStack = K;
-    unsigned long long e[kAoStack - kAoSmemStack];
+    unsigned long long e[CAP - kAoSmemStack];
 #ifdef LV_HOST_EMU   // host emulation: plain indexing instead of shared-window addresses + inline PTX
     unsigned long long* sm;
     __device__ __forceinline__ void init() {
@@ -324,15 +325,15 @@ template <int K> struct AoStack {
     }
 #endif
 };
-template <> struct AoStack<1> {
-    unsigned long long e[kAoStack];
+template <int CAP> struct AoStack<1, CAP> {
+    unsigned long long e[CAP];
     __device__ __forceinline__ void init() {}
     __device__ __forceinline__ void put(int i, uint32_t node, float t) { e[i] = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | node; }
     __device__ __forceinline__ unsigned long long get(int i) const { return e[i]; }
 };
 // pop until an entry whose box entry distance is still within reach; returns kDone if the stack runs empty
-template <int STACK>
-__device__ __forceinline__ uint32_t ao_stack_pop(const AoStack<STACK>& st, int& sp, float best) {
+template <int STACK, int CAP>
+__device__ __forceinline__ uint32_t ao_stack_pop(const AoStack<STACK, CAP>& st, int& sp, float best) {
     while (sp > 0) {
         --sp;
         const unsigned long long v = st.get(sp);
@@ -475,8 +476,10 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
 constexpr int kLeafQueue = 64;
 constexpr uint32_t kNoHitBits = 0x7F800000u;   // +inf
 
-// QN: traverse the 32-byte quantised nodes (NodeQ, lv_types.cuh) instead of Node64 -- experimental, capsules only.
-template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, bool QN = false>
+// NM = node format: 0 the 64-byte child-pair nodes (Node64); 1 the 32-byte quantised child-pair nodes (NodeQ, measured slower: the
+// integer-to-float conversions of its dequantisation cost more issue slots than the second load); 2 the 64-byte 4-WIDE quantised
+// nodes (NodeW4): four boxes per fetch, about half the dependent node fetches per ray, up to three pushes per step.  1 and 2: capsules only.
+template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, int NM = 0>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
               const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
@@ -495,7 +498,9 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     const float radius = S.radius;
     uint32_t steps = 0, isect = 0, rays = 0;
 
-    AoStack<STACK> pst;
+    constexpr bool QN = NM != 0;                       // quantised boxes: the record's exact AABB is tested in the leaf batch
+    constexpr int kCap = NM == 2 ? kAoStackWide : kAoStack;
+    AoStack<STACK, kCap> pst;
     pst.init();
     int sp = 0;
     uint32_t cur = kDone;
@@ -538,12 +543,46 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
 
         while (true) {
             // A: one inner-node step for every lane that holds an inner node
-            if (cur != kDone && !(cur & kLeafBit)) {
+            if (NM == 2) {
+              if (cur != kDone && !(cur & kLeafBit)) {
+                steps++;
+                float4 ha, hb2, hc, hd;
+                ldg256(S.wnodes + cur, ha, hb2);                                   // children 0, 1
+                ldg256(reinterpret_cast<const char*>(S.wnodes + cur) + 32, hc, hd);   // children 2, 3
+                const float ox = S.w_origin[0], oy = S.w_origin[1], oz = S.w_origin[2], sx = S.w_scale[0], sy = S.w_scale[1], sz = S.w_scale[2];
+                float tc[4]; uint32_t cw[4];
+#define LV_W4_CHILD(k, W0, W1, W2, CW) do { \
+                    const uint32_t w0 = __float_as_uint(W0), w1 = __float_as_uint(W1), w2 = __float_as_uint(W2); \
+                    cw[k] = __float_as_uint(CW); \
+                    float tn; \
+                    const bool h = cw[k] != kAbsentChild && \
+                        box_hit(rb, w4_dequant(w0 & 0xffffu, sx, ox), w4_dequant(w0 >> 16, sy, oy), w4_dequant(w1 & 0xffffu, sz, oz), \
+                                w4_dequant(w1 >> 16, sx, ox), w4_dequant(w2 & 0xffffu, sy, oy), w4_dequant(w2 >> 16, sz, oz), 0.0f, best, tn); \
+                    tc[k] = h ? tn : __int_as_float(0x7f800000); } while (0)
+                LV_W4_CHILD(0, ha.x, ha.y, ha.z, hb2.z);
+                LV_W4_CHILD(1, ha.w, hb2.x, hb2.y, hb2.w);
+                LV_W4_CHILD(2, hc.x, hc.y, hc.z, hd.z);
+                LV_W4_CHILD(3, hc.w, hd.x, hd.y, hd.w);
+#undef LV_W4_CHILD
+                // descend into the nearest hit child, push the other hit children (entries carry their entry distance and are culled
+                // against the closest hit when popped, so their order only matters for speed)
+                int near = 0; float tnear = tc[0];
+#pragma unroll
+                for (int k = 1; k < 4; k++) if (tc[k] < tnear) { tnear = tc[k]; near = k; }
+                if (tnear == __int_as_float(0x7f800000)) cur = ao_stack_pop(pst, sp, best);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k != near && tc[k] != __int_as_float(0x7f800000) && sp < kCap) { pst.put(sp, cw[k], tc[k]); sp++; }
+                    cur = cw[near];
+                }
+              }
+            } else if (cur != kDone && !(cur & kLeafBit)) {
                 steps++;
                 float tl, tr;
                 bool hl, hr;
                 uint32_t cl, cr;
-                if (QN) {
+                if (NM == 1) {
                     float4 qa, qb;
                     ldg256(S.qnodes + cur, qa, qb);   // the whole node in one request
                     const uint32_t w0 = __float_as_uint(qa.x), w1 = __float_as_uint(qa.y), w2 = __float_as_uint(qa.z);
@@ -658,10 +697,11 @@ __global__ void k_rtao_reduce(const __grid_constant__ FrameParams P, const float
 // PPLL.  addrGen: reference Data/Shaders/Utils/TiledAddress.glsl:53-85.
 __device__ __forceinline__ uint32_t addr_gen(const FrameParams& P, uint32_t x, uint32_t y) {
     if (P.addr_tw == 1 && P.addr_th == 1) return x + P.padded_w * y;
-    const uint32_t sw = P.padded_w / P.addr_tw;
-    const uint32_t tx = x / P.addr_tw, ty = y / P.addr_th;
-    const uint32_t base = (tx + sw * ty) * (P.addr_tw * P.addr_th);
-    return base | ((x & (P.addr_tw - 1)) + (y & (P.addr_th - 1)) * P.addr_tw);
+    // tile sizes are powers of two (checked by lv_set_option): the divisions of the reference are shifts
+    const uint32_t sw = P.padded_w >> P.addr_tw_log2;
+    const uint32_t tx = x >> P.addr_tw_log2, ty = y >> P.addr_th_log2;
+    const uint32_t base = (tx + sw * ty) << (P.addr_tw_log2 + P.addr_th_log2);
+    return base | ((x & (P.addr_tw - 1)) + ((y & (P.addr_th - 1)) << P.addr_tw_log2));
 }
 __device__ __forceinline__ uint32_t pack_unorm4x8(Vec4 c) {
     uint32_t r = uint32_t(floorf(clampf_(c.x, 0.0f, 1.0f) * 255.0f + 0.5f));
@@ -801,29 +841,57 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     flush_counter(&C->frags_generated, g.gen);
 }
 
-// S9 gather, OBJECT ORDER (b200_ppll_gather_mode = raster; like the reference, whose gather pass is a rasterisation of the tube
+// Per-pixel camera ray of the pixel centre, computed once per frame for the object-order gather: [2 * pixel] = (rd.xyz, |rd|^2),
+// [2 * pixel + 1] = (safe 1/rd).  The same expressions as camera_ray / make_rayq / make_raybox, evaluated once per pixel instead of
+// once per (pixel, segment) candidate.
+__global__ void __launch_bounds__(kBlockThreads)
+k_pixel_rays(const __grid_constant__ FrameParams P, float4* rays) {
+    uint32_t x, y;
+    if (!thread_pixel(P, x, y)) return;
+    Vec3 ro, rd;
+    camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
+    const RayQ rq = make_rayq(ro, rd);
+    const RayBox rb = make_raybox(ro, rd);
+    float4* o = rays + 2 * (size_t(y) * P.W + x);
+    o[0] = make_float4(rd.x, rd.y, rd.z, rq.dd);
+    o[1] = make_float4(rb.ix, rb.iy, rb.iz, 0.0f);
+}
+
+// S9 gather, OBJECT ORDER (b200_ppll_gather_mode = raster, the default; like the reference, whose gather pass is a rasterisation of the tube
 // geometry, LinkedListGather.glsl).  One warp takes one segment: a conservative screen rectangle of the capsule (the hull of the two
-// end spheres' projected bounding boxes, padded by a pixel), whose pixels the lanes test 32 at a time with EXACTLY the predicates of
-// the ray-cast gather -- the pixel-centre camera ray, the record's own-AABB slab test, capsule_hit, t in [1e-4, 1000] -- so the set of
-// fragments per pixel is the same, bit for bit; only the (race-dependent, in the reference too) order inside a list differs.
-// Fragments are appended the reference's way: one counter bump per warp round, atomicExch on the pixel's head.  No BVH is involved;
-// the work is proportional to the screen area of the tubes instead of the traversal's visits.  Tile-sharded frames: candidates outside
-// this rank's tiles are skipped (owned_tiles: one byte per tile of the frame).
+// end spheres' projected bounding boxes, padded by a pixel) thinned out by the 2-D distance to the projected axis; the surviving
+// candidate pixels are tested 32 at a time with EXACTLY the predicates of the ray-cast gather -- the pixel-centre camera ray (read from
+// the per-pixel ray table), the record's own-AABB slab test, capsule_hit, t in [1e-4, 1000] -- so the set of fragments per pixel is the
+// same, bit for bit; only the (race-dependent, in the reference too) order inside a list differs.  Hits are queued again and SHADED 32
+// at a time, so that both expensive stages run with full warps (measured on config 4 before the second queue: 30 of 32 lanes in the
+// test, 21.5 in the shading).  Everything that depends on the segment alone -- its AABB, cylinder axis, the tangent normalisations of
+// the shader -- is computed once per segment (warp-uniform), not once per fragment.  Fragments are appended the reference's way: one
+// counter bump per warp round, atomicExch on the pixel's head.  No BVH is involved; the work is proportional to the screen area of the
+// tubes.  Tile-sharded frames: candidates outside this rank's tiles are skipped (owned_tiles: one byte per tile of the frame).
 // STAGE (b200_ppll_gather_mode = raster_contiguous): fragments go to a staging array as (colour, depth, pixel address) and only the
 // per-pixel counts are bumped; an exclusive scan of the counts and k_ppll_fill then place every pixel's fragments in ONE contiguous
 // run of the node buffer (next = previous slot, head = last slot: still the reference's linked structure), which the resolve pass
 // reads by index instead of chasing pointers (k_ppll_resolve<.., CONTIG>).
-template <bool SAO, bool STAGE = false>
-__global__ void __launch_bounds__(kBlockThreads)
+constexpr int kRasterQueue = 64;
+template <bool SAO, bool STAGE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint32_t* heads, uint32_t* counts,
                      lv_ppll_node* nodes, unsigned long long* frag_counter, unsigned long long list_size, Counters* C,
-                     unsigned long long* work_counter, const unsigned char* owned_tiles, uint32_t tiles_x, unsigned long long n_pixels) {
-    __shared__ uint32_t s_cand[kBlockThreads / 32][64];   // per warp: queued candidate pixels (x | y << 16)
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t* queue = s_cand[threadIdx.x >> 5];
+                     unsigned long long* work_counter, const unsigned char* owned_tiles, uint32_t tiles_x, unsigned long long n_pixels,
+                     const float4* pixel_rays) {
+    __shared__ uint32_t s_cand[kBlockThreads / 32][kRasterQueue];   // per warp: queued candidate pixels (x | y << 16)
+    __shared__ uint32_t s_hpix[kBlockThreads / 32][kRasterQueue];   // per warp: queued hits -- pixel,
+    __shared__ uint32_t s_ht[kBlockThreads / 32][kRasterQueue];     //   t bits,
+    __shared__ uint32_t s_hkind[kBlockThreads / 32][kRasterQueue];  //   hit kind
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* queue = s_cand[warp];
+    uint32_t* hpix = s_hpix[warp]; uint32_t* ht = s_ht[warp]; uint32_t* hkind = s_hkind[warp];
     const float tmin = 0.0001f, tmax = 1000.0f;
     const bool capped = P.use_capped != 0;
     uint32_t isect = 0, gen = 0;
+    Vec3 ro;
+    { Vec4 o = mat_mul(P.inv_view, v4(0.0f, 0.0f, 0.0f, 1.0f)); ro = v3(o.x, o.y, o.z); }   // camera_ray's origin
     // radius of the end spheres in view space: scaled by the largest column of the view matrix's 3x3 (1 for a rigid camera), a little generous
     float sc2 = 0.0f;
 #pragma unroll
@@ -900,20 +968,41 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         const float ax = __shfl_sync(0xffffffffu, ccx, 0), ay = __shfl_sync(0xffffffffu, ccy, 0);      // lanes 0-7: end point a, 8-15: b
         const float ex = __shfl_sync(0xffffffffu, ccx, 8) - ax, ey = __shfl_sync(0xffffffffu, ccy, 8) - ay;
         const float l2 = ex * ex + ey * ey, inv_l2 = l2 > 0.0f ? 1.0f / l2 : 0.0f;
-        const float lim2 = (rad + 1.0f) * (rad + 1.0f);                                                 // + a pixel of slack
+        // Slack on top of the geometric bound.  The reference's float32 quadratics accept rays that pass OUTSIDE the capsule: the
+        // discriminant (d.oc)^2 - |d|^2 (|oc|^2 - r^2) carries a rounding error of a few ulp of |oc|^2 = D^2 (D = distance from the eye),
+        // which moves the accepted silhouette out by about k eps D^2 / (2 r) in world units.  Measured on config 4 (D 0.8, r 1e-3, 2.7
+        // pixel radius): a slack of 0.25 pixel = k 5 loses 542 of 158.9 M fragments, 0.5 pixel = k 10 loses none; k = 16 is used, times
+        // the pixels per world unit at the segment, plus b200_ppll_raster_slack pixels for the rounding of the projection itself.
+        const float dmax = sqrtf(fmaxf((va.x * va.x + va.y * va.y) + va.z * va.z, (vb.x * vb.x + vb.y * vb.y) + vb.z * vb.z)) + rv;
+        const float px_per_unit = persp ? focal_px / fmaxf(fminf(ca.w, cb.w), 1e-6f) : focal_px;
+        const float slack = P.raster_slack + (16.0f * 5.96e-8f) * dmax * dmax / (2.0f * S.radius) * px_per_unit;   // r = 0: inf, no cull (and no hits)
+        const float lim2 = (rad + slack) * (rad + slack);
         int x0 = int(floorf(xmin)) - 1, x1 = int(ceilf(xmax)) + 1, y0 = int(floorf(ymin)) - 1, y1 = int(ceilf(ymax)) + 1;
         const bool no_bound = full_frame || __ballot_sync(0xffffffffu, bad) != 0u;
         if (no_bound) { x0 = 0; y0 = 0; x1 = int(P.W) - 1; y1 = int(P.H) - 1; }
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, int(P.W) - 1); y1 = min(y1, int(P.H) - 1);
         if (x0 > x1 || y0 > y1) continue;                  // off screen
         const uint32_t bw = uint32_t(x1 - x0 + 1), area = bw * uint32_t(y1 - y0 + 1);
+        // row / column of candidate i: an exact float reciprocal division while (i + 0.5) / bw cannot come within rounding of an
+        // integer (area < 2^22), the integer division otherwise (whole-frame rectangles)
+        const bool fdiv = area < (1u << 22);
+        const float inv_bw = 1.0f / float(bw);
+        // segment-only terms of the acceptance test and of the shader (warp-uniform)
+        const float r = S.radius;
+        const float blx = fminf(s.a.x, s.b.x) - r, bly = fminf(s.a.y, s.b.y) - r, blz = fminf(s.a.z, s.b.z) - r;   // the record's own AABB,
+        const float bhx = fmaxf(s.a.x, s.b.x) + r, bhy = fmaxf(s.a.y, s.b.y) + r, bhz = fmaxf(s.a.z, s.b.z) + r;   // as in seg_box_hit
+        const SegShade pre = seg_shade(s);
+        const Vec3 axis = pre.tan0;                         // normalize(p1 - p0): cylinder_hit's axis is the shader's tangent
         // The cheap tests (ownership, 2-D cull) thin the rectangle out; their survivors are queued per warp and taken 32 at a time, so
-        // that the expensive part -- camera ray, slab test, capsule test, shading -- runs with full warps.
-        uint32_t q_count = 0;                               // uniform over the warp; <= 31 between rounds
+        // that the expensive parts -- slab test + capsule test, then shading -- run with full warps.
+        uint32_t q_count = 0, h_count = 0;                  // uniform over the warp; <= 31 between rounds
         for (uint32_t base = 0; base < area; base += 32u) {
             const uint32_t i = base + lane;
             uint32_t cx = 0, cy = 0;
-            if (i < area) { cx = uint32_t(x0) + i % bw; cy = uint32_t(y0) + i / bw; }
+            if (i < area) {
+                const uint32_t row = fdiv ? uint32_t((float(i) + 0.5f) * inv_bw) : i / bw;
+                cx = uint32_t(x0) + (i - row * bw); cy = uint32_t(y0) + row;
+            }
             // tile-sharded frames: only the pixels of this rank's tiles (1 byte per tile of the frame)
             bool cand = i < area && (!owned_tiles || owned_tiles[(cy / P.tile_size) * tiles_x + cx / P.tile_size]);
             if (cand && !no_bound) {   // 2-D distance from the projected axis; a NaN anywhere keeps the candidate
@@ -923,47 +1012,66 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
                 if (dx * dx + dy * dy > lim2) cand = false;
             }
             const unsigned cm = __ballot_sync(0xffffffffu, cand);
-            if (cand) queue[q_count + __popc(cm & ((1u << lane) - 1u))] = cx | (cy << 16);
+            if (cand) queue[q_count + __popc(cm & lt_mask)] = cx | (cy << 16);
             q_count += __popc(cm);
             __syncwarp();
             const bool last_round = base + 32u >= area;
-            while (q_count >= 32u || (last_round && q_count != 0u)) {
+            while (q_count >= 32u || (last_round && (q_count | h_count) != 0u)) {
+                // ---- test stage: the newest n candidates (n = 0 only when the rectangle is done and hits are still queued)
                 const uint32_t n = q_count < 32u ? q_count : 32u;
                 q_count -= n;
-                const uint32_t e = queue[q_count + (lane < n ? lane : 0u)];   // the newest n entries
-                const uint32_t px = e & 0xffffu, py = e >> 16;
-                bool keep = false;
-                uint32_t col = 0;
-                float depth = 0.0f;
+                const uint32_t e = queue[q_count + (lane < n ? lane : 0u)];
+                bool hit = false;
+                float t = 0.0f; uint32_t kind = 0;
                 if (lane < n) {
-                    Vec3 ro, rd;
-                    camera_ray(P, px, py, 0.5f, 0.5f, ro, rd);
-                    const RayBox rb = make_raybox(ro, rd);
+                    const float4* pr = pixel_rays + 2 * (size_t(e >> 16) * P.W + (e & 0xffffu));
+                    const float4 r0 = __ldg(pr), r1 = __ldg(pr + 1);
+                    RayQ rq; rq.o = ro; rq.d = v3(r0.x, r0.y, r0.z); rq.dd = r0.w;
+                    RayBox rb; rb.ix = r1.x; rb.iy = r1.y; rb.iz = r1.z;
+                    rb.cx = -(ro.x * rb.ix); rb.cy = -(ro.y * rb.iy); rb.cz = -(ro.z * rb.iz);
                     isect++;
-                    float t; uint32_t kind;
-                    if (seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(make_rayq(ro, rd), s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
-                        const Shaded sh = shade_hit<SAO>(P, ro, rd, t, kind, s, SAO && S.seg_aux ? S.seg_aux + seg : nullptr);
+                    float tn;
+                    hit = box_hit(rb, blx, bly, blz, bhx, bhy, bhz, tmin, tmax, tn) && capsule_hit(rq, s, axis, r, capped, t, kind) && t >= tmin && t <= tmax;
+                }
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hit) { const uint32_t k = h_count + __popc(hm & lt_mask); hpix[k] = e; ht[k] = __float_as_uint(t); hkind[k] = kind; }
+                h_count += __popc(hm);
+                __syncwarp();
+                // ---- shade stage: a full warp of hits, or what is left once the last candidates have been tested
+                const bool drained = last_round && q_count == 0u;
+                while (h_count >= 32u || (drained && h_count != 0u)) {
+                    const uint32_t m = h_count < 32u ? h_count : 32u;
+                    h_count -= m;
+                    const uint32_t hi = h_count + (lane < m ? lane : 0u);
+                    const uint32_t hp = hpix[hi];
+                    const uint32_t px = hp & 0xffffu, py = hp >> 16;
+                    bool keep = false;
+                    uint32_t col = 0;
+                    float depth = 0.0f;
+                    if (lane < m) {
+                        const float4 r0 = __ldg(pixel_rays + 2 * (size_t(py) * P.W + px));
+                        const Shaded sh = shade_hit<SAO>(P, ro, v3(r0.x, r0.y, r0.z), __uint_as_float(ht[hi]), hkind[hi], s, pre, SAO && S.seg_aux ? S.seg_aux + seg : nullptr);
                         if (!(sh.color.w < 0.001f)) { keep = true; col = pack_unorm4x8(sh.color); depth = sh.hit_t; }   // LinkedListGather.glsl:38
                     }
-                }
-                const unsigned km = __ballot_sync(0xffffffffu, keep);
-                if (km) {
-                    unsigned long long idx = 0;
-                    const int leader = __ffs(km) - 1;
-                    if (int(lane) == leader) idx = atomicAdd(frag_counter, (unsigned long long)__popc(km));   // fragCounter, LinkedListGather.glsl:55
-                    idx = __shfl_sync(0xffffffffu, idx, leader) + __popc(km & ((1u << lane) - 1u));
-                    if (keep) {
-                        gen++;
-                        if (idx < list_size) {                                                                 // :57
-                            const uint32_t a = addr_gen(P, px, py);
-                            lv_ppll_node nd; nd.color = col; nd.depth = depth;
-                            nd.next = STAGE ? a : atomicExch(heads + a, uint32_t(idx));                        // :60
-                            nodes[idx] = nd;                                                                   // STAGE: `nodes` is the staging array
-                            atomicAdd(counts + a, 1u);
+                    const unsigned km = __ballot_sync(0xffffffffu, keep);
+                    if (km) {
+                        unsigned long long idx = 0;
+                        const int leader = __ffs(km) - 1;
+                        if (int(lane) == leader) idx = atomicAdd(frag_counter, (unsigned long long)__popc(km));   // fragCounter, LinkedListGather.glsl:55
+                        idx = __shfl_sync(0xffffffffu, idx, leader) + __popc(km & lt_mask);
+                        if (keep) {
+                            gen++;
+                            if (idx < list_size) {                                                                 // :57
+                                const uint32_t a = addr_gen(P, px, py);
+                                lv_ppll_node nd; nd.color = col; nd.depth = depth;
+                                nd.next = STAGE ? a : atomicExch(heads + a, uint32_t(idx));                        // :60
+                                nodes[idx] = nd;                                                                   // STAGE: `nodes` is the staging array
+                                atomicAdd(counts + a, 1u);
+                            }
                         }
                     }
+                    __syncwarp();   // the entries just read may be overwritten by the next push
                 }
-                __syncwarp();   // the entries just read may be overwritten by the next push
             }
         }
       }

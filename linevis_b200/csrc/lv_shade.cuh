@@ -40,8 +40,9 @@ LV_DEV bool sphere_hit(const RayQ& r, Vec3 oc, float rad, float& t) {
 }
 
 // ray vs open finite cylinder (RayIntersectionTestsVulkan.glsl:78-119)
-LV_DEV bool cylinder_hit(const RayQ& r, Vec3 p0, Vec3 p1, Vec3 op0, float rad, float& t) {
-    Vec3 axis = normalize3(p1 - p0);
+// `axis` = normalize3(p1 - p0): a property of the segment, passed in so that callers that test one segment against many rays (the
+// object-order PPLL gather) compute it once; the arithmetic is the same either way.
+LV_DEV bool cylinder_hit(const RayQ& r, Vec3 p0, Vec3 p1, Vec3 axis, Vec3 op0, float rad, float& t) {
     Vec3 dperp = r.d - dot3(r.d, axis) * axis;
     Vec3 pperp = op0 - dot3(op0, axis) * axis;
     float A = (dperp.x * dperp.x + dperp.y * dperp.y) + dperp.z * dperp.z;
@@ -65,20 +66,24 @@ LV_DEV bool cylinder_hit(const RayQ& r, Vec3 p0, Vec3 p1, Vec3 op0, float rad, f
 }
 
 // IntersectionTube main (TubeRayTracing.glsl:452-494): min over body / sphere(p0) / sphere(p1).
-LV_DEV bool capsule_hit(const RayQ& r, const SegRec& s, float rad, bool capped, float& t, uint32_t& kind) {
+LV_DEV bool capsule_hit(const RayQ& r, const SegRec& s, Vec3 axis, float rad, bool capped, float& t, uint32_t& kind) {
     Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
     Vec3 op0 = r.o - p0;
     bool has = false;
     float best = 1e7f;
     uint32_t k = 0;
     float tt;
-    if (cylinder_hit(r, p0, p1, op0, rad, tt)) { best = tt; has = true; }
+    if (cylinder_hit(r, p0, p1, axis, op0, rad, tt)) { best = tt; has = true; }
     if (capped) {
         if (sphere_hit(r, op0, rad, tt) && tt < best) { best = tt; k = 1; has = true; }
         if (sphere_hit(r, r.o - p1, rad, tt) && tt < best) { best = tt; k = 2; has = true; }
     }
     t = best; kind = k;
     return has;
+}
+LV_DEV Vec3 seg_axis(const SegRec& s) { return normalize3(v3(s.b.x, s.b.y, s.b.z) - v3(s.a.x, s.a.y, s.a.z)); }
+LV_DEV bool capsule_hit(const RayQ& r, const SegRec& s, float rad, bool capped, float& t, uint32_t& kind) {
+    return capsule_hit(r, s, seg_axis(s), rad, capped, t, kind);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,29 +152,47 @@ LV_DEV float aa_factor(const FrameParams& P, float distance) {  // Utils/Antiali
 // ClosestHitTubeAnalytic + computeFragmentColor + blinnPhongShadingTube for one accepted hit.
 // SAO = prebaked object-space AO ("RTAO (Prebaker)") instead of the screen-space AO texture; a template parameter so that the
 // default instantiation carries none of its registers.  `aux`: the record's line-point data, read only with SAO.
+// The terms of shade_hit that depend on the segment alone (one segment, many fragments: the object-order PPLL gather hoists them).
+struct SegShade {
+    Vec3 seg;        // p1 - p0
+    float seg_dot;   // dot(seg, seg)
+    Vec3 tan0;       // normalize(seg)            TubeRayTracing.glsl:544
+    Vec3 tg;         // normalize(tan0)           RayHitCommon.glsl:144
+    Vec3 t2;         // normalize(tg)             Lighting.glsl:139
+};
+LV_DEV SegShade seg_shade(const SegRec& s) {
+    SegShade q;
+    q.seg = v3(s.b.x, s.b.y, s.b.z) - v3(s.a.x, s.a.y, s.a.z);
+    q.seg_dot = dot3(q.seg, q.seg);
+    q.tan0 = normalize3(q.seg);
+    q.tg = normalize3(q.tan0);
+    q.t2 = normalize3(q.tg);
+    return q;
+}
+
 template <bool SAO>
-LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegAux* aux) {
+LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegShade& q, const SegAux* aux) {
     const Vec3 cam = v3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
     Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
     Vec3 pos = ro + rd * t_hit;                                  // TubeRayTracing.glsl:517
-    Vec3 seg = p1 - p0;
+    const Vec3 seg = q.seg;
     Vec3 centre; float attr, u;
     if (kind == 0) {                                             // :524-530
-        u = dot3(seg, pos - p0) / dot3(seg, seg);
+        u = dot3(seg, pos - p0) / q.seg_dot;
         centre = p0 + u * seg;
         attr = (1.0f - u) * s.a.w + u * s.b.w;
     } else if (kind == 1) { centre = p0; attr = s.a.w; u = 0.0f; }
     else { centre = p1; attr = s.b.w; u = 1.0f; }
     // fragmentTangent / fragmentNormal are normalised at :544-545 and again inside computeFragmentColor (:141,:144)
     // and blinnPhongShadingTube (Lighting.glsl:138-139); the repeated normalisations are kept, they are not idempotent in float.
-    Vec3 tan0 = normalize3(seg);
+    const Vec3 tan0 = q.tan0;
     Vec3 nrm0 = normalize3(pos - centre);
     const bool is_cap = kind != 0;
 
     Vec4 base = tf_lookup(P, attr);                              // RayHitCommon.glsl:127
     const Vec3 n = normalize3(nrm0);
     const Vec3 v = normalize3(cam - pos);
-    const Vec3 tg = normalize3(tan0);
+    const Vec3 tg = q.tg;
     Vec3 helper = normalize3(cross3(tg, v));
     Vec3 new_v = normalize3(cross3(helper, tg));
     float ribbon = 0.0f;
@@ -213,7 +236,7 @@ LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uin
         kD = 0.9f * aof;
     }
     const Vec3 n2 = normalize3(n);
-    const Vec3 t2 = normalize3(tg);
+    const Vec3 t2 = q.t2;
     const Vec3 l = v;            // normalize(cameraPosition - fragmentPositionWorld), identical to v above
     const Vec3 h = normalize3(l + l);
     Vec3 helper_l = normalize3(cross3(t2, l));
@@ -242,6 +265,10 @@ LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uin
     out.color = v4(mixf_(col.x, P.fg[0], wmix), mixf_(col.y, P.fg[1], wmix), mixf_(col.z, P.fg[2], wmix), base.w * coverage);
     out.hit_t = depth;                                           // payload.hitT (:540)
     return out;
+}
+template <bool SAO>
+LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegAux* aux) {
+    return shade_hit<SAO>(P, ro, rd, t_hit, kind, s, seg_shade(s), aux);
 }
 
 }  // namespace lv

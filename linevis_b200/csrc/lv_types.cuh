@@ -58,6 +58,17 @@ struct __align__(32) NodeQ {
 };
 constexpr uint32_t kAbsentChild = 0x7FFFFFFDu;
 
+// 64-byte 4-WIDE quantised node for the AO ray stream (b200_ao_wide): a binary node collapsed with the children of its largest
+// children (lv_bvh.cuh: k_w4_round), four child boxes on the 16-bit grid of the scene bounds + four child words -- ONE 64-byte fetch
+// (two 256-bit loads) tests four boxes, the number of dependent node fetches per ray roughly halves.  Child c = 2 h + k lives in the
+// 32-byte half h: w[8 h + 3 k + 0] = lo.x | lo.y << 16, [.. + 1] = lo.z | hi.x << 16, [.. + 2] = hi.y | hi.z << 16, and its child word
+// (leaf bit | record, wide-node index, or kAbsentChild) in w[8 h + 6 + k].  Bounds are dequantised by w4_dequant (lv_bvh.cuh) and
+// rounded OUTWARD at build time against exactly that expression, like NodeQ: a quantised box always encloses the exact one, the
+// accepted set is decided by the record's own exact AABB in the leaf batch (rule 2).
+struct __align__(64) NodeW4 {
+    uint32_t w[16];
+};
+
 struct SceneDev {
     const SegRec* segs;        // [n_seg] BVH order
     const uint32_t* prim_ids;  // [n_seg] BVH order -> caller's segment index
@@ -65,6 +76,9 @@ struct SceneDev {
     const SegAux* seg_aux;     // [n_seg] BVH order, or nullptr (no line frames attached)
     const NodeQ* qnodes;       // [n_nodes] quantised copy of `nodes` (b200_ao_qnodes), or nullptr
     float q_origin[3], q_scale[3];
+    const NodeW4* wnodes;      // 4-wide quantised tree (b200_ao_wide), root = 0, breadth-first order; or nullptr
+    float w_origin[3], w_scale[3];   // w4_dequant's constants (origin already shifted by the conversion's magic number)
+    uint32_t w_top;            // the first w_top wide nodes are whole top levels (staged into shared memory by the AO ray stream)
     // triangle-tube mode of the AO passes (lv_tri.cuh); all nullptr / 0 unless the tube mesh has been built
     const TriRec* tris;        // [n_tri] BVH order
     const uint32_t* tri_ids;   // [n_tri] BVH order -> triangle index of the mesh
@@ -121,6 +135,8 @@ struct FrameParams {
     unsigned int* apron_marks;   // W*H stamps, only in tile-sharded + jittered mode (see k_rtao_primary)
     // PPLL addressing (reference Data/Shaders/Utils/TiledAddress.glsl)
     uint32_t padded_w, padded_h, addr_tw, addr_th;
+    uint32_t addr_tw_log2, addr_th_log2;   // the tile sizes are powers of two
+    float raster_slack;                    // object-order gather: pixels added to the projected radius bound in the 2-D cull
 };
 
 // per-launch counters accumulated with one atomic per warp

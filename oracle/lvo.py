@@ -262,10 +262,11 @@ class OracleScene:
         if ao is None:
             ao = np.zeros((cam.height, cam.width), np.float32)
         ao = _f32(ao)
-        stats = np.zeros(5, np.uint64)
+        stats = np.zeros(7, np.uint64)
         self.lib.lvo_render_rtao(ctypes.c_void_p(self.h), ctypes.byref(cam), ctypes.byref(opts), ctypes.c_uint32(frame_number),
                                  _p(ao, ctypes.c_float), _p(stats, ctypes.c_uint64))
-        return ao, dict(T=int(stats[0]), I=int(stats[1]), rays_primary=int(stats[2]), rays_ao=int(stats[3]), pixels_hit=int(stats[4]))
+        return ao, dict(T=int(stats[0]), I=int(stats[1]), rays_primary=int(stats[2]), rays_ao=int(stats[3]), pixels_hit=int(stats[4]),
+                        T_ao=int(stats[5]), I_ao=int(stats[6]))
 
     def render_tubes(self, cam, opts, tf, amin=0.0, amax=1.0, ao_tex=None, frame_number=0, rgba=None):
         tf = _f32(tf)
@@ -369,3 +370,24 @@ def per_pixel_lists(heads, nodes, cam, opts, oracle):
             if lst:
                 out[(x, y)] = sorted(lst)
     return out
+
+
+def per_pixel_multisets(heads, nodes):
+    """Vectorised form of per_pixel_lists for large frames: all lists are walked at once; returns a uint64 [n, 2] array of
+    (start-offset slot, (depth bits << 32) | colour) rows sorted lexicographically -- equal arrays <=> equal per-pixel multisets."""
+    nxt = nodes["next"].astype(np.int64)
+    key = (nodes["depth"].view(np.uint32).astype(np.uint64) << np.uint64(32)) | nodes["color"].astype(np.uint64)
+    cur = heads.astype(np.int64).ravel()
+    slot = np.arange(cur.size, dtype=np.int64)
+    rows = []
+    live = cur != 0xFFFFFFFF
+    cur, slot = cur[live], slot[live]
+    while cur.size:
+        rows.append(np.stack([slot.astype(np.uint64), key[cur]], axis=1))
+        cur = nxt[cur]
+        live = cur != 0xFFFFFFFF
+        cur, slot = cur[live], slot[live]
+    if not rows:
+        return np.zeros((0, 2), np.uint64)
+    r = np.concatenate(rows)
+    return r[np.lexsort((r[:, 1], r[:, 0]))]

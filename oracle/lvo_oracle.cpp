@@ -294,8 +294,8 @@ void lvo_render_rtao(void* h, const lv_camera* cam, const lvo_options* o, uint32
     const uint32_t globalFrameNumber = frame_number;  // useGlobalFrameNumber == false (VulkanRayTracedAmbientOcclusion.cpp:580-584)
     // subdivisionCorrectionFactor = cos(pi / tubeNumSubdivisions) -- VulkanRayTracedAmbientOcclusion.cpp:591
     const float subdivisionCorrectionFactor = float(std::cos(3.14159265358979323846 / double(o->tube_num_subdivisions)));
-    uint64_t T = 0, I = 0, RP = 0, RA = 0, PH = 0;
-#pragma omp parallel for schedule(dynamic, 2) reduction(+ : T, I, RP, RA, PH)
+    uint64_t T = 0, I = 0, RP = 0, RA = 0, PH = 0, TA = 0, IA = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : T, I, RP, RA, PH, TA, IA)
     for (int64_t yy = 0; yy < int64_t(H); yy++) {
         RayStats sp, sa;
         uint32_t y = uint32_t(yy);
@@ -337,9 +337,10 @@ void lvo_render_rtao(void* h, const lv_camera* cam, const lvo_options* o, uint32
             if (frame_number != 0) { float prev = ao_inout[idx]; aoFactor = mix(prev, aoFactor, 1.0f / float(frame_number + 1)); }  // :313-317
             ao_inout[idx] = aoFactor;
         }
-        T += sp.steps + sa.steps; I += sp.isect + sa.isect; RP += sp.rays; RA += sa.rays;
+        T += sp.steps + sa.steps; I += sp.isect + sa.isect; RP += sp.rays; RA += sa.rays; TA += sa.steps; IA += sa.isect;
     }
-    if (stats) { stats[0] = T; stats[1] = I; stats[2] = RP; stats[3] = RA; stats[4] = PH; }
+    // stats[5], [6]: traversal steps / primitive tests of the AO rays alone (T and I per AO ray on this backend's tree)
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = RP; stats[3] = RA; stats[4] = PH; stats[5] = TA; stats[6] = IA; }
 }
 
 // S1 ray-gen with S2/S3/S4: traceRayTransparent loop + running mean (TubeRayTracing.glsl:61-82,198-274).

@@ -417,6 +417,29 @@ def test_rtao_quantised_nodes(ectx, oracle, use_distance):
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_wide_quantised_tree(ectx, oracle, use_distance):
+    """b200_ao_wide: the AO ray stream over the 4-wide quantised tree (NodeW4: collapse of the child-pair nodes, 16-bit outward-rounded
+    boxes, magic-number dequantisation) gives the same AO image bit for bit, with the same number of rays, on a random soup, a helix
+    and a single segment (a root with one real child)."""
+    for data, width in (_random(), _helix(), _random(3), ((np.array([[-0.2, 0, 0], [0.2, 0.05, 0]], np.float32), np.array([0.1, 0.9], np.float32),
+                                                           np.array([[0, 1]], np.uint32)), 0.05)):
+        sc, osc = _pair(ectx, oracle, data, width)
+        cam = lv.make_camera(56, 36)
+        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
+                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True})
+        try:
+            ao, st = ectx.render_rtao(sc, cam, 0)
+            ectx.set_option("b200_ao_wide", False)
+            ao2, st2 = ectx.render_rtao(sc, cam, 0)
+        finally:
+            ectx.set_new_settings({"b200_ao_wide": False, "ambient_occlusion_radius": 0.1})
+        ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
+        assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+        if data[2].shape[0] > 100:   # the wide tree really is another tree: fewer steps per ray than the child-pair nodes
+            assert st["ao_traversal_steps"] < 0.75 * st2["ao_traversal_steps"], (st["ao_traversal_steps"], st2["ao_traversal_steps"])
+
+
 def test_frame_to_rgba8_and_library_owned_frames(ectx, oracle):
     """lv_frame_alloc / lv_frame_to_rgba8: rendering into a library-owned device frame and reading it back in the reference's
     RGBA8 UNORM output format (packUnorm4x8 per pixel); with a tile shard only the owned tiles are converted."""

@@ -124,10 +124,10 @@ def test_config3_ao_image_is_kernel_independent(random1m):
     want, wst = ctx.render_rtao(sc, cam, 0)
     assert wst["rays_ao"] == 16 * wst["pixels_hit"] > 0
     for variant in ({"b200_ao_queue": False}, {"b200_ao_qnodes": True}, {"b200_ao_stack": 1}, {"b200_ao_queue": False, "b200_ao_stack": 0},
-                    {"b200_ao_stack": 16, "b200_ao_min_blocks": 9}):
+                    {"b200_ao_stack": 16, "b200_ao_min_blocks": 9}, {"b200_ao_wide": True}, {"b200_ao_wide": False}, {"b200_ao_wide": True, "b200_ao_min_blocks": 9}):
         ctx.set_new_settings(variant)
         got, st = ctx.render_rtao(sc, cam, 0)
-        ctx.set_new_settings({"b200_ao_queue": True, "b200_ao_qnodes": False, "b200_ao_stack": 12, "b200_ao_min_blocks": 0})
+        ctx.set_new_settings({"b200_ao_queue": True, "b200_ao_qnodes": False, "b200_ao_stack": 12, "b200_ao_min_blocks": 0, "b200_ao_wide": False})
         assert st["rays_ao"] == wst["rays_ao"], variant
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), variant
     sc.close(); ctx.close()
@@ -217,3 +217,101 @@ def test_sharded_union_equals_full_frame_at_1080p(helix100k, tube_jitter):
     else:
         assert np.abs(acc - full).max() <= 2e-4
         assert rays == st_full["rays_primary"] + st_full["rays_ao"], "work is partitioned, not duplicated"
+
+
+# ----------------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json's own configurations against the oracle: a centre-crop camera of the full frame (same ray density, the whole scene),
+# rendered by the CUDA path and by the oracle on the REFERENCE's CPU BVH library (oracle/_ref; the portable oracle BVH where that
+# is not built).  Bars: AO image, PPLL counter / per-pixel multisets bit-exact; frames within 1e-3 (in practice bit-exact too).
+def _crop_camera(W, H, sw, sh):
+    import math
+    assert sw * H == sh * W, "the crop keeps the frame's aspect ratio, so that pixels keep their solid angle"
+    return lv.make_camera(sw, sh, fov_y=2.0 * math.atan(0.5 * sh / H))
+
+
+@pytest.fixture(scope="module")
+def oracle_best():
+    from oracle import lvo
+    try:
+        o = lvo.Oracle("ref")
+    except (FileNotFoundError, OSError):
+        o = lvo.Oracle("own")
+    o.set_num_threads()
+    return o
+
+
+def _tubes_rtao_crop_vs_oracle(data, W, H, sw, sh, spp, oracle):
+    from oracle import lvo
+    pos, attr, seg = data
+    cam = _crop_camera(W, H, sw, sh)
+    tf = scenes.standard_transfer_function()
+    ctx = lv.Context(0)
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"depth_cue_strength": 0.0, "ambient_occlusion_strength": 1.0, "ambient_occlusion_gamma": 1.0,
+                          "ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_iterations": 1, "ambient_occlusion_radius": 0.1,
+                          "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": True,
+                          "num_samples_per_frame": 1, "num_accumulated_frames": 1})     # bench.py's settings
+    sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
+    ao, sta = ctx.render_rtao(sc, cam, 0)
+    img, st = ctx.render_tubes(sc, cam, 0)
+    sc.close(); ctx.close()
+    osc = oracle.scene(pos, attr, seg, scenes.LINE_WIDTH)
+    opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_jitter_primary=1, ao_use_distance=1)
+    rao, s1 = osc.render_rtao(cam, opts, 0)
+    ref, s2 = osc.render_tubes(cam, opts, tf, ao_tex=rao)
+    assert sta["pixels_hit"] == s1["pixels_hit"] > 0.2 * sw * sh and sta["rays_ao"] == s1["rays_ao"] == spp * s1["pixels_hit"]
+    assert np.array_equal(ao.view(np.uint32), rao.view(np.uint32)), "AO image bit-exact"
+    assert np.isfinite(img).all() and np.abs(img - ref).max() <= 1e-3
+    assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), "frame expected bit-exact"
+
+
+def test_config3_crop_equals_oracle(random1m, oracle_best):
+    """Config 3 (1 M random segments, 1920x1080, tubes + 16-spp RTAO): the 480x270 centre crop, CUDA vs oracle."""
+    _tubes_rtao_crop_vs_oracle(random1m, 1920, 1080, 480, 270, 16, oracle_best)
+
+
+@pytest.fixture(scope="module")
+def curl10m():
+    import torch
+    return scenes.curl_noise_streamlines(n_lines=20000, n_points=501, seed=3003, device=torch.device("cuda", 0))    # config 5
+
+
+def test_config5_crop_equals_oracle(curl10m, oracle_best):
+    """Config 5, the headline (10 M curl-noise segments, 3840x2160, tubes + 64-spp RTAO): the 384x216 centre crop, CUDA vs oracle
+    (VulkanRayTracedAmbientOcclusion.glsl:178-319, TubeRayTracing.glsl:198-274)."""
+    _tubes_rtao_crop_vs_oracle(curl10m, 3840, 2160, 384, 216, 64, oracle_best)
+
+
+@pytest.mark.parametrize("mode", ["raster", "raycast", "raster_contiguous"])
+def test_config4_crop_equals_oracle(random1m, oracle_best, mode):
+    """Config 4 (1 M segments, 3840x2160, PPLL, MAX_NUM_FRAGS 256): the 480x270 centre crop -- fragment counter, per-pixel multisets of
+    (depth bits, colour) and the resolved frame, CUDA vs oracle (LinkedListGather.glsl:33-72, LinkedListResolve.glsl:57-105)."""
+    from oracle import lvo
+    pos, attr, seg = random1m
+    cam = _crop_camera(3840, 2160, 480, 270)
+    tf = scenes.standard_transfer_function(opacity=(0.1, 0.6))
+    ctx = lv.Context(0)
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "b200_ppll_gather_mode": mode})
+    sc = ctx.create_scene(pos, attr, seg, scenes.LINE_WIDTH)
+    size = 128 * 480 * 270        # the crop looks at the dense centre of the data: 76 fragments per pixel on average, nothing may be dropped
+    img, st = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="priority_queue", linked_list_size=size)
+    got = ctx.ppll_read()
+    imgb, stb = ctx.render_ppll(sc, cam, max_frags=256, sort_mode="bitonic", linked_list_size=size)
+    sc.close(); ctx.close()
+    osc = oracle_best.scene(pos, attr, seg, scenes.LINE_WIDTH)
+    opts = lvo.default_options()
+    ref = osc.ppll_gather(cam, opts, tf, linked_list_size=size)
+    assert got["counter"] == ref["counter"] == st["frags_generated"] > 10 * 480 * 270 and st["frags_dropped"] == 0
+    assert got["padded"] == ref["padded"]
+    assert np.array_equal(got["heads"] == 0xFFFFFFFF, ref["heads"] == 0xFFFFFFFF)
+    a = lvo.per_pixel_multisets(got["heads"], got["nodes"])
+    b = lvo.per_pixel_multisets(ref["heads"], ref["nodes"])
+    assert a.shape == b.shape == (ref["counter"], 2) and np.array_equal(a, b), "per-pixel multisets of (depth bits, colour) differ"
+    for mine, mst, m in ((img, st, 0), (imgb, stb, 5)):
+        rimg, rst = lvo.ppll_resolve(oracle_best, cam, opts, ref["heads"], ref["nodes"], 256, m, canonical=True)
+        assert mst["frags_sorted"] == rst["frags_sorted"] and mst["max_depth_complexity"] == rst["max_depth_complexity"]
+        nan = np.isnan(rimg)
+        assert np.array_equal(np.isnan(mine), nan)
+        assert np.abs(mine[~nan] - rimg[~nan]).max() <= 1e-3
+        assert np.array_equal(mine[~nan].view(np.uint32), rimg[~nan].view(np.uint32)), "resolved frame expected bit-exact"

@@ -15,7 +15,7 @@ ap.add_argument("--ppll-workload", default="config4")
 ap.add_argument("--frames", type=int, default=2)
 ap.add_argument("--skip-tubes", action="store_true")
 ap.add_argument("--skip-ppll", action="store_true")
-ap.add_argument("--opt", type=str, nargs="*", default=[], help="extra key=value options for the tube context")
+ap.add_argument("--opt", type=str, nargs="*", default=[], help="extra key=value options for the contexts")
 args = ap.parse_args()
 
 import torch
@@ -40,6 +40,11 @@ if not args.skip_ppll:
     pos, attr, seg = bench.generate(pw["gen"], dev)
     ctx = lv.Context(0)
     ctx.set_transfer_function(lv.scenes.standard_transfer_function(opacity=(0.1, 0.6)))
+    ctx.set_option("ambient_occlusion_strength", 0.0)
+    if "avg_depth" in pw:
+        ctx.set_option("b200_expected_avg_depth_complexity", pw["avg_depth"])
+    for kv in args.opt:
+        ctx.set_option(*kv.split("=", 1))
     sc = ctx.create_scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
     cam = lv.make_camera(pw["W"], pw["H"])
     frame = torch.zeros((pw["H"], pw["W"], 4), dtype=torch.float32, device=dev)
