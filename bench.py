@@ -351,12 +351,14 @@ class Dist:
         self.barrier()
         return self.reduce([e0.elapsed_time(e1) / steps], "max")[0]
 
-    def timed_wall(self, fn, steps):
+    def timed_wall(self, fn, steps, finish=None):
         """The end-to-end legs return data to the host, so they are timed by the host clock around synchronised calls."""
         self.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()                 # pipelined legs: the last frame's copy has landed inside the timed region
         self.torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / steps
         return self.reduce([ms], "max")[0]
@@ -365,6 +367,63 @@ class Dist:
         if self.world > 1:
             self.dist.barrier()
             self.dist.destroy_process_group()
+
+
+class Rgba8Pipeline:
+    """The end-to-end step with the frame delivered as RGBA8 UNORM (the reference's sceneTexture format) and the device->host copy of
+    frame i overlapping the kernels of frame i + 1.
+      one GPU: `render(out)` is the C-ABI call with a pinned HOST frame; the library double-buffers (b200_async_delivery) and
+               lv_synchronize() waits for the last copy;
+      N GPUs:  every rank's frame kernels store rgba8 pixels into one of TWO peer frames on rank 0 (alternating), the fence is a 1-element
+               all_reduce, rank 0 copies the finished frame to pinned host memory on a side stream while the next frame renders into the
+               other peer frame; rank 0 joins fence k only after copy k-1 has left its buffer."""
+
+    def __init__(self, D, ctx, W, H, render, peer):
+        import linevis_b200  # noqa: F401
+        from linevis_b200.sharding import PeerFrame
+        torch = D.torch
+        self.D, self.ctx, self.render, self.i = D, ctx, render, 0
+        ctx.set_new_settings({"b200_frame_format": "rgba8", "b200_async_delivery": True})
+        self.host = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.host_np = [h.numpy().view(np.uint32) for h in self.host]
+        self.pf = [PeerFrame(ctx, W, H, D.rank, D.world, D.dev) for _ in range(2)] if peer else None
+        if self.pf is not None and D.rank == 0:
+            self.copy_stream = torch.cuda.Stream(device=D.dev)
+            self.rendered = [torch.cuda.Event() for _ in range(2)]
+            self.copied = [None, None]
+
+    def step(self):
+        torch, j = self.D.torch, self.i & 1
+        self.i += 1
+        if self.pf is None:
+            self.render(self.host_np[j])                 # returns once the copy is enqueued
+            return
+        self.render(self.pf[j].ptr)
+        if self.D.rank == 0:
+            main = torch.cuda.current_stream()
+            if self.copied[j ^ 1] is not None:
+                main.wait_event(self.copied[j ^ 1])      # the other frame is written again after this fence: its copy must be done
+            self.pf[j].fence()
+            self.rendered[j].record(main)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.rendered[j])
+                self.host[j].copy_(self.pf[j].tensor_rgba8(), non_blocking=True)
+                self.copied[j] = torch.cuda.Event(); self.copied[j].record(self.copy_stream)
+        else:
+            self.pf[j].fence()
+
+    def finish(self):
+        self.ctx.synchronize()
+        if self.pf is not None and self.D.rank == 0:
+            self.copy_stream.synchronize()
+
+    def close(self):
+        self.finish()
+        self.ctx.set_new_settings({"b200_frame_format": "rgba32f", "b200_async_delivery": False})
+        if self.pf is not None:
+            self.D.barrier()
+            for p in self.pf:
+                p.close()
 
 
 def parallelism_note(world, peer):
@@ -474,6 +533,21 @@ def measure_ppll(D, args, name, extra_opts, hbm_peak, headline):
     for _ in range(2):
         step_e2e()
     e2e_ms = D.timed_wall(step_e2e, args.steps)
+    # the headline e2e: RGBA8 delivery (packed in the resolve kernel's epilogue), read back while the next frame renders
+    e2e8 = None
+    if fg is None:
+        pipe = Rgba8Pipeline(D, ctx, W, H, lambda out: ctx.render_ppll(scene, cam, pw["max_frags"], "priority_queue", 0, out=out, stats=False), peer)
+        for _ in range(3):
+            pipe.step()
+        pipe.finish()
+        ms8 = D.timed_wall(pipe.step, args.steps, finish=pipe.finish)
+        ok = bool(D.rank != 0 or (np.count_nonzero(pipe.host_np[0]) == W * H and np.array_equal(pipe.host_np[0], pipe.host_np[1])))
+        e2e8 = {"value": frags / (ms8 * 1e-3) / 1e6, "unit": "Mfrags/s", "ms_per_step": ms8, "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera),
+                "d2h_bytes_per_step": W * H * 4, "frames_complete_and_equal": ok,
+                "note": "lv_render_ppll, frame delivered as RGBA8 UNORM (the reference's sceneTexture format, packed in the resolve epilogue) to pinned host memory; "
+                        "the copy of frame i overlaps frame i + 1 (" + ("b200_async_delivery, lv_synchronize inside the timed region" if not peer else
+                                                                      "two alternating peer frames on rank 0, side-stream D2H") + ")"}
+        pipe.close()
     launches_per_step = 3 if mode != "raster_contiguous" else 6   # clear (memset) + gather + resolve (+ scan, fill)
 
     line = None
@@ -488,11 +562,12 @@ def measure_ppll(D, args, name, extra_opts, hbm_peak, headline):
                        "ms_clear": clr_ms, "ms_gather": gat_ms, "ms_resolve": res_ms, "resolve_only_Mfrags_per_s": frags / (res_ms * 1e-3) / 1e6,
                        "gather_mode": mode, "max_depth_complexity": st["max_depth_complexity"], **({"options": extra_opts} if extra_opts else {})},
             "roofline": dominant, "roofline_" + ("resolve" if dominant is r_gat else "gather"): other,
-            "e2e": {"value": frags / (e2e_ms * 1e-3) / 1e6, "unit": "Mfrags/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": W * H * 16,
-                    "ms_per_step": e2e_ms, "note": "lv_render_ppll with a pinned HOST framebuffer (RGBA32F out, lv_camera in; scene resident)" if pf is None else
-                    "every rank: lv_render_ppll into rank 0's peer frame + fence; rank 0: whole RGBA32F frame D2H into pinned host memory"},
+            "e2e_rgba32f": {"value": frags / (e2e_ms * 1e-3) / 1e6, "unit": "Mfrags/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": W * H * 16,
+                            "ms_per_step": e2e_ms, "note": "synchronous float delivery: lv_render_ppll with a pinned HOST framebuffer (RGBA32F out, lv_camera in; scene resident)" if pf is None else
+                            "synchronous float delivery: every rank renders into rank 0's peer frame + fence; rank 0: whole RGBA32F frame D2H into pinned host memory"},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
+        line["e2e"] = e2e8 if e2e8 is not None else line["e2e_rgba32f"]
         if D.world == 1:
             if not args.no_ncu:
                 cap = live_ncu("k_ppll_gather|k_ppll_resolve", ["--skip-tubes", "--ppll-workload", name] + opt_args(extra_opts))
@@ -619,25 +694,23 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
     for _ in range(2):
         step_e2e()
     e2e_ms = D.timed_wall(step_e2e, args.steps)
-    # ---- the same step with the frame delivered in the reference's own sceneTexture format (RGBA8 UNORM, lv_frame_to_rgba8): a quarter
-    # of the read-back bytes.  Reported beside `e2e` (which stays the RGBA32F delivery), single GPU only; never fatal.
+    # ---- the headline e2e: the frame delivered as RGBA8 UNORM -- the reference's own sceneTexture format (TubeRayTracing.glsl:42,
+    # src/Widgets/DataView.cpp:100-108) -- packed in k_tubes' epilogue, read back to pinned host memory while the next frame renders
     e2e8 = None
-    if world == 1:
-        try:
-            host8 = torch.zeros((H, W), dtype=torch.int32).pin_memory()
-            host8_np = host8.numpy().view(np.uint32)
-
-            def step_e2e8():
-                ctx.render_tubes(scene, cam, 0, out=frame, stats=False)
-                ctx.frame_to_rgba8(frame, W, H, out=host8_np)       # conversion kernel + D2H inside, synchronises
-            for _ in range(2):
-                step_e2e8()
-            ms8 = D.timed_wall(step_e2e8, args.steps)
-            e2e8 = {"value": tot_rays / (ms8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms8, "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera),
-                    "d2h_bytes_per_step": W * H * 4, "nonzero_pixels": int(np.count_nonzero(host8_np)),
-                    "note": "lv_render_tubes into a device frame + lv_frame_to_rgba8 into pinned host memory (RGBA8 UNORM, the reference's sceneTexture format)"}
-        except Exception as e:   # noqa: BLE001 -- an optional extra measurement must not cost the bench line
-            e2e8 = {"error": "%s: %s" % (type(e).__name__, e)}
+    if fg is None or peer:
+        pipe = Rgba8Pipeline(D, ctx, W, H, lambda out: ctx.render_tubes(scene, cam, 0, out=out, stats=False), peer)
+        for _ in range(3):
+            pipe.step()
+        pipe.finish()
+        ms8 = D.timed_wall(pipe.step, args.steps, finish=pipe.finish)
+        ok = bool(rank != 0 or (np.count_nonzero(pipe.host_np[0]) == W * H and np.array_equal(pipe.host_np[0], pipe.host_np[1])))
+        e2e8 = {"value": tot_rays / (ms8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms8, "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera),
+                "d2h_bytes_per_step": W * H * 4, "frames_complete_and_equal": ok,
+                "note": ("lv_render_tubes with a pinned HOST frame, b200_frame_format = rgba8 (packed in the tube kernel's epilogue), b200_async_delivery: "
+                         "the library copies frame i on a second stream while frame i + 1 renders; lv_synchronize inside the timed region") if not peer else
+                        ("every rank: lv_render_tubes (rgba8) into one of two alternating peer frames on rank 0 + fence; rank 0: D2H of the finished "
+                         "frame into pinned host memory on a side stream while the next frame renders; last copy inside the timed region")}
+        pipe.close()
     # bytes read back per step: the whole frame on rank 0 (single GPU, or peer assembly), else every rank's own tiles (rank 0's share is reported)
     d2h = (n_own * TILE * TILE if (world > 1 and pf is None) else W * H) * 16
 
@@ -674,16 +747,15 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
                          "bytes": "64 B x T + 32 B x I + 4 B per AO ray (SURVEY 8d) with the kernel's OWN T and I: T/ray %.2f, I/ray %.2f over %d AO rays (rank 0); "
                                   "cache-agnostic bookkeeping, not a DRAM measurement -- see traffic / limiter"
                                   % (st["ao_traversal_steps"] / max(st["rays_ao"], 1), st["ao_intersections"] / max(st["rays_ao"], 1), st["rays_ao"])},
-            "e2e": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "note": "lv_render_tubes with a pinned HOST framebuffer: lv_camera struct in (the scene is resident, like the reference's cached render data), RGBA32F frame out"
-                    if pf is None else "every rank: lv_render_tubes into rank 0's peer frame + fence; rank 0: whole RGBA32F frame D2H into pinned host memory; lv_camera struct in on every rank"},
+            "e2e_rgba32f": {"value": tot_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera), "d2h_bytes_per_step": int(d2h),
+                            "ms_per_step": e2e_ms, "note": "synchronous float delivery: lv_render_tubes with a pinned HOST framebuffer, lv_camera struct in (the scene is resident, like the reference's cached render data), RGBA32F frame out"
+                            if pf is None else "synchronous float delivery: every rank renders into rank 0's peer frame + fence; rank 0: whole RGBA32F frame D2H into pinned host memory"},
             # k_rtao_primary, AO ray stream, k_rtao_reduce, k_tubes (+ tile pack / unpack kernels in all_gather mode)
             "gpu_launches": (4 + (2 + (world - 1) if (world > 1 and not peer) else 0)) * args.steps,
             "clocks": clocks,
         }
         line.update(ppll_results)
-        if e2e8 is not None:
-            line["e2e_rgba8"] = e2e8
+        line["e2e"] = e2e8 if e2e8 is not None else line["e2e_rgba32f"]
         if gather_ms is not None:
             line["config"]["assemble_ms"] = gather_ms          # the frame fence (peer mode) or pack + all_gather + unpack alone, max over ranks
         line["config"]["k_rtao_rays_ms_per_rank"] = k_ms_ranks  # tile-shard load balance of the dominant kernel

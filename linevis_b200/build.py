@@ -33,7 +33,7 @@ def _stale(target, sources):
 
 def sources():
     inc = os.path.join(_HERE, "..", "include", "linevis_b200.h")
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [inc]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp", ".h"))] + [inc]
 
 
 def build(force=False, verbose=False):

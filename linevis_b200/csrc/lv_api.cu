@@ -44,7 +44,11 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
+    bool frame_rgba8 = false;           // b200_frame_format = rgba8: rgba_out of the render calls is RGBA8 UNORM (uint32 per pixel), packed in the frame kernels' epilogue
+    bool async_delivery = false;        // b200_async_delivery: an rgba8 frame for a HOST pointer is copied on a second stream from alternating staging buffers;
+                                        // the call returns once the copy is enqueued, lv_synchronize waits for it (frame i's D2H overlaps frame i+1's render)
     bool ao_wide = false;               // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
+    uint32_t ao_wide_reps = 1;          // ... node steps per pass of the traversal loop
     uint32_t ao_wide_top = 0;           // ... and serves the first levels (up to this many wide nodes) from shared memory (bulk-copied per block)
     bool ppll_raster_gather = true;     // b200_ppll_gather_mode = raster (default): object-order gather (one warp per segment); raycast = the BVH packet gather
     bool ppll_contiguous = false;       // ... = raster_contiguous: plus count -> scan -> fill, every list one contiguous run, pointer-free resolve
@@ -94,6 +98,8 @@ struct lv_ctx {
     // frame buffers
     DevBuf<unsigned int> apron_marks; unsigned int apron_stamp = 0;
     DevBuf<uint32_t> rgba8;
+    // asynchronous delivery of rgba8 frames to host memory: two staging frames, a copy stream, events
+    DevBuf<uint32_t> stage8[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[2] = {}, ev_copied[2] = {}; unsigned flip = 0; bool copies_pending = false;
     DevBuf<float4> image; DevBuf<float> ao, occ, depth_mm; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
     uint32_t ao_w = 0, ao_h = 0;
     DevBuf<Counters> counters; DevBuf<unsigned int> small;  // small[0] = ao hit count, small[2..3] = 64-bit ao work counter
@@ -124,6 +130,8 @@ struct lv_scene {
     // 4-wide quantised tree (ensure_wnodes): nodes in breadth-first order, level_end[l] = number of nodes in levels 0..l
     DevBuf<NodeW4> wnodes; float w_origin[3] = {0, 0, 0}, w_scale[3] = {1, 1, 1}; uint64_t n_wnodes = 0; uint32_t w_need = 0;
     std::vector<uint32_t> w_level_end; float w_build_ms = 0.0f; bool w_failed = false;
+    uint32_t w_top = 0;   // nodes of the whole top levels that fit b200_ao_wide_top (set before every AO launch)
+    void set_w_top(uint32_t cap) { w_top = 0; for (uint32_t e : w_level_end) { if (e <= cap && e <= n_wnodes) w_top = e; else break; } }
     // triangle-tube mode of the AO passes (ensure_tube_mesh): the reference's tube mesh + a BVH over its triangles
     DevBuf<TriRec> tris; DevBuf<uint32_t> tri_ids; DevBuf<Node64> tri_nodes; DevBuf<float4> tri_vattr, tri_line_pos, tri_line_tan;
     uint64_t n_tri = 0; uint32_t mesh_subdiv = 0; float tri_build_ms = 0.0f;
@@ -136,7 +144,7 @@ struct lv_scene {
         s.seg_aux = has_lines ? seg_aux.p : nullptr;
         s.qnodes = qnodes.p;
         for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; s.w_origin[k] = w_origin[k]; s.w_scale[k] = w_scale[k]; }
-        s.wnodes = n_wnodes ? wnodes.p : nullptr; s.w_top = 0;
+        s.wnodes = n_wnodes ? wnodes.p : nullptr; s.w_top = w_top;
         s.tris = tris.p; s.tri_ids = tri_ids.p; s.tri_nodes = tri_nodes.p; s.tri_vattr = tri_vattr.p;
         s.tri_line_pos = tri_line_pos.p; s.tri_line_tan = tri_line_tan.p; s.n_tri = uint32_t(n_tri);
         s.n_nodes = uint32_t(n_nodes); s.radius = line_width * 0.5f; s.line_width = line_width;
@@ -234,6 +242,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
     P.ao_refill_below = int(o.ao_refill_below);
     P.ao_leaf_vote = int(o.ao_leaf_vote);
+    P.ao_wide_reps = int(o.ao_wide_reps);
     P.spp = o.num_samples_per_frame;
     // useJitteredSamples = maxNumFrames > 1 || numSamplesPerFrame > 1 (reference VulkanRayTracer.cpp:421)
     P.use_jitter = (o.num_accumulated_frames > 1 || o.num_samples_per_frame > 1) ? 1 : 0;
@@ -300,6 +309,62 @@ int deliver(lv_ctx* c, const void* src, void* dst, uint32_t W, uint32_t H, size_
         }
     }
     if (!is_device_pointer(dst)) LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LV_OK;
+}
+
+// Where a frame kernel puts its pixels (b200_frame_format), and how they reach the caller afterwards.
+//   rgba32f: `image` = the caller's device frame, or the library's frame when the caller's pointer is host memory (then copied);
+//   rgba8:   `image` = the library's float accumulation image (running mean over frames), `out8` = the caller's device / peer frame, or
+//            a staging frame when the caller's pointer is host memory (then copied: synchronously, or -- b200_async_delivery -- on the
+//            copy stream from one of two alternating staging frames, so that the copy overlaps the next frame's kernels).
+struct FrameSink { float4* image = nullptr; uint32_t* out8 = nullptr; bool host = false; bool async = false; unsigned slot = 0; };
+
+int open_sink(lv_ctx* c, void* rgba_out, uint32_t W, uint32_t H, FrameSink& s) {
+    const size_t npx = size_t(W) * H;
+    s = FrameSink();
+    s.host = !is_device_pointer(rgba_out);
+    if (!c->opt.frame_rgba8) {
+        if (s.host) { LV_CUDA(c, c->image.ensure(npx)); s.image = c->image.p; }
+        else if (reinterpret_cast<uintptr_t>(rgba_out) & 15) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 16-byte aligned");
+        else s.image = reinterpret_cast<float4*>(rgba_out);
+        return LV_OK;
+    }
+    LV_CUDA(c, c->image.ensure(npx));
+    s.image = c->image.p;
+    if (!s.host) {
+        if (reinterpret_cast<uintptr_t>(rgba_out) & 3) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 4-byte aligned");
+        s.out8 = reinterpret_cast<uint32_t*>(rgba_out);
+        return LV_OK;
+    }
+    s.async = c->opt.async_delivery;
+    if (!s.async) { LV_CUDA(c, c->rgba8.ensure(npx)); s.out8 = c->rgba8.p; return LV_OK; }
+    if (!c->copy_stream) {
+        LV_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) { LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming)); LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming)); }
+    }
+    s.slot = c->flip & 1u; c->flip++;
+    const uint32_t* before = c->stage8[s.slot].p;
+    if (c->stage8[s.slot].n < npx) { LV_CUDA(c, cudaStreamSynchronize(c->copy_stream)); LV_CUDA(c, c->stage8[s.slot].ensure(npx)); }
+    if (before && before == c->stage8[s.slot].p) LV_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[s.slot], 0));   // the copy of two frames ago has left this buffer
+    s.out8 = c->stage8[s.slot].p;
+    return LV_OK;
+}
+
+int close_sink(lv_ctx* c, const FrameSink& s, void* rgba_out, uint32_t W, uint32_t H) {
+    if (!s.host) return LV_OK;
+    if (!c->opt.frame_rgba8) return deliver(c, s.image, rgba_out, W, H, 16);
+    if (!s.async) return deliver(c, s.out8, rgba_out, W, H, 4);
+    LV_CUDA(c, cudaEventRecord(c->ev_rendered[s.slot], c->stream));
+    LV_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[s.slot], 0));
+    if (c->world == 1) LV_CUDA(c, cudaMemcpyAsync(rgba_out, s.out8, size_t(W) * H * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    else
+        for (const uint2& t : c->tiles_host) {
+            const uint32_t x0 = t.x * c->tile_size, y0 = t.y * c->tile_size, w = std::min(c->tile_size, W - x0), h = std::min(c->tile_size, H - y0);
+            const size_t off = (size_t(y0) * W + x0) * 4;
+            LV_CUDA(c, cudaMemcpy2DAsync((char*)rgba_out + off, size_t(W) * 4, (const char*)s.out8 + off, size_t(W) * 4, w * 4, h, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    LV_CUDA(c, cudaEventRecord(c->ev_copied[s.slot], c->copy_stream));
+    c->copies_pending = true;
     return LV_OK;
 }
 
@@ -468,9 +533,12 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
         return c->opt.ao_min_blocks >= 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 1>) : launch(k_rtao_rays_q<8, BAKE, 12, 1>);
     const uint32_t stack = c->opt.ao_stack;
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
-    if (queue && c->opt.ao_wide && S.wnodes)     // 4-wide quantised tree
+    if (queue && c->opt.ao_wide && S.wnodes) {   // 4-wide quantised tree; S.w_top: how many top-level nodes the kernel stages into shared memory
+        if (S.w_top > 85) return launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 341>);
+        if (S.w_top > 0) return c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_q<7, BAKE, 12, 0, 2, 85>) : launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 85>);
         return c->opt.ao_min_blocks == 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 0, 2>) : c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_q<7, BAKE, 12, 0, 2>)
                                                                                                                 : launch(k_rtao_rays_q<8, BAKE, 12, 0, 2>);
+    }
     if (queue && c->opt.ao_qnodes && S.qnodes)   // experimental: quantised nodes (default register budget / stack only)
         return launch(k_rtao_rays_q<8, BAKE, 12, 0, 1>);
     const uint32_t mb = c->opt.ao_min_blocks ? c->opt.ao_min_blocks : (queue ? 8u : 9u);   // 0 = measured optimum of the variant
@@ -499,9 +567,8 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     if (c->ao_w != P.W || c->ao_h != P.H || !c->ao.p) {
         LV_CUDA(c, c->ao.ensure(npx));
         // untouched (not owned) texels must be finite for the bilinear lookup: initialise to "unoccluded"
-        std::vector<float> ones(npx, 1.0f);
-        LV_CUDA(c, cudaMemcpyAsync(c->ao.p, ones.data(), npx * 4, cudaMemcpyHostToDevice, c->stream));
-        LV_CUDA(c, cudaStreamSynchronize(c->stream));
+        k_fill_f32<<<uint32_t(c->num_sms) * 8u, 256, 0, c->stream>>>(c->ao.p, npx, 1.0f);
+        LV_CUDA(c, cudaGetLastError());
         c->ao_w = P.W; c->ao_h = P.H;
     }
     LV_CUDA(c, c->ao_hits.ensure(size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + 4 * c->tile_size + 4) + 1));
@@ -510,7 +577,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     P.frame_number = frame_number;
     const bool tri = c->opt.ao_triangles;
     if (tri) { int trc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)); if (trc) return trc; }
-    else if (c->opt.ao_wide) { int wrc = ensure_wnodes(c, const_cast<lv_scene*>(sc)); if (wrc) return wrc; }
+    else if (c->opt.ao_wide) { int wrc = ensure_wnodes(c, const_cast<lv_scene*>(sc)); if (wrc) return wrc; const_cast<lv_scene*>(sc)->set_w_top(c->opt.ao_wide_top); }
     else if (c->opt.ao_qnodes) { int qrc = ensure_qnodes(c, const_cast<lv_scene*>(sc)); if (qrc) return qrc; }
     const SceneDev S = sc->dev();
     const uint32_t grid = pixel_grid(c, P);
@@ -520,8 +587,10 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
     const bool apron = c->world > 1 && P.use_jitter;
     unsigned int stamp = 0;
     if (apron) {
+        const unsigned int* before = c->apron_marks.p;
         LV_CUDA(c, c->apron_marks.ensure(npx));
-        if (c->apron_stamp == 0) LV_CUDA(c, cudaMemsetAsync(c->apron_marks.p, 0, npx * 4, c->stream));
+        if (c->apron_marks.p != before) c->apron_stamp = 0;   // reallocated (the frame grew): the new words are uninitialised
+        if (c->apron_stamp == 0) LV_CUDA(c, cudaMemsetAsync(c->apron_marks.p, 0, c->apron_marks.n * 4, c->stream));
         stamp = ++c->apron_stamp;
         P.apron_marks = c->apron_marks.p;
     }
@@ -661,11 +730,11 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     FrameParams P;
     memset(&P, 0, sizeof(P));
     P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
-    P.ao_refill_below = int(o.ao_refill_below); P.ao_leaf_vote = int(o.ao_leaf_vote); P.frame_number = sc->bake_done;
+    P.ao_refill_below = int(o.ao_refill_below); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
     if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;
-    if (!o.ao_triangles && o.ao_wide && (rc = ensure_wnodes(c, sc))) return rc;
+    if (!o.ao_triangles && o.ao_wide) { if ((rc = ensure_wnodes(c, sc))) return rc; sc->set_w_top(o.ao_wide_top); }
     if (!o.ao_triangles && !o.ao_wide && o.ao_qnodes && (rc = ensure_qnodes(c, sc))) return rc;
     if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1, o.ao_triangles))) return rc;
     c->rtao_rays_timed = true;
@@ -728,9 +797,14 @@ int lv_ctx_create(lv_ctx** out, int device, void* cuda_stream) {
     c->device = device;
     c->stream = static_cast<cudaStream_t>(cuda_stream);
     cudaDeviceProp prop;
-    LV_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    cudaError_t err = cudaGetDeviceProperties(&prop, device);
     c->num_sms = prop.multiProcessorCount;
-    for (auto& e : c->ev) LV_CUDA(nullptr, cudaEventCreate(&e));
+    for (auto& e : c->ev) if (err == cudaSuccess) err = cudaEventCreate(&e);
+    if (err != cudaSuccess) {   // nothing of the half-built context survives a failure
+        for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+        delete c;
+        return fail(nullptr, LV_ERR_CUDA, std::string("lv_ctx_create: ") + cudaGetErrorString(err));
+    }
     *out = c;
     return LV_OK;
 }
@@ -739,7 +813,9 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (!c) return LV_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->rgba8.release(); c->pixel_rays.release();
+    c->rgba8.release(); c->pixel_rays.release(); c->stage8[0].release(); c->stage8[1].release();
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int k = 0; k < 2; k++) { if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
     c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -749,7 +825,9 @@ int lv_ctx_destroy(lv_ctx* c) {
 
 int lv_synchronize(lv_ctx* c) {
     if (!c) return LV_ERR_INVALID_ARGUMENT;
+    LV_CUDA(c, cudaSetDevice(c->device));
     LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->copy_stream && c->copies_pending) { LV_CUDA(c, cudaStreamSynchronize(c->copy_stream)); c->copies_pending = false; }   // b200_async_delivery
     return LV_OK;
 }
 
@@ -816,6 +894,12 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
     else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
     else if (k == "b200_ao_wide") o.ao_wide = parse_bool(value);
+    else if (k == "b200_frame_format") {
+        if (strcmp(value, "rgba32f") && strcmp(value, "rgba8")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_frame_format must be rgba32f or rgba8");
+        o.frame_rgba8 = !strcmp(value, "rgba8");
+    }
+    else if (k == "b200_async_delivery") o.async_delivery = parse_bool(value);
+    else if (k == "b200_ao_wide_reps") { if (u() == 0 || u() > 4) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_wide_reps must be in [1, 4]"); o.ao_wide_reps = u(); }
     else if (k == "b200_ao_wide_top") { if (u() > 1365) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_wide_top must be <= 1365 nodes"); o.ao_wide_top = u(); }
     else if (k == "b200_rtao_geometry") {
         if (!strcmp(value, "triangles")) o.ao_triangles = true;
@@ -873,7 +957,10 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_queue") v = b(o.ao_queue);
     else if (k == "b200_ao_qnodes") v = b(o.ao_qnodes);
     else if (k == "b200_ao_wide") v = b(o.ao_wide);
+    else if (k == "b200_frame_format") v = o.frame_rgba8 ? "rgba8" : "rgba32f";
+    else if (k == "b200_async_delivery") v = b(o.async_delivery);
     else if (k == "b200_ao_wide_top") v = std::to_string(o.ao_wide_top);
+    else if (k == "b200_ao_wide_reps") v = std::to_string(o.ao_wide_reps);
     else if (k == "b200_rtao_geometry") v = o.ao_triangles ? "triangles" : "capsules";
     else if (k == "b200_ao_stack") v = std::to_string(o.ao_stack);
     else if (k == "b200_ppll_binned_resolve") v = b(o.ppll_binned_resolve);
@@ -903,6 +990,7 @@ int lv_set_tile_shard(lv_ctx* c, uint32_t rank, uint32_t world, uint32_t tile_si
     c->rank = rank; c->world = world; c->tile_size = tile_size;
     c->tiles_w = c->tiles_h = 0;  // re-enumerate on next frame
     c->ao_w = c->ao_h = 0;
+    c->apron_stamp = 0;           // the stamp array is cleared again before its next use
     return LV_OK;
 }
 
@@ -1319,11 +1407,9 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
     int rc = make_params(c, sc, cam, frame_number, P);
     if (rc) return rc;
     if ((rc = reset_counters(c))) return rc;
-    const size_t npx = size_t(P.W) * P.H;
-    const bool dev = is_device_pointer(rgba_out);
-    float4* img = reinterpret_cast<float4*>(rgba_out);
-    if (!dev) { LV_CUDA(c, c->image.ensure(npx)); img = c->image.p; }
-    else if (reinterpret_cast<uintptr_t>(rgba_out) & 15) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 16-byte aligned");
+    FrameSink sink;
+    if ((rc = open_sink(c, rgba_out, P.W, P.H, sink))) return rc;
+    float4* img = sink.image;
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     const bool use_ao = c->opt.ao_strength > 0.0f && !c->opt.ao_prebaker;
     if ((rc = prepare_static_ao(c, sc, P))) return rc;
@@ -1337,12 +1423,12 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (P.n_tiles) {
-        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
-        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p);
+        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8);
+        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8);
     }
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    if (!dev && (rc = deliver(c, img, rgba_out, P.W, P.H, 16))) return rc;
+    if ((rc = close_sink(c, sink, rgba_out, P.W, P.H))) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         Counters h;
@@ -1454,11 +1540,10 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
     if (rc) return rc;
     if (P.padded_w != c->padded_w || P.padded_h != c->padded_h) return fail(c, LV_ERR_STATE, "lv_ppll_resolve: resolution changed since lv_ppll_clear");
     if ((rc = reset_counters(c))) return rc;
-    const size_t npx = size_t(P.W) * P.H;
-    const bool dev = is_device_pointer(rgba_out);
-    float4* img = reinterpret_cast<float4*>(rgba_out);
-    if (!dev) { LV_CUDA(c, c->image.ensure(npx)); img = c->image.p; }
-    else if (reinterpret_cast<uintptr_t>(rgba_out) & 15) return fail(c, LV_ERR_INVALID_ARGUMENT, "device rgba_out must be 16-byte aligned");
+    FrameSink sink;
+    if ((rc = open_sink(c, rgba_out, P.W, P.H, sink))) return rc;
+    float4* img = sink.image;
+    uint32_t* out8 = c->opt.ppll_binned_resolve ? nullptr : sink.out8;   // the binned kernels write floats; converted below
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     // All eight modes produce the depth-sorted order; only the priority queue stops blending at alpha >= 0.99
     // (reference LinkedListSort.glsl:217).  See DESIGN.md for the reference's bitonicSort defect.
@@ -1467,7 +1552,7 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
         // shared key tile per warp: the smallest of 256 / 512 / 1024 that is >= the option and can hold the longest list
         const uint32_t cap = std::max(c->opt.ppll_resolve_tile, max_frags) <= 256u ? 256u : (std::max(c->opt.ppll_resolve_tile, max_frags) <= 512u ? 512u : 1024u);
         const uint32_t grid = pixel_grid(c, P);
-#define LV_RESOLVE(RS, CAPV, CT) k_ppll_resolve<RS, CAPV, CT><<<grid, kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, nullptr, nullptr)
+#define LV_RESOLVE(RS, CAPV, CT) k_ppll_resolve<RS, CAPV, CT><<<grid, kBlockThreads, 0, c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, nullptr, nullptr, out8)
 #define LV_RESOLVE_CAP(RS, CT) do { if (cap == 256u) LV_RESOLVE(RS, 256, CT); else if (cap == 512u) LV_RESOLVE(RS, 512, CT); else LV_RESOLVE(RS, 1024, CT); } while (0)
         if (c->lists_contiguous) { if (c->opt.ppll_reg_sort) LV_RESOLVE_CAP(true, true); else LV_RESOLVE_CAP(false, true); }
         else { if (c->opt.ppll_reg_sort) LV_RESOLVE_CAP(true, false); else LV_RESOLVE_CAP(false, false); }
@@ -1487,7 +1572,7 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
         // surplus blocks exit on n_sorted[0]
         if (max_frags > 256u)
             k_ppll_resolve<false><<<uint32_t((n_own + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
-                P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, c->bin_order.p, nsort);
+                P, c->heads.p, c->counts.p, c->nodes.p, max_frags, early_out, img, c->counters.p, c->bin_order.p, nsort, nullptr);
         auto smem = [](int maxn, int warps) { return size_t(warps) * maxn * 32 * 8 + 256 * 4; };
         if (!c->binned_attr_set) {
             LV_CUDA(c, cudaFuncSetAttribute(k_ppll_resolve_binned<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem(256, 1))));
@@ -1499,9 +1584,10 @@ int lv_ppll_resolve(lv_ctx* c, const lv_camera* cam, uint32_t max_frags, uint32_
         if (max_frags > 32u) k_ppll_resolve_binned<64, 2, 3><<<pg, 64, smem(64, 2), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);
         k_ppll_resolve_binned<32, 4, 4><<<pg, 128, smem(32, 4), c->stream>>>(P, c->heads.p, c->counts.p, c->nodes.p, c->bin_order.p, nsort, max_frags, early_out, img, c->counters.p);
     }
+    if (P.n_tiles && sink.out8 && !out8) k_frame_to_rgba8<<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, img, sink.out8);   // binned resolve + rgba8
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    if (!dev && (rc = deliver(c, img, rgba_out, P.W, P.H, 16))) return rc;
+    if ((rc = close_sink(c, sink, rgba_out, P.W, P.H))) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         Counters h;

@@ -258,6 +258,11 @@ __global__ void k_quantize_nodes(const Node64* nodes, uint32_t n, float ox, floa
 //     bound = fma(as_float(0x4B000000 | q), scale, origin_m),   origin_m = origin - 8388608 * scale (rounded once, on the host).
 // The builder rounds against exactly this expression, so its rounding errors are part of the grid, not of the bound.
 LV_DEV float w4_dequant(uint32_t q, float scale, float origin_m) { return __fmaf_rn(__uint_as_float(0x4B000000u | q), scale, origin_m); }
+// the same value from a packed word lo | hi << 16: `sel` = 0x7610 takes the low half, 0x7632 the high half (one PRMT)
+LV_DEV float w4_dequant_packed(uint32_t w, uint32_t sel, float scale, float origin_m) {
+    return __fmaf_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), scale, origin_m);
+}
+constexpr uint32_t kW4SelLo = 0x7610u, kW4SelHi = 0x7632u;
 
 __device__ __forceinline__ uint32_t w4_quantize(float b, float o, float s, float om, bool up) {
     float g = (b - o) / s;
@@ -312,14 +317,14 @@ __global__ void k_w4_round(const Node64* nodes, const uint3* in_q, uint32_t n_in
     NodeW4 w;
     int inner_i = 0;
     for (int k = 0; k < 4; k++) {
-        uint32_t* bw = w.w + 8 * (k >> 1) + 3 * (k & 1);
-        uint32_t& cw = w.w[8 * (k >> 1) + 6 + (k & 1)];
+        uint32_t* bw = w.w + 3 * k;
+        uint32_t& cw = w.w[12 + k];
         if (k >= n) { bw[0] = bw[1] = bw[2] = 0u; cw = kAbsentChild; continue; }
         const uint32_t ax = w4_quantize(lo[k].x, G.o[0], G.s[0], G.om[0], false), ay = w4_quantize(lo[k].y, G.o[1], G.s[1], G.om[1], false),
                        az = w4_quantize(lo[k].z, G.o[2], G.s[2], G.om[2], false);
         const uint32_t bx = w4_quantize(hi[k].x, G.o[0], G.s[0], G.om[0], true), by = w4_quantize(hi[k].y, G.o[1], G.s[1], G.om[1], true),
                        bz = w4_quantize(hi[k].z, G.o[2], G.s[2], G.om[2], true);
-        bw[0] = ax | (ay << 16); bw[1] = az | (bx << 16); bw[2] = by | (bz << 16);
+        bw[0] = ax | (bx << 16); bw[1] = ay | (by << 16); bw[2] = az | (bz << 16);
         const uint32_t word = __float_as_uint(lo[k].w);
         if (word & 0x80000000u) cw = word;
         else {

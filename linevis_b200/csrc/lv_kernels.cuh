@@ -34,6 +34,15 @@ __device__ __forceinline__ void flush_counter(unsigned long long* dst, unsigned 
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
 
+// packUnorm4x8 (GLSL 4.60 spec 8.4): round(clamp(c, 0, 1) * 255) per channel
+__device__ __forceinline__ uint32_t pack_unorm4x8(Vec4 c) {
+    uint32_t r = uint32_t(floorf(clampf_(c.x, 0.0f, 1.0f) * 255.0f + 0.5f));
+    uint32_t g = uint32_t(floorf(clampf_(c.y, 0.0f, 1.0f) * 255.0f + 0.5f));
+    uint32_t b = uint32_t(floorf(clampf_(c.z, 0.0f, 1.0f) * 255.0f + 0.5f));
+    uint32_t a = uint32_t(floorf(clampf_(c.w, 0.0f, 1.0f) * 255.0f + 0.5f));
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
 // RayGen camera ray (reference TubeRayTracing.glsl:202,219-226)
 __device__ __forceinline__ void camera_ray(const FrameParams& P, uint32_t px, uint32_t py, float xix, float xiy, Vec3& ro, Vec3& rd) {
     Vec4 o = mat_mul(P.inv_view, v4(0.0f, 0.0f, 0.0f, 1.0f));
@@ -106,9 +115,12 @@ k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDe
 // ------------------------------------------------------------------------------------------------
 // S1 ray-gen with the traceRayTransparent loop, S3/S4 shading and the running mean over frames
 // (reference TubeRayTracing.glsl:61-82,198-274).  `image` is the accumulation image (float RGBA).
+// out8 != nullptr (b200_frame_format = rgba8): the frame is ALSO stored as RGBA8 UNORM -- the reference's own sceneTexture format
+// (TubeRayTracing.glsl:42, src/Widgets/DataView.cpp:100-108) -- in the same epilogue; `image` then is the library's own float
+// accumulation image and out8 the delivered frame (4 B / pixel: a quarter of the peer-store and read-back traffic).
 template <bool SAO>
 __global__ void __launch_bounds__(kBlockThreads)
-k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C) {
+k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C, uint32_t* out8) {
     __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
     uint32_t* stack = s_stack[threadIdx.x >> 5];
     uint32_t x, y;
@@ -163,6 +175,7 @@ k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev 
             fr = mixf_(prev.x, fr, a); fg = mixf_(prev.y, fg, a); fb = mixf_(prev.z, fb, a); fa = mixf_(prev.w, fa, a);
         }
         *px = make_float4(fr, fg, fb, fa);
+        if (out8) out8[size_t(y) * P.W + x] = pack_unorm4x8(v4(fr, fg, fb, fa));
     }
     flush_counter(&C->rays_primary, rays);
     flush_counter(&C->steps, steps);
@@ -479,7 +492,10 @@ constexpr uint32_t kNoHitBits = 0x7F800000u;   // +inf
 // NM = node format: 0 the 64-byte child-pair nodes (Node64); 1 the 32-byte quantised child-pair nodes (NodeQ, measured slower: the
 // integer-to-float conversions of its dequantisation cost more issue slots than the second load); 2 the 64-byte 4-WIDE quantised
 // nodes (NodeW4): four boxes per fetch, about half the dependent node fetches per ray, up to three pushes per step.  1 and 2: capsules only.
-template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, int NM = 0>
+// TOP (NM = 2 only): the first min(TOP, S.w_top) wide nodes -- whole top levels of the breadth-first tree, the nodes every ray walks --
+// are staged into shared memory once per persistent block with ONE bulk-async copy (cp.async.bulk.shared::cluster.global, completion on
+// an mbarrier: the TMA engine moves the bytes, no thread touches them) and steps on them are served from there.
+template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, int NM = 0, int TOP = 0>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
               const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
@@ -498,6 +514,34 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     const float radius = S.radius;
     uint32_t steps = 0, isect = 0, rays = 0;
 
+    __shared__ __align__(128) NodeW4 s_top[TOP > 0 ? TOP : 1];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    uint32_t n_top = 0;
+    if (NM == 2 && TOP > 0) {
+        n_top = S.w_top < uint32_t(TOP) ? S.w_top : uint32_t(TOP);
+#ifdef LV_HOST_EMU
+        for (uint32_t i = threadIdx.x; i < n_top * 16u; i += kBlockThreads) reinterpret_cast<uint32_t*>(s_top)[i] = reinterpret_cast<const uint32_t*>(S.wnodes)[i];
+        __syncthreads();
+#else
+        const uint32_t bar = uint32_t(__cvta_generic_to_shared(&s_mbar)), dst = uint32_t(__cvta_generic_to_shared(s_top));
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (n_top) {
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = n_top * 64u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(S.wnodes), "r"(bytes), "r"(bar) : "memory");
+            }
+            uint32_t done = 0;   // every thread waits for phase 0 of the barrier: the copy's bytes have landed
+            while (!done)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+        }
+#endif
+    }
     constexpr bool QN = NM != 0;                       // quantised boxes: the record's exact AABB is tested in the leaf batch
     constexpr int kCap = NM == 2 ? kAoStackWide : kAoStack;
     AoStack<STACK, kCap> pst;
@@ -511,6 +555,7 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     bool found = false;
     rq.o = v3(0, 0, 0); rq.d = v3(0, 0, 1); rq.dd = 1.0f; rb = make_raybox(rq.o, rq.d);
     uint32_t q_head = 0, q_count = 0;   // uniform over the warp
+    uint32_t w4nx = kW4SelLo, w4ny = kW4SelLo, w4nz = kW4SelLo;
     wpend[lane] = 0;
     __syncwarp();
 
@@ -532,6 +577,9 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                     ao_ray_from_record<BAKE>(hit_list + slot, sample, spp, P.frame_number, org, dir);
                     rq = make_rayq(org, dir);
                     rb = make_raybox(org, dir);
+                    if (NM == 2) {   // which bound of each axis the ray enters first (rb.i* is never 0 or NaN for a ray that is traversed)
+                        w4nx = rb.ix >= 0.0f ? kW4SelLo : kW4SelHi; w4ny = rb.iy >= 0.0f ? kW4SelLo : kW4SelHi; w4nz = rb.iz >= 0.0f ? kW4SelLo : kW4SelHi;
+                    }
                     best = P.ao_radius; found = false;
                     sp = 0; cur = ao_ray_valid(rq) ? 0u : kDone;                     // root (a NaN ray hits nothing and must not be traversed, see k_rtao_rays)
                     has_ray = true;
@@ -544,37 +592,51 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
         while (true) {
             // A: one inner-node step for every lane that holds an inner node
             if (NM == 2) {
+              // ao_wide_reps steps per pass of the loop: the queue / refill bookkeeping below is paid once per pass
+              for (int rep = 0; rep < P.ao_wide_reps; rep++)
               if (cur != kDone && !(cur & kLeafBit)) {
                 steps++;
                 float4 ha, hb2, hc, hd;
-                ldg256(S.wnodes + cur, ha, hb2);                                   // children 0, 1
-                ldg256(reinterpret_cast<const char*>(S.wnodes + cur) + 32, hc, hd);   // children 2, 3
+                if (TOP > 0 && cur < n_top) {                                          // a top-level node: from the staged copy
+                    const float4* tp = reinterpret_cast<const float4*>(s_top + cur);
+                    ha = tp[0]; hb2 = tp[1]; hc = tp[2]; hd = tp[3];
+                } else {
+                    ldg256(S.wnodes + cur, ha, hb2);                                   // children 0, 1
+                    ldg256(reinterpret_cast<const char*>(S.wnodes + cur) + 32, hc, hd);   // children 2, 3
+                }
                 const float ox = S.w_origin[0], oy = S.w_origin[1], oz = S.w_origin[2], sx = S.w_scale[0], sy = S.w_scale[1], sz = S.w_scale[2];
-                float tc[4]; uint32_t cw[4];
-#define LV_W4_CHILD(k, W0, W1, W2, CW) do { \
-                    const uint32_t w0 = __float_as_uint(W0), w1 = __float_as_uint(W1), w2 = __float_as_uint(W2); \
-                    cw[k] = __float_as_uint(CW); \
-                    float tn; \
-                    const bool h = cw[k] != kAbsentChild && \
-                        box_hit(rb, w4_dequant(w0 & 0xffffu, sx, ox), w4_dequant(w0 >> 16, sy, oy), w4_dequant(w1 & 0xffffu, sz, oz), \
-                                w4_dequant(w1 >> 16, sx, ox), w4_dequant(w2 & 0xffffu, sy, oy), w4_dequant(w2 >> 16, sz, oz), 0.0f, best, tn); \
-                    tc[k] = h ? tn : __int_as_float(0x7f800000); } while (0)
-                LV_W4_CHILD(0, ha.x, ha.y, ha.z, hb2.z);
-                LV_W4_CHILD(1, ha.w, hb2.x, hb2.y, hb2.w);
-                LV_W4_CHILD(2, hc.x, hc.y, hc.z, hd.z);
-                LV_W4_CHILD(3, hc.w, hd.x, hd.y, hd.w);
+                // Per axis the ray's direction sign says which bound is entered first: t = fma(b, inv, c) is monotone in b, so
+                // min(t(lo), t(hi)) = t(near bound) bit for bit -- the canonical slab test without its six min / max, and the
+                // selection costs nothing because the byte-permute that builds the float does it (w4n*: PRMT selectors of the ray).
+                const uint32_t fx = w4nx ^ 0x0022u, fy = w4ny ^ 0x0022u, fz = w4nz ^ 0x0022u;
+                const float kInf = __int_as_float(0x7f800000);
+#define LV_W4_CHILD(T, WX, WY, WZ, CW) do { \
+                    const uint32_t wx = __float_as_uint(WX), wy = __float_as_uint(WY), wz = __float_as_uint(WZ); \
+                    const float nx = __fmaf_rn(w4_dequant_packed(wx, w4nx, sx, ox), rb.ix, rb.cx), gx = __fmaf_rn(w4_dequant_packed(wx, fx, sx, ox), rb.ix, rb.cx); \
+                    const float ny = __fmaf_rn(w4_dequant_packed(wy, w4ny, sy, oy), rb.iy, rb.cy), gy = __fmaf_rn(w4_dequant_packed(wy, fy, sy, oy), rb.iy, rb.cy); \
+                    const float nz = __fmaf_rn(w4_dequant_packed(wz, w4nz, sz, oz), rb.iz, rb.cz), gz = __fmaf_rn(w4_dequant_packed(wz, fz, sz, oz), rb.iz, rb.cz); \
+                    const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f)), hi = fminf(fminf(gx, gy), fminf(gz, best)); \
+                    T = (lo <= hi) & (__float_as_uint(CW) != kAbsentChild) ? lo : kInf; } while (0)
+                float t0, t1, t2, t3;
+                LV_W4_CHILD(t0, ha.x, ha.y, ha.z, hd.x);
+                LV_W4_CHILD(t1, ha.w, hb2.x, hb2.y, hd.y);
+                LV_W4_CHILD(t2, hb2.z, hb2.w, hc.x, hd.z);
+                LV_W4_CHILD(t3, hc.y, hc.z, hc.w, hd.w);
 #undef LV_W4_CHILD
+                const uint32_t c0 = __float_as_uint(hd.x), c1 = __float_as_uint(hd.y), c2 = __float_as_uint(hd.z), c3 = __float_as_uint(hd.w);
                 // descend into the nearest hit child, push the other hit children (entries carry their entry distance and are culled
                 // against the closest hit when popped, so their order only matters for speed)
-                int near = 0; float tnear = tc[0];
-#pragma unroll
-                for (int k = 1; k < 4; k++) if (tc[k] < tnear) { tnear = tc[k]; near = k; }
-                if (tnear == __int_as_float(0x7f800000)) cur = ao_stack_pop(pst, sp, best);
+                int near = 0; float tnear = t0; uint32_t cnear = c0;
+                if (t1 < tnear) { tnear = t1; cnear = c1; near = 1; }
+                if (t2 < tnear) { tnear = t2; cnear = c2; near = 2; }
+                if (t3 < tnear) { tnear = t3; cnear = c3; near = 3; }
+                if (tnear == kInf) cur = ao_stack_pop(pst, sp, best);
                 else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (k != near && tc[k] != __int_as_float(0x7f800000) && sp < kCap) { pst.put(sp, cw[k], tc[k]); sp++; }
-                    cur = cw[near];
+                    if (near != 0 && t0 != kInf && sp < kCap) { pst.put(sp, c0, t0); sp++; }
+                    if (near != 1 && t1 != kInf && sp < kCap) { pst.put(sp, c1, t1); sp++; }
+                    if (near != 2 && t2 != kInf && sp < kCap) { pst.put(sp, c2, t2); sp++; }
+                    if (near != 3 && t3 != kInf && sp < kCap) { pst.put(sp, c3, t3); sp++; }
+                    cur = cnear;
                 }
               }
             } else if (cur != kDone && !(cur & kLeafBit)) {
@@ -703,13 +765,6 @@ __device__ __forceinline__ uint32_t addr_gen(const FrameParams& P, uint32_t x, u
     const uint32_t base = (tx + sw * ty) << (P.addr_tw_log2 + P.addr_th_log2);
     return base | ((x & (P.addr_tw - 1)) + ((y & (P.addr_th - 1)) << P.addr_tw_log2));
 }
-__device__ __forceinline__ uint32_t pack_unorm4x8(Vec4 c) {
-    uint32_t r = uint32_t(floorf(clampf_(c.x, 0.0f, 1.0f) * 255.0f + 0.5f));
-    uint32_t g = uint32_t(floorf(clampf_(c.y, 0.0f, 1.0f) * 255.0f + 0.5f));
-    uint32_t b = uint32_t(floorf(clampf_(c.z, 0.0f, 1.0f) * 255.0f + 0.5f));
-    uint32_t a = uint32_t(floorf(clampf_(c.w, 0.0f, 1.0f) * 255.0f + 0.5f));
-    return r | (g << 8) | (b << 16) | (a << 24);
-}
 
 // S9 gather.  The fragment source is the all-hits enumeration of the pixel-centre ray: every accepted candidate
 // in [1e-4, 1000] is shaded (S3) and appended.  One thread owns one pixel, so the list head lives in a register and is
@@ -778,7 +833,10 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     uint32_t x, y;
     const bool valid = thread_pixel(P, x, y);
     uint32_t steps = 0, isect = 0;
+    // the pixel's list so far (lv_ppll_clear: empty): a second gather between two clears APPENDS, like the reference's atomicExchange chain
     GatherState g; g.head = kNone; g.stored = 0; g.gen = 0;
+    uint32_t list_addr = 0;
+    if (valid) { list_addr = addr_gen(P, x, y); g.head = heads[list_addr]; g.stored = counts[list_addr]; }
     Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
     if (valid) camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
     const RayQ rq = make_rayq(ro, rd);
@@ -831,9 +889,8 @@ k_ppll_gather(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
         gather_flush<SAO>(P, S, ro, rd, lane, s_queue, qn, g, nodes, frag_counter, list_size);
     }
     if (valid) {
-        const uint32_t a = addr_gen(P, x, y);
-        heads[a] = g.head;
-        counts[a] = g.stored;
+        heads[list_addr] = g.head;
+        counts[list_addr] = g.stored;
     }
     flush_counter(&C->rays_primary, valid ? 1 : 0);
     flush_counter(&C->steps, steps);
@@ -1179,7 +1236,7 @@ __device__ __forceinline__ void warp_bitonic_sort_reg(unsigned long long* s, uin
 template <bool REGSORT, int CAP = kResolveCap, bool CONTIG = false>
 __global__ void __launch_bounds__(kBlockThreads)
 k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, const uint32_t* counts, const lv_ppll_node* nodes,
-               uint32_t max_frags, int early_out, float4* image, Counters* C, const uint32_t* order, const unsigned int* n_sorted) {
+               uint32_t max_frags, int early_out, float4* image, Counters* C, const uint32_t* order, const unsigned int* n_sorted, uint32_t* out8) {
     __shared__ unsigned long long s_keys[kResolveWarps * CAP];
     __shared__ float s_unorm[256];   // unpackUnorm4x8: float(b) / 255.0f, tabulated once (4 IEEE divisions per fragment otherwise)
     for (uint32_t i = threadIdx.x; i < 256u; i += kBlockThreads) s_unorm[i] = float(i) / 255.0f;
@@ -1197,7 +1254,10 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
     uint32_t head = kNone, total = 0;
     if (valid) { const uint32_t a = addr_gen(P, x, y); head = heads[a]; total = counts[a]; }
     const uint32_t cnt = min(total, max_frags);
-    if (valid && cnt == 0) image[size_t(y) * P.W + x] = make_float4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]);  // discard -> clear colour
+    if (valid && cnt == 0) {   // discard -> clear colour
+        if (out8) out8[size_t(y) * P.W + x] = pack_unorm4x8(v4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]));
+        else image[size_t(y) * P.W + x] = make_float4(P.bg[0], P.bg[1], P.bg[2], P.bg[3]);
+    }
     unsigned remaining = __ballot_sync(0xffffffffu, cnt > 0);
     while (remaining) {
         const uint32_t c = ((remaining >> lane) & 1u) ? cnt : 0u;
@@ -1269,8 +1329,9 @@ k_ppll_resolve(const __grid_constant__ FrameParams P, const uint32_t* heads, con
             }
             r = r / a; g = g / a; b = b / a;
             // BACK_TO_FRONT_STRAIGHT_ALPHA over the clear colour (PerPixelLinkedListLineRenderer.cpp:70)
-            image[size_t(y) * P.W + x] = make_float4(r * a + P.bg[0] * (1.0f - a), g * a + P.bg[1] * (1.0f - a),
-                                                      b * a + P.bg[2] * (1.0f - a), a + P.bg[3] * (1.0f - a));
+            const Vec4 px = v4(r * a + P.bg[0] * (1.0f - a), g * a + P.bg[1] * (1.0f - a), b * a + P.bg[2] * (1.0f - a), a + P.bg[3] * (1.0f - a));
+            if (out8) out8[size_t(y) * P.W + x] = pack_unorm4x8(px);   // b200_frame_format = rgba8: the resolved pixel in the sceneTexture's format
+            else image[size_t(y) * P.W + x] = make_float4(px.x, px.y, px.z, px.w);
         }
         remaining &= ~selmask;
         __syncwarp();
@@ -1404,6 +1465,10 @@ k_ppll_resolve_binned(const __grid_constant__ FrameParams P, const uint32_t* hea
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0 && mx) atomicMax(&C->max_depth_complexity, mx);
+}
+
+__global__ void k_fill_f32(float* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) p[i] = v;
 }
 
 // RGBA32F frame -> RGBA8 UNORM (the reference's sceneTexture format), owned tiles only

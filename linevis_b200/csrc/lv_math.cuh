@@ -19,6 +19,12 @@ inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); r
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 template <class T> inline T __ldg(const T* p) { return *p; }
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {   // PRMT, default mode: result byte i = byte (nibble i of s) of {y, x}
+    const uint64_t v = (uint64_t(y) << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= uint32_t((v >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 // integer min / max overloads nvcc provides in the global namespace
 inline int max(int a, int b) { return a < b ? b : a; }
 inline int min(int a, int b) { return b < a ? b : a; }

@@ -60,11 +60,11 @@ constexpr uint32_t kAbsentChild = 0x7FFFFFFDu;
 
 // 64-byte 4-WIDE quantised node for the AO ray stream (b200_ao_wide): a binary node collapsed with the children of its largest
 // children (lv_bvh.cuh: k_w4_round), four child boxes on the 16-bit grid of the scene bounds + four child words -- ONE 64-byte fetch
-// (two 256-bit loads) tests four boxes, the number of dependent node fetches per ray roughly halves.  Child c = 2 h + k lives in the
-// 32-byte half h: w[8 h + 3 k + 0] = lo.x | lo.y << 16, [.. + 1] = lo.z | hi.x << 16, [.. + 2] = hi.y | hi.z << 16, and its child word
-// (leaf bit | record, wide-node index, or kAbsentChild) in w[8 h + 6 + k].  Bounds are dequantised by w4_dequant (lv_bvh.cuh) and
-// rounded OUTWARD at build time against exactly that expression, like NodeQ: a quantised box always encloses the exact one, the
-// accepted set is decided by the record's own exact AABB in the leaf batch (rule 2).
+// (two 256-bit loads) tests four boxes, the number of dependent node fetches per ray roughly halves.  Child k: w[3 k + a] = lo_a |
+// hi_a << 16 for the axes a = 0, 1, 2 (the two bounds of an axis share a word: one byte-permute both picks the bound that is NEAR for
+// the ray's direction sign and builds the float 2^23 + q, see w4_dequant); w[12 + k] = child word (leaf bit | record, wide-node index,
+// or kAbsentChild).  Bounds are rounded OUTWARD at build time against exactly the traversal's dequantisation, like NodeQ: a quantised
+// box always encloses the exact one, the accepted set is decided by the record's own exact AABB in the leaf batch (rule 2).
 struct __align__(64) NodeW4 {
     uint32_t w[16];
 };
@@ -114,6 +114,7 @@ struct FrameParams {
     float subdiv_corr;        // cos(pi / tubeNumSubdivisions)
     int ao_refill_below;      // k_rtao_rays refills a warp once fewer lanes than this are live
     int ao_leaf_vote;         // ... and intersects postponed leaves once this many lanes hold one
+    int ao_wide_reps;         // wide-tree stream: node steps per pass of the traversal loop
     uint32_t spp;             // numSamplesPerFrame
     int use_jitter, det_sampling;
     uint32_t max_depth;       // maxDepthComplexity

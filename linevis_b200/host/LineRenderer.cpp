@@ -113,6 +113,15 @@ bool LineRenderer::setNewSettings(const SettingsMap& settings) {
     return shallReloadGatherShader;
 }
 
+void LineRenderer::setNewState(const InternalState& newState) {
+    // MainApp::setNewState -> LineRenderer::setNewTilingMode (LineRenderer.cpp:739-760): the PPLL start-offset addressing tile
+    if (newState.tilingWidth > 0 && newState.tilingHeight > 0) {
+        check(lv_set_option(ctx, "b200_tiling_width", std::to_string(newState.tilingWidth).c_str()), "tilingWidth");
+        check(lv_set_option(ctx, "b200_tiling_height", std::to_string(newState.tilingHeight).c_str()), "tilingHeight");
+    }
+    reRender = true;
+}
+
 void LineRenderer::fillCamera(lv_camera& cam) const {
     // LineData::updateVulkanUniformBuffers, src/LineData/LineData.cpp:1275-1319
     std::memcpy(cam.view, sceneData->viewMatrix, 64);
@@ -147,7 +156,43 @@ void B200RayTracer::onResolutionChanged() {
 
 bool B200RayTracer::needsReRender() {
     if (accumulatedFramesCounter < maxNumAccumulatedFrames) return true;
+    // the AO pass is still collecting iterations: frames keep coming (and the frame counter keeps counting, VulkanRayTracer.cpp:153)
+    if (ambientOcclusionStrength > 0.0f && accumulatedFramesCounter < ambientOcclusionIterations) return true;
     return LineRenderer::needsReRender();
+}
+
+void B200RayTracer::setNewState(const InternalState& newState) {
+    LineRenderer::setNewState(newState);
+    const SettingsMap& rs = newState.rendererSettings;
+    std::string geometryMode;
+    bool useAnalyticIntersections = true;
+    // only the analytic tube primitive exists here (RayTracingGeometryMode::AABBS / "Analytic Tubes", VulkanRayTracer.hpp:54-63):
+    // a state that asks for the triangle mesh is refused loudly instead of being measured under the wrong name
+    if (rs.getValueOpt("geometryMode", geometryMode)) {
+        if (geometryMode != "AABBs (analytic)")   // RAY_TRACING_GEOMETRY_MODE_NAMES, VulkanRayTracer.hpp:58-63
+            throw std::runtime_error("setNewState: geometryMode '" + geometryMode + "' is not available (only 'AABBs (analytic)')");
+        accumulatedFramesCounter = 0;
+    } else if (rs.getValueOpt("useAnalyticIntersections", useAnalyticIntersections)) {
+        if (!useAnalyticIntersections) throw std::runtime_error("setNewState: useAnalyticIntersections = false is not available (analytic tubes only)");
+        accumulatedFramesCounter = 0;
+    }
+    if (rs.getValueOpt("numSamplesPerFrame", numSamplesPerFrame)) {
+        check(lv_set_option(ctx, "num_samples_per_frame", std::to_string(numSamplesPerFrame).c_str()), "numSamplesPerFrame");
+        accumulatedFramesCounter = 0;
+    }
+    if (rs.getValueOpt("maxNumAccumulatedFrames", maxNumAccumulatedFrames)) {
+        check(lv_set_option(ctx, "num_accumulated_frames", std::to_string(maxNumAccumulatedFrames).c_str()), "maxNumAccumulatedFrames");
+        accumulatedFramesCounter = 0;
+    }
+    bool b = false;
+    if (rs.getValueOpt("useDeterministicSampling", b)) {
+        check(lv_set_option(ctx, "use_deterministic_sampling", b ? "true" : "false"), "useDeterministicSampling");
+        accumulatedFramesCounter = 0;
+    }
+    if (rs.getValueOpt("useMlat", b)) {
+        if (b) throw std::runtime_error("setNewState: useMlat is not available");
+        accumulatedFramesCounter = 0;
+    }
 }
 
 bool B200RayTracer::setNewSettings(const SettingsMap& settings) {
@@ -156,6 +201,7 @@ bool B200RayTracer::setNewSettings(const SettingsMap& settings) {
     if (settings.getValueOpt("num_accumulated_frames", maxNumAccumulatedFrames)) accumulatedFramesCounter = 0;
     bool b;
     if (settings.getValueOpt("use_deterministic_sampling", b)) accumulatedFramesCounter = 0;
+    if (settings.getValueOpt("ambient_occlusion_iterations", ambientOcclusionIterations)) accumulatedFramesCounter = 0;
     return r;
 }
 
@@ -173,6 +219,11 @@ void B200RayTracer::render() {
 // ---------------------------------------------------------------------------------------------- PPLL
 B200PerPixelLinkedListLineRenderer::B200PerPixelLinkedListLineRenderer(SceneData* sd, TransferFunction& tf, int device, void* stream)
     : LineRenderer("Per-Pixel Linked List Renderer (B200)", sd, tf, device, stream) {}
+
+void B200PerPixelLinkedListLineRenderer::setNewState(const InternalState& newState) {
+    LineRenderer::setNewState(newState);
+    currentStateName = newState.name;   // the name the per-state timings are filed under (PerPixelLinkedListLineRenderer.cpp:99)
+}
 
 void B200PerPixelLinkedListLineRenderer::updateLargeMeshMode() {
     const bool large = lineData && lineData->getNumLineSegments() > size_t(1e6);

@@ -30,6 +30,19 @@ struct SceneData {
     std::vector<float> sceneTexture;  // viewportWidth * viewportHeight * 4
 };
 
+// Stand-in for InternalState (src/Utils/InternalState.hpp:171-199): what a --perf state hands to LineRenderer::setNewState.
+// rendererSettings carries the camelCase keys of the performance-measurement modes (InternalState.cpp), not the snake_case
+// keys of the replay scripts.
+struct InternalState {
+    std::string name;
+    int renderingMode = 0;
+    SettingsMap rendererSettings;
+    int tilingWidth = 2, tilingHeight = 8;        // setNewTilingMode (LineRenderer.cpp:739-760)
+    bool useMortonCodeForTiling = false;
+    std::string transferFunctionName;
+    int windowResolution[2] = {0, 0};
+};
+
 enum RenderingMode { RENDERING_MODE_PER_PIXEL_LINKED_LIST = 1, RENDERING_MODE_VULKAN_RAY_TRACER = 9 };  // src/Renderers/RenderingModes.hpp:32-53
 
 class LineRenderer {
@@ -53,6 +66,9 @@ public:
     virtual void notifyReRenderTriggeredExternally() { internalReRender = false; }
     /// Same keys as the reference (src/Renderers/LineRenderer.cpp:433-498); returns whether a gather-shader reload would be needed.
     virtual bool setNewSettings(const SettingsMap& settings);
+    /// Called when a new performance-measurement state is set (LineRenderer.hpp:109-110; MainApp::setNewState).  The base applies the
+    /// state's PPLL addressing tile (setNewTilingMode); renderers override it for their rendererSettings keys.
+    virtual void setNewState(const InternalState& newState);
 
     static void setLineWidth(float width) { lineWidth = width; }
     static float getLineWidth() { return lineWidth; }
@@ -87,10 +103,15 @@ public:
     bool needsReRender() override;                       // VulkanRayTracer.cpp:330-336
     void notifyReRenderTriggeredExternally() override { internalReRender = false; accumulatedFramesCounter = 0; }
     bool setNewSettings(const SettingsMap& settings) override;  // VulkanRayTracer.cpp:226-278
+    void setNewState(const InternalState& newState) override;   // VulkanRayTracer.cpp:280-328
     void render() override;                              // VulkanRayTracer.cpp:131-154
+    uint32_t getAccumulatedFramesCounter() const { return accumulatedFramesCounter; }
 
 private:
     uint32_t numSamplesPerFrame = 2, maxNumAccumulatedFrames = 32, accumulatedFramesCounter = 0;  // VulkanRayTracer.hpp:137-142
+    // the screen-space RTAO pass accumulates its own iterations (VulkanRayTracedAmbientOcclusion.hpp:150: maxNumAccumulatedFrames 64);
+    // LineRenderer::renderBase keeps forcing frames while it is still running (LineRenderer.cpp:257-264)
+    uint32_t ambientOcclusionIterations = 64;
 };
 
 // Counterpart of PerPixelLinkedListLineRenderer (src/Renderers/OIT/PerPixelLinkedListLineRenderer.{hpp,cpp})
@@ -101,6 +122,8 @@ public:
     void setLineData(LineDataPtr& lineData, bool isNewData) override;
     void onResolutionChanged() override;
     void render() override;                              // PerPixelLinkedListLineRenderer.cpp:399-427
+    void setNewState(const InternalState& newState) override;   // PerPixelLinkedListLineRenderer.cpp:98-107
+    const std::string& getCurrentStateName() const { return currentStateName; }
     void setSortingAlgorithmMode(lv_sort_mode mode) { sortingAlgorithmMode = mode; reRender = true; }
 
 private:
@@ -109,4 +132,5 @@ private:
     lv_sort_mode sortingAlgorithmMode = LV_SORT_PRIORITY_QUEUE;   // .hpp:113
     int expectedAvgDepthComplexity = 20, expectedMaxDepthComplexity = 100;  // MESH_MODE_DEPTH_COMPLEXITIES_PPLL, .hpp:45-49
     uint64_t fragmentBufferSize = 0;
+    std::string currentStateName;
 };

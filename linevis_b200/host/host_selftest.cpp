@@ -77,6 +77,22 @@ int main() {
         std::printf("ray tracer: %llu rays, %zu non-background pixels, mean R %.4f\n",
                     (unsigned long long)(rt.getLastStats().rays_primary + rt.getLastStats().rays_ao), nonbg, sum / (sd.sceneTexture.size() / 4));
         if (nonbg == 0 || rt.getLastStats().rays_ao == 0) { std::printf("FAIL: empty frame\n"); return 1; }
+        // a --perf state (camelCase keys, VulkanRayTracer.cpp:280-328): resets the accumulation, applies samples / frames; AO keeps frames coming
+        InternalState st; st.name = "RT 1spp"; st.rendererSettings.addKeyValue("numSamplesPerFrame", 1); st.rendererSettings.addKeyValue("maxNumAccumulatedFrames", 2);
+        st.rendererSettings.addKeyValue("useAnalyticIntersections", true);
+        rt.setNewState(st);
+        if (rt.getAccumulatedFramesCounter() != 0 || !rt.needsReRender()) { std::printf("FAIL: setNewState\n"); return 1; }
+        SettingsMap aoit; aoit.addKeyValue("ambient_occlusion_iterations", 3);
+        rt.setNewSettings(aoit);
+        rt.LineRenderer::needsReRender();   // consume the "settings changed" flag: only the accumulation logic is left
+        int frames = 0;
+        while (rt.needsReRender() && frames < 10) { rt.render(); frames++; }
+        if (frames != 3) { std::printf("FAIL: %d frames rendered, expected 3 (2 accumulated frames, 3 AO iterations)\n", frames); return 1; }
+        bool refused = false;
+        InternalState bad; bad.rendererSettings.addKeyValue("geometryMode", std::string("Triangle Mesh"));
+        try { rt.setNewState(bad); } catch (const std::runtime_error&) { refused = true; }
+        if (!refused) { std::printf("FAIL: triangle-mesh geometry mode was not refused\n"); return 1; }
+        rt.setNewSettings(once);
         // object-space AO prebaker: the first frames each run one baking iteration, then only look the factors up
         SettingsMap pre; pre.addKeyValue("ambient_occlusion_mode", std::string("RTAO (Prebaker)")); pre.addKeyValue("b200_prebaker_iterations", 2);
         pre.addKeyValue("b200_prebaker_param_segment_length", 0.01f);

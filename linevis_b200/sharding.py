@@ -102,8 +102,8 @@ class FrameGather:
 class _RawCudaArray:
     """Zero-copy view of a raw device address for torch.as_tensor (CUDA array interface v2)."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 class PeerFrame:
@@ -131,6 +131,11 @@ class PeerFrame:
         """[H, W, 4] float32 view of the frame (root only)."""
         assert self.rank == self.root
         return torch.as_tensor(_RawCudaArray(self.local, (self.H, self.W, 4)), device=self.device)
+
+    def tensor_rgba8(self):
+        """[H, W] int32 view of the frame's first W*H*4 bytes (root only): the frame when the ranks render with b200_frame_format = rgba8."""
+        assert self.rank == self.root
+        return torch.as_tensor(_RawCudaArray(self.local, (self.H, self.W), "<i4"), device=self.device)
 
     def close(self):
         if self.ptr is None:

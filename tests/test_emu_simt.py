@@ -417,8 +417,9 @@ def test_rtao_quantised_nodes(ectx, oracle, use_distance):
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("top", [0, 85, 341])
 @pytest.mark.parametrize("use_distance", [True, False])
-def test_rtao_wide_quantised_tree(ectx, oracle, use_distance):
+def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top):
     """b200_ao_wide: the AO ray stream over the 4-wide quantised tree (NodeW4: collapse of the child-pair nodes, 16-bit outward-rounded
     boxes, magic-number dequantisation) gives the same AO image bit for bit, with the same number of rays, on a random soup, a helix
     and a single segment (a root with one real child)."""
@@ -427,17 +428,47 @@ def test_rtao_wide_quantised_tree(ectx, oracle, use_distance):
         sc, osc = _pair(ectx, oracle, data, width)
         cam = lv.make_camera(56, 36)
         ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
-                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True})
+                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True, "b200_ao_wide_top": top})
         try:
             ao, st = ectx.render_rtao(sc, cam, 0)
             ectx.set_option("b200_ao_wide", False)
             ao2, st2 = ectx.render_rtao(sc, cam, 0)
         finally:
-            ectx.set_new_settings({"b200_ao_wide": False, "ambient_occlusion_radius": 0.1})
+            ectx.set_new_settings({"b200_ao_wide": False, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1})
         ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
         if data[2].shape[0] > 100:   # the wide tree really is another tree: fewer steps per ray than the child-pair nodes
             assert st["ao_traversal_steps"] < 0.75 * st2["ao_traversal_steps"], (st["ao_traversal_steps"], st2["ao_traversal_steps"])
+
+
+@pytest.mark.parametrize("async_delivery", [False, True])
+def test_rgba8_frame_format(ectx, oracle, async_delivery):
+    """b200_frame_format = rgba8: the tube pass and the PPLL resolve deliver RGBA8 UNORM frames packed in their epilogues -- equal to
+    packUnorm4x8 of the float frame, for a host frame (synchronous and b200_async_delivery + lv_synchronize) and over frame accumulation."""
+    data, width = _helix()
+    sc, osc = _pair(ectx, oracle, data, width)
+    cam = lv.make_camera(64, 40)
+    tf = scenes.standard_transfer_function(opacity=(0.3, 0.9))
+    ectx.set_transfer_function(tf)
+    ectx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 4, "num_samples_per_frame": 1, "num_accumulated_frames": 2})
+    try:
+        f0, _ = ectx.render_tubes(sc, cam, 0)
+        f1, _ = ectx.render_tubes(sc, cam, 1, out=f0.copy())
+        pp, _ = ectx.render_ppll(sc, cam, max_frags=64, sort_mode="priority_queue")
+        ectx.set_new_settings({"b200_frame_format": "rgba8", "b200_async_delivery": async_delivery})
+        a0 = np.zeros((40, 64), np.uint32); a1 = np.zeros((40, 64), np.uint32); ap = np.zeros((40, 64), np.uint32)
+        ectx.render_tubes(sc, cam, 0, out=a0)
+        ectx.render_tubes(sc, cam, 1, out=a1)          # the running mean lives in the library's own float image
+        ectx.render_ppll(sc, cam, max_frags=64, sort_mode="priority_queue", out=ap)
+        ectx.synchronize()
+    finally:
+        ectx.set_new_settings({"b200_frame_format": "rgba32f", "b200_async_delivery": False, "ambient_occlusion_strength": 0.0, "num_accumulated_frames": 1})
+
+    def pack(img):
+        q = np.floor(np.clip(img, 0.0, 1.0).astype(np.float32) * np.float32(255.0) + np.float32(0.5)).astype(np.uint32)
+        return q[..., 0] | (q[..., 1] << 8) | (q[..., 2] << 16) | (q[..., 3] << 24)
+    assert np.array_equal(a0, pack(f0)) and np.array_equal(a1, pack(f1)) and not np.array_equal(a0, a1)
+    assert np.array_equal(ap, pack(np.nan_to_num(pp)))
 
 
 def test_frame_to_rgba8_and_library_owned_frames(ectx, oracle):
