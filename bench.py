@@ -238,7 +238,12 @@ def run_reference(args, name):
     o, kind = load_oracle()
     ppll = name in PPLL_WORKLOADS
     wl = PPLL_WORKLOADS[name] if ppll else WORKLOADS[name]
-    pos, attr, seg = generate(wl["gen"])
+    gen_device = None
+    if wl["gen"][0] == "curl":   # 10 M RK4-integrated points: torch on the CPU with every host thread (torchrun exports OMP_NUM_THREADS=1), ~15 s instead of a minute
+        import torch
+        torch.set_num_threads(o.num_threads())
+        gen_device = torch.device("cpu")
+    pos, attr, seg = generate(wl["gen"], gen_device)
     t0 = time.time()
     sc = o.scene(pos, attr, seg, lv.scenes.LINE_WIDTH)
     build_s = time.time() - t0
@@ -429,7 +434,7 @@ class Rgba8Pipeline:
 def parallelism_note(world, peer):
     if world == 1:
         return "single GPU"
-    return "tile-sharded x%d (64x64 tiles, Morton round-robin); " % world + (
+    return "tile-sharded x%d (%dx%d tiles, Morton round-robin); " % (world, TILE, TILE) + (
         "frame assembled on rank 0 by NVLink peer stores from the frame kernels, 1-element all_reduce as fence" if peer
         else "1 NCCL all_gather/frame + unpack on rank 0")
 
@@ -805,6 +810,7 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
 
 
 def main():
+    global TILE
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -820,17 +826,20 @@ def main():
                     help="centre crop (pixels) of the frame the CPU legs render: ~90 M rays on config 5, about 5-10 s per step on 16 host cores; "
                          "--impl reference shrinks it to fit --ref-budget")
     ap.add_argument("--ppll-sample", type=int, nargs=2, default=[480, 270], help="centre crop of the PPLL headline's CPU baseline / parity leg")
-    ap.add_argument("--ref-budget", type=float, default=100.0, help="--impl reference: seconds of CPU rendering for warm-up + steps together")
+    ap.add_argument("--ref-budget", type=float, default=80.0, help="--impl reference: seconds of CPU rendering for warm-up + steps together")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu pass (roofline.traffic then comes from the committed capture, labelled stale)")
     ap.add_argument("--assemble", default="peer", choices=["peer", "allgather"],
                     help="N > 1: how rank 0 gets the whole frame -- 'peer': every rank's kernels store their tiles straight into rank 0's "
                          "frame over NVLink (lv_frame_alloc / lv_ipc_*), one 1-element all_reduce as frame fence; 'allgather': pack + NCCL "
                          "all_gather + unpack")
+    ap.add_argument("--tile", type=int, default=0, help="N > 1: tile size of the image shards in pixels (multiple of 16; default %d)" % TILE)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="extra lv_set_option settings for A/B runs (e.g. b200_ao_qnodes=true, b200_ppll_reg_sort=true); recorded in config.options")
     args = ap.parse_args()
     extra_opts = dict(o.split("=", 1) for o in args.opt)
+    if args.tile:
+        TILE = args.tile
     if args.impl == "reference":
         run_reference(args, args.workload)
         return

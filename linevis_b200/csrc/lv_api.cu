@@ -38,7 +38,7 @@ struct Options {
     uint32_t max_depth_complexity = 1024;
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
-    uint32_t ao_refill_below = 24;
+    uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 30 with b200_ao_raybuf (refilling is cheap), 24 without
     uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
     bool ao_qnodes = false;           // experimental: AO ray stream over 32-byte quantised nodes (k_quantize_nodes, NodeQ); capsules + leaf queue only
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
@@ -47,13 +47,14 @@ struct Options {
     bool frame_rgba8 = false;           // b200_frame_format = rgba8: rgba_out of the render calls is RGBA8 UNORM (uint32 per pixel), packed in the frame kernels' epilogue
     bool async_delivery = false;        // b200_async_delivery: an rgba8 frame for a HOST pointer is copied on a second stream from alternating staging buffers;
                                         // the call returns once the copy is enqueued, lv_synchronize waits for it (frame i's D2H overlaps frame i+1's render)
-    bool ao_wide = false;               // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
+    bool ao_raybuf = true;              // b200_ao_raybuf: the AO stream generates rays 32 at a time by the whole warp into a shared batch
+    bool ao_wide = true;                // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
     uint32_t ao_wide_reps = 1;          // ... node steps per pass of the traversal loop
     uint32_t ao_wide_top = 0;           // ... and serves the first levels (up to this many wide nodes) from shared memory (bulk-copied per block)
     bool ppll_raster_gather = true;     // b200_ppll_gather_mode = raster (default): object-order gather (one warp per segment); raycast = the BVH packet gather
     bool ppll_contiguous = false;       // ... = raster_contiguous: plus count -> scan -> fill, every list one contiguous run, pointer-free resolve
     float ppll_raster_slack = 0.1f;     // object-order gather: pixels added to the 2-D cull's bound on top of the float-error term (see the kernel)
-    uint32_t ppll_raster_min_blocks = 4;  // ... blocks per SM the kernel is compiled for (4 / 5 / 6: 128 / 102 / 85 registers)
+    uint32_t ppll_raster_min_blocks = 6;  // ... blocks per SM the kernel is compiled for (4 / 5 / 6: 128 / 102 / 85 registers; config 4: 16.6 / 15.0 / 14.0 ms)
     uint32_t ppll_resolve_tile = 1024;  // plain resolve: keys per warp in the shared tile (256 / 512 / 1024; raised to hold max_frags)
     bool ppll_reg_sort = true;          // plain resolve: lists of 65..256 keys are sorted in registers (shuffles) instead of shared memory (config 4: 4.84 -> 2.87 ms)
     bool ppll_binned_resolve = false;   // count-binned resolve: faster on sparse scenes (config 2), slower on dense ones (config 4)
@@ -240,7 +241,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.ao_strength = o.ao_strength; P.ao_gamma = o.ao_gamma; P.ao_radius = o.ao_radius;
     P.ao_spp = o.ao_spp; P.ao_use_distance = o.ao_use_distance; P.ao_jitter = o.ao_jitter_primary;
     P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
-    P.ao_refill_below = int(o.ao_refill_below);
+    P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? 30u : 24u));
     P.ao_leaf_vote = int(o.ao_leaf_vote);
     P.ao_wide_reps = int(o.ao_wide_reps);
     P.spp = o.num_samples_per_frame;
@@ -533,7 +534,10 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
         return c->opt.ao_min_blocks >= 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 1>) : launch(k_rtao_rays_q<8, BAKE, 12, 1>);
     const uint32_t stack = c->opt.ao_stack;
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
-    if (queue && c->opt.ao_wide && S.wnodes) {   // 4-wide quantised tree; S.w_top: how many top-level nodes the kernel stages into shared memory
+    const bool default_tuning = stack == 12 && (c->opt.ao_min_blocks == 0 || c->opt.ao_min_blocks == 8) && !c->opt.ao_qnodes;
+    if (queue && c->opt.ao_raybuf && default_tuning && !(c->opt.ao_wide && S.wnodes && S.w_top))   // warp-wide ray generation into a shared batch (default tuning only)
+        return (c->opt.ao_wide && S.wnodes) ? launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 0, true>) : launch(k_rtao_rays_q<8, BAKE, 12, 0, 0, 0, true>);
+    if (queue && c->opt.ao_wide && S.wnodes && stack == 12 && !c->opt.ao_qnodes) {   // 4-wide quantised tree; S.w_top: how many top-level nodes the kernel stages into shared memory
         if (S.w_top > 85) return launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 341>);
         if (S.w_top > 0) return c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_q<7, BAKE, 12, 0, 2, 85>) : launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 85>);
         return c->opt.ao_min_blocks == 9 ? launch(k_rtao_rays_q<9, BAKE, 12, 0, 2>) : c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_q<7, BAKE, 12, 0, 2>)
@@ -730,7 +734,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     FrameParams P;
     memset(&P, 0, sizeof(P));
     P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
-    P.ao_refill_below = int(o.ao_refill_below); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
+    P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? 30u : 24u)); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
     if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;
@@ -894,6 +898,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ao_queue") o.ao_queue = parse_bool(value);
     else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
     else if (k == "b200_ao_wide") o.ao_wide = parse_bool(value);
+    else if (k == "b200_ao_raybuf") o.ao_raybuf = parse_bool(value);
     else if (k == "b200_frame_format") {
         if (strcmp(value, "rgba32f") && strcmp(value, "rgba8")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_frame_format must be rgba32f or rgba8");
         o.frame_rgba8 = !strcmp(value, "rgba8");
@@ -908,7 +913,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     }
     else if (k == "b200_ao_stack") { if (u() != 0 && u() != 1 && u() != 8 && u() != 12 && u() != 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_stack must be 0, 1, 8, 12 or 16"); o.ao_stack = u(); }
     else if (k == "b200_ao_leaf_vote") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_leaf_vote must be in [1, 32]"); o.ao_leaf_vote = u(); }
-    else if (k == "b200_ao_refill_below") { if (u() == 0 || u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [1, 32]"); o.ao_refill_below = u(); }
+    else if (k == "b200_ao_refill_below") { if (u() > 32) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_refill_below must be in [0, 32] (0 = automatic)"); o.ao_refill_below = u(); }
     else return fail(c, LV_ERR_UNKNOWN_OPTION, "unknown option '" + k + "'");
     return LV_OK;
 }
@@ -957,6 +962,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_queue") v = b(o.ao_queue);
     else if (k == "b200_ao_qnodes") v = b(o.ao_qnodes);
     else if (k == "b200_ao_wide") v = b(o.ao_wide);
+    else if (k == "b200_ao_raybuf") v = b(o.ao_raybuf);
     else if (k == "b200_frame_format") v = o.frame_rgba8 ? "rgba8" : "rgba32f";
     else if (k == "b200_async_delivery") v = b(o.async_delivery);
     else if (k == "b200_ao_wide_top") v = std::to_string(o.ao_wide_top);
@@ -1157,6 +1163,13 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     s->n_nodes = uint64_t(n_inner);
     cleanup();
 #undef LV_BUILD
+    // the AO stream's 4-wide tree is part of the scene build when it is going to be used (b200_ao_wide at creation time), so that
+    // its cost shows in the build time and not in the first frame; switched on later, it is built on first use
+    if (c->opt.ao_wide && s->leaf_size == 1) {
+        const int wrc = ensure_wnodes(c, s);
+        if (wrc) { lv_scene_destroy(s); return wrc; }
+        s->build_ms += s->w_build_ms;
+    }
     *out = s;
     return LV_OK;
 }

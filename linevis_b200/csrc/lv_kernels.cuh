@@ -409,7 +409,7 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
         if (__ballot_sync(0xffffffffu, cur != kDone) == 0u) {
             // nobody traverses: the stream is drained, or every ray just fetched was invalid -- those are finished here (nothing hit) and the
             // warp fetches again (leaving instead would drop their results, and the rest of the stream if this is the last warp running)
-            if (!exhausted && ray_id < total) { occ[ray_id] = 1.0f; ray_id = total; }
+            if (!exhausted && ray_id < total) { occ[ray_id] = P.ao_radius; ray_id = total; }
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
             continue;
         }
@@ -462,7 +462,7 @@ k_rtao_rays(const __grid_constant__ FrameParams P, const __grid_constant__ Scene
             }
             if (cur == kDone && !exhausted && ray_id < total) {
                 // ray finished: traceAoRay result (:158-175)
-                occ[ray_id] = found ? (any_mode ? 0.0f : best / P.ao_radius) : 1.0f;
+                occ[ray_id] = found ? (any_mode ? 0.0f : best) : P.ao_radius;   // the numerator of traceAoRay's t / radius; k_rtao_reduce divides
                 ray_id = total;   // written
             }
             if (__popc(__ballot_sync(0xffffffffu, cur != kDone)) < P.ao_refill_below) break;
@@ -495,13 +495,14 @@ constexpr uint32_t kNoHitBits = 0x7F800000u;   // +inf
 // TOP (NM = 2 only): the first min(TOP, S.w_top) wide nodes -- whole top levels of the breadth-first tree, the nodes every ray walks --
 // are staged into shared memory once per persistent block with ONE bulk-async copy (cp.async.bulk.shared::cluster.global, completion on
 // an mbarrier: the TMA engine moves the bytes, no thread touches them) and steps on them are served from there.
-template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, int NM = 0, int TOP = 0>
+template <int MIN_BLOCKS, bool BAKE, int STACK, int PRIM = 0, int NM = 0, int TOP = 0, bool RBUF = false>
 __global__ void __launch_bounds__(kBlockThreads, MIN_BLOCKS)
 k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float* occ, const AoHit* hit_list,
               const unsigned int* hit_count, unsigned long long* work_counter, Counters* C) {
     __shared__ uint32_t s_queue[kBlockThreads / 32][kLeafQueue];   // record index | owner lane << 27
     __shared__ uint32_t s_hit[kBlockThreads / 32][32];             // nearest accepted hit (float bits) delivered to a lane by the current batch
     __shared__ int s_pend[kBlockThreads / 32][32];                 // queue entries of a lane that are not processed yet
+    __shared__ float s_rbuf[RBUF ? kBlockThreads / 32 : 1][9][32];  // RBUF: the warp's batch of generated rays (origin, direction, safe 1/direction)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* queue = s_queue[warp];
     uint32_t* whit = s_hit[warp];
@@ -559,16 +560,68 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     wpend[lane] = 0;
     __syncwarp();
 
+    // Ray generation is decoupled from the refill (RBUF): the whole warp generates the next 32 rays of the stream together -- TEA seed,
+    // LCG, hemisphere sample, the three IEEE reciprocals of the slab test: ~600 instructions per ray, which the lanes that happened to
+    // be idle used to execute alone (10 of 32 lanes, 8 % of the kernel's warp instructions) -- into a shared-memory batch; a lane
+    // without a ray then just takes the next entry.  Refilling is cheap that way, so it can happen as soon as lanes are idle.
+    uint32_t rb_next = 32u;                // next unread entry of the warp's batch (32 = empty); uniform over the warp
+    unsigned long long rb_base = 0;        // ray number of entry 0
+    bool stream_done = false;              // the last batch reached the end of the stream
+    float (*rbuf)[32] = s_rbuf[RBUF ? warp : 0];
+
     while (true) {
         // ---- refill lanes without a ray
-        const bool idle = !has_ray && !exhausted;
-        const unsigned need = __ballot_sync(0xffffffffu, idle);
-        if (need) {
+        unsigned need = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
+        while (need) {
+            if (RBUF) {
+                if (rb_next >= 32u) {
+                    if (stream_done) { if (!has_ray) exhausted = true; break; }
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(work_counter, 32ull);
+                    rb_base = __shfl_sync(0xffffffffu, base, 0);
+                    rb_next = 0u;
+                    const unsigned long long id = rb_base + lane;
+                    Vec3 org = v3(0, 0, 0), dir = v3(0, 0, 1);
+                    if (id < total) {
+                        const uint32_t slot = uint32_t(id / spp), sample = uint32_t(id - (unsigned long long)slot * spp);
+                        ao_ray_from_record<BAKE>(hit_list + slot, sample, spp, P.frame_number, org, dir);
+                    }
+                    const RayBox gb = make_raybox(org, dir);
+                    rbuf[0][lane] = org.x; rbuf[1][lane] = org.y; rbuf[2][lane] = org.z;
+                    rbuf[3][lane] = dir.x; rbuf[4][lane] = dir.y; rbuf[5][lane] = dir.z;
+                    rbuf[6][lane] = gb.ix; rbuf[7][lane] = gb.iy; rbuf[8][lane] = gb.iz;
+                    if (rb_base + 32ull >= total) stream_done = true;
+                    __syncwarp();
+                }
+                const uint32_t avail = 32u - rb_next, rank = __popc(need & lt_mask);
+                if (((need >> lane) & 1u) && rank < avail) {
+                    const uint32_t e = rb_next + rank;
+                    ray_id = rb_base + e;
+                    if (ray_id >= total) exhausted = true;
+                    else {
+                        const Vec3 org = v3(rbuf[0][e], rbuf[1][e], rbuf[2][e]), dir = v3(rbuf[3][e], rbuf[4][e], rbuf[5][e]);
+                        rq = make_rayq(org, dir);
+                        rb.ix = rbuf[6][e]; rb.iy = rbuf[7][e]; rb.iz = rbuf[8][e];
+                        rb.cx = -(org.x * rb.ix); rb.cy = -(org.y * rb.iy); rb.cz = -(org.z * rb.iz);   // as in make_raybox
+                        if (NM == 2) {   // which bound of each axis the ray enters first (rb.i* is never 0 or NaN for a ray that is traversed)
+                            w4nx = rb.ix >= 0.0f ? kW4SelLo : kW4SelHi; w4ny = rb.iy >= 0.0f ? kW4SelLo : kW4SelHi; w4nz = rb.iz >= 0.0f ? kW4SelLo : kW4SelHi;
+                        }
+                        best = P.ao_radius; found = false;
+                        sp = 0; cur = ao_ray_valid(rq) ? 0u : kDone;                 // root (a NaN ray hits nothing and must not be traversed, see k_rtao_rays)
+                        has_ray = true;
+                        rays++;
+                    }
+                }
+                rb_next += min(uint32_t(__popc(need)), avail);
+                __syncwarp();   // the entries have been read before the next batch overwrites them
+                need = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
+                continue;
+            }
             unsigned long long base = 0;
             const int leader = __ffs(need) - 1;
             if (int(lane) == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (idle) {
+            if ((need >> lane) & 1u) {
                 ray_id = base + __popc(need & lt_mask);
                 if (ray_id >= total) exhausted = true;
                 else {
@@ -586,6 +639,7 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
                     rays++;
                 }
             }
+            break;   // one pass: every idle lane has fetched a ray number
         }
         if (__ballot_sync(0xffffffffu, has_ray) == 0u) break;
 
@@ -728,7 +782,7 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
             }
             // a ray is finished when its stack is empty and none of its queue entries is pending: traceAoRay result (:158-175)
             if (has_ray && cur == kDone && wpend[lane] == 0) {
-                occ[ray_id] = found ? (any_mode ? 0.0f : best / P.ao_radius) : 1.0f;
+                occ[ray_id] = found ? (any_mode ? 0.0f : best) : P.ao_radius;   // the numerator of traceAoRay's t / radius; k_rtao_reduce divides
                 has_ray = false;
             }
             if (__popc(__ballot_sync(0xffffffffu, has_ray)) < P.ao_refill_below) break;
@@ -746,8 +800,10 @@ __global__ void k_rtao_reduce(const __grid_constant__ FrameParams P, const float
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_hit; slot += gridDim.x * blockDim.x) {
         const uint32_t pixel = __float_as_uint(hit_list[slot].nrm_px.w);
         const float* q = occ + size_t(slot) * spp;
+        // the stream stores hit distances (radius for a miss, 0 for an any-hit): t / radius (:170) is taken here, coalesced and by all
+        // lanes, instead of by the few lanes of a warp whose ray has just finished
         float sum = 0.0f;
-        for (uint32_t i = 0; i < spp; i++) sum += q[i];
+        for (uint32_t i = 0; i < spp; i++) sum += q[i] / P.ao_radius;
         float v = sum / float(spp);
         float* p = ao + pixel;
         if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));

@@ -417,6 +417,26 @@ def test_rtao_quantised_nodes(ectx, oracle, use_distance):
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_ray_batches(ectx, oracle, use_distance, wide):
+    """b200_ao_raybuf: the AO stream generates its rays 32 at a time by the whole warp into a shared-memory batch and idle lanes take
+    entries from it -- same rays, same AO image bit for bit (also when the stream is shorter than a batch, or ends inside one)."""
+    for data, width, frame in ((_random(), 0.01, (56, 36)), (_helix(), 0.012, (56, 36)), (_random(3), 0.01, (24, 16))):
+        data = data[0] if isinstance(data, tuple) and len(data) == 2 else data
+        sc, osc = _pair(ectx, oracle, data, width)
+        cam = lv.make_camera(*frame)
+        for spp in (5, 1):
+            ectx.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": use_distance,
+                                   "ambient_occlusion_radius": 0.4, "b200_ao_raybuf": True, "b200_ao_wide": wide, "b200_ao_refill_below": 32})
+            try:
+                ao, st = ectx.render_rtao(sc, cam, 0)
+            finally:
+                ectx.set_new_settings({"b200_ao_raybuf": True, "b200_ao_wide": True, "ambient_occlusion_radius": 0.1, "b200_ao_refill_below": 0})
+            ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
+            assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("top", [0, 85, 341])
 @pytest.mark.parametrize("use_distance", [True, False])
 def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top):
@@ -434,7 +454,7 @@ def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top):
             ectx.set_option("b200_ao_wide", False)
             ao2, st2 = ectx.render_rtao(sc, cam, 0)
         finally:
-            ectx.set_new_settings({"b200_ao_wide": False, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1})
+            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1})
         ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
         if data[2].shape[0] > 100:   # the wide tree really is another tree: fewer steps per ray than the child-pair nodes

@@ -83,11 +83,14 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     ctx.set_option("b200_bvh_leaf_size", 1)
     spp = int(rng.integers(1, 7)); dist = bool(rng.integers(0, 2)); jit = bool(rng.integers(0, 2)); radius = float(rng.choice([0.05, 0.1, 0.5]))
     queue = bool(rng.integers(0, 2)); stack = int(rng.choice([0, 1, 8, 12, 16])); qn = bool(rng.integers(0, 2))
+    wide = bool(rng.integers(0, 2)); raybuf = bool(rng.integers(0, 2)); wtop = int(rng.choice([0, 0, 85, 341])); wreps = int(rng.choice([1, 1, 2]))
+    refill = int(rng.choice([24, 24, 28, 32, 8]))
     capped = bool(rng.integers(0, 4) > 0); halos = bool(rng.integers(0, 2))
     tf = scenes.standard_transfer_function(opacity=(float(rng.random()), float(rng.random())))
     ctx.set_transfer_function(tf)
     ctx.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": dist, "use_jittered_primary_rays": jit,
                           "ambient_occlusion_radius": radius, "b200_ao_queue": queue, "b200_ao_stack": stack, "b200_ao_qnodes": qn,
+                          "b200_ao_wide": wide, "b200_ao_raybuf": raybuf, "b200_ao_wide_top": wtop, "b200_ao_wide_reps": wreps, "b200_ao_refill_below": refill,
                           "use_capped_tubes": capped, "use_halos": halos, "ambient_occlusion_strength": 1.0, "num_samples_per_frame": 1,
                           "num_accumulated_frames": 1, "depth_cue_strength": 0.0, "b200_rtao_geometry": "capsules", "ambient_occlusion_mode": "RTAO (Screen Space)"})
     opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(dist), ao_jitter_primary=int(jit), ao_radius=radius,
