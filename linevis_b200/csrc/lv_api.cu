@@ -38,6 +38,8 @@ struct Options {
     uint32_t max_depth_complexity = 1024;
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
+    bool bvh_ploc = false;              // b200_bvh_builder = ploc: parallel locally-ordered clustering instead of the Morton radix tree (one-record leaves only)
+    uint32_t bvh_ploc_radius = 16;      // ... neighbours searched to either side per round
     uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 30 with b200_ao_raybuf (refilling is cheap), 24 without
     uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
     bool ao_qnodes = false;           // experimental: AO ray stream over 32-byte quantised nodes (k_quantize_nodes, NodeQ); capsules + leaf queue only
@@ -881,6 +883,10 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         uint32_t v = u();
         if (v == 0 || (v & (v - 1))) return fail(c, LV_ERR_INVALID_ARGUMENT, "tiling sizes must be powers of two");
         (k == "b200_tiling_width" ? o.tiling_w : o.tiling_h) = v;
+    } else if (k == "b200_bvh_builder") {
+        if (strcmp(value, "lbvh") && strcmp(value, "ploc")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_builder must be lbvh or ploc");
+        o.bvh_ploc = !strcmp(value, "ploc");
+    } else if (k == "b200_bvh_ploc_radius") { if (u() == 0 || u() > 64) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_ploc_radius must be in [1, 64]"); o.bvh_ploc_radius = u();
     } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
     else if (k == "b200_ppll_binned_resolve") o.ppll_binned_resolve = parse_bool(value);
@@ -955,6 +961,8 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_tiling_width") v = std::to_string(o.tiling_w);
     else if (k == "b200_tiling_height") v = std::to_string(o.tiling_h);
     else if (k == "b200_bvh_leaf_size") v = std::to_string(o.bvh_leaf_size);
+    else if (k == "b200_bvh_builder") v = o.bvh_ploc ? "ploc" : "lbvh";
+    else if (k == "b200_bvh_ploc_radius") v = std::to_string(o.bvh_ploc_radius);
     else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
     else if (k == "b200_ao_leaf_vote") v = std::to_string(o.ao_leaf_vote);
@@ -1143,12 +1151,51 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     LV_BUILD(children.ensure(n_inner)); LV_BUILD(ranges.ensure(n_inner)); LV_BUILD(parent.ensure(2 * size_t(n)));
     LV_BUILD(boxes.ensure(6 * (2 * size_t(n)))); LV_BUILD(flags.ensure(n_inner));
     LV_BUILD(cudaMemsetAsync(flags.p, 0, size_t(n_inner) * 4, st));
-    if (n > 1) k_radix_tree<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys2.p, n, children.p, ranges.p, parent.p);
-    k_fit<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, n, r, children.p, parent.p, boxes.p, flags.p);
+    const bool ploc = c->opt.bvh_ploc && c->opt.bvh_leaf_size == 1 && n >= 2;
     LV_BUILD(s->nodes.ensure(n_inner));
-    k_emit_nodes<<<(n_inner + 255) / 256, 256, 0, st>>>(n, int(c->opt.bvh_leaf_size), children.p, ranges.p, boxes.p, s->nodes.p);
-    LV_BUILD(cudaMemsetAsync(flags.p, 0, 4, st));   // reuse flags[0] as the depth accumulator
-    k_tree_depth<<<(n + 255) / 256, 256, 0, st>>>(n, parent.p, flags.p);
+    if (ploc) {
+        // PLOC (lv_bvh.cuh): rounds of nearest-neighbour search in Morton order + merge + ordered compaction; one host read per round
+        DevBuf<PlocCluster> ca, cb; DevBuf<uint32_t> nn; DevBuf<unsigned long long> pf, ps;
+        auto pcleanup = [&]() { ca.release(); cb.release(); nn.release(); pf.release(); ps.release(); };
+#define LV_PLOC(expr) do { cudaError_t e2__ = (expr); if (e2__ != cudaSuccess) { pcleanup(); LV_BUILD(e2__); } } while (0)
+        LV_PLOC(ca.ensure(n)); LV_PLOC(cb.ensure(n)); LV_PLOC(nn.ensure(n)); LV_PLOC(pf.ensure(size_t(n) + 1)); LV_PLOC(ps.ensure(size_t(n) + 1));
+        size_t scan_bytes = 0;
+        LV_PLOC(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, pf.p, ps.p, n + 1, st));
+        LV_PLOC(cubtmp.ensure(std::max(scan_bytes, cub_bytes) + 16));
+        k_ploc_init<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, uint32_t(n), r, ca.p);
+        uint32_t m = uint32_t(n), created = 0;
+        PlocCluster *cin = ca.p, *cout = cb.p;
+        const int radius = int(c->opt.bvh_ploc_radius);
+        while (m > 1) {
+            const uint32_t g = (m + 255) / 256;
+            k_ploc_nearest<<<g, 256, 0, st>>>(cin, m, radius, nn.p);
+            k_ploc_flags<<<g, 256, 0, st>>>(nn.p, m, pf.p);
+            LV_PLOC(cudaMemsetAsync(pf.p + m, 0, 8, st));       // the scan's last element = the totals
+            LV_PLOC(cub::DeviceScan::ExclusiveSum(cubtmp.p, scan_bytes, pf.p, ps.p, int(m) + 1, st));
+            k_ploc_apply<<<g, 256, 0, st>>>(cin, nn.p, pf.p, ps.p, m, created, uint32_t(n_inner), s->nodes.p, cout);
+            unsigned long long tot = 0;
+            LV_PLOC(cudaMemcpyAsync(&tot, ps.p + m, 8, cudaMemcpyDeviceToHost, st));
+            LV_PLOC(cudaStreamSynchronize(st));
+            const uint32_t merged = uint32_t(tot >> 32);
+            if (merged == 0) { pcleanup(); LV_BUILD(cudaErrorUnknown); }   // cannot happen: the pair with the globally smallest area is always mutual
+            created += merged; m = uint32_t(tot);
+            std::swap(cin, cout);
+        }
+        PlocCluster root;
+        LV_PLOC(cudaMemcpyAsync(&root, cin, sizeof(root), cudaMemcpyDeviceToHost, st));
+        LV_PLOC(cudaStreamSynchronize(st));
+        uint32_t height; memcpy(&height, &root.hi.w, 4);
+        LV_PLOC(cudaMemcpyAsync(flags.p, &height, 4, cudaMemcpyHostToDevice, st));    // where the depth is read from below
+        LV_PLOC(cudaStreamSynchronize(st));
+        pcleanup();
+#undef LV_PLOC
+    } else {
+        if (n > 1) k_radix_tree<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys2.p, n, children.p, ranges.p, parent.p);
+        k_fit<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, n, r, children.p, parent.p, boxes.p, flags.p);
+        k_emit_nodes<<<(n_inner + 255) / 256, 256, 0, st>>>(n, int(c->opt.bvh_leaf_size), children.p, ranges.p, boxes.p, s->nodes.p);
+        LV_BUILD(cudaMemsetAsync(flags.p, 0, 4, st));   // reuse flags[0] as the depth accumulator
+        k_tree_depth<<<(n + 255) / 256, 256, 0, st>>>(n, parent.p, flags.p);
+    }
     LV_BUILD(cudaGetLastError());
     LV_BUILD(cudaEventRecord(c->ev[1], st));
     LV_BUILD(cudaMemcpyAsync(s->bounds, bounds.p, 24, cudaMemcpyDeviceToHost, st));

@@ -252,6 +252,75 @@ __global__ void k_quantize_nodes(const Node64* nodes, uint32_t n, float ox, floa
     out[i] = q;
 }
 
+// ---- PLOC builder (b200_bvh_builder = ploc) -----------------------------------------------------------------------------------
+// Parallel locally-ordered clustering (Meister & Bittner 2018; the reference library's LocallyOrderedClusteringBuilder,
+// submodules/bvh/include/bvh/locally_ordered_clustering_builder.hpp, is the CPU form): the records in Morton order are the initial
+// clusters; every round each cluster looks `radius` neighbours to either side for the partner with the smallest merged surface area,
+// mutual nearest neighbours merge into a new child-pair node, the survivors are compacted in order, until one cluster is left.
+// A cluster = its box, the child word that refers to it (leaf | record, or node index) and the height of its subtree.
+struct PlocCluster {
+    float4 lo;   // min.xyz, as_float(child word)
+    float4 hi;   // max.xyz, as_float(subtree height)
+};
+
+__global__ void k_ploc_init(const SegRec* segs, uint32_t n, float r, PlocCluster* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SegRec s = segs[i];
+    PlocCluster c;
+    c.lo = make_float4(fminf(s.a.x, s.b.x) - r, fminf(s.a.y, s.b.y) - r, fminf(s.a.z, s.b.z) - r, __uint_as_float(0x80000000u | i));   // the record's own AABB, as in k_fit
+    c.hi = make_float4(fmaxf(s.a.x, s.b.x) + r, fmaxf(s.a.y, s.b.y) + r, fmaxf(s.a.z, s.b.z) + r, __uint_as_float(0u));
+    out[i] = c;
+}
+
+__global__ void k_ploc_nearest(const PlocCluster* cl, uint32_t m, int radius, uint32_t* nn) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float4 lo = cl[i].lo, hi = cl[i].hi;
+    const int j0 = int(i) - radius < 0 ? 0 : int(i) - radius, j1 = int(i) + radius >= int(m) ? int(m) - 1 : int(i) + radius;
+    float best = INFINITY; uint32_t arg = i == 0 ? 1u : i - 1u;
+    for (int j = j0; j <= j1; j++) {
+        if (j == int(i)) continue;
+        const float4 l2 = cl[j].lo, h2 = cl[j].hi;
+        const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+        const float a = dx * dy + dy * dz + dz * dx;     // the same expression for (i, j) and (j, i): mutual choices are consistent
+        if (a < best) { best = a; arg = uint32_t(j); }  // ties: the lowest index
+    }
+    nn[i] = arg;
+}
+
+// flags[i]: bit 0 = cluster i survives the round (it is not the higher-indexed half of a merging pair), bit 32 = it merges (lower half)
+__global__ void k_ploc_flags(const uint32_t* nn, uint32_t m, unsigned long long* flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t j = nn[i];
+    const bool mutual = nn[j] == i;
+    flags[i] = (mutual && j < i ? 0ull : 1ull) | (mutual && i < j ? (1ull << 32) : 0ull);
+}
+
+// scan[i] = exclusive sums of flags (low word: output slot; high word: how many merges precede).  Nodes are numbered backwards from
+// n_inner - 1, so that the last merge -- the root -- is node 0.
+__global__ void k_ploc_apply(const PlocCluster* in, const uint32_t* nn, const unsigned long long* flags, const unsigned long long* scan, uint32_t m,
+                             uint32_t created, uint32_t n_inner, Node64* nodes, PlocCluster* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const unsigned long long f = flags[i];
+    if (!(f & 1ull)) return;                               // merged into its partner
+    PlocCluster c = in[i];
+    if (f >> 32) {
+        const PlocCluster d = in[nn[i]];
+        const uint32_t node = n_inner - 1u - (created + uint32_t(scan[i] >> 32));
+        Node64 nd;
+        nd.l0 = c.lo; nd.l1 = make_float4(c.hi.x, c.hi.y, c.hi.z, __uint_as_float((__float_as_uint(c.lo.w) & 0x80000000u) ? 1u : 0u));
+        nd.r0 = d.lo; nd.r1 = make_float4(d.hi.x, d.hi.y, d.hi.z, __uint_as_float((__float_as_uint(d.lo.w) & 0x80000000u) ? 1u : 0u));
+        nodes[node] = nd;
+        const uint32_t h = max(__float_as_uint(c.hi.w), __float_as_uint(d.hi.w)) + 1u;
+        c.lo = make_float4(fminf(c.lo.x, d.lo.x), fminf(c.lo.y, d.lo.y), fminf(c.lo.z, d.lo.z), __uint_as_float(node));
+        c.hi = make_float4(fmaxf(c.hi.x, d.hi.x), fmaxf(c.hi.y, d.hi.y), fmaxf(c.hi.z, d.hi.z), __uint_as_float(h));
+    }
+    out[uint32_t(scan[i])] = c;
+}
+
 // ---- 4-wide quantised tree (NodeW4) -------------------------------------------------------------------------------------------
 // Dequantisation of a 16-bit grid coordinate q: 0x4B000000 | q is the float 8388608 + q (exact), so ONE logic operation + ONE fma
 // replace an integer-to-float conversion (a quarter-rate instruction; it is what made the 32-byte NodeQ kernel lose) + an fma:

@@ -93,14 +93,14 @@ __global__ void k_depth_range(const __grid_constant__ FrameParams P, const SegRe
 // closest-hit only (parity / debugging entry point lv_trace_primary)
 __global__ void __launch_bounds__(kBlockThreads)
 k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, lv_hit* hits, Counters* C) {
-    __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
+    __shared__ PacketScratch s_scratch[kBlockThreads / 32];
     uint32_t x, y;
     const bool valid = thread_pixel(P, x, y);
     uint32_t steps = 0, isect = 0, nhit = 0;
     Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
     if (valid) camera_ray(P, x, y, 0.5f, 0.5f, ro, rd);
     HitRec h;
-    const bool hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_stack[threadIdx.x >> 5], steps, isect);
+    const bool hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_scratch[threadIdx.x >> 5], steps, isect);
     if (valid) {
         lv_hit out; out.t = 0.0f; out.prim = kNone; out.kind = 0; out.pad = 0;
         if (hit) { out.t = h.t; out.prim = h.prim; out.kind = h.kind; nhit = 1; }
@@ -121,8 +121,8 @@ k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDe
 template <bool SAO>
 __global__ void __launch_bounds__(kBlockThreads)
 k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C, uint32_t* out8) {
-    __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
-    uint32_t* stack = s_stack[threadIdx.x >> 5];
+    __shared__ PacketScratch s_scratch[kBlockThreads / 32];
+    PacketScratch& stack = s_scratch[threadIdx.x >> 5];
     uint32_t x, y;
     const bool valid = thread_pixel(P, x, y);
     uint32_t steps = 0, isect = 0, rays = 0, nhit = 0;
@@ -222,7 +222,7 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
     bool hit = false;
     AoHit rec;
     if (valid && !apron_mark && apron_stamp) apron_mark_owned(P, x, y, apron_stamp);
-    __shared__ uint32_t s_stack[kBlockThreads / 32][kStackSize];
+    __shared__ PacketScratch s_scratch[kBlockThreads / 32];
     Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
     if (valid) {
         uint32_t seed = tea(x + y * P.W, P.frame_number);
@@ -232,8 +232,8 @@ k_rtao_primary(const __grid_constant__ FrameParams P, const __grid_constant__ Sc
     }
     HitRec h;
     TriHitRec th;
-    if (PRIM == 1) hit = bvh_trace_packet_tri(S, valid, ro, rd, 0.0001f, 1000.0f, th, s_stack[threadIdx.x >> 5], steps, isect);
-    else hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_stack[threadIdx.x >> 5], steps, isect);
+    if (PRIM == 1) hit = bvh_trace_packet_tri(S, valid, ro, rd, 0.0001f, 1000.0f, th, s_scratch[threadIdx.x >> 5].stack, steps, isect);
+    else hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_scratch[threadIdx.x >> 5], steps, isect);
     if (valid) {
         if (hit && PRIM == 1) {
             rec = tri_ao_frame(S, load_tri(S.tris + th.idx), th.u, th.v, P.subdiv_corr, y * P.W + x);   // the shader's barycentric fetch (:213-276)

@@ -98,21 +98,69 @@ struct HitRec {
 // tie margin) passes, near child first by majority vote, and every node / record is fetched once per warp.  Each lane keeps
 // its own closest hit (acceptance rule above, ties -> lowest segment index); the order in which candidates are met does not
 // influence the result.
-// Must be called by all 32 lanes; `active` = this lane has a ray.  `stack` = kStackSize words of shared memory per warp.
+// Leaf tests are DEFERRED and BATCHED: at a leaf only the lanes whose own box test passed want the record (ncu on k_tubes: the
+// capsule test ran with 5 - 9 of 32 lanes, 40 % of the kernel's warp instructions).  They append (lane, record) to a warp queue; as
+// soon as 32 entries are queued every lane runs ONE test -- entry i on lane i, the owner's ray fetched with shuffles -- and hands the
+// result to the owner through a 64-bit shared word: key = (hit distance bits << 32) | caller-side segment index, merged with
+// atomicMin, which IS the result rule (smallest distance, ties -> lowest segment index).  The record index / hit kind of the winning
+// key are written by the lane that holds it after the batch.  Owners cull with the distance they know so far.
+// Must be called by all 32 lanes; `active` = this lane has a ray.  `scratch` = one PacketScratch of shared memory per warp.
+struct PacketScratch {
+    unsigned long long key[32];   // per lane: closest accepted hit so far
+    uint32_t aux[32];             // ... its record index (BVH order) | hit kind << 28
+    uint32_t queue[64];           // ring of deferred tests: record index | owner lane << 27
+    uint32_t stack[kStackSize];
+};
+
+__device__ __forceinline__ void packet_flush(const SceneDev& S, PacketScratch& sc, uint32_t lane, uint32_t n, uint32_t& q_head, uint32_t& q_count,
+                                             const RayQ& rq, const RayBox& rb, float tmin, float tmax, bool capped, float& best_t) {
+    const uint32_t e = sc.queue[(q_head + (lane < n ? lane : 0u)) & 63u];
+    const uint32_t owner = e >> 27, rec = e & kRefMask;
+    RayQ r2; RayBox b2;
+    r2.o.x = __shfl_sync(0xffffffffu, rq.o.x, owner); r2.o.y = __shfl_sync(0xffffffffu, rq.o.y, owner); r2.o.z = __shfl_sync(0xffffffffu, rq.o.z, owner);
+    r2.d.x = __shfl_sync(0xffffffffu, rq.d.x, owner); r2.d.y = __shfl_sync(0xffffffffu, rq.d.y, owner); r2.d.z = __shfl_sync(0xffffffffu, rq.d.z, owner);
+    r2.dd = __shfl_sync(0xffffffffu, rq.dd, owner);
+    b2.ix = __shfl_sync(0xffffffffu, rb.ix, owner); b2.iy = __shfl_sync(0xffffffffu, rb.iy, owner); b2.iz = __shfl_sync(0xffffffffu, rb.iz, owner);
+    b2.cx = __shfl_sync(0xffffffffu, rb.cx, owner); b2.cy = __shfl_sync(0xffffffffu, rb.cy, owner); b2.cz = __shfl_sync(0xffffffffu, rb.cz, owner);
+    const float tmin2 = __shfl_sync(0xffffffffu, tmin, owner);
+    unsigned long long mykey = ~0ull;
+    uint32_t kind = 0;
+    if (lane < n) {
+        const SegRec s = load_seg(S.segs + rec);
+        float t;
+        if (seg_box_hit(b2, s, S.radius, tmin2, tmax) && capsule_hit(r2, s, S.radius, capped, t, kind) && t >= tmin2 && t <= tmax) {
+            mykey = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | __ldg(S.prim_ids + rec);   // t > 0: the bit pattern orders like the value
+            atomicMin(&sc.key[owner], mykey);
+        }
+    }
+    __syncwarp();
+    if (mykey != ~0ull && sc.key[owner] == mykey) sc.aux[owner] = rec | (kind << 28);   // the winner (segment indices are unique) names its record
+    __syncwarp();
+    best_t = __uint_as_float(uint32_t(sc.key[lane] >> 32));
+    q_head = (q_head + n) & 63u;
+    q_count -= n;
+}
+
 __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active, Vec3 o, Vec3 d, float tmin, float tmax, bool capped,
-                                                 HitRec& best, uint32_t* stack, uint32_t& steps, uint32_t& isect) {
+                                                 HitRec& best, PacketScratch& sc, uint32_t& steps, uint32_t& isect) {
     best.t = tmax; best.idx = 0; best.prim = 0xFFFFFFFFu; best.kind = 0;
-    bool found = false;
     if (S.n_seg == 0 || __ballot_sync(0xffffffffu, active) == 0u) return false;
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const RayQ rq = make_rayq(o, d);
     const RayBox rb = make_raybox(o, d);
+    const unsigned long long no_hit = (static_cast<unsigned long long>(__float_as_uint(tmax)) << 32) | 0xFFFFFFFFull;
+    sc.key[lane] = no_hit;
+    sc.aux[lane] = 0u;
+    __syncwarp();
+    float best_t = tmax;
+    uint32_t q_head = 0, q_count = 0;   // uniform over the warp
     uint32_t node = 0;
     int sp = 0;
     while (true) {
         const Node64 nd = load_node(S.nodes + node);
         steps += (lane == 0);
-        const float tcull = best.t + S.line_width;
+        const float tcull = best_t + S.line_width;
         float tl, tr;
         const bool hl = active && box_hit(rb, nd.l0, nd.l1, tmin, tcull, tl);
         const bool hr = active && box_hit(rb, nd.r0, nd.r1, tmin, tcull, tr);
@@ -128,15 +176,12 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
                 const uint32_t ref = w & kRefMask, cnt = ((w >> 27) & 15u) + 1u;
                 isect += (lane == 0) ? cnt : 0u;
                 const bool mine = side ? hr : hl;
+                const uint32_t nm = __popc(mk[side]);
                 for (uint32_t i = 0; i < cnt; i++) {
-                    const SegRec s = load_seg(S.segs + ref + i);
-                    float t; uint32_t kind;
-                    if (mine && seg_box_hit(rb, s, S.radius, tmin, tmax) && capsule_hit(rq, s, S.radius, capped, t, kind) && t >= tmin && t <= tmax) {
-                        if (!found || t <= best.t) {
-                            const uint32_t prim = __ldg(S.prim_ids + ref + i);
-                            if (!found || t < best.t || prim < best.prim) { best.t = t; best.idx = ref + i; best.prim = prim; best.kind = kind; found = true; }
-                        }
-                    }
+                    if (mine) sc.queue[(q_head + q_count + __popc(mk[side] & lt_mask)) & 63u] = (ref + i) | (lane << 27);
+                    q_count += nm;
+                    __syncwarp();
+                    if (q_count >= 32u) packet_flush(S, sc, lane, 32u, q_head, q_count, rq, rb, tmin, tmax, capped, best_t);
                 }
             } else inner[n_inner++] = w;
         }
@@ -145,7 +190,7 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
             const unsigned right_near = __ballot_sync(0xffffffffu, hr && (!hl || tr < tl));
             const unsigned left_near = __ballot_sync(0xffffffffu, hl && (!hr || tl <= tr));
             const bool rf = __popc(right_near) > __popc(left_near);
-            if (lane == 0) stack[sp] = rf ? inner[0] : inner[1];
+            if (lane == 0) sc.stack[sp] = rf ? inner[0] : inner[1];
             sp++;
             node = rf ? inner[1] : inner[0];
         } else if (n_inner == 1) node = inner[0];
@@ -153,11 +198,17 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
             if (sp == 0) break;
             --sp;
             __syncwarp();
-            node = stack[sp];
+            node = sc.stack[sp];
         }
         __syncwarp();
     }
-    return found;
+    if (q_count) packet_flush(S, sc, lane, q_count, q_head, q_count, rq, rb, tmin, tmax, capped, best_t);
+    const unsigned long long k = sc.key[lane];
+    const uint32_t a = sc.aux[lane];
+    __syncwarp();   // the scratch is reused by the next packet of this warp
+    if (k == no_hit) return false;
+    best.t = __uint_as_float(uint32_t(k >> 32)); best.prim = uint32_t(k); best.idx = a & kRefMask; best.kind = a >> 28;
+    return true;
 }
 #endif  // warp-collective code
 

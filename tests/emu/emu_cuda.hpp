@@ -267,6 +267,7 @@ template <class T> inline T emu_atomic_minmax(T* p, T v, bool is_min) {
 }
 inline int atomicMin(int* p, int v) { return emu_atomic_minmax(p, v, true); }
 inline unsigned atomicMin(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, true); }
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { return emu_atomic_minmax(p, v, true); }
 inline int atomicMax(int* p, int v) { return emu_atomic_minmax(p, v, false); }
 inline unsigned atomicMax(unsigned* p, unsigned v) { return emu_atomic_minmax(p, v, false); }
 

@@ -417,6 +417,44 @@ def test_rtao_quantised_nodes(ectx, oracle, use_distance):
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("radius", [1, 16])
+def test_ploc_builder(ectx, oracle, radius):
+    """b200_bvh_builder = ploc: the tree built by parallel locally-ordered clustering is a valid BVH over the same records (every
+    record referenced once, boxes enclose), and primary hits, AO image (wide tree collapsed from it) and PPLL fragments are the
+    LBVH's / the oracle's bit for bit -- results do not depend on the tree (rule 2)."""
+    for data, width in (_random(), _helix(), _random(2), _random(3)):
+        ectx.set_new_settings({"b200_bvh_builder": "ploc", "b200_bvh_ploc_radius": radius})
+        try:
+            sc, osc = _pair(ectx, oracle, data, width)
+        finally:
+            ectx.set_new_settings({"b200_bvh_builder": "lbvh", "b200_bvh_ploc_radius": 16})
+        n = data[2].shape[0]
+        nodes = sc.bvh_nodes()
+        assert len(nodes) == max(1, n - 1)
+        seen, stack = np.zeros(n, np.int32), [0]
+        while stack:
+            nd = nodes[stack.pop()]
+            for side in ("l", "r"):
+                ref, cnt = int(nd[side + "ref"]), int(nd[side + "count"])
+                if cnt:
+                    seen[ref & 0x07FFFFFF] += 1
+                else:
+                    ch = nodes[ref]
+                    assert (np.minimum(ch["lmin"], ch["rmin"]) >= nd[side + "min"]).all() and (np.maximum(ch["lmax"], ch["rmax"]) <= nd[side + "max"]).all()
+                    stack.append(ref)
+        assert (seen == 1).all()
+        cam = lv.make_camera(56, 36)
+        hits, _ = ectx.trace_primary(sc, cam); ref, _ = osc.trace_primary(cam)
+        assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32)) and np.array_equal(hits["prim"], ref["prim"])
+        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 5, "ambient_occlusion_radius": 0.4})
+        try:
+            ao, st = ectx.render_rtao(sc, cam, 0)
+        finally:
+            ectx.set_new_settings({"ambient_occlusion_radius": 0.1})
+        rao, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=5, ao_radius=0.4), 0)
+        assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), rao.view(np.uint32))
+
+
 @pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("use_distance", [True, False])
 def test_rtao_ray_batches(ectx, oracle, use_distance, wide):
