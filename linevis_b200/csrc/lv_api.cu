@@ -46,6 +46,7 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
+    bool tube_prepass = true;           // b200_tube_prepass: the tube pass's first hits are traced on a second stream beside the RTAO pass
     bool frame_rgba8 = false;           // b200_frame_format = rgba8: rgba_out of the render calls is RGBA8 UNORM (uint32 per pixel), packed in the frame kernels' epilogue
     bool async_delivery = false;        // b200_async_delivery: an rgba8 frame for a HOST pointer is copied on a second stream from alternating staging buffers;
                                         // the call returns once the copy is enqueued, lv_synchronize waits for it (frame i's D2H overlaps frame i+1's render)
@@ -102,6 +103,7 @@ struct lv_ctx {
     DevBuf<unsigned int> apron_marks; unsigned int apron_stamp = 0;
     DevBuf<uint32_t> rgba8;
     // asynchronous delivery of rgba8 frames to host memory: two staging frames, a copy stream, events
+    DevBuf<uint2> first_hits; cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // b200_tube_prepass
     DevBuf<uint32_t> stage8[2]; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[2] = {}, ev_copied[2] = {}; unsigned flip = 0; bool copies_pending = false;
     DevBuf<float4> image; DevBuf<float> ao, occ, depth_mm; DevBuf<lv_hit> hits; DevBuf<AoHit> ao_hits;
     uint32_t ao_w = 0, ao_h = 0;
@@ -821,6 +823,8 @@ int lv_ctx_destroy(lv_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->rgba8.release(); c->pixel_rays.release(); c->stage8[0].release(); c->stage8[1].release();
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+    c->first_hits.release();
     for (int k = 0; k < 2; k++) { if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
     c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
@@ -910,6 +914,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         o.frame_rgba8 = !strcmp(value, "rgba8");
     }
     else if (k == "b200_async_delivery") o.async_delivery = parse_bool(value);
+    else if (k == "b200_tube_prepass") o.tube_prepass = parse_bool(value);
     else if (k == "b200_ao_wide_reps") { if (u() == 0 || u() > 4) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_wide_reps must be in [1, 4]"); o.ao_wide_reps = u(); }
     else if (k == "b200_ao_wide_top") { if (u() > 1365) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_wide_top must be <= 1365 nodes"); o.ao_wide_top = u(); }
     else if (k == "b200_rtao_geometry") {
@@ -973,6 +978,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_raybuf") v = b(o.ao_raybuf);
     else if (k == "b200_frame_format") v = o.frame_rgba8 ? "rgba8" : "rgba32f";
     else if (k == "b200_async_delivery") v = b(o.async_delivery);
+    else if (k == "b200_tube_prepass") v = b(o.tube_prepass);
     else if (k == "b200_ao_wide_top") v = std::to_string(o.ao_wide_top);
     else if (k == "b200_ao_wide_reps") v = std::to_string(o.ao_wide_reps);
     else if (k == "b200_rtao_geometry") v = o.ao_triangles ? "triangles" : "capsules";
@@ -1473,18 +1479,35 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
     LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     const bool use_ao = c->opt.ao_strength > 0.0f && !c->opt.ao_prebaker;
     if ((rc = prepare_static_ao(c, sc, P))) return rc;
+    const uint2* first = nullptr;
     if (use_ao) {
         // LineRenderer::renderBase -> ambientOcclusionBaker->updateIterative (reference LineRenderer.cpp:259-265): one RTAO
         // iteration per rendered frame until maxNumAccumulatedFrames (VulkanRayTracedAmbientOcclusion.cpp:89-107).
-        if (frame_number < c->opt.ao_iterations || !c->ao.p || c->ao_w != P.W || c->ao_h != P.H)
+        if (frame_number < c->opt.ao_iterations || !c->ao.p || c->ao_w != P.W || c->ao_h != P.H) {
+            if (c->opt.tube_prepass && P.n_tiles && sc->n_seg) {
+                // fork: the tube pass's first-hit traversal on the second stream, beside the RTAO pass (joined in front of k_tubes)
+                if (!c->aux_stream) {
+                    LV_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+                    LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); LV_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+                }
+                LV_CUDA(c, c->first_hits.ensure(size_t(P.W) * P.H));
+                LV_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+                LV_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+                k_tube_first<<<pixel_grid(c, P), kBlockThreads, 0, c->aux_stream>>>(P, sc->dev(), c->first_hits.p, c->counters.p);
+                LV_CUDA(c, cudaGetLastError());
+                LV_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
+                first = c->first_hits.p;
+            }
             if ((rc = run_rtao(c, sc, P, frame_number))) return rc;
+            if (first) LV_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        }
         P.use_ao = 1; P.ao_tex = c->ao.p;
     }
     if ((rc = run_depth_range(c, sc, P))) return rc;
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (P.n_tiles) {
-        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8);
-        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8);
+        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
+        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
     }
     LV_CUDA(c, cudaGetLastError());
     LV_CUDA(c, cudaEventRecord(c->ev[2], c->stream));

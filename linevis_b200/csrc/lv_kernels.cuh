@@ -115,12 +115,36 @@ k_primary(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDe
 // ------------------------------------------------------------------------------------------------
 // S1 ray-gen with the traceRayTransparent loop, S3/S4 shading and the running mean over frames
 // (reference TubeRayTracing.glsl:61-82,198-274).  `image` is the accumulation image (float RGBA).
+// First hit of the tube pass's first sample, traced AHEAD of k_tubes on a second stream (b200_tube_prepass): the closest-hit
+// traversal does not depend on the AO image, so it runs beside k_rtao_primary and in the shadow of the AO ray stream's tail (a
+// persistent kernel drains unevenly: ~0.3 ms during which most SMs idle -- 1 % of a one-GPU frame, 7 % of an 8-GPU one).
+// first[pixel] = (t bits, record index | hit kind << 28 | hit << 31).
+__global__ void __launch_bounds__(kBlockThreads)
+k_tube_first(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, uint2* first, Counters* C) {
+    __shared__ PacketScratch s_scratch[kBlockThreads / 32];
+    uint32_t x, y;
+    const bool valid = thread_pixel(P, x, y);
+    uint32_t steps = 0, isect = 0;
+    float xix = 0.5f, xiy = 0.5f;
+    if (P.use_jitter) {   // sample 0 of k_tubes
+        uint32_t seed = P.det_sampling ? tea(19u, P.frame_number * P.spp) : tea(x + y * P.W, P.frame_number * P.spp);
+        xix = rnd(seed); xiy = rnd(seed);
+    }
+    Vec3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);
+    if (valid) camera_ray(P, x, y, xix, xiy, ro, rd);
+    HitRec h;
+    const bool hit = bvh_trace_packet(S, valid, ro, rd, 0.0001f, 1000.0f, P.use_capped != 0, h, s_scratch[threadIdx.x >> 5], steps, isect);
+    if (valid) first[size_t(y) * P.W + x] = hit ? make_uint2(__float_as_uint(h.t), h.idx | (h.kind << 28) | 0x80000000u) : make_uint2(0u, 0u);
+    flush_counter(&C->steps, steps);
+    flush_counter(&C->isect, isect);
+}
+
 // out8 != nullptr (b200_frame_format = rgba8): the frame is ALSO stored as RGBA8 UNORM -- the reference's own sceneTexture format
 // (TubeRayTracing.glsl:42, src/Widgets/DataView.cpp:100-108) -- in the same epilogue; `image` then is the library's own float
 // accumulation image and out8 the delivered frame (4 B / pixel: a quarter of the peer-store and read-back traffic).
 template <bool SAO>
 __global__ void __launch_bounds__(kBlockThreads)
-k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C, uint32_t* out8) {
+k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev S, float4* image, Counters* C, uint32_t* out8, const uint2* first) {
     __shared__ PacketScratch s_scratch[kBlockThreads / 32];
     PacketScratch& stack = s_scratch[threadIdx.x >> 5];
     uint32_t x, y;
@@ -144,7 +168,12 @@ k_tubes(const __grid_constant__ FrameParams P, const __grid_constant__ SceneDev 
         for (uint32_t hi = 0; hi < P.max_depth; hi++) {
             if (__ballot_sync(0xffffffffu, live) == 0u) break;
             HitRec h;
-            const bool hit = bvh_trace_packet(S, live, ro, rd, tmin, 1000.0f, P.use_capped != 0, h, stack, steps, isect);
+            bool hit;
+            if (first && hi == 0 && si == 0) {   // traced ahead by k_tube_first (same ray, same acceptance rule)
+                const uint2 f = valid ? first[size_t(y) * P.W + x] : make_uint2(0u, 0u);
+                hit = (f.y >> 31) != 0u;
+                h.t = __uint_as_float(f.x); h.idx = f.y & kRefMask; h.kind = (f.y >> 28) & 3u; h.prim = 0u;
+            } else hit = bvh_trace_packet(S, live, ro, rd, tmin, 1000.0f, P.use_capped != 0, h, stack, steps, isect);
             if (live) {
                 rays++;
                 Vec4 hc; float hit_t;

@@ -100,11 +100,18 @@ struct HitRec {
 // influence the result.
 // Leaf tests are DEFERRED and BATCHED: at a leaf only the lanes whose own box test passed want the record (ncu on k_tubes: the
 // capsule test ran with 5 - 9 of 32 lanes, 40 % of the kernel's warp instructions).  They append (lane, record) to a warp queue; as
-// soon as 32 entries are queued every lane runs ONE test -- entry i on lane i, the owner's ray fetched with shuffles -- and hands the
+// soon as kPacketFlush entries are queued the lanes run ONE test each -- entry i on lane i, the owner's ray fetched with shuffles -- and hands the
 // result to the owner through a 64-bit shared word: key = (hit distance bits << 32) | caller-side segment index, merged with
 // atomicMin, which IS the result rule (smallest distance, ties -> lowest segment index).  The record index / hit kind of the winning
 // key are written by the lane that holds it after the batch.  Owners cull with the distance they know so far.
 // Must be called by all 32 lanes; `active` = this lane has a ray.  `scratch` = one PacketScratch of shared memory per warp.
+// Queued tests at which a batch runs.  32 = only full batches: best for dense data (config 5: 3.79 -> 3.14 ms for the two packet kernels),
+// but a packet that meets fewer than 32 candidates on its whole way then never learns a hit distance to cull with (config 3: 1.55 ->
+// 1.88 ms).  LV_PACKET_FLUSH is the compromise measured on both.
+#ifndef LV_PACKET_FLUSH
+#define LV_PACKET_FLUSH 12
+#endif
+constexpr uint32_t kPacketFlush = LV_PACKET_FLUSH;
 struct PacketScratch {
     unsigned long long key[32];   // per lane: closest accepted hit so far
     uint32_t aux[32];             // ... its record index (BVH order) | hit kind << 28
@@ -181,7 +188,7 @@ __device__ __forceinline__ bool bvh_trace_packet(const SceneDev& S, bool active,
                     if (mine) sc.queue[(q_head + q_count + __popc(mk[side] & lt_mask)) & 63u] = (ref + i) | (lane << 27);
                     q_count += nm;
                     __syncwarp();
-                    if (q_count >= 32u) packet_flush(S, sc, lane, 32u, q_head, q_count, rq, rb, tmin, tmax, capped, best_t);
+                    if (q_count >= kPacketFlush) packet_flush(S, sc, lane, q_count < 32u ? q_count : 32u, q_head, q_count, rq, rb, tmin, tmax, capped, best_t);
                 }
             } else inner[n_inner++] = w;
         }

@@ -90,7 +90,7 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     ctx.set_transfer_function(tf)
     ctx.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": dist, "use_jittered_primary_rays": jit,
                           "ambient_occlusion_radius": radius, "b200_ao_queue": queue, "b200_ao_stack": stack, "b200_ao_qnodes": qn,
-                          "b200_ao_wide": wide, "b200_ao_raybuf": raybuf, "b200_ao_wide_top": wtop, "b200_ao_wide_reps": wreps, "b200_ao_refill_below": refill,
+                          "b200_ao_wide": wide, "b200_ao_raybuf": raybuf, "b200_tube_prepass": bool(rng.integers(0, 2)), "b200_ao_wide_top": wtop, "b200_ao_wide_reps": wreps, "b200_ao_refill_below": refill,
                           "use_capped_tubes": capped, "use_halos": halos, "ambient_occlusion_strength": 1.0, "num_samples_per_frame": 1,
                           "num_accumulated_frames": 1, "depth_cue_strength": 0.0, "b200_rtao_geometry": "capsules", "ambient_occlusion_mode": "RTAO (Screen Space)"})
     opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(dist), ao_jitter_primary=int(jit), ao_radius=radius,
