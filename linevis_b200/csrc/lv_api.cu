@@ -38,6 +38,7 @@ struct Options {
     uint32_t max_depth_complexity = 1024;
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
+    bool bvh_cubic_morton = true;       // b200_bvh_morton = cubic: one scale for all axes in the Morton codes (per_axis: each axis to [0, 1])
     bool bvh_ploc = false;              // b200_bvh_builder = ploc: parallel locally-ordered clustering instead of the Morton radix tree (one-record leaves only)
     uint32_t bvh_ploc_radius = 16;      // ... neighbours searched to either side per round
     uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 30 with b200_ao_raybuf (refilling is cheap), 24 without
@@ -46,6 +47,7 @@ struct Options {
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
     bool ao_queue = true;             // AO rays: leaf-queue kernel k_rtao_rays_q (one-record leaves), else the leaf-vote kernel k_rtao_rays
     uint32_t ao_min_blocks = 0;       // resident 128-thread blocks per SM the AO ray kernel is compiled for (8 / 9 / 10); 0 = best measured (queue 8, vote 9)
+    bool tube_triangles = false;        // geometry_mode = "Triangle Mesh": the tube pass traces and shades the reference's triangulated tubes
     bool tube_prepass = true;           // b200_tube_prepass: the tube pass's first hits are traced on a second stream beside the RTAO pass
     bool frame_rgba8 = false;           // b200_frame_format = rgba8: rgba_out of the render calls is RGBA8 UNORM (uint32 per pixel), packed in the frame kernels' epilogue
     bool async_delivery = false;        // b200_async_delivery: an rgba8 frame for a HOST pointer is copied on a second stream from alternating staging buffers;
@@ -465,6 +467,7 @@ int ensure_tube_mesh(lv_ctx* c, lv_scene* sc) {
         vline[i] = m.vertices[i].line_point;
     }
     for (size_t i = 0; i < nl; i++) { lpos[i] = make_float4(m.line_pos[i].x, m.line_pos[i].y, m.line_pos[i].z, 0.0f); ltan[i] = make_float4(m.line_tan[i].x, m.line_tan[i].y, m.line_tan[i].z, 0.0f); }
+    for (uint32_t src : m.line_src) if (src >= sc->n_pt) return fail(c, LV_ERR_STATE, "triangle-tube mode: the polylines of lv_scene_set_lines do not match the scene's points");
     cudaStream_t st = c->stream;
     const int n = int(nt);
     DevBuf<float> d_vpos, d_vnrm, bounds, boxes; DevBuf<uint32_t> d_idx, d_vline, vals; DevBuf<unsigned long long> keys, keys2;
@@ -482,6 +485,20 @@ int ensure_tube_mesh(lv_ctx* c, lv_scene* sc) {
     LV_TRI(cudaMemcpyAsync(sc->tri_line_pos.p, lpos.data(), 16 * nl, cudaMemcpyHostToDevice, st));
     LV_TRI(cudaMemcpyAsync(sc->tri_line_tan.p, ltan.data(), 16 * nl, cudaMemcpyHostToDevice, st));
     k_tri_vertex_attr<<<uint32_t(std::min<size_t>((nv + 255) / 256, 65535)), 256, 0, st>>>(d_vnrm.p, d_vline.p, uint32_t(nv), sc->tri_vattr.p);
+    {   // lineAttribute of the mesh's line points -> tri_line_tan.w (the triangle geometry mode of the tube pass interpolates it)
+        DevBuf<float> pt_attr; DevBuf<uint32_t> d_src;
+        cudaError_t e = pt_attr.ensure(sc->n_pt);
+        if (e == cudaSuccess) e = d_src.ensure(nl);
+        if (e == cudaSuccess) e = cudaMemsetAsync(pt_attr.p, 0, sc->n_pt * 4, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_src.p, m.line_src.data(), 4 * nl, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            k_point_attr<<<uint32_t(std::min<size_t>((sc->n_seg + 255) / 256, 65535)), 256, 0, st>>>(sc->segs.p, sc->prim_ids.p, sc->seg_idx.p, uint32_t(sc->n_seg), pt_attr.p);
+            k_tri_line_attr<<<uint32_t(std::min<size_t>((nl + 255) / 256, 65535)), 256, 0, st>>>(pt_attr.p, d_src.p, uint32_t(nl), sc->tri_line_tan.p);
+            e = cudaStreamSynchronize(st);
+        }
+        pt_attr.release(); d_src.release();
+        LV_TRI(e);
+    }
     LV_TRI(bounds.ensure(6)); LV_TRI(keys.ensure(n)); LV_TRI(keys2.ensure(n)); LV_TRI(vals.ensure(n));
     LV_TRI(sc->tri_ids.ensure(size_t(n) + 1)); LV_TRI(sc->tris.ensure(size_t(n) + 1));   // + the dummy record of an absent child (k_emit_nodes)
     LV_TRI(cudaMemsetAsync(sc->tris.p + n, 0xFF, sizeof(TriRec), st));
@@ -864,10 +881,12 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "use_jittered_primary_rays") o.ao_jitter_primary = parse_bool(value);
     else if (k == "ambient_occlusion_denoiser") {
         if (strcmp(value, "None")) return fail(c, LV_ERR_INVALID_ARGUMENT, "denoisers are out of scope; use ambient_occlusion_denoiser = None");
-    } else if (k == "geometry_mode") {
-        if (strcmp(value, "AABBs (analytic)")) return fail(c, LV_ERR_INVALID_ARGUMENT, "only geometry_mode = 'AABBs (analytic)' is implemented");
-    } else if (k == "use_analytic_intersections") {
-        if (!parse_bool(value)) return fail(c, LV_ERR_INVALID_ARGUMENT, "only analytic tube intersections are implemented");
+    } else if (k == "geometry_mode") {   // RAY_TRACING_GEOMETRY_MODE_NAMES, VulkanRayTracer.hpp:58-63
+        if (strcmp(value, "AABBs (analytic)") && strcmp(value, "Triangle Mesh"))
+            return fail(c, LV_ERR_INVALID_ARGUMENT, "geometry_mode must be 'AABBs (analytic)' or 'Triangle Mesh' (linear swept spheres are not implemented)");
+        o.geometry_mode = value; o.tube_triangles = !strcmp(value, "Triangle Mesh");
+    } else if (k == "use_analytic_intersections") {   // the older spelling of the same switch (VulkanRayTracer.cpp:244-251)
+        o.tube_triangles = !parse_bool(value); o.geometry_mode = o.tube_triangles ? "Triangle Mesh" : "AABBs (analytic)";
     } else if (k == "num_samples_per_frame") { if (u() == 0) return fail(c, LV_ERR_INVALID_ARGUMENT, "num_samples_per_frame must be >= 1"); o.num_samples_per_frame = u(); }
     else if (k == "num_accumulated_frames") o.num_accumulated_frames = u();
     else if (k == "use_deterministic_sampling") o.use_deterministic_sampling = parse_bool(value);
@@ -890,6 +909,9 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     } else if (k == "b200_bvh_builder") {
         if (strcmp(value, "lbvh") && strcmp(value, "ploc")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_builder must be lbvh or ploc");
         o.bvh_ploc = !strcmp(value, "ploc");
+    } else if (k == "b200_bvh_morton") {
+        if (strcmp(value, "cubic") && strcmp(value, "per_axis")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_morton must be cubic or per_axis");
+        o.bvh_cubic_morton = !strcmp(value, "cubic");
     } else if (k == "b200_bvh_ploc_radius") { if (u() == 0 || u() > 64) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_ploc_radius must be in [1, 64]"); o.bvh_ploc_radius = u();
     } else if (k == "b200_bvh_leaf_size") { if (u() == 0 || u() > 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_leaf_size must be in [1, 16]"); o.bvh_leaf_size = u(); }
     else if (k == "b200_expected_avg_depth_complexity") o.expected_avg_depth_complexity = u();
@@ -948,7 +970,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "use_jittered_primary_rays") v = b(o.ao_jitter_primary);
     else if (k == "ambient_occlusion_denoiser") v = o.denoiser;
     else if (k == "geometry_mode") v = o.geometry_mode;
-    else if (k == "use_analytic_intersections") v = "true";
+    else if (k == "use_analytic_intersections") v = b(!o.tube_triangles);
     else if (k == "num_samples_per_frame") v = std::to_string(o.num_samples_per_frame);
     else if (k == "num_accumulated_frames") v = std::to_string(o.num_accumulated_frames);
     else if (k == "use_deterministic_sampling") v = b(o.use_deterministic_sampling);
@@ -967,6 +989,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_tiling_height") v = std::to_string(o.tiling_h);
     else if (k == "b200_bvh_leaf_size") v = std::to_string(o.bvh_leaf_size);
     else if (k == "b200_bvh_builder") v = o.bvh_ploc ? "ploc" : "lbvh";
+    else if (k == "b200_bvh_morton") v = o.bvh_cubic_morton ? "cubic" : "per_axis";
     else if (k == "b200_bvh_ploc_radius") v = std::to_string(o.bvh_ploc_radius);
     else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
     else if (k == "b200_ao_refill_below") v = std::to_string(o.ao_refill_below);
@@ -1147,7 +1170,7 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     LV_BUILD(cudaMemcpyAsync(s->seg_idx.p, d_idx, size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
     k_init_bounds<<<1, 32, 0, st>>>(bounds.p);
     k_scene_bounds<<<std::min(1024, (n + 255) / 256), 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p);
-    k_morton<<<(n + 255) / 256, 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p, keys.p, vals.p);
+    k_morton<<<(n + 255) / 256, 256, 0, st>>>(d_pos, d_idx, uint32_t(n), r, bounds.p, keys.p, vals.p, c->opt.bvh_cubic_morton);
     size_t cub_bytes = 0;
     LV_BUILD(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys.p, keys2.p, vals.p, s->prim_ids.p, n, 0, 63, st));
     LV_BUILD(cubtmp.ensure(cub_bytes + 16));
@@ -1484,7 +1507,7 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
         // LineRenderer::renderBase -> ambientOcclusionBaker->updateIterative (reference LineRenderer.cpp:259-265): one RTAO
         // iteration per rendered frame until maxNumAccumulatedFrames (VulkanRayTracedAmbientOcclusion.cpp:89-107).
         if (frame_number < c->opt.ao_iterations || !c->ao.p || c->ao_w != P.W || c->ao_h != P.H) {
-            if (c->opt.tube_prepass && P.n_tiles && sc->n_seg) {
+            if (c->opt.tube_prepass && P.n_tiles && sc->n_seg && !c->opt.tube_triangles) {
                 // fork: the tube pass's first-hit traversal on the second stream, beside the RTAO pass (joined in front of k_tubes)
                 if (!c->aux_stream) {
                     LV_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
@@ -1504,8 +1527,14 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
         P.use_ao = 1; P.ao_tex = c->ao.p;
     }
     if ((rc = run_depth_range(c, sc, P))) return rc;
+    const bool tri_tubes = c->opt.tube_triangles && sc->n_seg;
+    if (tri_tubes) {
+        if (P.use_static_ao) return fail(c, LV_ERR_INVALID_ARGUMENT, "geometry_mode = 'Triangle Mesh' does not support ambient_occlusion_mode = 'RTAO (Prebaker)'");
+        if ((rc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)))) return rc;
+    }
     LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    if (P.n_tiles) {
+    if (P.n_tiles && tri_tubes) k_tubes<false, 1><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, nullptr);
+    else if (P.n_tiles) {
         if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
         else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
     }

@@ -68,15 +68,19 @@ __device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
 }
 
 __global__ void k_morton(const float* pos, const uint32_t* idx, uint32_t n, float r, const float* bounds,
-                         unsigned long long* keys, uint32_t* vals) {
+                         unsigned long long* keys, uint32_t* vals, bool cubic) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float mn[3], mx[3];
     seg_box(pos, idx, i, r, mn, mx);
     unsigned long long code = 0;
+    // ONE scale for the three axes (the largest extent): Morton cells are cubes whatever the aspect of the scene box, so the radix
+    // tree's splits halve the longest side first instead of cutting a short axis of a flat box (config 5's 2:1:2 box) too early.
+    // b200_bvh_morton = per_axis keeps the old normalisation (each axis to [0, 1]).
+    const float ext_max = fmaxf(fmaxf(bounds[3] - bounds[0], bounds[4] - bounds[1]), bounds[5] - bounds[2]);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float lo = bounds[k], ext = bounds[3 + k] - lo;
+        float lo = bounds[k], ext = cubic ? ext_max : bounds[3 + k] - lo;
         float c = 0.5f * (mn[k] + mx[k]);
         float u = ext > 0.0f ? (c - lo) / ext : 0.0f;
         u = fminf(fmaxf(u, 0.0f), 1.0f);

@@ -170,29 +170,15 @@ LV_DEV SegShade seg_shade(const SegRec& s) {
     return q;
 }
 
+// computeFragmentColor + blinnPhongShadingTube for a surface point (RayHitCommon.glsl:74-543): what both hit shaders -- the analytic
+// tube's (shade_hit below) and the triangle mesh's (shade_tri_hit, lv_tri.cuh) -- end in.  tg = normalize(tan0), t2 = normalize(tg);
+// u / aux: the analytic hit's segment parameter and line-point data for the prebaked AO lookup (SAO only).
 template <bool SAO>
-LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegShade& q, const SegAux* aux) {
+LV_DEV Shaded shade_surface(const FrameParams& P, Vec3 pos, Vec3 nrm0, Vec3 tan0, Vec3 tg, Vec3 t2, bool is_cap, float attr, float u, const SegAux* aux) {
     const Vec3 cam = v3(P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]);
-    Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
-    Vec3 pos = ro + rd * t_hit;                                  // TubeRayTracing.glsl:517
-    const Vec3 seg = q.seg;
-    Vec3 centre; float attr, u;
-    if (kind == 0) {                                             // :524-530
-        u = dot3(seg, pos - p0) / q.seg_dot;
-        centre = p0 + u * seg;
-        attr = (1.0f - u) * s.a.w + u * s.b.w;
-    } else if (kind == 1) { centre = p0; attr = s.a.w; u = 0.0f; }
-    else { centre = p1; attr = s.b.w; u = 1.0f; }
-    // fragmentTangent / fragmentNormal are normalised at :544-545 and again inside computeFragmentColor (:141,:144)
-    // and blinnPhongShadingTube (Lighting.glsl:138-139); the repeated normalisations are kept, they are not idempotent in float.
-    const Vec3 tan0 = q.tan0;
-    Vec3 nrm0 = normalize3(pos - centre);
-    const bool is_cap = kind != 0;
-
     Vec4 base = tf_lookup(P, attr);                              // RayHitCommon.glsl:127
     const Vec3 n = normalize3(nrm0);
     const Vec3 v = normalize3(cam - pos);
-    const Vec3 tg = q.tg;
     Vec3 helper = normalize3(cross3(tg, v));
     Vec3 new_v = normalize3(cross3(helper, tg));
     float ribbon = 0.0f;
@@ -236,7 +222,6 @@ LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uin
         kD = 0.9f * aof;
     }
     const Vec3 n2 = normalize3(n);
-    const Vec3 t2 = q.t2;
     const Vec3 l = v;            // normalize(cameraPosition - fragmentPositionWorld), identical to v above
     const Vec3 h = normalize3(l + l);
     Vec3 helper_l = normalize3(cross3(t2, l));
@@ -265,6 +250,23 @@ LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uin
     out.color = v4(mixf_(col.x, P.fg[0], wmix), mixf_(col.y, P.fg[1], wmix), mixf_(col.z, P.fg[2], wmix), base.w * coverage);
     out.hit_t = depth;                                           // payload.hitT (:540)
     return out;
+}
+// ClosestHitTubeAnalytic (TubeRayTracing.glsl:512-613) for one accepted hit of the analytic tube.
+template <bool SAO>
+LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegShade& q, const SegAux* aux) {
+    Vec3 p0 = v3(s.a.x, s.a.y, s.a.z), p1 = v3(s.b.x, s.b.y, s.b.z);
+    Vec3 pos = ro + rd * t_hit;                                  // TubeRayTracing.glsl:517
+    const Vec3 seg = q.seg;
+    Vec3 centre; float attr, u;
+    if (kind == 0) {                                             // :524-530
+        u = dot3(seg, pos - p0) / q.seg_dot;
+        centre = p0 + u * seg;
+        attr = (1.0f - u) * s.a.w + u * s.b.w;
+    } else if (kind == 1) { centre = p0; attr = s.a.w; u = 0.0f; }
+    else { centre = p1; attr = s.b.w; u = 1.0f; }
+    // fragmentTangent / fragmentNormal are normalised at :544-545 and again inside computeFragmentColor (:141,:144)
+    // and blinnPhongShadingTube (Lighting.glsl:138-139); the repeated normalisations are kept, they are not idempotent in float.
+    return shade_surface<SAO>(P, pos, normalize3(pos - centre), q.tan0, q.tg, q.t2, kind != 0, attr, u, aux);
 }
 template <bool SAO>
 LV_DEV Shaded shade_hit(const FrameParams& P, Vec3 ro, Vec3 rd, float t_hit, uint32_t kind, const SegRec& s, const SegAux* aux) {

@@ -141,10 +141,22 @@ __global__ void k_tri_fit(const TriRec* tris, int n, const int2* children, const
     }
 }
 
-// per-vertex attributes of the mesh for the barycentric fetch: (normal.xyz, as_float(line point index without the cap bit))
+// per-vertex attributes of the mesh for the barycentric fetch: (normal.xyz, as_float(vertexLinePointIndex: line point index, bit 31 = cap vertex))
 __global__ void k_tri_vertex_attr(const float* vnrm, const uint32_t* vline, uint32_t n, float4* out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        out[i] = make_float4(vnrm[3 * size_t(i)], vnrm[3 * size_t(i) + 1], vnrm[3 * size_t(i) + 2], __uint_as_float(vline[i] & 0x7FFFFFFFu));
+        out[i] = make_float4(vnrm[3 * size_t(i)], vnrm[3 * size_t(i) + 1], vnrm[3 * size_t(i) + 2], __uint_as_float(vline[i]));
+}
+
+// lineAttribute of the mesh's line points (the w lane of tri_line_tan): per-point attributes are recovered from the segment records
+// (record r holds the attributes of the two points seg_idx[prim_ids[r]] names), then gathered through the mesh's source-point indices
+__global__ void k_point_attr(const SegRec* segs, const uint32_t* prim_ids, const uint2* seg_idx, uint32_t n_seg, float* pt_attr) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_seg; r += gridDim.x * blockDim.x) {
+        const uint2 ix = seg_idx[prim_ids[r]];
+        pt_attr[ix.x] = segs[r].a.w; pt_attr[ix.y] = segs[r].b.w;
+    }
+}
+__global__ void k_tri_line_attr(const float* pt_attr, const uint32_t* line_src, uint32_t n, float4* line_tan) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) line_tan[i].w = pt_attr[line_src[i]];
 }
 
 struct TriHitRec { float t, u, v; uint32_t idx, prim; };   // idx = record (BVH order), prim = triangle index of the mesh
@@ -219,7 +231,7 @@ LV_DEV AoHit tri_ao_frame(const SceneDev& S, const TriRec& r, float u, float v, 
     Vec3 p0, p1, p2;
     tri_positions(r, p0, p1, p2);
     const float4 a0 = __ldg(S.tri_vattr + __float_as_uint(r.a.w)), a1 = __ldg(S.tri_vattr + __float_as_uint(r.b.w)), a2 = __ldg(S.tri_vattr + __float_as_uint(r.c.w));
-    const uint32_t l0 = __float_as_uint(a0.w), l1 = __float_as_uint(a1.w), l2 = __float_as_uint(a2.w);
+    const uint32_t l0 = __float_as_uint(a0.w) & 0x7FFFFFFFu, l1 = __float_as_uint(a1.w) & 0x7FFFFFFFu, l2 = __float_as_uint(a2.w) & 0x7FFFFFFFu;
     const Vec3 pos = interp3(p0, p1, p2, w);
     const Vec3 nrm = normalize3(interp3(xyz4(a0), xyz4(a1), xyz4(a2), w));
     const Vec3 line_pos = interp3(xyz4(__ldg(S.tri_line_pos + l0)), xyz4(__ldg(S.tri_line_pos + l1)), xyz4(__ldg(S.tri_line_pos + l2)), w);
@@ -230,6 +242,25 @@ LV_DEV AoHit tri_ao_frame(const SceneDev& S, const TriRec& r, float u, float v, 
     rec.nrm_px = make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(pixel));
     rec.tng = make_float4(tng.x, tng.y, tng.z, 0.0f);
     return rec;
+}
+
+// ClosestHitTubeTriangles + LineAttributesBarycentric.glsl:1-39 (TubeRayTracing.glsl:301-351): the tube pass's hit shader in the
+// triangle-mesh geometry mode -- barycentric position / normal / tangent / attribute, cap flag from the vertices, then the common
+// computeFragmentColor (shade_surface).  The prebaked-AO lookup (phi / vertex id interpolation) is not part of this mode.
+LV_DEV Shaded shade_tri_hit(const FrameParams& P, const SceneDev& S, const TriRec& r, float u, float v) {
+    const Vec3 w = v3(1.0f - u - v, u, v);
+    Vec3 p0, p1, p2;
+    tri_positions(r, p0, p1, p2);
+    const float4 a0 = __ldg(S.tri_vattr + __float_as_uint(r.a.w)), a1 = __ldg(S.tri_vattr + __float_as_uint(r.b.w)), a2 = __ldg(S.tri_vattr + __float_as_uint(r.c.w));
+    const uint32_t v0 = __float_as_uint(a0.w), v1 = __float_as_uint(a1.w), v2 = __float_as_uint(a2.w);
+    const bool is_cap = ((v0 | v1 | v2) >> 31) != 0u;
+    const float4 t0 = __ldg(S.tri_line_tan + (v0 & 0x7FFFFFFFu)), t1 = __ldg(S.tri_line_tan + (v1 & 0x7FFFFFFFu)), t2v = __ldg(S.tri_line_tan + (v2 & 0x7FFFFFFFu));
+    const Vec3 pos = interp3(p0, p1, p2, w);
+    const Vec3 nrm0 = normalize3(interp3(xyz4(a0), xyz4(a1), xyz4(a2), w));
+    const Vec3 tan0 = normalize3(interp3(xyz4(t0), xyz4(t1), xyz4(t2v), w));
+    const float attr = (t0.w * w.x + t1.w * w.y) + t2v.w * w.z;          // interpolateFloat, BarycentricInterpolation.glsl:35-37
+    const Vec3 tg = normalize3(tan0);
+    return shade_surface<false>(P, pos, nrm0, tan0, tg, normalize3(tg), is_cap, attr, 0.0f, nullptr);
 }
 
 }  // namespace lv

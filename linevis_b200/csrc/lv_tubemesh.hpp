@@ -28,6 +28,7 @@ struct TubeMesh {
     std::vector<Vertex> vertices;
     std::vector<uint32_t> indices;              // 3 per triangle
     std::vector<V3> line_pos, line_tan, line_nrm;
+    std::vector<uint32_t> line_src;             // index of the input point each mesh line point was made from
 };
 
 constexpr float kPi = 3.1415926535897932f, kTwoPi = kPi * 2.0f, kHalfPi = kPi / 2.0f;   // sgl/Math/Math.hpp:47-49
@@ -106,12 +107,12 @@ inline void build(const float* pos, const uint64_t* offsets, uint64_t n_lines, f
                 v.phi = float(k) / float(N) * kTwoPi;
                 m.vertices.push_back(v);
             }
-            m.line_pos.push_back(c); m.line_tan.push_back(tangent); m.line_nrm.push_back(normal);
+            m.line_pos.push_back(c); m.line_tan.push_back(tangent); m.line_nrm.push_back(normal); m.line_src.push_back(uint32_t(first + i));
             valid++;
         }
         if (valid <= 1) {                                                     // nothing (or a single point) left: the polyline vanishes
             m.vertices.resize(cap0_v); m.indices.resize(cap0_i);
-            m.line_pos.resize(line_base); m.line_tan.resize(line_base); m.line_nrm.resize(line_base);
+            m.line_pos.resize(line_base); m.line_tan.resize(line_base); m.line_nrm.resize(line_base); m.line_src.resize(line_base);
             continue;
         }
         for (int i = 0; i < valid - 1; i++)

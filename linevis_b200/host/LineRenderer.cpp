@@ -166,14 +166,13 @@ void B200RayTracer::setNewState(const InternalState& newState) {
     const SettingsMap& rs = newState.rendererSettings;
     std::string geometryMode;
     bool useAnalyticIntersections = true;
-    // only the analytic tube primitive exists here (RayTracingGeometryMode::AABBS / "Analytic Tubes", VulkanRayTracer.hpp:54-63):
-    // a state that asks for the triangle mesh is refused loudly instead of being measured under the wrong name
+    // RAY_TRACING_GEOMETRY_MODE_NAMES (VulkanRayTracer.hpp:58-63): "Triangle Mesh" and "AABBs (analytic)" exist here; anything else
+    // (linear swept spheres) is refused loudly by the library instead of being measured under the wrong name
     if (rs.getValueOpt("geometryMode", geometryMode)) {
-        if (geometryMode != "AABBs (analytic)")   // RAY_TRACING_GEOMETRY_MODE_NAMES, VulkanRayTracer.hpp:58-63
-            throw std::runtime_error("setNewState: geometryMode '" + geometryMode + "' is not available (only 'AABBs (analytic)')");
+        check(lv_set_option(ctx, "geometry_mode", geometryMode.c_str()), "geometryMode");
         accumulatedFramesCounter = 0;
     } else if (rs.getValueOpt("useAnalyticIntersections", useAnalyticIntersections)) {
-        if (!useAnalyticIntersections) throw std::runtime_error("setNewState: useAnalyticIntersections = false is not available (analytic tubes only)");
+        check(lv_set_option(ctx, "use_analytic_intersections", useAnalyticIntersections ? "true" : "false"), "useAnalyticIntersections");
         accumulatedFramesCounter = 0;
     }
     if (rs.getValueOpt("numSamplesPerFrame", numSamplesPerFrame)) {

@@ -89,9 +89,19 @@ int main() {
         while (rt.needsReRender() && frames < 10) { rt.render(); frames++; }
         if (frames != 3) { std::printf("FAIL: %d frames rendered, expected 3 (2 accumulated frames, 3 AO iterations)\n", frames); return 1; }
         bool refused = false;
-        InternalState bad; bad.rendererSettings.addKeyValue("geometryMode", std::string("Triangle Mesh"));
+        InternalState bad; bad.rendererSettings.addKeyValue("geometryMode", std::string("Linear Swept Spheres"));
         try { rt.setNewState(bad); } catch (const std::runtime_error&) { refused = true; }
-        if (!refused) { std::printf("FAIL: triangle-mesh geometry mode was not refused\n"); return 1; }
+        if (!refused) { std::printf("FAIL: an unknown geometry mode was not refused\n"); return 1; }
+        // the triangle-mesh geometry mode: same scene, the tube pass traces and shades the reference's tube mesh
+        InternalState tri; tri.rendererSettings.addKeyValue("geometryMode", std::string("Triangle Mesh"));
+        rt.setNewState(tri);
+        rt.render();
+        size_t nonbgTri = 0;
+        for (size_t i = 0; i < sd.sceneTexture.size(); i += 4) if (sd.sceneTexture[i] < 0.999f) nonbgTri++;
+        std::printf("triangle-mesh mode: %zu non-background pixels (analytic: %zu)\n", nonbgTri, nonbg);
+        if (nonbgTri == 0 || nonbgTri > 2 * nonbg) { std::printf("FAIL: triangle-mesh frame\n"); return 1; }
+        InternalState ana; ana.rendererSettings.addKeyValue("geometryMode", std::string("AABBs (analytic)"));
+        rt.setNewState(ana);
         rt.setNewSettings(once);
         // object-space AO prebaker: the first frames each run one baking iteration, then only look the factors up
         SettingsMap pre; pre.addKeyValue("ambient_occlusion_mode", std::string("RTAO (Prebaker)")); pre.addKeyValue("b200_prebaker_iterations", 2);

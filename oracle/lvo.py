@@ -333,6 +333,20 @@ class TubeMesh:
         self.lib.lvo_tubemesh_copy(ctypes.c_void_p(self.h), v.ctypes.data_as(ctypes.c_void_p), t.ctypes.data_as(ctypes.c_void_p))
         return v, t
 
+    def render_tubes(self, attr, cam, opts, tf, amin=0.0, amax=1.0, ao_tex=None, frame_number=0, rgba=None):
+        """The tube pass in the reference's triangle-mesh geometry mode (ClosestHitTubeTriangles); attr = lineAttribute per input point."""
+        tf, attr = _f32(tf), _f32(attr)
+        if rgba is None:
+            rgba = np.zeros((cam.height, cam.width, 4), np.float32)
+        rgba = _f32(rgba)
+        stats = np.zeros(3, np.uint64)
+        ao = _f32(ao_tex) if ao_tex is not None else None
+        self.lib.lvo_tubemesh_render_tubes(ctypes.c_void_p(self.h), _p(attr, ctypes.c_float), ctypes.byref(cam), ctypes.byref(opts), _p(tf, ctypes.c_float),
+                                           ctypes.c_uint32(tf.shape[0]), ctypes.c_float(amin), ctypes.c_float(amax),
+                                           _p(ao, ctypes.c_float) if ao is not None else None, ctypes.c_uint32(frame_number),
+                                           _p(rgba, ctypes.c_float), _p(stats, ctypes.c_uint64))
+        return rgba, dict(T=int(stats[0]), I=int(stats[1]), rays=int(stats[2]))
+
     def render_rtao(self, cam, opts, frame_number=0, ao=None):
         if ao is None:
             ao = np.zeros((cam.height, cam.width), np.float32)

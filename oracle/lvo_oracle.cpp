@@ -701,6 +701,64 @@ void lvo_tubemesh_copy(void* h, float* vertices, uint32_t* indices) {
     if (indices) std::memcpy(indices, t.mesh.triangleIndices.data(), t.mesh.triangleIndices.size() * 4);
 }
 
+// The tube pass in the triangle-mesh geometry mode (RayTracingGeometryMode::TRIANGLE_MESH, VulkanRayTracer.hpp:54-63): ray-gen +
+// traceRayTransparent as in lvo_render_tubes, closest hit against the tube mesh, ClosestHitTubeTriangles.  attr: per input point.
+// stats = {T, I, rays}
+void lvo_tubemesh_render_tubes(void* h, const float* attr, const lv_camera* cam, const lvo_options* o, const float* tf, uint32_t K, float amin, float amax,
+                               const float* ao_tex, uint32_t frame_number, float* rgba_inout, uint64_t* stats) {
+    TubeMeshScene& ts = *static_cast<TubeMeshScene*>(h);
+    Scene dummy; dummy.lineWidth = ts.lineWidth;
+    lvo_options o2 = *o; o2.use_static_ao = 0; o2.depth_cue_strength = 0.0f;
+    Uniforms u = makeUniforms(dummy, *cam, o2, tf, K, amin, amax, ao_tex);
+    const uint32_t W = cam->width, H = cam->height;
+    uint64_t T = 0, I = 0, R = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : T, I, R)
+    for (int64_t yy = 0; yy < int64_t(H); yy++) {
+        uint64_t steps = 0, isect = 0, rays = 0;
+        const uint32_t y = uint32_t(yy);
+        for (uint32_t x = 0; x < W; x++) {
+            vec4 fragmentColor{0, 0, 0, 0};
+            const uint32_t nspp = o->use_jittered_rays ? o->num_samples_per_frame : 1u;
+            for (uint32_t sampleIdx = 0; sampleIdx < nspp; sampleIdx++) {
+                float xix = 0.5f, xiy = 0.5f;
+                if (o->use_jittered_rays) {
+                    uint32_t seed = o->use_deterministic_sampling ? tea(19u, frame_number * o->num_samples_per_frame + sampleIdx)
+                                                                  : tea(x + y * W, frame_number * o->num_samples_per_frame + sampleIdx);
+                    xix = rnd(seed); xiy = rnd(seed);
+                }
+                vec3 ro, rd; cameraRay(u, x, y, xix, xiy, ro, rd);
+                vec4 fc{0, 0, 0, 0};
+                float tMin = 0.0001f;
+                for (uint32_t hitIdx = 0; hitIdx < o->max_depth_complexity; hitIdx++) {   // traceRayTransparent :61-82
+                    TriHit hit; HitColor pl;
+                    rays++;
+                    if (traceTriangles(ts.bvh, ro, rd, tMin, 1000.0f, false, hit, steps, isect, ts.lineWidth)) pl = closestHitTubeTriangles(u, ts.mesh, attr, hit);
+                    else pl = missShader(u);
+                    tMin = pl.hitT + fmax_(pl.hitT * 1e-5f, 1e-7f);
+                    fc.x = fc.x + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.x;
+                    fc.y = fc.y + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.y;
+                    fc.z = fc.z + (1.0f - fc.w) * pl.hitColor.w * pl.hitColor.z;
+                    fc.w = fc.w + (1.0f - fc.w) * pl.hitColor.w;
+                    if (!pl.hasHit || fc.w > 0.99f) break;
+                }
+                fragmentColor.x += fc.x; fragmentColor.y += fc.y; fragmentColor.z += fc.z; fragmentColor.w += fc.w;
+            }
+            if (o->use_jittered_rays) {
+                const float d = float(o->num_samples_per_frame);
+                fragmentColor.x /= d; fragmentColor.y /= d; fragmentColor.z /= d; fragmentColor.w /= d;
+            }
+            float* px = rgba_inout + 4 * (size_t(y) * W + x);
+            if (frame_number != 0) {
+                const float a = 1.0f / float(frame_number + 1);
+                fragmentColor = vec4{mix(px[0], fragmentColor.x, a), mix(px[1], fragmentColor.y, a), mix(px[2], fragmentColor.z, a), mix(px[3], fragmentColor.w, a)};
+            }
+            px[0] = fragmentColor.x; px[1] = fragmentColor.y; px[2] = fragmentColor.z; px[3] = fragmentColor.w;
+        }
+        T += steps; I += isect; R += rays;
+    }
+    if (stats) { stats[0] = T; stats[1] = I; stats[2] = R; }
+}
+
 // The screen-space RTAO pass exactly as the reference runs it: against the TRIANGULATED tubes, with the barycentric vertex
 // fetch (Data/Shaders/AO/RTAO/VulkanRayTracedAmbientOcclusion.glsl:178-319).  stats = {T, I, rays_primary, rays_ao, pixels_hit}
 void lvo_render_rtao_triangles(void* h, const lv_camera* cam, const lvo_options* o, uint32_t frame_number, float* ao_inout, uint64_t* stats) {

@@ -35,6 +35,7 @@ struct TubeMesh {
     std::vector<uint32_t> triangleIndices;
     std::vector<TubeTriangleVertexData> vertexDataList;
     std::vector<vec3> linePositions, lineTangents, lineNormals;   // tubeTriangleLinePointDataList (LineDataFlow.cpp:1997-2012)
+    std::vector<uint32_t> lineSources;                            // index of the input point a mesh line point was made from (its lineAttribute)
 };
 
 namespace sglc {   // sgl/Math/Math.hpp:47-49
@@ -212,6 +213,7 @@ inline void createCappedTriangleTubes(const float* pos, const uint64_t* line_off
             m.lineTangents.push_back(tangent);
             m.lineNormals.push_back(lastLineNormal);
             m.linePositions.push_back(lineCenters(i));
+            m.lineSources.push_back(uint32_t(b + i));
             numValidLinePoints++;
         }
         if (numValidLinePoints == 1) {
@@ -219,7 +221,7 @@ inline void createCappedTriangleTubes(const float* pos, const uint64_t* line_off
             // (the reference leaves the reserved cap triangle indices in place here; they would reference removed vertices --
             //  a latent defect for polylines that degenerate to one point; dropped here)
             triangleIndices.resize(triOffsetCapStart);
-            m.lineTangents.pop_back(); m.lineNormals.pop_back(); m.linePositions.pop_back();
+            m.lineTangents.pop_back(); m.lineNormals.pop_back(); m.linePositions.pop_back(); m.lineSources.pop_back();
         }
         if (numValidLinePoints <= 1) {
             if (numValidLinePoints == 0) { vertexDataList.resize(indexOffsetCapStart); triangleIndices.resize(triOffsetCapStart); }
@@ -369,6 +371,28 @@ inline bool traceTriangles(const TriBvh& bvh, vec3 o, vec3 d, float tmin, float 
 
 static inline vec3 interpolateVec3(vec3 v0, vec3 v1, vec3 v2, vec3 b) {   // BarycentricInterpolation.glsl:39-41
     return (v0 * b.x + v1 * b.y) + v2 * b.z;
+}
+static inline float interpolateFloat(float v0, float v1, float v2, vec3 b) {   // BarycentricInterpolation.glsl:35-37
+    return (v0 * b.x + v1 * b.y) + v2 * b.z;
+}
+
+// ClosestHitTubeTriangles main + LineAttributesBarycentric.glsl:1-39 (TubeRayTracing.glsl:301-351): the tube pass's hit shader in
+// the triangle-mesh geometry mode.  attr = lineAttribute per INPUT point (mesh line points refer to them through lineSources).
+// Variant as elsewhere: USE_CAPPED_TUBES, no bands / multi-var / helicity; the screen-space AO texture is supported, the prebaked
+// AO lookup (phi / fragmentVertexId interpolation) is not part of this mode here.
+static inline HitColor closestHitTubeTriangles(const Uniforms& u, const TubeMesh& m, const float* attr, const TriHit& hit) {
+    const uint32_t* ix = &m.triangleIndices[3 * size_t(hit.tri)];
+    const vec3 barycentricCoordinates = V3(1.0f - hit.u - hit.v, hit.u, hit.v);
+    const TubeTriangleVertexData& v0 = m.vertexDataList[ix[0]];
+    const TubeTriangleVertexData& v1 = m.vertexDataList[ix[1]];
+    const TubeTriangleVertexData& v2 = m.vertexDataList[ix[2]];
+    const vec3 fragmentPositionWorld = interpolateVec3(v0.vertexPosition, v1.vertexPosition, v2.vertexPosition, barycentricCoordinates);
+    const uint32_t l0 = v0.vertexLinePointIndex & 0x7FFFFFFFu, l1 = v1.vertexLinePointIndex & 0x7FFFFFFFu, l2 = v2.vertexLinePointIndex & 0x7FFFFFFFu;
+    const bool isCap = (v0.vertexLinePointIndex >> 31) != 0u || (v1.vertexLinePointIndex >> 31) != 0u || (v2.vertexLinePointIndex >> 31) != 0u;
+    vec3 fragmentNormal = normalize(interpolateVec3(v0.vertexNormal, v1.vertexNormal, v2.vertexNormal, barycentricCoordinates));
+    vec3 fragmentTangent = normalize(interpolateVec3(m.lineTangents[l0], m.lineTangents[l1], m.lineTangents[l2], barycentricCoordinates));
+    const float fragmentAttribute = interpolateFloat(attr[m.lineSources[l0]], attr[m.lineSources[l1]], attr[m.lineSources[l2]], barycentricCoordinates);
+    return computeFragmentColor(u, fragmentPositionWorld, fragmentNormal, fragmentTangent, isCap, 0.0f, 0.0f, fragmentAttribute);
 }
 
 }  // namespace lvo

@@ -385,6 +385,44 @@ def test_triangle_tube_frame_and_prebaker(ectx, oracle):
                                "ambient_occlusion_radius": 0.1})
 
 
+
+@pytest.mark.parametrize("n_sub,ao,jitter", [(6, False, False), (8, True, False), (6, True, True)])
+def test_triangle_geometry_mode_of_the_tube_pass(ectx, oracle, n_sub, ao, jitter):
+    """geometry_mode = "Triangle Mesh" (RayTracingGeometryMode::TRIANGLE_MESH): the tube pass traces the reference's triangulated tubes and
+    shades with ClosestHitTubeTriangles (barycentric normal / tangent / attribute, cap flag) -- frame bit-exact against the oracle's
+    restatement, with the RTAO texture traced against the same mesh, with jittered multi-sample frames and accumulation."""
+    d, sc, osc, width = _tube_scene(ectx, oracle, 8, 21)
+    tm = lvo.TubeMesh(oracle, d["pos"], d["line_offsets"], width, n_sub)
+    cam = lv.make_camera(64, 40)
+    tf = scenes.standard_transfer_function(opacity=(0.4, 1.0))
+    ctx = ectx
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"geometry_mode": "Triangle Mesh", "tube_num_subdivisions": n_sub, "b200_rtao_geometry": "triangles",
+                          "ambient_occlusion_strength": 1.0 if ao else 0.0, "ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_radius": 0.2,
+                          "num_samples_per_frame": 2 if jitter else 1, "num_accumulated_frames": 2 if jitter else 1})
+    try:
+        assert ctx.get_option("use_analytic_intersections") == "false"
+        opts = lvo.default_options(ao_strength=1.0 if ao else 0.0, ao_spp=4, ao_radius=0.2, tube_num_subdivisions=n_sub,
+                                   num_samples_per_frame=2 if jitter else 1, use_jittered_rays=int(jitter))
+        img, ref = None, None
+        for frame in range(2 if jitter else 1):
+            img, st = ctx.render_tubes(sc, cam, frame, out=img)
+            rao = tm.render_rtao(cam, opts, frame, ao=rao if frame else None)[0] if ao else None
+            ref, ost = tm.render_tubes(d["attr"], cam, opts, tf, ao_tex=rao, frame_number=frame, rgba=ref)
+            assert st["pixels_hit"] > 0 and np.isfinite(img).all()
+            assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), frame
+        analytic, _ = osc.render_tubes(cam, lvo.default_options(), tf)
+        assert not np.array_equal(analytic, ref)            # it really is the other geometry
+        ctx.set_new_settings({"ambient_occlusion_mode": "RTAO (Prebaker)", "ambient_occlusion_strength": 1.0})
+        with pytest.raises(lv.LineVisError):
+            ctx.render_tubes(sc, cam, 0)
+        with pytest.raises(lv.LineVisError):
+            ctx.set_option("geometry_mode", "Linear Swept Spheres")
+    finally:
+        ctx.set_new_settings({"geometry_mode": "AABBs (analytic)", "b200_rtao_geometry": "capsules", "ambient_occlusion_mode": "RTAO (Screen Space)",
+                              "ambient_occlusion_strength": 0.0, "ambient_occlusion_radius": 0.1, "tube_num_subdivisions": 6,
+                              "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+
 def test_triangle_mode_needs_polylines(ectx):
     data, width = _helix()
     sc = ectx.create_scene(*data, width)
@@ -446,7 +484,8 @@ def test_ploc_builder(ectx, oracle, radius):
         cam = lv.make_camera(56, 36)
         hits, _ = ectx.trace_primary(sc, cam); ref, _ = osc.trace_primary(cam)
         assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32)) and np.array_equal(hits["prim"], ref["prim"])
-        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 5, "ambient_occlusion_radius": 0.4})
+        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 5, "ambient_occlusion_radius": 0.4, "ambient_occlusion_distance_based": True,
+                               "use_jittered_primary_rays": True, "tube_num_subdivisions": 6, "b200_rtao_geometry": "capsules"})
         try:
             ao, st = ectx.render_rtao(sc, cam, 0)
         finally:

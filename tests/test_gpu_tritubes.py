@@ -73,3 +73,42 @@ def test_triangle_tube_frame_and_prebaker_bit_exact(tri_ctx, oracle):
         ref_f, ost = osc.ao_bake_iteration(sl, it, factors=ref_f, radius=0.05, n_subdiv=8, spp=4, tube_mesh=tm)
         assert st["rays_ao"] == ost["rays"]
         assert np.array_equal(sc.ao_read()["factors"].reshape(-1).view(np.uint32), ref_f.view(np.uint32)), it
+
+
+@pytest.mark.parametrize("n_sub,ao,jitter", [(6, False, False), (8, True, False), (6, True, True)])
+def test_triangle_geometry_mode_of_the_tube_pass(tri_ctx, oracle, n_sub, ao, jitter):
+    """geometry_mode = "Triangle Mesh" (RayTracingGeometryMode::TRIANGLE_MESH): the tube pass traces the reference's triangulated tubes and
+    shades with ClosestHitTubeTriangles (barycentric normal / tangent / attribute, cap flag) -- frame bit-exact against the oracle's
+    restatement, with the RTAO texture traced against the same mesh, with jittered multi-sample frames and accumulation."""
+    d, sc, osc, width = _scene(tri_ctx, oracle, 40, 61, 0.006) + (0.006,)
+    tm = lvo.TubeMesh(oracle, d["pos"], d["line_offsets"], width, n_sub)
+    cam = lv.make_camera(200, 120)
+    tf = scenes.standard_transfer_function(opacity=(0.4, 1.0))
+    ctx = tri_ctx
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"geometry_mode": "Triangle Mesh", "tube_num_subdivisions": n_sub, "b200_rtao_geometry": "triangles",
+                          "ambient_occlusion_strength": 1.0 if ao else 0.0, "ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_radius": 0.2,
+                          "num_samples_per_frame": 2 if jitter else 1, "num_accumulated_frames": 2 if jitter else 1})
+    try:
+        assert ctx.get_option("use_analytic_intersections") == "false"
+        opts = lvo.default_options(ao_strength=1.0 if ao else 0.0, ao_spp=4, ao_radius=0.2, tube_num_subdivisions=n_sub,
+                                   num_samples_per_frame=2 if jitter else 1, use_jittered_rays=int(jitter))
+        img, ref = None, None
+        for frame in range(2 if jitter else 1):
+            img, st = ctx.render_tubes(sc, cam, frame, out=img)
+            rao = tm.render_rtao(cam, opts, frame, ao=rao if frame else None)[0] if ao else None
+            ref, ost = tm.render_tubes(d["attr"], cam, opts, tf, ao_tex=rao, frame_number=frame, rgba=ref)
+            assert st["pixels_hit"] > 0 and np.isfinite(img).all()
+            assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)), frame
+        analytic, _ = osc.render_tubes(cam, lvo.default_options(), tf)
+        assert not np.array_equal(analytic, ref)            # it really is the other geometry
+        ctx.set_new_settings({"ambient_occlusion_mode": "RTAO (Prebaker)", "ambient_occlusion_strength": 1.0})
+        with pytest.raises(lv.LineVisError):
+            ctx.render_tubes(sc, cam, 0)
+        with pytest.raises(lv.LineVisError):
+            ctx.set_option("geometry_mode", "Linear Swept Spheres")
+    finally:
+        ctx.set_new_settings({"geometry_mode": "AABBs (analytic)", "b200_rtao_geometry": "capsules", "ambient_occlusion_mode": "RTAO (Screen Space)",
+                              "ambient_occlusion_strength": 0.0, "ambient_occlusion_radius": 0.1, "tube_num_subdivisions": 6,
+                              "num_samples_per_frame": 1, "num_accumulated_frames": 1})
+
