@@ -243,7 +243,16 @@ int lv_ao_read(lv_scene* scene, float* factors, size_t factors_cap, float* blend
  * LineRenderer::renderBase -> RTAO updateIterative (if ambient_occlusion_strength > 0) -> traceRays(W,H,1).
  * frame_number is RayTracerSettings::frameNumber (running mean over frames, TubeRayTracing.glsl:268-273);
  * the accumulation image is `rgba_out` itself, exactly like the reference's storage image.
- * rgba_out: W*H*4 floats, device or host (detected).  stats may be NULL. */
+ * rgba_out: W*H*4 floats, device or host (detected).  stats may be NULL.
+ * Frame format (option b200_frame_format, the reference's sceneTexture is RGBA8 / RGBA16 UNORM, src/Widgets/DataView.cpp:100-108):
+ *   "rgba32f" (default)  as above;
+ *   "rgba8"              rgba_out is a uint32_t[W*H] RGBA8 UNORM frame (packUnorm4x8 of the float pixel, written in the frame kernel's
+ *                        epilogue); the float accumulation image then lives inside the context.  The same holds for lv_render_ppll /
+ *                        lv_ppll_resolve.  With b200_async_delivery = true a HOST rgba8 frame is copied on a second stream from one of
+ *                        two staging frames: the call returns once the copy is enqueued and lv_synchronize() waits for it, so that the
+ *                        read-back of frame i overlaps the kernels of frame i + 1 (pinned memory; at most two frames in flight).
+ * geometry_mode = "Triangle Mesh" (RayTracingGeometryMode::TRIANGLE_MESH, VulkanRayTracer.hpp:54-63; needs lv_scene_set_lines):
+ * the pass traces the reference's triangulated tubes and shades with ClosestHitTubeTriangles (TubeRayTracing.glsl:301-351). */
 int lv_render_tubes(lv_ctx* ctx, const lv_scene* scene, const lv_camera* cam, uint32_t frame_number,
                     float* rgba_out, lv_stats* stats);
 

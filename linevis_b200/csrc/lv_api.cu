@@ -38,7 +38,7 @@ struct Options {
     uint32_t max_depth_complexity = 1024;
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
-    bool bvh_cubic_morton = true;       // b200_bvh_morton = cubic: one scale for all axes in the Morton codes (per_axis: each axis to [0, 1])
+    bool bvh_cubic_morton = false;      // b200_bvh_morton = cubic: one scale for all axes in the Morton codes (default per_axis: each axis to [0, 1]; measured equal)
     bool bvh_ploc = false;              // b200_bvh_builder = ploc: parallel locally-ordered clustering instead of the Morton radix tree (one-record leaves only)
     uint32_t bvh_ploc_radius = 16;      // ... neighbours searched to either side per round
     uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 30 with b200_ao_raybuf (refilling is cheap), 24 without

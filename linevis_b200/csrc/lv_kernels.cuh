@@ -1134,7 +1134,9 @@ k_ppll_gather_raster(const __grid_constant__ FrameParams P, const __grid_constan
         if (x0 > x1 || y0 > y1) continue;                  // off screen
         if (owned_tiles) {
             // tile-sharded frame: a segment whose rectangle touches none of this rank's tiles is done here -- without this every rank
-            // enumerated every segment's candidates and only skipped the pixels (8 GPUs: gather 5.1 ms for 14.7 / 8 = 1.8 ms of work)
+            // enumerated every segment's candidates and only skipped the pixels (8 GPUs: gather 5.1 -> 3.6 ms per rank for 14.7 / 8 =
+            // 1.8 ms of work; a one-segment-per-lane prefilter in front of the warp-wide set-up made it 4.0 ms and was dropped: what is
+            // left is the per-segment flush of the two queues, whose rounds are mostly empty when a rank owns an eighth of a segment's pixels)
             const uint32_t tx0 = uint32_t(x0) / P.tile_size, ty0 = uint32_t(y0) / P.tile_size;
             const uint32_t ntx = uint32_t(x1) / P.tile_size - tx0 + 1u, nt = ntx * (uint32_t(y1) / P.tile_size - ty0 + 1u);
             bool any = false;

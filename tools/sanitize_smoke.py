@@ -7,22 +7,30 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import linevis_b200 as lv
 
 fast = len(sys.argv) > 1 and sys.argv[1] == "fast"
-pos, attr, seg = lv.scenes.helix_lines(12, 41)
 cam = lv.make_camera(64, 48)
 tf = lv.scenes.standard_transfer_function(opacity=(0.3, 0.8))
-variants = [{}] if fast else [{}, {"b200_ao_queue": False, "b200_bvh_leaf_size": 4}, {"b200_ao_qnodes": True},
-                              {"b200_ppll_gather_mode": "raster"}, {"b200_ppll_gather_mode": "raster_contiguous", "b200_ppll_reg_sort": True},
-                              {"b200_ppll_binned_resolve": True}, {"depth_cue_strength": 0.8}]
+variants = [{}] if fast else [{}, {"b200_ao_queue": False, "b200_bvh_leaf_size": 4}, {"b200_ao_qnodes": True, "b200_ao_wide": False, "b200_ao_raybuf": False},
+                              {"b200_ao_wide": False, "b200_ao_raybuf": False, "b200_tube_prepass": False, "b200_ppll_gather_mode": "raycast", "b200_ppll_reg_sort": False},
+                              {"b200_ao_wide_top": 85}, {"b200_bvh_builder": "ploc"}, {"b200_frame_format": "rgba8", "b200_async_delivery": True},
+                              {"b200_ppll_gather_mode": "raster_contiguous"}, {"b200_ppll_binned_resolve": True}, {"depth_cue_strength": 0.8},
+                              {"geometry_mode": "Triangle Mesh", "b200_rtao_geometry": "triangles"}]
+d = lv.scenes.helix_polylines(12, 41)
+pos, attr, seg = d["pos"], d["attr"], d["seg"]
 for v in variants:
     ctx = lv.Context(0)
     ctx.set_transfer_function(tf)
     ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 4, "num_samples_per_frame": 1, "num_accumulated_frames": 1})
     ctx.set_new_settings(v)
     sc = ctx.create_scene(pos, attr, seg, 0.006)
-    img, st = ctx.render_tubes(sc, cam)
-    pp, st2 = ctx.render_ppll(sc, cam, max_frags=128, sort_mode="priority_queue")
+    sc.set_lines(d["pos"], d["tangent"], d["normal"], d["line_offsets"])
+    rgba8 = v.get("b200_frame_format") == "rgba8"
+    out = (lambda: np.zeros((cam.height, cam.width), np.uint32)) if rgba8 else (lambda: None)
+    img, st = ctx.render_tubes(sc, cam, out=out())
+    pp, st2 = ctx.render_ppll(sc, cam, max_frags=128, sort_mode="priority_queue", out=out())
     ctx.set_tile_shard(1, 2, 16)
-    img2, _ = ctx.render_tubes(sc, cam)
-    print(v, "rays", st["rays_primary"] + st["rays_ao"], "frags", st2["frags_sorted"], "finite", bool(np.isfinite(img).all()), flush=True)
+    img2, _ = ctx.render_tubes(sc, cam, out=out())
+    pp2, _ = ctx.render_ppll(sc, cam, max_frags=128, sort_mode="bitonic", out=out())
+    ctx.synchronize()
+    print(v, "rays", st["rays_primary"] + st["rays_ao"], "frags", st2["frags_sorted"], "finite", bool(rgba8 or np.isfinite(img).all()), flush=True)
     sc.close(); ctx.close()
 print("sanitize_smoke done")
