@@ -54,6 +54,7 @@ struct Options {
                                         // the call returns once the copy is enqueued, lv_synchronize waits for it (frame i's D2H overlaps frame i+1's render)
     bool ao_raybuf = true;              // b200_ao_raybuf: the AO stream generates rays 32 at a time by the whole warp into a shared batch
     bool ao_wide = true;                // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
+    bool ao_packed = true;              // b200_ao_packed: ... with k_rtao_rays_w (lv_aostream.cuh: packed fp32x2 box tests, rays in shared memory)
     uint32_t ao_wide_reps = 1;          // ... node steps per pass of the traversal loop
     uint32_t ao_wide_top = 0;           // ... and serves the first levels (up to this many wide nodes) from shared memory (bulk-copied per block)
     bool ppll_raster_gather = true;     // b200_ppll_gather_mode = raster (default): object-order gather (one warp per segment); raycast = the BVH packet gather
@@ -151,6 +152,8 @@ struct lv_scene {
         s.seg_aux = has_lines ? seg_aux.p : nullptr;
         s.qnodes = qnodes.p;
         for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; s.w_origin[k] = w_origin[k]; s.w_scale[k] = w_scale[k]; }
+        s.w_pk[0] = w_scale[0]; s.w_pk[1] = w_scale[1]; s.w_pk[2] = w_origin[0]; s.w_pk[3] = w_origin[1];
+        s.w_pk[4] = s.w_pk[5] = w_scale[2]; s.w_pk[6] = s.w_pk[7] = w_origin[2];
         s.wnodes = n_wnodes ? wnodes.p : nullptr; s.w_top = w_top;
         s.tris = tris.p; s.tri_ids = tri_ids.p; s.tri_nodes = tri_nodes.p; s.tri_vattr = tri_vattr.p;
         s.tri_line_pos = tri_line_pos.p; s.tri_line_tan = tri_line_tan.p; s.n_tri = uint32_t(n_tri);
@@ -432,7 +435,7 @@ int ensure_wnodes(lv_ctx* c, lv_scene* sc) {
     while (n_in) {
         sc->w_level_end.push_back(total);
         LV_W4(cudaMemsetAsync(ctr.p, 0, 4, st));
-        k_w4_round<<<(n_in + 127) / 128, 128, 0, st>>>(sc->nodes.p, in, n_in, out, ctr.p, ctr.p + 1, sc->wnodes.p, ctr.p + 2, G);
+        k_w4_round<<<(n_in + 127) / 128, 128, 0, st>>>(sc->nodes.p, in, n_in, out, ctr.p, ctr.p + 1, sc->wnodes.p, ctr.p + 2, G, uint32_t(sc->n_seg));
         unsigned int h[3];
         LV_W4(cudaMemcpyAsync(h, ctr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
         LV_W4(cudaStreamSynchronize(st));
@@ -540,7 +543,7 @@ int ensure_tube_mesh(lv_ctx* c, lv_scene* sc) {
 // persistent AO ray-stream kernel over the records in ctx->ao_hits (count in small[0], work counter in small[2..3]) into ctx->occ;
 // timed with ev[4] / ev[5].  BAKE selects the prebaker's random stream / ray origin (lv_bake.cuh).
 template <bool BAKE>
-int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves, bool tri = false) {
+int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves, unsigned long long max_rays, bool tri = false) {
     auto launch = [&](auto kern) -> int {
         int per_sm = 0;
         LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
@@ -556,6 +559,9 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
     const uint32_t stack = c->opt.ao_stack;
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
     const bool default_tuning = stack == 12 && (c->opt.ao_min_blocks == 0 || c->opt.ao_min_blocks == 8) && !c->opt.ao_qnodes;
+    // the packed-arithmetic stream (32-bit ray numbers: `max_rays` bounds records x samples)
+    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 12 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
+        return c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_w<7, BAKE>) : c->opt.ao_min_blocks == 9 ? launch(k_rtao_rays_w<9, BAKE>) : launch(k_rtao_rays_w<8, BAKE>);
     if (queue && c->opt.ao_raybuf && default_tuning && !(c->opt.ao_wide && S.wnodes && S.w_top))   // warp-wide ray generation into a shared batch (default tuning only)
         return (c->opt.ao_wide && S.wnodes) ? launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 0, true>) : launch(k_rtao_rays_q<8, BAKE, 12, 0, 0, 0, true>);
     if (queue && c->opt.ao_wide && S.wnodes && stack == 12 && !c->opt.ao_qnodes) {   // 4-wide quantised tree; S.w_top: how many top-level nodes the kernel stages into shared memory
@@ -635,7 +641,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
         // one float per (hit pixel, sample); worst case every owned pixel (and ring pixel) is hit
         const size_t max_hits = size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + (apron ? ring : 0));
         LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
-        int lrc = launch_ao_rays<false>(c, P, S, sc->leaf_size == 1, tri);
+        int lrc = launch_ao_rays<false>(c, P, S, sc->leaf_size == 1, (unsigned long long)max_hits * P.ao_spp, tri);
         if (lrc) return lrc;
         c->rtao_rays_timed = true;
         k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, c->ao.p);
@@ -761,7 +767,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;
     if (!o.ao_triangles && o.ao_wide) { if ((rc = ensure_wnodes(c, sc))) return rc; sc->set_w_top(o.ao_wide_top); }
     if (!o.ao_triangles && !o.ao_wide && o.ao_qnodes && (rc = ensure_qnodes(c, sc))) return rc;
-    if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1, o.ao_triangles))) return rc;
+    if ((rc = launch_ao_rays<true>(c, P, sc->dev(), sc->leaf_size == 1, (unsigned long long)n_rec * o.bake_spp, o.ao_triangles))) return rc;
     c->rtao_rays_timed = true;
     k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, c->occ.p, c->ao_hits.p, c->small.p, sc->factors.p);
     LV_CUDA(c, cudaGetLastError());
@@ -931,6 +937,7 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ao_qnodes") o.ao_qnodes = parse_bool(value);
     else if (k == "b200_ao_wide") o.ao_wide = parse_bool(value);
     else if (k == "b200_ao_raybuf") o.ao_raybuf = parse_bool(value);
+    else if (k == "b200_ao_packed") o.ao_packed = parse_bool(value);
     else if (k == "b200_frame_format") {
         if (strcmp(value, "rgba32f") && strcmp(value, "rgba8")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_frame_format must be rgba32f or rgba8");
         o.frame_rgba8 = !strcmp(value, "rgba8");
@@ -999,6 +1006,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_qnodes") v = b(o.ao_qnodes);
     else if (k == "b200_ao_wide") v = b(o.ao_wide);
     else if (k == "b200_ao_raybuf") v = b(o.ao_raybuf);
+    else if (k == "b200_ao_packed") v = b(o.ao_packed);
     else if (k == "b200_frame_format") v = o.frame_rgba8 ? "rgba8" : "rgba32f";
     else if (k == "b200_async_delivery") v = b(o.async_delivery);
     else if (k == "b200_tube_prepass") v = b(o.tube_prepass);

@@ -354,7 +354,7 @@ struct W4Grid { float o[3], s[3], om[3]; };
 // consecutive wide indices from `alloc` and go to the next round's queue.  `need` = the worst-case traversal stack: a step pushes
 // every hit child but the one it descends into, so a path needs sum (children - 1) entries.
 __global__ void k_w4_round(const Node64* nodes, const uint3* in_q, uint32_t n_in, uint3* out_q, unsigned int* out_count, unsigned int* alloc,
-                           NodeW4* wnodes, unsigned int* need, const W4Grid G) {
+                           NodeW4* wnodes, unsigned int* need, const W4Grid G, uint32_t n_rec) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_in) return;
     const uint3 item = in_q[i];
@@ -392,7 +392,9 @@ __global__ void k_w4_round(const Node64* nodes, const uint3* in_q, uint32_t n_in
     for (int k = 0; k < 4; k++) {
         uint32_t* bw = w.w + 3 * k;
         uint32_t& cw = w.w[12 + k];
-        if (k >= n) { bw[0] = bw[1] = bw[2] = 0u; cw = kAbsentChild; continue; }
+        // an absent child is an EMPTY box (lo = 65535 > hi = 0 on every axis: its near bound lies behind its far bound whatever the ray's signs
+        // are, so the slab test fails without a look at the child word); the word refers to the all-NaN dummy record, like k_emit_nodes'
+        if (k >= n) { bw[0] = bw[1] = bw[2] = 0x0000FFFFu; cw = 0x80000000u | n_rec; continue; }
         const uint32_t ax = w4_quantize(lo[k].x, G.o[0], G.s[0], G.om[0], false), ay = w4_quantize(lo[k].y, G.o[1], G.s[1], G.om[1], false),
                        az = w4_quantize(lo[k].z, G.o[2], G.s[2], G.om[2], false);
         const uint32_t bx = w4_quantize(hi[k].x, G.o[0], G.s[0], G.om[0], true), by = w4_quantize(hi[k].y, G.o[1], G.s[1], G.om[1], true),

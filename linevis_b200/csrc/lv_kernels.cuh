@@ -830,6 +830,10 @@ k_rtao_rays_q(const __grid_constant__ FrameParams P, const __grid_constant__ Sce
     flush_counter(&C->ao_isect, isect);
 }
 
+}  // namespace lv
+#include "lv_aostream.cuh"
+namespace lv {
+
 __global__ void k_rtao_reduce(const __grid_constant__ FrameParams P, const float* occ, const AoHit* hit_list,
                               const unsigned int* hit_count, float* ao) {
     const uint32_t n_hit = *hit_count;

@@ -78,6 +78,7 @@ struct SceneDev {
     float q_origin[3], q_scale[3];
     const NodeW4* wnodes;      // 4-wide quantised tree (b200_ao_wide), root = 0, breadth-first order; or nullptr
     float w_origin[3], w_scale[3];   // w4_dequant's constants (origin already shifted by the conversion's magic number)
+    alignas(8) float w_pk[8];        // the same as aligned pairs for the packed fp32x2 box tests: {sx, sy}, {ox, oy}, {sz, sz}, {oz, oz}
     uint32_t w_top;            // the first w_top wide nodes are whole top levels (staged into shared memory by the AO ray stream)
     // triangle-tube mode of the AO passes (lv_tri.cuh); all nullptr / 0 unless the tube mesh has been built
     const TriRec* tris;        // [n_tri] BVH order

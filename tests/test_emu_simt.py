@@ -514,9 +514,9 @@ def test_rtao_ray_batches(ectx, oracle, use_distance, wide):
             assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("top", [0, 85, 341])
+@pytest.mark.parametrize("top,packed", [(0, True), (0, False), (85, True), (341, True)])
 @pytest.mark.parametrize("use_distance", [True, False])
-def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top):
+def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top, packed):
     """b200_ao_wide: the AO ray stream over the 4-wide quantised tree (NodeW4: collapse of the child-pair nodes, 16-bit outward-rounded
     boxes, magic-number dequantisation) gives the same AO image bit for bit, with the same number of rays, on a random soup, a helix
     and a single segment (a root with one real child)."""
@@ -525,13 +525,13 @@ def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top):
         sc, osc = _pair(ectx, oracle, data, width)
         cam = lv.make_camera(56, 36)
         ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
-                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True, "b200_ao_wide_top": top})
+                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True, "b200_ao_wide_top": top, "b200_ao_packed": packed})
         try:
             ao, st = ectx.render_rtao(sc, cam, 0)
             ectx.set_option("b200_ao_wide", False)
             ao2, st2 = ectx.render_rtao(sc, cam, 0)
         finally:
-            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1})
+            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1, "b200_ao_packed": True})
         ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
         if data[2].shape[0] > 100:   # the wide tree really is another tree: fewer steps per ray than the child-pair nodes
