@@ -560,6 +560,10 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
     const bool default_tuning = stack == 12 && (c->opt.ao_min_blocks == 0 || c->opt.ao_min_blocks == 8) && !c->opt.ao_qnodes;
     // the packed-arithmetic stream (32-bit ray numbers: `max_rays` bounds records x samples)
+    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 8 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
+        return launch(k_rtao_rays_w<8, BAKE, 8>);
+    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 16 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
+        return launch(k_rtao_rays_w<8, BAKE, 6>);   // experiment: 6 entries
     if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 12 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
         return c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_w<7, BAKE>) : c->opt.ao_min_blocks == 9 ? launch(k_rtao_rays_w<9, BAKE>) : launch(k_rtao_rays_w<8, BAKE>);
     if (queue && c->opt.ao_raybuf && default_tuning && !(c->opt.ao_wide && S.wnodes && S.w_top))   // warp-wide ray generation into a shared batch (default tuning only)
