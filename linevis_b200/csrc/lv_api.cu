@@ -154,6 +154,7 @@ struct lv_scene {
         for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; s.w_origin[k] = w_origin[k]; s.w_scale[k] = w_scale[k]; }
         s.w_pk[0] = w_scale[0]; s.w_pk[1] = w_scale[1]; s.w_pk[2] = w_origin[0]; s.w_pk[3] = w_origin[1];
         s.w_pk[4] = s.w_pk[5] = w_scale[2]; s.w_pk[6] = s.w_pk[7] = w_origin[2];
+        s.w_tq_bits = std::max<uint64_t>(n_wnodes, n_seg + 1) < (1ull << 24) ? 7u : 4u;
         s.wnodes = n_wnodes ? wnodes.p : nullptr; s.w_top = w_top;
         s.tris = tris.p; s.tri_ids = tri_ids.p; s.tri_nodes = tri_nodes.p; s.tri_vattr = tri_vattr.p;
         s.tri_line_pos = tri_line_pos.p; s.tri_line_tan = tri_line_tan.p; s.n_tri = uint32_t(n_tri);
@@ -253,6 +254,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? 30u : 24u));
     P.ao_leaf_vote = int(o.ao_leaf_vote);
     P.ao_wide_reps = int(o.ao_wide_reps);
+    P.ao_tq_lo = (1.0f / P.ao_radius) * (1.0f - 1.0f / 4096.0f); P.ao_tq_hi = (1.0f / P.ao_radius) * (1.0f + 1.0f / 4096.0f);
     P.spp = o.num_samples_per_frame;
     // useJitteredSamples = maxNumFrames > 1 || numSamplesPerFrame > 1 (reference VulkanRayTracer.cpp:421)
     P.use_jitter = (o.num_accumulated_frames > 1 || o.num_samples_per_frame > 1) ? 1 : 0;
@@ -560,12 +562,8 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
     const bool queue = c->opt.ao_queue && one_record_leaves && stack != 0;   // the leaf-queue kernel needs one-record leaves and a packed stack
     const bool default_tuning = stack == 12 && (c->opt.ao_min_blocks == 0 || c->opt.ao_min_blocks == 8) && !c->opt.ao_qnodes;
     // the packed-arithmetic stream (32-bit ray numbers: `max_rays` bounds records x samples)
-    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 8 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
-        return launch(k_rtao_rays_w<8, BAKE, 8>);
-    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 16 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
-        return launch(k_rtao_rays_w<8, BAKE, 6>);   // experiment: 6 entries
-    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && stack == 12 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
-        return c->opt.ao_min_blocks == 7 ? launch(k_rtao_rays_w<7, BAKE>) : c->opt.ao_min_blocks == 9 ? launch(k_rtao_rays_w<9, BAKE>) : launch(k_rtao_rays_w<8, BAKE>);
+    if (queue && c->opt.ao_raybuf && c->opt.ao_packed && default_tuning && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
+        return S.w_tq_bits == 7u ? launch(k_rtao_rays_w<8, BAKE, 7>) : launch(k_rtao_rays_w<8, BAKE, 4>);
     if (queue && c->opt.ao_raybuf && default_tuning && !(c->opt.ao_wide && S.wnodes && S.w_top))   // warp-wide ray generation into a shared batch (default tuning only)
         return (c->opt.ao_wide && S.wnodes) ? launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 0, true>) : launch(k_rtao_rays_q<8, BAKE, 12, 0, 0, 0, true>);
     if (queue && c->opt.ao_wide && S.wnodes && stack == 12 && !c->opt.ao_qnodes) {   // 4-wide quantised tree; S.w_top: how many top-level nodes the kernel stages into shared memory
@@ -766,6 +764,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     memset(&P, 0, sizeof(P));
     P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
     P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? 30u : 24u)); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
+    P.ao_tq_lo = (1.0f / P.ao_radius) * (1.0f - 1.0f / 4096.0f); P.ao_tq_hi = (1.0f / P.ao_radius) * (1.0f + 1.0f / 4096.0f);
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
     if (o.ao_triangles && (rc = ensure_tube_mesh(c, sc))) return rc;

@@ -79,6 +79,7 @@ struct SceneDev {
     const NodeW4* wnodes;      // 4-wide quantised tree (b200_ao_wide), root = 0, breadth-first order; or nullptr
     float w_origin[3], w_scale[3];   // w4_dequant's constants (origin already shifted by the conversion's magic number)
     alignas(8) float w_pk[8];        // the same as aligned pairs for the packed fp32x2 box tests: {sx, sy}, {ox, oy}, {sz, sz}, {oz, oz}
+    uint32_t w_tq_bits;        // k_rtao_rays_w: 7 if every wide node / record index (incl. the dummy record) is below 2^24, else 4
     uint32_t w_top;            // the first w_top wide nodes are whole top levels (staged into shared memory by the AO ray stream)
     // triangle-tube mode of the AO passes (lv_tri.cuh); all nullptr / 0 unless the tube mesh has been built
     const TriRec* tris;        // [n_tri] BVH order
@@ -116,6 +117,7 @@ struct FrameParams {
     int ao_refill_below;      // k_rtao_rays refills a warp once fewer lanes than this are live
     int ao_leaf_vote;         // ... and intersects postponed leaves once this many lanes hold one
     int ao_wide_reps;         // wide-tree stream: node steps per pass of the traversal loop
+    float ao_tq_lo, ao_tq_hi; // k_rtao_rays_w: (1 / ao_radius) (1 -+ 2^-12), the scales of its 4-bit stack entry distances
     uint32_t spp;             // numSamplesPerFrame
     int use_jitter, det_sampling;
     uint32_t max_depth;       // maxDepthComplexity

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
 O=gpurun_out
-python tools/ao_ab.py --workload config5 --variant "b200_ao_packed=false" --variant "b200_ao_refill_below=28" --variant "b200_ao_stack=8,b200_ao_refill_below=28" --variant "b200_ao_stack=16,b200_ao_refill_below=28" --variant "b200_ao_refill_below=26"  > $O/r2p_ab5.log 2>&1; echo "ab5 rc=$?"; cat $O/r2p_ab5.log | tail -8
+python tools/ao_ab.py --workload config5 --variant "b200_ao_packed=false" --variant "" --variant "b200_ao_refill_below=28" --variant "b200_ao_refill_below=29" --variant "b200_ao_leaf_vote=6"  > $O/r2p_ab5.log 2>&1; echo "ab5 rc=$?"; cat $O/r2p_ab5.log | tail -8
