@@ -345,13 +345,19 @@ class Dist:
         self.dist.all_gather(out, t)
         return [float(x.item()) for x in out]
 
-    def timed(self, fn, steps):
-        """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides; CUDA events; ms per step, max over ranks."""
+    def timed(self, fn, steps, fork=None, join=None):
+        """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides; CUDA events; ms per step, max over ranks.
+        fork / join: when `fn` enqueues on other streams than the current one, fork() makes them wait for the start event and join()
+        makes the current stream wait for them before the end event is recorded."""
         self.barrier()
         e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
         e0.record()
+        if fork is not None:
+            fork()
         for _ in range(steps):
             fn()
+        if join is not None:
+            join()
         e1.record()
         self.barrier()
         return self.reduce([e0.elapsed_time(e1) / steps], "max")[0]
@@ -621,12 +627,15 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
         "ambient_occlusion_samples_per_frame": wl["ao_spp"], "ambient_occlusion_iterations": 1, "ambient_occlusion_radius": 0.1,
         "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": True,
         "num_samples_per_frame": 1, "num_accumulated_frames": 1, "use_deterministic_sampling": False}
-    ctx = lv.Context(D.local, stream)
-    ctx.set_transfer_function(lv.scenes.standard_transfer_function())
-    ctx.set_new_settings(settings)
-    ctx.set_new_settings(extra_opts)
-    if world > 1:
-        ctx.set_tile_shard(rank, world, TILE)
+    def make_tube_ctx(cuda_stream):
+        c = lv.Context(D.local, cuda_stream)
+        c.set_transfer_function(lv.scenes.standard_transfer_function())
+        c.set_new_settings(settings)
+        c.set_new_settings(extra_opts)
+        if world > 1:
+            c.set_tile_shard(rank, world, TILE)
+        return c
+    ctx = make_tube_ctx(stream)
     t0 = time.time()
     d_pos, d_attr, d_seg = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (pos, attr, seg.view(np.int32)))
     scene = ctx.create_scene(d_pos, d_attr, d_seg, lv.scenes.LINE_WIDTH)
@@ -665,10 +674,42 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
         st["rays_primary"] + st["rays_ao"], st["traversal_steps"], st["intersections"], st["rays_primary"], st["rays_ao"],
         st["ao_traversal_steps"], st["ao_intersections"]])
 
-    # ---- timed region: exactly K steps, barrier + synchronize on both sides, CUDA events, max over ranks
+    # ---- timed region: exactly K steps, barrier + synchronize on both sides, CUDA events, max over ranks.
+    # --frames-in-flight 2 (an experiment, off by default): frames alternate between two contexts on two streams that share the scene, so frame i + 1's packet
+    # kernels run in the tail of frame i's persistent AO stream (linevis_b200.sharding.FramesInFlight; every frame is still one complete
+    # lv_render_tubes frame, the frames are independent: no temporal accumulation in this workload).  ms_one_frame_in_flight is the
+    # same loop with a single context, i.e. the latency of a frame.
+    fif = None
+    ms_single = D.timed(step, args.steps) if args.frames_in_flight == 2 else None
+    if args.frames_in_flight == 2:
+        from linevis_b200.sharding import FramesInFlight
+        streams2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        ctxs2 = [make_tube_ctx(s_.cuda_stream) for s_ in streams2]
+        frames2 = [torch.zeros((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if not peer else None
+        pfs2 = [PeerFrame(ctxs2[j], W, H, rank, world, dev) for j in range(2)] if peer else None
+
+        def render2(c, j):
+            c.render_tubes(scene, cam, 0, out=(pfs2[j].ptr if pfs2 is not None else frames2[j]), stats=False)
+            if pfs2 is not None:
+                pfs2[j].fence()
+            elif fg is not None:
+                fg.gather(frames2[j], assemble_on=(0,))
+        fif = FramesInFlight(ctxs2, streams2, render2)
+        for _ in range(max(4, args.warmup)):
+            fif.step()
+        torch.cuda.synchronize()
     sampler = ClockSampler(D.local) if rank == 0 else None
-    ms = D.timed(step, args.steps)
+    ms = D.timed(fif.step, args.steps, fork=fif.fork, join=fif.join) if fif is not None else D.timed(step, args.steps)
     clocks = sampler.stop() if sampler else None
+    if fif is not None:
+        # the pipelined frames are complete and identical to the single-context frame
+        torch.cuda.synchronize()
+        ref_frame = pf.tensor() if (pf is not None and rank == 0) else frame
+        fif_equal = True
+        if rank == 0 or not peer:
+            for j in range(2):
+                got = pfs2[j].tensor() if pfs2 is not None else frames2[j]
+                fif_equal = fif_equal and bool(torch.equal(got.view(torch.int32), ref_frame.view(torch.int32)))
 
     # ---- dominant kernel (the AO ray stream) live timing for the roofline: CUDA events around that kernel inside the library
     kt = []
@@ -733,10 +774,13 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
     line = None
     if rank == 0:
         ao_kernel = "k_rtao_rays_q" if ctx.get_option("b200_ao_queue") == "true" else "k_rtao_rays"
+        if ao_kernel == "k_rtao_rays_q" and all(ctx.get_option(k_) == "true" for k_ in ("b200_ao_packed", "b200_ao_wide", "b200_ao_raybuf")):
+            ao_kernel = "k_rtao_rays_w"
         line = {
             "metric": "Mrays/s (tube+RTAO)", "value": tot_rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "frame": [W, H], "segments": int(info["n_seg"]), "bvh_nodes": int(info["n_nodes"]),
+                       **({"frames_in_flight": 2, "ms_one_frame_in_flight": ms_single, "frames_in_flight_equal_to_single": fif_equal} if fif is not None else {}),
                        "scene_bytes": int(scene_bytes), "l2": "inputs larger than L2 (segments + BVH = %.2f GB)" % (scene_bytes / 1e9)
                        if scene_bytes > 200e6 else "scene fits L2; the 126 MB L2 is not flushed between frames",
                        "parallelism": parallelism_note(world, peer),
@@ -772,7 +816,7 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
                 line["roofline"]["traffic"] = c["dram_bytes"]; line["roofline"]["limiter"] = c["limiter"]
                 line["roofline"]["traffic_source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum, measured inside this run"
         if world == 1 and line["roofline"]["traffic"] is None:
-            line["roofline"]["traffic"] = committed_traffic("k_rtao_rays_q", name)
+            line["roofline"]["traffic"] = committed_traffic(ao_kernel, name)
             line["roofline"]["traffic_source"] = "STALE: committed capture profiles/traffic.json (no live ncu pass in this run)"
         if not args.no_cpu_baseline and world == 1:
             # CPU baseline on a centre crop + parity of the CUDA path against it on exactly that crop + T / I of the reference library's tree
@@ -802,10 +846,18 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
                                             "own_I_per_ao_ray_same_crop": own_I, "bytes_ratio_ref_over_own": scale,
                                             "note": "T / I of the %s tree for the AO rays of the %dx%d crop (oracle Statistics) against this kernel's counters on the same rays; "
                                                     "frac_ref_tree = frac x that ratio: it rises when our tree needs fewer steps" % (o.lib.lvo_backend_name().decode(), sw, sh)}
+    if fif is not None:
+        D.barrier()
+        if pfs2 is not None:
+            for p_ in pfs2:
+                p_.close()
     if pf is not None:
         D.barrier()
         pf.close()
     scene.close(); ctx.close()
+    if fif is not None:
+        for c_ in ctxs2:
+            c_.close()
     return line
 
 
@@ -827,6 +879,10 @@ def main():
                          "--impl reference shrinks it to fit --ref-budget")
     ap.add_argument("--ppll-sample", type=int, nargs=2, default=[480, 270], help="centre crop of the PPLL headline's CPU baseline / parity leg")
     ap.add_argument("--ref-budget", type=float, default=80.0, help="--impl reference: seconds of CPU rendering for warm-up + steps together")
+    ap.add_argument("--frames-in-flight", type=int, default=1, choices=[1, 2],
+                    help="tube + RTAO headline: 2 = frames alternate between two contexts / streams sharing the scene (measured: no gain, "
+                         "27.86 vs 27.83 ms on config 5 -- blocks of the next frame's packet kernels do not get onto SMs that still hold blocks of the "
+                         "persistent AO stream); 1 = one context (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu pass (roofline.traffic then comes from the committed capture, labelled stale)")
     ap.add_argument("--assemble", default="peer", choices=["peer", "allgather"],

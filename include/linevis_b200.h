@@ -144,6 +144,14 @@ int lv_set_transfer_function(lv_ctx* ctx, const float* rgba, uint32_t K, float a
  * context renders the whole frame.  With world > 1 render calls only touch owned pixels; all other
  * pixels of the output buffer are left untouched. */
 int lv_set_tile_shard(lv_ctx* ctx, uint32_t rank, uint32_t world, uint32_t tile_size);
+/* Cost-balanced tile ownership (new).  lv_get_tile_costs: per tile of the width x height frame, in the Morton order of the
+ * enumeration, the hit pixels of this context's last RTAO pass (0 for tiles of other ranks) -- summed over the ranks this is the
+ * AO-ray cost map of the frame.  lv_set_tile_owners replaces "tile i -> rank i % world" by an explicit owner per tile (same order,
+ * same map on every rank) for frames of exactly this size, until the next lv_set_tile_shard; the frame kernels, the peer-frame
+ * stores and the tile pack / unpack follow it.  linevis_b200/sharding.py::balance_tiles builds the map (longest processing time
+ * first).  The reference has no counterpart: its frame is rendered by one GPU. */
+int lv_get_tile_costs(lv_ctx* ctx, uint32_t width, uint32_t height, uint32_t* costs, uint32_t n_tiles);
+int lv_set_tile_owners(lv_ctx* ctx, uint32_t width, uint32_t height, const unsigned char* owners, uint32_t n_tiles);
 /* Number of tiles this context owns for a W x H frame and their (tile_x, tile_y) coordinates. */
 int lv_get_owned_tiles(const lv_ctx* ctx, uint32_t width, uint32_t height,
                        uint32_t* tiles_xy /* n_owned*2 or NULL */, uint32_t* n_owned);

@@ -24,6 +24,7 @@ class Context:
             raise LineVisError(rc, self.lib.lv_last_global_error().decode())
         self.h = h
         self.device = device
+        self._tile_size = 64
 
     def close(self):
         if getattr(self, "h", None):
@@ -64,6 +65,20 @@ class Context:
     # -- sharding
     def set_tile_shard(self, rank, world, tile_size=64):
         self._check(self.lib.lv_set_tile_shard(self.h, rank, world, tile_size))
+        self._tile_size = tile_size
+
+    def tile_costs(self, width, height):
+        """Hit pixels of this context's last RTAO pass per tile of the frame (Morton order of the tile enumeration; 0 for other ranks' tiles)."""
+        ts = self._tile_size
+        n = ((width + ts - 1) // ts) * ((height + ts - 1) // ts)
+        out = np.zeros(n, np.uint32)
+        self._check(self.lib.lv_get_tile_costs(self.h, width, height, _ptr(out), n))
+        return out
+
+    def set_tile_owners(self, width, height, owners):
+        """Explicit owner rank per tile (Morton order) for frames of this size; see sharding.balance_tiles."""
+        owners = np.ascontiguousarray(owners, np.uint8)
+        self._check(self.lib.lv_set_tile_owners(self.h, width, height, _ptr(owners), owners.size))
 
     def owned_tiles(self, width, height):
         n = ctypes.c_uint32()

@@ -23,7 +23,7 @@ SORT_MODES = {"priority_queue": 0, "bubble": 1, "insertion": 2, "shell": 3, "max
 # every symbol include/linevis_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "lv_ctx_create", "lv_ctx_destroy", "lv_last_error", "lv_last_global_error", "lv_abi_version", "lv_set_option",
-    "lv_get_option", "lv_set_transfer_function", "lv_set_tile_shard", "lv_get_owned_tiles", "lv_pack_owned_tiles",
+    "lv_get_option", "lv_set_transfer_function", "lv_set_tile_shard", "lv_get_tile_costs", "lv_set_tile_owners", "lv_get_owned_tiles", "lv_pack_owned_tiles",
     "lv_unpack_tiles", "lv_scene_create", "lv_scene_create_device", "lv_scene_destroy", "lv_scene_info",
     "lv_scene_copy_bvh", "lv_render_tubes", "lv_render_ppll", "lv_trace_primary", "lv_render_rtao", "lv_ppll_clear",
     "lv_ppll_gather", "lv_ppll_resolve", "lv_ppll_read", "lv_synchronize",
@@ -85,6 +85,8 @@ def load_library(path=None):
     L.lv_get_option.argtypes = [vp, cp, cp, ctypes.c_size_t]
     L.lv_set_transfer_function.argtypes = [vp, vp, u32, f32, f32]
     L.lv_set_tile_shard.argtypes = [vp, u32, u32, u32]
+    L.lv_get_tile_costs.argtypes = [vp, u32, u32, vp, u32]
+    L.lv_set_tile_owners.argtypes = [vp, u32, u32, vp, u32]
     L.lv_get_owned_tiles.argtypes = [vp, u32, u32, vp, P(u32)]
     L.lv_pack_owned_tiles.argtypes = [vp, vp, u32, u32, vp]
     L.lv_unpack_tiles.argtypes = [vp, vp, u32, u32, u32, u32, vp]

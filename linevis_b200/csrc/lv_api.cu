@@ -41,7 +41,7 @@ struct Options {
     bool bvh_cubic_morton = false;      // b200_bvh_morton = cubic: one scale for all axes in the Morton codes (default per_axis: each axis to [0, 1]; measured equal)
     bool bvh_ploc = false;              // b200_bvh_builder = ploc: parallel locally-ordered clustering instead of the Morton radix tree (one-record leaves only)
     uint32_t bvh_ploc_radius = 16;      // ... neighbours searched to either side per round
-    uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 30 with b200_ao_raybuf (refilling is cheap), 24 without
+    uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 28 for k_rtao_rays_w, 30 for the other streams with b200_ao_raybuf (refilling is cheap), 24 without
     uint32_t ao_stack = 12;           // traversal stack of the AO ray kernel: 0 local 2x32-bit, 1 local packed 64-bit, K = 8 / 12 / 16 packed entries in shared memory + local spill
     bool ao_qnodes = false;           // experimental: AO ray stream over 32-byte quantised nodes (k_quantize_nodes, NodeQ); capsules + leaf queue only
     bool ao_triangles = false;        // b200_rtao_geometry = triangles: AO passes trace the reference's triangulated tubes (lv_tri.cuh)
@@ -54,6 +54,8 @@ struct Options {
                                         // the call returns once the copy is enqueued, lv_synchronize waits for it (frame i's D2H overlaps frame i+1's render)
     bool ao_raybuf = true;              // b200_ao_raybuf: the AO stream generates rays 32 at a time by the whole warp into a shared batch
     bool ao_wide = true;                // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
+    uint32_t ao_tq_bits = 0;            // b200_ao_tq_bits: bits of the packed stream's stack entry distances (0 = what the scene's index range allows: 7 or 4)
+    int packet_carveout = -1;           // b200_packet_carveout (see lv_set_option)
     bool ao_packed = true;              // b200_ao_packed: ... with k_rtao_rays_w (lv_aostream.cuh: packed fp32x2 box tests, rays in shared memory)
     uint32_t ao_wide_reps = 1;          // ... node steps per pass of the traversal loop
     uint32_t ao_wide_top = 0;           // ... and serves the first levels (up to this many wide nodes) from shared memory (bulk-copied per block)
@@ -100,6 +102,8 @@ struct lv_ctx {
     // sharding
     uint32_t rank = 0, world = 1, tile_size = 64;
     std::vector<uint2> tiles_host; DevBuf<uint2> tiles_dev; uint32_t tiles_w = 0, tiles_h = 0;
+    std::vector<unsigned char> tile_owner; uint32_t owner_w = 0, owner_h = 0;   // lv_set_tile_owners: explicit owner per tile (Morton order) of an owner_w x owner_h frame
+    DevBuf<unsigned int> tile_hist;
     DevBuf<unsigned char> owned_map; uint32_t tiles_x = 0;   // world > 1: 1 byte per tile of the frame, 1 = owned (object-order PPLL gather)
     DevBuf<uint2> tiles_tmp; std::vector<uint32_t> peer_off; uint32_t peer_w = 0, peer_h = 0, peer_world = 0, peer_tile = 0;
     // frame buffers
@@ -191,19 +195,31 @@ uint32_t morton2(uint32_t x, uint32_t y) {
 }
 
 // tiles of a W x H frame in Morton order; tile i belongs to rank i % world
-void enumerate_tiles(uint32_t W, uint32_t H, uint32_t ts, uint32_t rank, uint32_t world, std::vector<uint2>& out) {
+// tiles of a W x H frame in Morton order
+void morton_tiles(uint32_t W, uint32_t H, uint32_t ts, std::vector<uint2>& out) {
     uint32_t tx = (W + ts - 1) / ts, ty = (H + ts - 1) / ts;
     std::vector<std::pair<uint32_t, uint2>> all;
     all.reserve(size_t(tx) * ty);
     for (uint32_t y = 0; y < ty; y++) for (uint32_t x = 0; x < tx; x++) all.push_back({morton2(x, y), make_uint2(x, y)});
     std::sort(all.begin(), all.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
     out.clear();
-    for (size_t i = 0; i < all.size(); i++) if (i % world == rank) out.push_back(all[i].second);
+    for (const auto& a : all) out.push_back(a.second);
+}
+// the tiles `rank` owns: tile i of the Morton order belongs to rank i % world, or to owners[i] when an explicit map is given
+void enumerate_tiles(uint32_t W, uint32_t H, uint32_t ts, uint32_t rank, uint32_t world, std::vector<uint2>& out, const std::vector<unsigned char>* owners = nullptr) {
+    std::vector<uint2> all;
+    morton_tiles(W, H, ts, all);
+    out.clear();
+    const bool use = owners && owners->size() == all.size();
+    for (size_t i = 0; i < all.size(); i++) if ((use ? uint32_t((*owners)[i]) : uint32_t(i % world)) == rank) out.push_back(all[i]);
+}
+const std::vector<unsigned char>* tile_owners_for(const lv_ctx* c, uint32_t W, uint32_t H) {
+    return (!c->tile_owner.empty() && c->owner_w == W && c->owner_h == H) ? &c->tile_owner : nullptr;
 }
 
 int ensure_tiles(lv_ctx* c, uint32_t W, uint32_t H) {
     if (c->tiles_w == W && c->tiles_h == H && c->tiles_dev.p) return LV_OK;
-    enumerate_tiles(W, H, c->tile_size, c->rank, c->world, c->tiles_host);
+    enumerate_tiles(W, H, c->tile_size, c->rank, c->world, c->tiles_host, tile_owners_for(c, W, H));
     LV_CUDA(c, c->tiles_dev.ensure(std::max<size_t>(1, c->tiles_host.size())));
     if (!c->tiles_host.empty())
         LV_CUDA(c, cudaMemcpyAsync(c->tiles_dev.p, c->tiles_host.data(), c->tiles_host.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
@@ -251,7 +267,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.ao_strength = o.ao_strength; P.ao_gamma = o.ao_gamma; P.ao_radius = o.ao_radius;
     P.ao_spp = o.ao_spp; P.ao_use_distance = o.ao_use_distance; P.ao_jitter = o.ao_jitter_primary;
     P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
-    P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? 30u : 24u));
+    P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? (o.ao_packed && o.ao_wide ? 28u : 30u) : 24u));
     P.ao_leaf_vote = int(o.ao_leaf_vote);
     P.ao_wide_reps = int(o.ao_wide_reps);
     P.ao_tq_lo = (1.0f / P.ao_radius) * (1.0f - 1.0f / 4096.0f); P.ao_tq_hi = (1.0f / P.ao_radius) * (1.0f + 1.0f / 4096.0f);
@@ -563,7 +579,7 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
     const bool default_tuning = stack == 12 && (c->opt.ao_min_blocks == 0 || c->opt.ao_min_blocks == 8) && !c->opt.ao_qnodes;
     // the packed-arithmetic stream (32-bit ray numbers: `max_rays` bounds records x samples)
     if (queue && c->opt.ao_raybuf && c->opt.ao_packed && default_tuning && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
-        return S.w_tq_bits == 7u ? launch(k_rtao_rays_w<8, BAKE, 7>) : launch(k_rtao_rays_w<8, BAKE, 4>);
+        return (S.w_tq_bits == 7u && c->opt.ao_tq_bits != 4u) ? launch(k_rtao_rays_w<8, BAKE, 7>) : launch(k_rtao_rays_w<8, BAKE, 4>);
     if (queue && c->opt.ao_raybuf && default_tuning && !(c->opt.ao_wide && S.wnodes && S.w_top))   // warp-wide ray generation into a shared batch (default tuning only)
         return (c->opt.ao_wide && S.wnodes) ? launch(k_rtao_rays_q<8, BAKE, 12, 0, 2, 0, true>) : launch(k_rtao_rays_q<8, BAKE, 12, 0, 0, 0, true>);
     if (queue && c->opt.ao_wide && S.wnodes && stack == 12 && !c->opt.ao_qnodes) {   // 4-wide quantised tree; S.w_top: how many top-level nodes the kernel stages into shared memory
@@ -763,7 +779,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     FrameParams P;
     memset(&P, 0, sizeof(P));
     P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
-    P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? 30u : 24u)); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
+    P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? (o.ao_packed && o.ao_wide ? 28u : 30u) : 24u)); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
     P.ao_tq_lo = (1.0f / P.ao_radius) * (1.0f - 1.0f / 4096.0f); P.ao_tq_hi = (1.0f / P.ao_radius) * (1.0f + 1.0f / 4096.0f);
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
     c->rtao_rays_timed = false;
@@ -852,7 +868,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
     c->first_hits.release();
     for (int k = 0; k < 2; k++) { if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
-    c->tf.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
+    c->tf.release(); c->tile_hist.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -941,6 +957,21 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ao_wide") o.ao_wide = parse_bool(value);
     else if (k == "b200_ao_raybuf") o.ao_raybuf = parse_bool(value);
     else if (k == "b200_ao_packed") o.ao_packed = parse_bool(value);
+    else if (k == "b200_ao_tq_bits") { if (u() != 0 && u() != 4 && u() != 7) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_tq_bits must be 0 (automatic), 4 or 7"); o.ao_tq_bits = u(); }
+    else if (k == "b200_packet_carveout") {
+        // shared-memory carveout (percent of the SM's L1 / shared array) the packet kernels of the tube + RTAO frame ask for.  An SM has
+        // ONE carveout at a time: blocks of a kernel that wants another one cannot start on an SM until every block of the persistent AO
+        // stream (which needs the largest carveout) has left it.  100 lets them share SMs with the draining stream; -1 = the driver's choice.
+        const int pct = std::atoi(value);
+        if (pct < -1 || pct > 100) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_packet_carveout must be -1 (default) or 0..100");
+        LV_CUDA(c, cudaSetDevice(c->device));
+        LV_CUDA(c, cudaFuncSetAttribute(k_rtao_primary<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        LV_CUDA(c, cudaFuncSetAttribute(k_tube_first, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        LV_CUDA(c, cudaFuncSetAttribute(k_tubes<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        LV_CUDA(c, cudaFuncSetAttribute(k_tubes<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        LV_CUDA(c, cudaFuncSetAttribute(k_rtao_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        o.packet_carveout = pct;
+    }
     else if (k == "b200_frame_format") {
         if (strcmp(value, "rgba32f") && strcmp(value, "rgba8")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_frame_format must be rgba32f or rgba8");
         o.frame_rgba8 = !strcmp(value, "rgba8");
@@ -1010,6 +1041,8 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_wide") v = b(o.ao_wide);
     else if (k == "b200_ao_raybuf") v = b(o.ao_raybuf);
     else if (k == "b200_ao_packed") v = b(o.ao_packed);
+    else if (k == "b200_packet_carveout") v = std::to_string(o.packet_carveout);
+    else if (k == "b200_ao_tq_bits") v = std::to_string(o.ao_tq_bits);
     else if (k == "b200_frame_format") v = o.frame_rgba8 ? "rgba8" : "rgba32f";
     else if (k == "b200_async_delivery") v = b(o.async_delivery);
     else if (k == "b200_tube_prepass") v = b(o.tube_prepass);
@@ -1042,16 +1075,56 @@ int lv_set_tile_shard(lv_ctx* c, uint32_t rank, uint32_t world, uint32_t tile_si
     if (!c || world == 0 || rank >= world) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_set_tile_shard: need rank < world");
     if (tile_size == 0 || tile_size % 16) return fail(c, LV_ERR_INVALID_ARGUMENT, "tile_size must be a positive multiple of 16");
     c->rank = rank; c->world = world; c->tile_size = tile_size;
+    c->tile_owner.clear(); c->owner_w = c->owner_h = 0; c->peer_w = c->peer_h = 0;
     c->tiles_w = c->tiles_h = 0;  // re-enumerate on next frame
     c->ao_w = c->ao_h = 0;
     c->apron_stamp = 0;           // the stamp array is cleared again before its next use
     return LV_OK;
 }
 
+int lv_set_tile_owners(lv_ctx* c, uint32_t width, uint32_t height, const unsigned char* owners, uint32_t n_tiles) {
+    if (!c) return LV_ERR_INVALID_ARGUMENT;
+    const uint32_t tx = (width + c->tile_size - 1) / c->tile_size, ty = (height + c->tile_size - 1) / c->tile_size;
+    if (!owners || n_tiles != tx * ty) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_set_tile_owners: need one owner per tile of the frame (" + std::to_string(tx * ty) + ")");
+    for (uint32_t i = 0; i < n_tiles; i++) if (owners[i] >= c->world) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_set_tile_owners: owner >= world");
+    c->tile_owner.assign(owners, owners + n_tiles); c->owner_w = width; c->owner_h = height;
+    c->tiles_w = c->tiles_h = 0; c->peer_w = c->peer_h = 0;   // re-enumerate on next frame
+    c->ao_w = c->ao_h = 0;
+    c->apron_stamp = 0;
+    return LV_OK;
+}
+
+// per tile (Morton order, all tiles of the frame; 0 for tiles of other ranks): hit pixels of the last RTAO pass of this context
+__global__ void k_tile_hist(const AoHit* hits, const unsigned int* n_hit, uint32_t W, uint32_t tile_size, uint32_t tiles_x, unsigned int* hist) {
+    const uint32_t n = *n_hit;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t px = __float_as_uint(hits[i].nrm_px.w);
+        atomicAdd(&hist[((px / W) / tile_size) * tiles_x + (px % W) / tile_size], 1u);
+    }
+}
+
+int lv_get_tile_costs(lv_ctx* c, uint32_t width, uint32_t height, uint32_t* costs, uint32_t n_tiles) {
+    if (!c || !costs) return LV_ERR_INVALID_ARGUMENT;
+    const uint32_t tx = (width + c->tile_size - 1) / c->tile_size, ty = (height + c->tile_size - 1) / c->tile_size;
+    if (n_tiles != tx * ty) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_get_tile_costs: need room for one cost per tile of the frame");
+    if (!c->ao_hits.p || !c->small.p || c->ao_w != width || c->ao_h != height) return fail(c, LV_ERR_STATE, "lv_get_tile_costs: no RTAO pass of this frame size has run");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    LV_CUDA(c, c->tile_hist.ensure(n_tiles));
+    LV_CUDA(c, cudaMemsetAsync(c->tile_hist.p, 0, size_t(n_tiles) * 4, c->stream));
+    k_tile_hist<<<c->num_sms * 4, 256, 0, c->stream>>>(c->ao_hits.p, c->small.p, width, c->tile_size, tx, c->tile_hist.p);
+    std::vector<unsigned int> lin(n_tiles);
+    LV_CUDA(c, cudaMemcpyAsync(lin.data(), c->tile_hist.p, size_t(n_tiles) * 4, cudaMemcpyDeviceToHost, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<uint2> all;
+    morton_tiles(width, height, c->tile_size, all);
+    for (uint32_t i = 0; i < n_tiles; i++) costs[i] = lin[size_t(all[i].y) * tx + all[i].x];
+    return LV_OK;
+}
+
 int lv_get_owned_tiles(const lv_ctx* c, uint32_t width, uint32_t height, uint32_t* tiles_xy, uint32_t* n_owned) {
     if (!c || !n_owned) return LV_ERR_INVALID_ARGUMENT;
     std::vector<uint2> t;
-    enumerate_tiles(width, height, c->tile_size, c->rank, c->world, t);
+    enumerate_tiles(width, height, c->tile_size, c->rank, c->world, t, tile_owners_for(c, width, height));
     *n_owned = uint32_t(t.size());
     if (tiles_xy) for (size_t i = 0; i < t.size(); i++) { tiles_xy[2 * i] = t[i].x; tiles_xy[2 * i + 1] = t[i].y; }
     return LV_OK;
@@ -1079,7 +1152,7 @@ int lv_unpack_tiles(lv_ctx* c, const float* packed, uint32_t src_rank, uint32_t 
         c->peer_off.assign(world + 1, 0);
         for (uint32_t r = 0; r < world; r++) {
             std::vector<uint2> t;
-            enumerate_tiles(W, H, c->tile_size, r, world, t);
+            enumerate_tiles(W, H, c->tile_size, r, world, t, tile_owners_for(c, W, H));
             all.insert(all.end(), t.begin(), t.end());
             c->peer_off[r + 1] = uint32_t(all.size());
         }

@@ -166,3 +166,88 @@ def exchange_baked_slices(factors, n_param, n_subdiv, rank, world):
         if count:
             dist.broadcast(factors[first * n_subdiv:(first + count) * n_subdiv], src=r)
     return factors
+
+
+class FramesInFlight:
+    """Two frames in flight: successive frames are rendered alternately by two contexts on two CUDA streams that share ONE scene, so
+    the packet kernels of frame i + 1 (k_rtao_primary, k_tube_first) fill the SMs that the tail of frame i's persistent AO ray stream
+    leaves idle, and frame i's k_rtao_reduce / k_tubes run beside the start of frame i + 1's stream.  Every frame is the same complete
+    frame as with one context; only valid while frames do not depend on each other (no temporal accumulation: num_accumulated_frames
+    = ambient_occlusion_iterations = 1, as in a benchmark replay or an animation), because each context keeps its own running means.
+
+    contexts: two Context objects created on the two `streams` (torch.cuda.Stream) with identical settings; render(ctx, slot) enqueues
+    one frame of that context (and, on several GPUs, its frame fence) -- it is called inside `with torch.cuda.stream(streams[slot])`."""
+
+    def __init__(self, contexts, streams, render):
+        assert len(contexts) == 2 and len(streams) == 2
+        self.contexts, self.streams, self.render, self.i = contexts, streams, render, 0
+
+    def step(self):
+        j = self.i & 1
+        self.i += 1
+        with torch.cuda.stream(self.streams[j]):
+            self.render(self.contexts[j], j)
+
+    def fork(self, stream=None):
+        """both render streams wait for everything enqueued on `stream` (default: the current stream) so far"""
+        stream = stream or torch.cuda.current_stream()
+        ev = torch.cuda.Event(); ev.record(stream)
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def join(self, stream=None):
+        """`stream` (default: the current stream) waits for both render streams"""
+        stream = stream or torch.cuda.current_stream()
+        for s in self.streams:
+            ev = torch.cuda.Event(); ev.record(s)
+            stream.wait_event(ev)
+
+
+# ------------------------------------------------------------------------------------------------ cost-balanced tile ownership
+def balance_tiles_contiguous(costs, world, tile_pixels=64 * 64, spp=64, pixel_weight=1.5):
+    """Owner rank per tile (Morton order, uint8): the Morton order is cut into `world` CONTIGUOUS runs of equal cost (prefix sums), so
+    that a rank's tiles form a compact screen region -- its rays then touch about 1 / world of the scene instead of all of it
+    (interleaved tiles make every rank pull the whole visible BVH through its L2 every frame, a cost that does not shrink with N)."""
+    c = np.asarray(costs, np.float64) * float(spp) + float(pixel_weight) * float(tile_pixels)
+    cum = np.cumsum(c)
+    mid = cum - 0.5 * c                               # a tile belongs to the run its cost midpoint falls into
+    owners = np.minimum((mid / (cum[-1] / world)).astype(np.int64), world - 1)
+    return owners.astype(np.uint8)
+
+
+def balance_tiles(costs, world, tile_pixels=64 * 64, spp=64, pixel_weight=1.5):
+    """Owner rank per tile (Morton order, uint8) from the frame's cost map: cost of a tile = its AO rays (hit pixels x spp) + its pixels
+    x `pixel_weight` (what the packet kernels of a pixel cost in AO-ray units: 0.8 ns against 0.53 ns on config 5).  Longest processing
+    time first: tiles in order of decreasing cost, each to the rank with the smallest load so far (ties: the lowest rank; equal costs keep
+    the Morton order) -- the same map on every rank for the same cost map.  With Morton round-robin the ranks' AO-ray counts differ by
+    up to 16 % on config 5 (6.18 M .. 7.19 M of 52 M); balanced they differ by less than one tile."""
+    costs = np.asarray(costs, np.float64) * float(spp) + float(pixel_weight) * float(tile_pixels)
+    order = np.argsort(-costs, kind="stable")
+    load = np.zeros(world, np.float64)
+    owners = np.zeros(costs.size, np.uint8)
+    for i in order:
+        r = int(np.argmin(load))
+        owners[i] = r
+        load[r] += costs[i]
+    return owners
+
+
+def rebalance(ctx, width, height, world, spp, tile=64, pixel_weight=1.5):
+    """Every rank: cost map of the last frame (lv_get_tile_costs, summed over the ranks) -> balance_tiles -> lv_set_tile_owners.
+    Call between two frames; the next frame is rendered with the new ownership (peer-frame assembly follows it by itself)."""
+    costs = torch.from_numpy(ctx.tile_costs(width, height).astype(np.int64))
+    if world > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        costs = costs.to(dev)
+        dist.all_reduce(costs)
+        costs = costs.cpu()
+    owners = balance_tiles(costs.numpy(), world, tile * tile, spp, pixel_weight)
+    ctx.set_tile_owners(width, height, owners)
+    return owners
+
+
+def tile_costs_single_gpu(ctx, scene, cam, tile, frame):
+    """Cost map of the whole frame from ONE context (tools/shard_emul.py): render unsharded once, read the per-tile hit counts."""
+    ctx.set_tile_shard(0, 1, tile)
+    ctx.render_tubes(scene, cam, 0, out=frame, stats=False)
+    return ctx.tile_costs(cam.width, cam.height)

@@ -286,6 +286,52 @@ def test_tile_shards_union_is_the_frame(ectx, oracle):
     assert np.abs(acc - full).max() < 2e-3 and (acc == full).mean() > 0.98
 
 
+def test_balanced_tile_owners_union_is_the_frame(ectx, oracle):
+    """lv_get_tile_costs / lv_set_tile_owners: the cost map of a frame (hit pixels per tile, Morton order) adds up to the frame's hit
+    pixels; with the longest-processing-time ownership built from it (sharding.balance_tiles) the ranks' shards are still disjoint, cover
+    the frame bit for bit (jittered AO rays: the apron makes sharded frames exact) and their AO-ray counts are closer than round-robin's."""
+    from linevis_b200 import sharding
+    data, width = _helix()
+    sc = ectx.create_scene(*data, width)
+    cam = lv.make_camera(96, 64)
+    ectx.set_transfer_function(scenes.standard_transfer_function(opacity=(1.0, 1.0)))
+    ectx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 2, "num_samples_per_frame": 2, "num_accumulated_frames": 1})
+    world, tile = 3, 16
+    try:
+        ectx.set_tile_shard(0, 1, tile)
+        full, fst = ectx.render_tubes(sc, cam)
+        costs = ectx.tile_costs(96, 64)
+        assert costs.size == 24 and 2 * int(costs.sum()) == fst["rays_ao"] > 0
+        owners = sharding.balance_tiles(costs, world, tile * tile, 2)
+        assert owners.shape == (24,) and set(owners.tolist()) == {0, 1, 2}
+
+        def shards(own):
+            acc = np.full_like(full, np.nan)
+            rays = []
+            for r in range(world):
+                ectx.set_tile_shard(r, world, tile)
+                if own is not None:
+                    ectx.set_tile_owners(96, 64, own)
+                    want = {(int(x), int(y)) for (x, y), o in zip(sharding.all_tiles(96, 64, tile), own) if o == r}
+                    assert {tuple(t) for t in ectx.owned_tiles(96, 64).tolist()} == want
+                part = np.full_like(full, np.nan)
+                _, st = ectx.render_tubes(sc, cam, out=part)
+                m = ~np.isnan(part[..., 0])
+                assert not (m & ~np.isnan(acc[..., 0])).any()
+                acc[m] = part[m]
+                rays.append(st["rays_ao"])
+            return acc, rays
+        acc_rr, rays_rr = shards(None)
+        acc_b, rays_b = shards(owners)
+        assert np.array_equal(acc_b.view(np.uint32), full.view(np.uint32)) and np.array_equal(acc_rr.view(np.uint32), full.view(np.uint32))
+        assert max(rays_b) - min(rays_b) <= max(rays_rr) - min(rays_rr)
+        with pytest.raises(lv.LineVisError):
+            ectx.set_tile_owners(96, 64, owners[:-1])
+    finally:
+        ectx.set_tile_shard(0, 1, 64)
+        ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1})
+
+
 @pytest.mark.parametrize("gather", ["raycast", "raster", "raster_contiguous"])
 def test_ppll_tile_shards_union_is_the_frame(ectx, oracle, gather):
     """PPLL with tile sharding, both gather modes: every rank gathers and resolves only its tiles; the union is the unsharded frame bit
@@ -514,7 +560,7 @@ def test_rtao_ray_batches(ectx, oracle, use_distance, wide):
             assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("top,packed", [(0, True), (0, False), (85, True), (341, True)])
+@pytest.mark.parametrize("top,packed", [(0, True), (0, 4), (0, False), (85, True), (341, True)])
 @pytest.mark.parametrize("use_distance", [True, False])
 def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top, packed):
     """b200_ao_wide: the AO ray stream over the 4-wide quantised tree (NodeW4: collapse of the child-pair nodes, 16-bit outward-rounded
@@ -525,13 +571,14 @@ def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top, packed):
         sc, osc = _pair(ectx, oracle, data, width)
         cam = lv.make_camera(56, 36)
         ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
-                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True, "b200_ao_wide_top": top, "b200_ao_packed": packed})
+                               "ambient_occlusion_radius": 0.4, "b200_ao_wide": True, "b200_ao_wide_top": top, "b200_ao_packed": bool(packed),
+                               "b200_ao_tq_bits": 4 if packed == 4 else 0})
         try:
             ao, st = ectx.render_rtao(sc, cam, 0)
             ectx.set_option("b200_ao_wide", False)
             ao2, st2 = ectx.render_rtao(sc, cam, 0)
         finally:
-            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1, "b200_ao_packed": True})
+            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1, "b200_ao_packed": True, "b200_ao_tq_bits": 0})
         ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
         if data[2].shape[0] > 100:   # the wide tree really is another tree: fewer steps per ray than the child-pair nodes

@@ -124,13 +124,13 @@ def test_config3_ao_image_is_kernel_independent(random1m):
     want, wst = ctx.render_rtao(sc, cam, 0)
     assert wst["rays_ao"] == 16 * wst["pixels_hit"] > 0
     for variant in ({"b200_ao_queue": False}, {"b200_ao_qnodes": True}, {"b200_ao_stack": 1}, {"b200_ao_queue": False, "b200_ao_stack": 0},
-                    {"b200_ao_stack": 16, "b200_ao_min_blocks": 9}, {"b200_ao_wide": False}, {"b200_ao_wide": False, "b200_ao_raybuf": False},
+                    {"b200_ao_stack": 16, "b200_ao_min_blocks": 9}, {"b200_ao_packed": False}, {"b200_ao_tq_bits": 4}, {"b200_ao_wide": False}, {"b200_ao_wide": False, "b200_ao_raybuf": False},
                     {"b200_ao_raybuf": False}, {"b200_ao_raybuf": False, "b200_ao_min_blocks": 9}, {"b200_ao_wide_top": 85}, {"b200_ao_refill_below": 32},
                     {"b200_ao_wide": False, "b200_ao_raybuf": False, "b200_ao_queue": False}):
         ctx.set_new_settings(variant)
         got, st = ctx.render_rtao(sc, cam, 0)
         ctx.set_new_settings({"b200_ao_queue": True, "b200_ao_qnodes": False, "b200_ao_stack": 12, "b200_ao_min_blocks": 0, "b200_ao_wide": True,
-                              "b200_ao_raybuf": True, "b200_ao_wide_top": 0, "b200_ao_refill_below": 0})
+                              "b200_ao_raybuf": True, "b200_ao_wide_top": 0, "b200_ao_refill_below": 0, "b200_ao_packed": True, "b200_ao_tq_bits": 0})
         assert st["rays_ao"] == wst["rays_ao"], variant
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), variant
     sc.close(); ctx.close()

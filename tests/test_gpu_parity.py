@@ -134,6 +134,27 @@ def test_rtao_kernel_variants_bit_exact(ctx, oracle, queue, stack, minb, use_dis
     assert st["rays_ao"] == ost["rays_ao"] > 0
 
 
+@pytest.mark.parametrize("packed,tq_bits", [(True, 0), (True, 4), (False, 0)])
+@pytest.mark.parametrize("use_distance", [True, False])
+def test_rtao_packed_stream_bit_exact(ctx, oracle, use_distance, packed, tq_bits):
+    """k_rtao_rays_w (b200_ao_packed, the default stream on the 4-wide tree): packed fp32x2 box tests, the ray in shared memory, one-word
+    stack entries whose entry distance sits in the 7 (small scenes) or 4 free index bits -- the oracle's AO image bit for bit, like the
+    stream it replaces (packed = False).  The long AO radius makes the stacks deep and the hit-distance culling matter."""
+    for name in ("random", "helix"):
+        data, width = DATASETS[name]()
+        sc, osc = _scene_pair(ctx, oracle, data, width)
+        cam = lv.make_camera(120, 80)
+        ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 8, "ambient_occlusion_distance_based": use_distance,
+                              "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.3, "b200_ao_packed": packed, "b200_ao_tq_bits": tq_bits})
+        try:
+            ao, st = ctx.render_rtao(sc, cam, 0)
+        finally:
+            ctx.set_new_settings({"b200_ao_packed": True, "b200_ao_tq_bits": 0, "ambient_occlusion_radius": 0.1})
+        opts = lvo.default_options(ao_strength=1.0, ao_spp=8, ao_use_distance=int(use_distance), ao_jitter_primary=1, ao_radius=0.3)
+        ref, ost = osc.render_rtao(cam, opts, 0)
+        assert st["rays_ao"] == ost["rays_ao"] > 0 and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("use_distance", [True, False])
 def test_rtao_quantised_nodes_bit_exact(ctx, oracle, use_distance):
     """b200_ao_qnodes (experimental, off by default): 32-byte nodes with 16-bit outward-rounded child boxes -- same AO image."""
