@@ -437,9 +437,13 @@ class Rgba8Pipeline:
                 p.close()
 
 
-def parallelism_note(world, peer):
+def parallelism_note(world, peer, shard="tiles"):
     if world == 1:
         return "single GPU"
+    if shard == "samples":
+        return ("pixels tile-sharded x%d (%dx%d tiles, Morton round-robin), AO rays sharded by SAMPLE batch (every rank: spp / %d samples of every hit "
+                "pixel); per frame: all-gather of the hit lists, all-to-all of the per-sample results, " % (world, TILE, TILE, world) +
+                ("peer-store frame assembly + 1-element fence" if peer else "all_gather frame assembly"))
     return "tile-sharded x%d (%dx%d tiles, Morton round-robin); " % (world, TILE, TILE) + (
         "frame assembled on rank 0 by NVLink peer stores from the frame kernels, 1-element all_reduce as fence" if peer
         else "1 NCCL all_gather/frame + unpack on rank 0")
@@ -655,13 +659,25 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
     fg = FrameGather(W, H, TILE, rank, world, dev, ctx=ctx) if world > 1 else None     # also the e2e leg's device-side collective
     pf = PeerFrame(ctx, W, H, rank, world, dev) if peer else None
 
+    # --shard samples (N > 1): the AO rays are split by SAMPLE instead of by tile (lv_sao_*, sharding.SampleShards): every rank traces
+    # spp / N samples of every hit pixel of the frame; two more collectives per frame (hit lists, per-sample results)
+    ss = None
+    if world > 1 and args.shard == "samples":
+        from linevis_b200.sharding import SampleShards
+        ss = SampleShards(ctx, rank, world, wl["ao_spp"], dev)
+
+    def render_frame(out, stats=False):
+        if ss is not None:
+            return ss.render(scene, cam, 0, out, stats=stats)[1]
+        return ctx.render_tubes(scene, cam, 0, out=out, stats=stats)[1]
+
     def step(stats=False):
         if pf is not None:
             # every rank's frame kernels store their tiles straight into rank 0's frame (NVLink peer stores); the fence is the frame's only collective
-            st = ctx.render_tubes(scene, cam, 0, out=pf.ptr, stats=stats)[1]
+            st = render_frame(pf.ptr, stats)
             pf.fence()
             return st
-        st = ctx.render_tubes(scene, cam, 0, out=frame, stats=stats)[1]
+        st = render_frame(frame, stats)
         if fg is not None:
             fg.gather(frame, assemble_on=(0,))   # the single collective of the frame: every rank's packed tile block -> all ranks; rank 0 assembles
         return st
@@ -714,7 +730,7 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
     # ---- dominant kernel (the AO ray stream) live timing for the roofline: CUDA events around that kernel inside the library
     kt = []
     for _ in range(max(3, args.steps)):
-        kt.append(ctx.render_tubes(scene, cam, 0, out=frame, stats=True)[1]["ms_rtao_rays"])
+        kt.append(render_frame(frame, True)["ms_rtao_rays"])
     k_ms = float(np.mean(kt))
     my_ao_bytes = 64 * st["ao_traversal_steps"] + 32 * st["ao_intersections"] + 4 * st["rays_ao"]
     achieved = my_ao_bytes / (k_ms * 1e-3) / 1e9
@@ -783,7 +799,7 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
                        **({"frames_in_flight": 2, "ms_one_frame_in_flight": ms_single, "frames_in_flight_equal_to_single": fif_equal} if fif is not None else {}),
                        "scene_bytes": int(scene_bytes), "l2": "inputs larger than L2 (segments + BVH = %.2f GB)" % (scene_bytes / 1e9)
                        if scene_bytes > 200e6 else "scene fits L2; the 126 MB L2 is not flushed between frames",
-                       "parallelism": parallelism_note(world, peer),
+                       "parallelism": parallelism_note(world, peer, args.shard),
                        "rays_per_step": tot_rays, "rays_primary": tot_rp, "rays_ao": tot_ra,
                        "T_per_ao_ray": ao_T / max(tot_ra, 1), "I_per_ao_ray": ao_I / max(tot_ra, 1),
                        "primary_packet_steps_per_ray": (tot_T - ao_T) / max(tot_rp, 1), "primary_packet_records_per_ray": (tot_I - ao_I) / max(tot_rp, 1),
@@ -883,6 +899,8 @@ def main():
                     help="tube + RTAO headline: 2 = frames alternate between two contexts / streams sharing the scene (measured: no gain, "
                          "27.86 vs 27.83 ms on config 5 -- blocks of the next frame's packet kernels do not get onto SMs that still hold blocks of the "
                          "persistent AO stream); 1 = one context (default)")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
+                    help="N > 1, tube + RTAO: tiles = image tiles only (default); samples = tiles for the pixels, AO rays split by sample batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu pass (roofline.traffic then comes from the committed capture, labelled stale)")
     ap.add_argument("--assemble", default="peer", choices=["peer", "allgather"],

@@ -264,6 +264,24 @@ int lv_ao_read(lv_scene* scene, float* factors, size_t factors_cap, float* blend
 int lv_render_tubes(lv_ctx* ctx, const lv_scene* scene, const lv_camera* cam, uint32_t frame_number,
                     float* rgba_out, lv_stats* stats);
 
+/* AO-sample-batch shards (new; SURVEY 8e, the second shard axis): lv_render_tubes in three stages, so that N ranks split the SAMPLES of
+ * the screen-space RTAO pass -- the samples of a pixel are independent, their seeds are tea(pixel, frameNumber * spp + sample)
+ * (Data/Shaders/AO/RTAO/VulkanRayTracedAmbientOcclusion.glsl:289-292).  With lv_set_tile_shard(rank, world) in force:
+ *   lv_sao_primary  the RTAO pass's camera rays on the rank's own tiles (.glsl:178-276); returns the device address and length of the
+ *                   rank's hit list (48-byte start frames: position + ray origin offset, normal + pixel, tangent);
+ *   -- the caller concatenates the ranks' lists in rank order (all-gather), linevis_b200/sharding.py::SampleShards --
+ *   lv_sao_trace    AO rays [sample_first, sample_first + sample_count) of EVERY record of `hits_device` (.glsl:158-175,289-305) into
+ *                   occ_device[record * sample_count + k]: the numerator of traceAoRay's t / radius.  sample_count divides spp;
+ *   -- the caller returns each record's values to its owner (all-to-all): occ_parts[part][own record][k] --
+ *   lv_sao_finish   sums every own record's spp values IN SAMPLE ORDER (.glsl:301-317: bit for bit the one-GPU sum), then the tube pass
+ *                   of lv_render_tubes on the rank's tiles into rgba_out (peer frame, device or host).
+ * Needs the default AO ray stream; frames are identical to lv_render_tubes' whatever N is. */
+int lv_sao_primary(lv_ctx* ctx, const lv_scene* scene, const lv_camera* cam, uint32_t frame_number, const void** hits_device, uint32_t* n_hits);
+int lv_sao_trace(lv_ctx* ctx, const lv_scene* scene, const lv_camera* cam, uint32_t frame_number, const void* hits_device, uint32_t n_hits,
+                 uint32_t sample_first, uint32_t sample_count, float* occ_device);
+int lv_sao_finish(lv_ctx* ctx, const lv_scene* scene, const lv_camera* cam, uint32_t frame_number, const float* occ_parts, uint32_t n_parts,
+                  float* rgba_out, lv_stats* stats);
+
 /* Replaces PerPixelLinkedListLineRenderer::render() (src/Renderers/OIT/PerPixelLinkedListLineRenderer.cpp:399-427):
  * clear() -> gather() -> resolve().  max_frags == MAX_NUM_FRAGS (expectedMaxDepthComplexity),
  * linked_list_size == fragmentBufferSize (0 = expectedAvgDepthComplexity * paddedW * paddedH like

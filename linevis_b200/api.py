@@ -185,6 +185,21 @@ class Context:
         self._check(self.lib.lv_render_tubes(self.h, scene.h, ctypes.byref(cam), frame_number, _ptr(out), ctypes.byref(st) if stats else None))
         return out, st.as_dict()
 
+    # AO-sample-batch shards: lv_render_tubes in three stages (include/linevis_b200.h); sharding.SampleShards drives them
+    def sao_primary(self, scene, cam, frame_number=0):
+        """-> (device address of this rank's hit list, number of 48-byte records)"""
+        ptr, n = ctypes.c_void_p(), ctypes.c_uint32()
+        self._check(self.lib.lv_sao_primary(self.h, scene.h, ctypes.byref(cam), frame_number, ctypes.byref(ptr), ctypes.byref(n)))
+        return int(ptr.value or 0), int(n.value)
+
+    def sao_trace(self, scene, cam, frame_number, hits, n_hits, sample_first, sample_count, occ):
+        self._check(self.lib.lv_sao_trace(self.h, scene.h, ctypes.byref(cam), frame_number, _ptr(hits), n_hits, sample_first, sample_count, _ptr(occ)))
+
+    def sao_finish(self, scene, cam, frame_number, occ_parts, n_parts, out, stats=True):
+        st = LvStats()
+        self._check(self.lib.lv_sao_finish(self.h, scene.h, ctypes.byref(cam), frame_number, _ptr(occ_parts), n_parts, _ptr(out), ctypes.byref(st) if stats else None))
+        return out, st.as_dict()
+
     def render_ppll(self, scene, cam, max_frags=100, sort_mode="priority_queue", linked_list_size=0, out=None, stats=True):
         if out is None:
             out = np.zeros((cam.height, cam.width, 4), np.float32)

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "lv_ctx_create", "lv_ctx_destroy", "lv_last_error", "lv_last_global_error", "lv_abi_version", "lv_set_option",
     "lv_get_option", "lv_set_transfer_function", "lv_set_tile_shard", "lv_get_tile_costs", "lv_set_tile_owners", "lv_get_owned_tiles", "lv_pack_owned_tiles",
     "lv_unpack_tiles", "lv_scene_create", "lv_scene_create_device", "lv_scene_destroy", "lv_scene_info",
-    "lv_scene_copy_bvh", "lv_render_tubes", "lv_render_ppll", "lv_trace_primary", "lv_render_rtao", "lv_ppll_clear",
+    "lv_scene_copy_bvh", "lv_render_tubes", "lv_sao_primary", "lv_sao_trace", "lv_sao_finish", "lv_render_ppll", "lv_trace_primary", "lv_render_rtao", "lv_ppll_clear",
     "lv_ppll_gather", "lv_ppll_resolve", "lv_ppll_read", "lv_synchronize",
     "lv_scene_set_lines", "lv_ao_parametrize", "lv_ao_bake", "lv_ao_bake_reset", "lv_ao_read",
     "lv_frame_alloc", "lv_frame_free", "lv_ipc_export", "lv_ipc_open", "lv_ipc_close", "lv_tube_mesh", "lv_frame_to_rgba8", "lv_ao_set_vertex_range", "lv_ao_factors",
@@ -96,6 +96,9 @@ def load_library(path=None):
     L.lv_scene_info.argtypes = [vp, P(u64), P(u64), P(f32), vp]
     L.lv_scene_copy_bvh.argtypes = [vp, vp, ctypes.c_size_t]
     L.lv_render_tubes.argtypes = [vp, vp, P(LvCamera), u32, vp, P(LvStats)]
+    L.lv_sao_primary.argtypes = [vp, vp, P(LvCamera), u32, P(vp), P(u32)]
+    L.lv_sao_trace.argtypes = [vp, vp, P(LvCamera), u32, vp, u32, u32, u32, vp]
+    L.lv_sao_finish.argtypes = [vp, vp, P(LvCamera), u32, vp, u32, vp, P(LvStats)]
     L.lv_render_ppll.argtypes = [vp, vp, P(LvCamera), u32, u32, u64, vp, P(LvStats)]
     L.lv_trace_primary.argtypes = [vp, vp, P(LvCamera), vp, P(LvStats)]
     L.lv_render_rtao.argtypes = [vp, vp, P(LvCamera), u32, vp, P(LvStats)]

@@ -103,7 +103,7 @@ struct lv_ctx {
     uint32_t rank = 0, world = 1, tile_size = 64;
     std::vector<uint2> tiles_host; DevBuf<uint2> tiles_dev; uint32_t tiles_w = 0, tiles_h = 0;
     std::vector<unsigned char> tile_owner; uint32_t owner_w = 0, owner_h = 0;   // lv_set_tile_owners: explicit owner per tile (Morton order) of an owner_w x owner_h frame
-    DevBuf<unsigned int> tile_hist;
+    DevBuf<unsigned int> tile_hist, small2;   // small2: record count + work counter of an lv_sao_trace launch
     DevBuf<unsigned char> owned_map; uint32_t tiles_x = 0;   // world > 1: 1 byte per tile of the frame, 1 = owned (object-order PPLL gather)
     DevBuf<uint2> tiles_tmp; std::vector<uint32_t> peer_off; uint32_t peer_w = 0, peer_h = 0, peer_world = 0, peer_tile = 0;
     // frame buffers
@@ -266,6 +266,7 @@ int make_params(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t fr
     P.near_dist = cam->near_dist; P.far_dist = cam->far_dist;
     P.ao_strength = o.ao_strength; P.ao_gamma = o.ao_gamma; P.ao_radius = o.ao_radius;
     P.ao_spp = o.ao_spp; P.ao_use_distance = o.ao_use_distance; P.ao_jitter = o.ao_jitter_primary;
+    P.ao_spp_local = o.ao_spp; P.ao_sample_first = 0;
     P.subdiv_corr = float(std::cos(3.14159265358979323846 / double(o.tube_num_subdivisions)));
     P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? (o.ao_packed && o.ao_wide ? 28u : 30u) : 24u));
     P.ao_leaf_vote = int(o.ao_leaf_vote);
@@ -561,14 +562,20 @@ int ensure_tube_mesh(lv_ctx* c, lv_scene* sc) {
 // persistent AO ray-stream kernel over the records in ctx->ao_hits (count in small[0], work counter in small[2..3]) into ctx->occ;
 // timed with ev[4] / ev[5].  BAKE selects the prebaker's random stream / ray origin (lv_bake.cuh).
 template <bool BAKE>
-int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves, unsigned long long max_rays, bool tri = false) {
+int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_record_leaves, unsigned long long max_rays, bool tri = false,
+                   const AoHit* ext_hits = nullptr, unsigned int* ext_small = nullptr, float* ext_occ = nullptr) {
+    const AoHit* hits = ext_hits ? ext_hits : c->ao_hits.p;
+    unsigned int* small = ext_small ? ext_small : c->small.p;      // [0] record count, [2..3] the stream's work counter
+    float* occ = ext_occ ? ext_occ : c->occ.p;
+    if (P.ao_spp_local != P.ao_spp && !(c->opt.ao_queue && one_record_leaves && c->opt.ao_raybuf && c->opt.ao_packed && c->opt.ao_stack == 12 &&
+                                        c->opt.ao_min_blocks == 0 && !c->opt.ao_qnodes && c->opt.ao_wide && S.wnodes && !S.w_top && !tri && max_rays < 0xFF000000ull))
+        return fail(c, LV_ERR_STATE, "AO-sample-batch shards need the default AO ray stream (k_rtao_rays_w)");
     auto launch = [&](auto kern) -> int {
         int per_sm = 0;
         LV_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
         const uint32_t pgrid = uint32_t(std::max(1, per_sm) * c->num_sms);
         LV_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-        kern<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, c->occ.p, c->ao_hits.p, c->small.p,
-                                                     reinterpret_cast<unsigned long long*>(c->small.p + 2), c->counters.p);
+        kern<<<pgrid, kBlockThreads, 0, c->stream>>>(P, S, occ, hits, small, reinterpret_cast<unsigned long long*>(small + 2), c->counters.p);
         LV_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
         return LV_OK;
     };
@@ -610,7 +617,9 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
 }
 
 // ---- RTAO pass (S5) into ctx->ao --------------------------------------------------------------
-int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number) {
+// stages: kRtaoAll = the whole pass; kRtaoPrimaryOnly = up to the hit list (AO-sample-batch shards trace and reduce separately)
+enum { kRtaoAll = 0, kRtaoPrimaryOnly = 1 };
+int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number, int stage = kRtaoAll) {
     const size_t npx = size_t(P.W) * P.H;
     c->rtao_rays_timed = false;
     if (c->ao_w != P.W || c->ao_h != P.H || !c->ao.p) {
@@ -655,7 +664,7 @@ int run_rtao(lv_ctx* c, const lv_scene* sc, FrameParams P, uint32_t frame_number
             k_rtao_primary<0><<<P.n_tiles * ((ring + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, c->stream>>>(
                 P, S, c->ao.p, c->ao_hits.p, c->small.p, c->counters.p, c->apron_marks.p, stamp);
     }
-    {
+    if (stage == kRtaoAll) {
         // one float per (hit pixel, sample); worst case every owned pixel (and ring pixel) is hit
         const size_t max_hits = size_t(P.n_tiles) * (size_t(c->tile_size) * c->tile_size + (apron ? ring : 0));
         LV_CUDA(c, c->occ.ensure(max_hits * P.ao_spp));
@@ -778,7 +787,7 @@ int run_bake_iteration(lv_ctx* c, lv_scene* sc) {
     B.first_vertex = uint32_t(first); B.n_vertices = uint32_t(count);
     FrameParams P;
     memset(&P, 0, sizeof(P));
-    P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_use_distance = o.bake_use_distance;
+    P.use_capped = o.use_capped_tubes; P.ao_radius = o.bake_radius; P.ao_spp = o.bake_spp; P.ao_spp_local = o.bake_spp; P.ao_sample_first = 0; P.ao_use_distance = o.bake_use_distance;
     P.ao_refill_below = int(o.ao_refill_below ? o.ao_refill_below : (o.ao_raybuf ? (o.ao_packed && o.ao_wide ? 28u : 30u) : 24u)); P.ao_leaf_vote = int(o.ao_leaf_vote); P.ao_wide_reps = int(o.ao_wide_reps); P.frame_number = sc->bake_done;
     P.ao_tq_lo = (1.0f / P.ao_radius) * (1.0f - 1.0f / 4096.0f); P.ao_tq_hi = (1.0f / P.ao_radius) * (1.0f + 1.0f / 4096.0f);
     k_bake_setup<<<c->num_sms * 8, 256, 0, c->stream>>>(B, c->ao_hits.p);
@@ -868,7 +877,7 @@ int lv_ctx_destroy(lv_ctx* c) {
     if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
     c->first_hits.release();
     for (int k = 0; k < 2; k++) { if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
-    c->tf.release(); c->tile_hist.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
+    c->tf.release(); c->tile_hist.release(); c->small2.release(); c->tiles_dev.release(); c->owned_map.release(); c->stage.release(); c->list_offs.release(); c->fill_cursor.release(); c->scan_tmp.release(); c->tiles_tmp.release(); c->image.release(); c->ao.release(); c->apron_marks.release(); c->occ.release(); c->depth_mm.release(); c->hits.release(); c->ao_hits.release();
     c->counters.release(); c->small.release(); c->heads.release(); c->counts.release(); c->bin_order.release(); c->bin_hist.release(); c->nodes.release(); c->frag_counter.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -1572,6 +1581,38 @@ int lv_render_rtao(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t
     return LV_OK;
 }
 
+// the tube pass proper (k_tubes into the sink) and the frame's statistics: the tail of lv_render_tubes / lv_sao_finish
+int tube_pass(lv_ctx* c, const lv_scene* sc, FrameParams& P, FrameSink& sink, void* rgba_out, const uint2* first, bool use_ao, lv_stats* stats) {
+    int rc;
+    float4* img = sink.image;
+    if ((rc = run_depth_range(c, sc, P))) return rc;
+    const bool tri_tubes = c->opt.tube_triangles && sc->n_seg;
+    if (tri_tubes) {
+        if (P.use_static_ao) return fail(c, LV_ERR_INVALID_ARGUMENT, "geometry_mode = 'Triangle Mesh' does not support ambient_occlusion_mode = 'RTAO (Prebaker)'");
+        if ((rc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)))) return rc;
+    }
+    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (P.n_tiles && tri_tubes) k_tubes<false, 1><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, nullptr);
+    else if (P.n_tiles) {
+        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
+        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
+    }
+    LV_CUDA(c, cudaGetLastError());
+    LV_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = close_sink(c, sink, rgba_out, P.W, P.H))) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        Counters h;
+        if ((rc = read_counters(c, h))) return rc;
+        fill_stats(stats, h);
+        stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
+        if (use_ao && c->rtao_rays_timed) stats->ms_rtao_rays = elapsed(c->ev[4], c->ev[5]);
+        stats->ms_trace = elapsed(c->ev[1], c->ev[2]);
+        stats->ms_total = elapsed(c->ev[0], c->ev[2]);
+    }
+    return LV_OK;
+}
+
 int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, float* rgba_out, lv_stats* stats) {
     if (!c || !sc || !rgba_out) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_render_tubes: NULL argument");
     if (!c->tf.p) return fail(c, LV_ERR_STATE, "lv_render_tubes: no transfer function set (lv_set_transfer_function)");
@@ -1610,32 +1651,73 @@ int lv_render_tubes(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_
         }
         P.use_ao = 1; P.ao_tex = c->ao.p;
     }
-    if ((rc = run_depth_range(c, sc, P))) return rc;
-    const bool tri_tubes = c->opt.tube_triangles && sc->n_seg;
-    if (tri_tubes) {
-        if (P.use_static_ao) return fail(c, LV_ERR_INVALID_ARGUMENT, "geometry_mode = 'Triangle Mesh' does not support ambient_occlusion_mode = 'RTAO (Prebaker)'");
-        if ((rc = ensure_tube_mesh(c, const_cast<lv_scene*>(sc)))) return rc;
-    }
-    LV_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    if (P.n_tiles && tri_tubes) k_tubes<false, 1><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, nullptr);
-    else if (P.n_tiles) {
-        if (P.use_static_ao) k_tubes<true><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
-        else k_tubes<false><<<pixel_grid(c, P), kBlockThreads, 0, c->stream>>>(P, sc->dev(), img, c->counters.p, sink.out8, first);
-    }
-    LV_CUDA(c, cudaGetLastError());
-    LV_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    if ((rc = close_sink(c, sink, rgba_out, P.W, P.H))) return rc;
-    if (stats) {
-        memset(stats, 0, sizeof(*stats));
-        Counters h;
-        if ((rc = read_counters(c, h))) return rc;
-        fill_stats(stats, h);
-        stats->ms_rtao = elapsed(c->ev[0], c->ev[1]);
-        if (use_ao && c->rtao_rays_timed) stats->ms_rtao_rays = elapsed(c->ev[4], c->ev[5]);
-        stats->ms_trace = elapsed(c->ev[1], c->ev[2]);
-        stats->ms_total = elapsed(c->ev[0], c->ev[2]);
-    }
+    return tube_pass(c, sc, P, sink, rgba_out, first, use_ao, stats);
+}
+
+// ---- AO-sample-batch shards (north_star's second shard axis) ----------------------------------------------------------
+// The RTAO pass of a frame in three stages, so that N ranks can split its SAMPLES instead of (only) its pixels: every rank finds the
+// hit pixels of its own tiles (stage 1), the hit lists are all-gathered by the caller (torch.distributed / NCCL, sharding.py::
+// SampleShards), every rank traces samples [r spp / N, (r + 1) spp / N) of EVERY hit pixel of the frame (stage 2: perfectly balanced by
+// construction -- the seeds are sample-indexed, VulkanRayTracedAmbientOcclusion.glsl:289-292), the per-sample results return to the
+// pixel's owner (all-to-all), which sums them in sample order -- bit for bit the sum of a one-GPU frame -- and renders its tiles (stage 3).
+int lv_sao_primary(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, const void** hits_device, uint32_t* n_hits) {
+    if (!c || !sc || !hits_device || !n_hits) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_sao_primary: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, frame_number, P);
+    if (rc) return rc;
+    if (!(c->opt.ao_strength > 0.0f) || c->opt.ao_prebaker) return fail(c, LV_ERR_STATE, "lv_sao_primary: screen-space RTAO is off");
+    if ((rc = reset_counters(c))) return rc;
+    LV_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = run_rtao(c, sc, P, frame_number, kRtaoPrimaryOnly))) return rc;
+    unsigned int n = 0;
+    LV_CUDA(c, cudaMemcpyAsync(&n, c->small.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    LV_CUDA(c, cudaStreamSynchronize(c->stream));
+    *hits_device = c->ao_hits.p; *n_hits = n;
     return LV_OK;
+}
+
+int lv_sao_trace(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, const void* hits_device, uint32_t n_hits,
+                 uint32_t sample_first, uint32_t sample_count, float* occ_device) {
+    if (!c || !sc || !occ_device || (!hits_device && n_hits)) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_sao_trace: NULL argument");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, frame_number, P);
+    if (rc) return rc;
+    if (sample_count == 0 || sample_first + sample_count > P.ao_spp || P.ao_spp % sample_count || sample_first % sample_count)
+        return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_sao_trace: the sample range must be one of spp / count equal batches");
+    P.frame_number = frame_number; P.ao_spp_local = sample_count; P.ao_sample_first = sample_first;
+    if (c->opt.ao_wide) { if ((rc = ensure_wnodes(c, const_cast<lv_scene*>(sc)))) return rc; const_cast<lv_scene*>(sc)->set_w_top(c->opt.ao_wide_top); }
+    LV_CUDA(c, c->small2.ensure(4));
+    const unsigned int init[4] = {n_hits, 0u, 0u, 0u};
+    LV_CUDA(c, cudaMemcpyAsync(c->small2.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    if (n_hits == 0) return LV_OK;
+    if ((rc = launch_ao_rays<false>(c, P, sc->dev(), sc->leaf_size == 1, (unsigned long long)n_hits * sample_count, false,
+                                    static_cast<const AoHit*>(hits_device), c->small2.p, occ_device))) return rc;
+    c->rtao_rays_timed = true;
+    LV_CUDA(c, cudaGetLastError());
+    return LV_OK;
+}
+
+int lv_sao_finish(lv_ctx* c, const lv_scene* sc, const lv_camera* cam, uint32_t frame_number, const float* occ_parts, uint32_t n_parts,
+                  float* rgba_out, lv_stats* stats) {
+    if (!c || !sc || !rgba_out || !occ_parts) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_sao_finish: NULL argument");
+    if (!c->tf.p) return fail(c, LV_ERR_STATE, "lv_sao_finish: no transfer function set (lv_set_transfer_function)");
+    LV_CUDA(c, cudaSetDevice(c->device));
+    FrameParams P;
+    int rc = make_params(c, sc, cam, frame_number, P);
+    if (rc) return rc;
+    if (n_parts == 0 || P.ao_spp % n_parts) return fail(c, LV_ERR_INVALID_ARGUMENT, "lv_sao_finish: spp must be a multiple of the number of parts");
+    if (!c->ao.p || c->ao_w != P.W || c->ao_h != P.H || !c->small.p) return fail(c, LV_ERR_STATE, "lv_sao_finish: lv_sao_primary has not run for this frame size");
+    FrameSink sink;
+    if ((rc = open_sink(c, rgba_out, P.W, P.H, sink))) return rc;
+    if ((rc = prepare_static_ao(c, sc, P))) return rc;
+    P.frame_number = frame_number; P.ao_spp_local = P.ao_spp / n_parts;
+    k_rtao_reduce<<<c->num_sms * 4, 256, 0, c->stream>>>(P, occ_parts, c->ao_hits.p, c->small.p, c->ao.p);
+    LV_CUDA(c, cudaGetLastError());
+    P.ao_spp_local = P.ao_spp;
+    P.use_ao = 1; P.ao_tex = c->ao.p;
+    return tube_pass(c, sc, P, sink, rgba_out, nullptr, true, stats);
 }
 
 int lv_ppll_clear(lv_ctx* c, const lv_camera* cam, uint64_t linked_list_size) {

@@ -837,14 +837,17 @@ namespace lv {
 __global__ void k_rtao_reduce(const __grid_constant__ FrameParams P, const float* occ, const AoHit* hit_list,
                               const unsigned int* hit_count, float* ao) {
     const uint32_t n_hit = *hit_count;
-    const uint32_t spp = P.ao_spp;
+    const uint32_t spp = P.ao_spp, spl = P.ao_spp_local;
+    // AO-sample-batch shards (spl < spp): `occ` holds spp / spl parts, part j = samples [j spl, (j + 1) spl) of every record, traced by rank j
+    const size_t part_stride = size_t(n_hit) * spl;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_hit; slot += gridDim.x * blockDim.x) {
         const uint32_t pixel = __float_as_uint(hit_list[slot].nrm_px.w);
-        const float* q = occ + size_t(slot) * spp;
+        const float* q = occ + size_t(slot) * spl;
         // the stream stores hit distances (radius for a miss, 0 for an any-hit): t / radius (:170) is taken here, coalesced and by all
-        // lanes, instead of by the few lanes of a warp whose ray has just finished
+        // lanes, instead of by the few lanes of a warp whose ray has just finished.  Summed in sample order, whoever traced the sample.
         float sum = 0.0f;
-        for (uint32_t i = 0; i < spp; i++) sum += q[i] / P.ao_radius;
+        for (uint32_t j = 0; j * spl < spp; j++)
+            for (uint32_t i = 0; i < spl; i++) sum += q[j * part_stride + i] / P.ao_radius;
         float v = sum / float(spp);
         float* p = ao + pixel;
         if (P.frame_number != 0) v = mixf_(*p, v, 1.0f / float(P.frame_number + 1));

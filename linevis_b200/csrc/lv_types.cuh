@@ -112,6 +112,7 @@ struct FrameParams {
     const float* depth_min_max;    // device: {minDepth, maxDepth} of this frame (k_depth_range)
     float near_dist, far_dist;
     uint32_t ao_spp;
+    uint32_t ao_spp_local, ao_sample_first;   // AO-sample-batch shards: this launch traces samples [first, first + local) of every record (default: all)
     int ao_use_distance, ao_jitter;
     float subdiv_corr;        // cos(pi / tubeNumSubdivisions)
     int ao_refill_below;      // k_rtao_rays refills a warp once fewer lanes than this are live

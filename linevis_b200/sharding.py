@@ -251,3 +251,67 @@ def tile_costs_single_gpu(ctx, scene, cam, tile, frame):
     ctx.set_tile_shard(0, 1, tile)
     ctx.render_tubes(scene, cam, 0, out=frame, stats=False)
     return ctx.tile_costs(cam.width, cam.height)
+
+
+# ------------------------------------------------------------------------------------------------ AO-sample-batch shards
+def _device_floats(ptr, shape, device):
+    """float32 tensor view of library-owned device memory (host memory when the library is the CPU emulation of the test-suite)"""
+    if torch.device(device).type == "cuda":
+        return torch.as_tensor(_RawCudaArray(ptr, shape), device=device)
+    import ctypes
+    n = int(np.prod(shape))
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))).view(*shape)
+
+
+class SampleShards:
+    """The second shard axis of the tube + RTAO frame (lv_sao_primary / lv_sao_trace / lv_sao_finish): pixels stay tile-sharded, the AO
+    rays are split by SAMPLE -- rank r traces samples [r spp / N, (r + 1) spp / N) of every hit pixel of the frame, so every rank traces
+    exactly the same number of rays through the same pixels (no tile imbalance).  Per frame: an all-gather of the ranks' hit lists
+    (48 B per hit pixel) in front of the ray stream, an all-to-all of the per-sample results (4 B per ray) behind it; the owner sums its
+    pixels' samples in sample order, so the frame is bit-identical to the tile-sharded and to the one-GPU frame.
+    Needs spp % world == 0."""
+
+    def __init__(self, ctx, rank, world, spp, device):
+        if spp % world:
+            raise ValueError("ambient_occlusion_samples_per_frame must be a multiple of the world size")
+        self.ctx, self.rank, self.world, self.spp, self.spl, self.device = ctx, rank, world, spp, spp // world, device
+        self._bufs = {}
+
+    def _buf(self, name, n):
+        b = self._bufs.get(name)
+        if b is None or b.numel() < n:
+            b = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)
+            self._bufs[name] = b
+        return b[:n]
+
+    def render(self, scene, cam, frame_number, out, stats=False):
+        ctx, W = self.ctx, self.world
+        ptr, n = ctx.sao_primary(scene, cam, frame_number)
+        mine = _device_floats(ptr, (max(n, 1), 12), self.device)[:n]
+        if W > 1:
+            cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
+            cnts = torch.empty(W, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(cnts, cnt)
+            counts = [int(c) for c in cnts.tolist()]
+            total = sum(counts)
+            # one padded all-gather (equal sizes: a single collective on NCCL, and what gloo supports), then the lists are packed in rank order
+            cap = max(max(counts), 1)
+            send = self._buf("send", cap * 12).view(cap, 12)
+            send[:n] = mine
+            padded = self._buf("padded", W * cap * 12).view(W, cap, 12)
+            dist.all_gather_into_tensor(padded.view(-1), send.view(-1))
+            hits = self._buf("hits", total * 12).view(total, 12)
+            o = 0
+            for r, c in enumerate(counts):
+                hits[o:o + c] = padded[r, :c]
+                o += c
+        else:
+            counts, total, hits = [n], n, mine
+        occ = self._buf("occ", total * self.spl)
+        ctx.sao_trace(scene, cam, frame_number, hits, total, self.rank * self.spl, self.spl, occ)
+        if W > 1:
+            parts = self._buf("parts", W * n * self.spl)
+            dist.all_to_all_single(parts, occ, output_split_sizes=[n * self.spl] * W, input_split_sizes=[c * self.spl for c in counts])
+        else:
+            parts = occ
+        return ctx.sao_finish(scene, cam, frame_number, parts, W, out, stats=stats)

@@ -332,6 +332,124 @@ def test_balanced_tile_owners_union_is_the_frame(ectx, oracle):
         ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1})
 
 
+def _host_floats(addr, n):
+    """numpy view of n floats at a 'device' address of the emulated library (host memory)"""
+    import ctypes
+    return np.ctypeslib.as_array((ctypes.c_float * max(n, 1)).from_address(addr))[:n]
+
+
+@pytest.mark.parametrize("world,jitter", [(1, False), (2, True), (4, False)])
+def test_ao_sample_batch_shards(ectx, oracle, world, jitter):
+    """lv_sao_primary / lv_sao_trace / lv_sao_finish: the ranks' tiles + every rank tracing spp / world samples of ALL hit pixels, with the
+    exchanges done by hand (the emulated 'device' memory is host memory) -- the union of the ranks' frames is the one-context frame bit
+    for bit (the per-sample values are summed in sample order by the pixel's owner), and every rank traces the same number of rays."""
+    data, width = _helix()
+    sc = ectx.create_scene(*data, width)
+    cam = lv.make_camera(96, 64)
+    spp, tile = 8, 16
+    spl = spp // world
+    ectx.set_transfer_function(scenes.standard_transfer_function(opacity=(1.0, 1.0)))
+    ectx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_iterations": 1,
+                           "num_samples_per_frame": 2 if jitter else 1, "num_accumulated_frames": 1})
+    try:
+        full, fst = ectx.render_tubes(sc, cam)
+        # stage 1 on every rank (one context plays the ranks in turn, so the hit lists are copied out)
+        lists = []
+        for r in range(world):
+            ectx.set_tile_shard(r, world, tile)
+            ptr, n = ectx.sao_primary(sc, cam, 0)
+            lists.append(_host_floats(ptr, n * 12).reshape(n, 12).copy())
+        counts = [h.shape[0] for h in lists]
+        hits = np.ascontiguousarray(np.concatenate(lists, axis=0))
+        # stage 2: rank r traces samples [r spl, (r + 1) spl) of all records
+        occs = []
+        for r in range(world):
+            ectx.set_tile_shard(r, world, tile)
+            occ = np.zeros(hits.shape[0] * spl, np.float32)
+            ectx.sao_trace(sc, cam, 0, hits, hits.shape[0], r * spl, spl, occ)
+            ectx.synchronize()
+            occs.append(occ.reshape(hits.shape[0], spl))
+        # stage 3: the owner gets its records' values from every rank (the all-to-all) and finishes its tiles.  The context's own hit list
+        # must be the owner's again, so stage 1 is repeated for it (deterministic up to the order of the list: match rows by pixel)
+        acc = np.full_like(full, np.nan)
+        off = np.concatenate([[0], np.cumsum(counts)])
+        for r in range(world):
+            ectx.set_tile_shard(r, world, tile)
+            ptr, n = ectx.sao_primary(sc, cam, 0)
+            assert n == counts[r]
+            now = _host_floats(ptr, n * 12).reshape(n, 12)
+            pix_now, pix_then = now[:, 7].view(np.uint32), lists[r][:, 7].view(np.uint32)
+            order = np.argsort(pix_then, kind="stable")[np.searchsorted(np.sort(pix_then), pix_now)]   # row of `lists[r]` holding now[i]'s pixel
+            assert np.array_equal(pix_then[order], pix_now)
+            parts = np.ascontiguousarray(np.stack([occs[j][off[r]:off[r + 1]][order] for j in range(world)], axis=0))
+            part = np.full_like(full, np.nan)
+            ectx.sao_finish(sc, cam, 0, parts, world, part)
+            m = ~np.isnan(part[..., 0])
+            assert not (m & ~np.isnan(acc[..., 0])).any()
+            acc[m] = part[m]
+        assert not np.isnan(acc).any()
+        if jitter or world == 1:   # with jittered tube rays the apron makes sharded frames exact; without, border texels differ by ~1e-4 (DESIGN 5)
+            assert np.array_equal(acc.view(np.uint32), full.view(np.uint32))
+        else:
+            assert np.abs(acc - full).max() < 2e-3 and (acc == full).mean() > 0.98
+    finally:
+        ectx.set_tile_shard(0, 1, 64)
+        ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1, "ambient_occlusion_samples_per_frame": 4})
+
+
+def _sample_shard_worker(rank, world, port, lib_path, q):
+    import torch
+    import torch.distributed as dist
+    from linevis_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = lv.Context(0, lib_path=lib_path)
+        data, width = _helix()
+        sc = c.create_scene(*data, width)
+        cam = lv.make_camera(96, 64)
+        c.set_transfer_function(scenes.standard_transfer_function(opacity=(1.0, 1.0)))
+        c.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 8, "ambient_occlusion_iterations": 1,
+                            "num_samples_per_frame": 2, "num_accumulated_frames": 1})
+        full = None
+        if rank == 0:
+            full, _ = c.render_tubes(sc, cam)
+        c.set_tile_shard(rank, world, 16)
+        ss = sharding.SampleShards(c, rank, world, 8, "cpu")
+        part = np.full((64, 96, 4), np.nan, np.float32)
+        _, st = ss.render(sc, cam, 0, part, stats=True)
+        parts = [None] * world
+        dist.all_gather_object(parts, (part, st["rays_ao"]))
+        if rank == 0:
+            acc = np.full_like(full, np.nan)
+            for p, _ in parts:
+                m = ~np.isnan(p[..., 0])
+                assert not (m & ~np.isnan(acc[..., 0])).any()
+                acc[m] = p[m]
+            q.put((bool(np.array_equal(acc.view(np.uint32), full.view(np.uint32))), [r for _, r in parts]))
+        sc.close(); c.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ao_sample_batch_shards_over_gloo(ectx):
+    """sharding.SampleShards with two processes over gloo on the emulated library: counts all-gather, hit-list all-gather, per-sample
+    all-to-all; the union of the two ranks' frames is the one-context frame bit for bit and both ranks trace the same number of AO rays."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sample_shard_worker, args=(r, 2, port, ectx.lib_path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, rays = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and rays[0] == rays[1] > 0
+
+
 @pytest.mark.parametrize("gather", ["raycast", "raster", "raster_contiguous"])
 def test_ppll_tile_shards_union_is_the_frame(ectx, oracle, gather):
     """PPLL with tile sharding, both gather modes: every rank gathers and resolves only its tiles; the union is the unsharded frame bit

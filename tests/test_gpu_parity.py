@@ -527,3 +527,63 @@ def test_frame_to_rgba8(ctx, oracle):
     assert (got == want).mean() > 0.999
     with pytest.raises(lv.LineVisError):
         ctx.frame_to_rgba8(f, 160, 100)      # a host float frame is refused
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ao_sample_batch_shards_one_gpu_plays_the_ranks(ctx, oracle, world):
+    """lv_sao_primary / lv_sao_trace / lv_sao_finish (AO rays sharded by sample batch): one context plays the ranks in turn, the exchanges are
+    tensor copies; the union of the ranks' frames is the oracle's frame bit for bit and every rank traces the same number of AO rays."""
+    import torch
+    from linevis_b200 import sharding
+    data, width = DATASETS["helix"]()
+    sc, osc = _scene_pair(ctx, oracle, data, width)
+    W, H, spp, tile = 160, 96, 8, 16
+    spl = spp // world
+    cam = lv.make_camera(W, H)
+    tf = scenes.standard_transfer_function(opacity=(1.0, 1.0))
+    ctx.set_transfer_function(tf)
+    ctx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_iterations": 1,
+                          "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": True, "ambient_occlusion_radius": 0.1,
+                          "num_samples_per_frame": 2, "num_accumulated_frames": 1})
+    try:
+        full, _ = ctx.render_tubes(sc, cam)
+        lists = []
+        for r in range(world):
+            ctx.set_tile_shard(r, world, tile)
+            ptr, n = ctx.sao_primary(sc, cam, 0)
+            lists.append(sharding._device_floats(ptr, (max(n, 1), 12), "cuda")[:n].clone())
+        counts = [h.shape[0] for h in lists]
+        hits = torch.cat(lists, dim=0).contiguous()
+        occs, rays = [], []
+        for r in range(world):
+            ctx.set_tile_shard(r, world, tile)
+            occ = torch.zeros(hits.shape[0] * spl, device="cuda")
+            ctx.sao_trace(sc, cam, 0, hits, hits.shape[0], r * spl, spl, occ)
+            ctx.synchronize()
+            occs.append(occ.view(hits.shape[0], spl))
+        acc = np.full_like(full, np.nan)
+        off = np.concatenate([[0], np.cumsum(counts)])
+        for r in range(world):
+            ctx.set_tile_shard(r, world, tile)
+            ptr, n = ctx.sao_primary(sc, cam, 0)        # the context's own hit list is rank r's again (same pixels, maybe another order)
+            assert n == counts[r]
+            now = sharding._device_floats(ptr, (max(n, 1), 12), "cuda")[:n]
+            pix_now = now[:, 7].contiguous().view(torch.int32).cpu().numpy()
+            pix_then = lists[r][:, 7].contiguous().view(torch.int32).cpu().numpy()
+            order = np.argsort(pix_then, kind="stable")[np.searchsorted(np.sort(pix_then), pix_now)]
+            assert np.array_equal(pix_then[order], pix_now)
+            idx = torch.from_numpy(order.astype(np.int64)).cuda()
+            parts = torch.stack([occs[j][off[r]:off[r + 1]][idx] for j in range(world)], dim=0).contiguous()
+            part = torch.full((H, W, 4), float("nan"), device="cuda")
+            _, st = ctx.sao_finish(sc, cam, 0, parts, world, part)
+            p = part.cpu().numpy()
+            m = ~np.isnan(p[..., 0])
+            assert not (m & ~np.isnan(acc[..., 0])).any()
+            acc[m] = p[m]
+        assert np.array_equal(acc.view(np.uint32), full.view(np.uint32))
+        opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=1, ao_jitter_primary=1, num_samples_per_frame=2, use_jittered_rays=1)
+        ref, _ = osc.render_tubes(cam, opts, tf, ao_tex=osc.render_rtao(cam, opts, 0)[0])
+        assert np.abs(acc - ref).max() <= TOL
+    finally:
+        ctx.set_tile_shard(0, 1, 64)
+        ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1, "ambient_occlusion_samples_per_frame": 4})
