@@ -389,27 +389,29 @@ class Rgba8Pipeline:
                all_reduce, rank 0 copies the finished frame to pinned host memory on a side stream while the next frame renders into the
                other peer frame; rank 0 joins fence k only after copy k-1 has left its buffer."""
 
-    def __init__(self, D, ctx, W, H, render, peer):
+    def __init__(self, D, ctxs, W, H, render, peer, streams=None):
+        """ctxs: one context, or two (frames in flight: frame i is rendered by context i & 1 on streams[i & 1]); render(ctx, out)."""
         import linevis_b200  # noqa: F401
         from linevis_b200.sharding import PeerFrame
         torch = D.torch
-        self.D, self.ctx, self.render, self.i = D, ctx, render, 0
-        ctx.set_new_settings({"b200_frame_format": "rgba8", "b200_async_delivery": True})
+        self.D, self.ctxs, self.render, self.i = D, list(ctxs), render, 0
+        self.streams = streams if (streams is not None and len(self.ctxs) == 2) else None
+        for c in self.ctxs:
+            c.set_new_settings({"b200_frame_format": "rgba8", "b200_async_delivery": True})
         self.host = [torch.zeros((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
         self.host_np = [h.numpy().view(np.uint32) for h in self.host]
-        self.pf = [PeerFrame(ctx, W, H, D.rank, D.world, D.dev) for _ in range(2)] if peer else None
+        self.pf = [PeerFrame(self.ctxs[0], W, H, D.rank, D.world, D.dev) for _ in range(2)] if peer else None
         if self.pf is not None and D.rank == 0:
             self.copy_stream = torch.cuda.Stream(device=D.dev)
             self.rendered = [torch.cuda.Event() for _ in range(2)]
             self.copied = [None, None]
 
-    def step(self):
-        torch, j = self.D.torch, self.i & 1
-        self.i += 1
+    def _frame(self, j):
+        torch, ctx = self.D.torch, self.ctxs[j % len(self.ctxs)]
         if self.pf is None:
-            self.render(self.host_np[j])                 # returns once the copy is enqueued
+            self.render(ctx, self.host_np[j])            # returns once the copy is enqueued
             return
-        self.render(self.pf[j].ptr)
+        self.render(ctx, self.pf[j].ptr)
         if self.D.rank == 0:
             main = torch.cuda.current_stream()
             if self.copied[j ^ 1] is not None:
@@ -423,14 +425,28 @@ class Rgba8Pipeline:
         else:
             self.pf[j].fence()
 
+    def step(self):
+        j = self.i & 1
+        self.i += 1
+        if self.streams is None:
+            self._frame(j)
+        else:
+            with self.D.torch.cuda.stream(self.streams[j]):
+                self._frame(j)
+
     def finish(self):
-        self.ctx.synchronize()
+        for c in self.ctxs:
+            c.synchronize()
+        if self.streams is not None:
+            for s_ in self.streams:
+                s_.synchronize()
         if self.pf is not None and self.D.rank == 0:
             self.copy_stream.synchronize()
 
     def close(self):
         self.finish()
-        self.ctx.set_new_settings({"b200_frame_format": "rgba32f", "b200_async_delivery": False})
+        for c in self.ctxs:
+            c.set_new_settings({"b200_frame_format": "rgba32f", "b200_async_delivery": False})
         if self.pf is not None:
             self.D.barrier()
             for p in self.pf:
@@ -551,7 +567,7 @@ def measure_ppll(D, args, name, extra_opts, hbm_peak, headline):
     # the headline e2e: RGBA8 delivery (packed in the resolve kernel's epilogue), read back while the next frame renders
     e2e8 = None
     if fg is None:
-        pipe = Rgba8Pipeline(D, ctx, W, H, lambda out: ctx.render_ppll(scene, cam, pw["max_frags"], "priority_queue", 0, out=out, stats=False), peer)
+        pipe = Rgba8Pipeline(D, [ctx], W, H, lambda c_, out: c_.render_ppll(scene, cam, pw["max_frags"], "priority_queue", 0, out=out, stats=False), peer)
         for _ in range(3):
             pipe.step()
         pipe.finish()
@@ -691,13 +707,13 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
         st["ao_traversal_steps"], st["ao_intersections"]])
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, CUDA events, max over ranks.
-    # --frames-in-flight 2 (an experiment, off by default): frames alternate between two contexts on two streams that share the scene, so frame i + 1's packet
+    # --frames-in-flight 2 (default): frames alternate between two contexts on two streams that share the scene, so frame i + 1's packet
     # kernels run in the tail of frame i's persistent AO stream (linevis_b200.sharding.FramesInFlight; every frame is still one complete
     # lv_render_tubes frame, the frames are independent: no temporal accumulation in this workload).  ms_one_frame_in_flight is the
     # same loop with a single context, i.e. the latency of a frame.
     fif = None
-    ms_single = D.timed(step, args.steps) if args.frames_in_flight == 2 else None
-    if args.frames_in_flight == 2:
+    ms_single = D.timed(step, args.steps) if (args.frames_in_flight == 2 and ss is None) else None
+    if args.frames_in_flight == 2 and ss is None:
         from linevis_b200.sharding import FramesInFlight
         streams2 = [torch.cuda.Stream(device=dev) for _ in range(2)]
         ctxs2 = [make_tube_ctx(s_.cuda_stream) for s_ in streams2]
@@ -760,14 +776,15 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
     # src/Widgets/DataView.cpp:100-108) -- packed in k_tubes' epilogue, read back to pinned host memory while the next frame renders
     e2e8 = None
     if fg is None or peer:
-        pipe = Rgba8Pipeline(D, ctx, W, H, lambda out: ctx.render_tubes(scene, cam, 0, out=out, stats=False), peer)
+        pipe = Rgba8Pipeline(D, ctxs2 if fif is not None else [ctx], W, H, lambda c_, out: c_.render_tubes(scene, cam, 0, out=out, stats=False), peer,
+                             streams=streams2 if fif is not None else None)
         for _ in range(3):
             pipe.step()
         pipe.finish()
         ms8 = D.timed_wall(pipe.step, args.steps, finish=pipe.finish)
         ok = bool(rank != 0 or (np.count_nonzero(pipe.host_np[0]) == W * H and np.array_equal(pipe.host_np[0], pipe.host_np[1])))
         e2e8 = {"value": tot_rays / (ms8 * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms8, "h2d_bytes_per_step": ctypes.sizeof(lv.LvCamera),
-                "d2h_bytes_per_step": W * H * 4, "frames_complete_and_equal": ok,
+                "d2h_bytes_per_step": W * H * 4, "frames_complete_and_equal": ok, "frames_in_flight": 2 if fif is not None else 1,
                 "note": ("lv_render_tubes with a pinned HOST frame, b200_frame_format = rgba8 (packed in the tube kernel's epilogue), b200_async_delivery: "
                          "the library copies frame i on a second stream while frame i + 1 renders; lv_synchronize inside the timed region") if not peer else
                         ("every rank: lv_render_tubes (rgba8) into one of two alternating peer frames on rank 0 + fence; rank 0: D2H of the finished "
@@ -895,10 +912,10 @@ def main():
                          "--impl reference shrinks it to fit --ref-budget")
     ap.add_argument("--ppll-sample", type=int, nargs=2, default=[480, 270], help="centre crop of the PPLL headline's CPU baseline / parity leg")
     ap.add_argument("--ref-budget", type=float, default=80.0, help="--impl reference: seconds of CPU rendering for warm-up + steps together")
-    ap.add_argument("--frames-in-flight", type=int, default=1, choices=[1, 2],
-                    help="tube + RTAO headline: 2 = frames alternate between two contexts / streams sharing the scene (measured: no gain, "
-                         "27.86 vs 27.83 ms on config 5 -- blocks of the next frame's packet kernels do not get onto SMs that still hold blocks of the "
-                         "persistent AO stream); 1 = one context (default)")
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
+                    help="tube + RTAO headline: 2 (default) = frames alternate between two contexts / streams sharing the scene, so one frame's fence, "
+                         "launch gaps and stream tail overlap the next frame's kernels (config 5: nothing on one GPU, 27.86 vs 27.83 ms; 4.10 vs 4.49 ms "
+                         "on 8); 1 = one context.  The line always carries ms_one_frame_in_flight as well")
     ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                     help="N > 1, tube + RTAO: tiles = image tiles only (default); samples = tiles for the pixels, AO rays split by sample batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
