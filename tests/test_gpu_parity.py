@@ -586,4 +586,4 @@ def test_ao_sample_batch_shards_one_gpu_plays_the_ranks(ctx, oracle, world):
         assert np.abs(acc - ref).max() <= TOL
     finally:
         ctx.set_tile_shard(0, 1, 64)
-        ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1, "ambient_occlusion_samples_per_frame": 4})
+        ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1, "ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_iterations": 64})
