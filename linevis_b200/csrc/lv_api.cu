@@ -15,6 +15,7 @@
 #include "lv_kernels.cuh"
 #include "lv_bake.cuh"
 #include "lv_tubemesh.hpp"
+#include "lv_sah_host.hpp"
 
 using namespace lv;
 
@@ -39,6 +40,7 @@ struct Options {
     uint32_t tiling_w = 2, tiling_h = 8;
     uint32_t bvh_leaf_size = 1;
     bool bvh_cubic_morton = false;      // b200_bvh_morton = cubic: one scale for all axes in the Morton codes (default per_axis: each axis to [0, 1]; measured equal)
+    bool bvh_sah_host = false;          // b200_bvh_builder = sah: top-down binned SAH on the host threads (lv_sah_host.hpp; a measurement of builder quality)
     bool bvh_ploc = false;              // b200_bvh_builder = ploc: parallel locally-ordered clustering instead of the Morton radix tree (one-record leaves only)
     uint32_t bvh_ploc_radius = 16;      // ... neighbours searched to either side per round
     uint32_t ao_refill_below = 0;       // 0 = the measured optimum of the kernel in use: 28 for k_rtao_rays_w, 30 for the other streams with b200_ao_raybuf (refilling is cheap), 24 without
@@ -947,8 +949,8 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
         if (v == 0 || (v & (v - 1))) return fail(c, LV_ERR_INVALID_ARGUMENT, "tiling sizes must be powers of two");
         (k == "b200_tiling_width" ? o.tiling_w : o.tiling_h) = v;
     } else if (k == "b200_bvh_builder") {
-        if (strcmp(value, "lbvh") && strcmp(value, "ploc")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_builder must be lbvh or ploc");
-        o.bvh_ploc = !strcmp(value, "ploc");
+        if (strcmp(value, "lbvh") && strcmp(value, "ploc") && strcmp(value, "sah")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_builder must be lbvh, ploc or sah");
+        o.bvh_ploc = !strcmp(value, "ploc"); o.bvh_sah_host = !strcmp(value, "sah");
     } else if (k == "b200_bvh_morton") {
         if (strcmp(value, "cubic") && strcmp(value, "per_axis")) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_bvh_morton must be cubic or per_axis");
         o.bvh_cubic_morton = !strcmp(value, "cubic");
@@ -1045,7 +1047,7 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_tiling_width") v = std::to_string(o.tiling_w);
     else if (k == "b200_tiling_height") v = std::to_string(o.tiling_h);
     else if (k == "b200_bvh_leaf_size") v = std::to_string(o.bvh_leaf_size);
-    else if (k == "b200_bvh_builder") v = o.bvh_ploc ? "ploc" : "lbvh";
+    else if (k == "b200_bvh_builder") v = o.bvh_sah_host ? "sah" : o.bvh_ploc ? "ploc" : "lbvh";
     else if (k == "b200_bvh_morton") v = o.bvh_cubic_morton ? "cubic" : "per_axis";
     else if (k == "b200_bvh_ploc_radius") v = std::to_string(o.bvh_ploc_radius);
     else if (k == "b200_expected_avg_depth_complexity") v = std::to_string(o.expected_avg_depth_complexity);
@@ -1319,6 +1321,16 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
         LV_PLOC(cudaStreamSynchronize(st));
         pcleanup();
 #undef LV_PLOC
+    } else if (c->opt.bvh_sah_host && c->opt.bvh_leaf_size == 1 && n >= 2) {
+        // binned SAH on the host (lv_sah_host.hpp): the Morton-ordered records come back, the finished nodes go up
+        std::vector<float> h_segs; h_segs.resize(size_t(n) * 8);
+        std::vector<Node64> h_nodes; h_nodes.resize(size_t(n_inner));
+        LV_BUILD(cudaMemcpyAsync(h_segs.data(), s->segs.p, size_t(n) * sizeof(SegRec), cudaMemcpyDeviceToHost, st));
+        LV_BUILD(cudaStreamSynchronize(st));
+        const uint32_t depth = lvsah::build(h_segs.data(), uint32_t(n), r, h_nodes.data());
+        LV_BUILD(cudaMemcpyAsync(s->nodes.p, h_nodes.data(), size_t(n_inner) * sizeof(Node64), cudaMemcpyHostToDevice, st));
+        LV_BUILD(cudaMemcpyAsync(flags.p, &depth, 4, cudaMemcpyHostToDevice, st));
+        LV_BUILD(cudaStreamSynchronize(st));
     } else {
         if (n > 1) k_radix_tree<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys2.p, n, children.p, ranges.p, parent.p);
         k_fit<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, n, r, children.p, parent.p, boxes.p, flags.p);

@@ -620,6 +620,36 @@ def test_rtao_quantised_nodes(ectx, oracle, use_distance):
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
+def test_host_sah_builder(ectx, oracle):
+    """b200_bvh_builder = sah: the binned-SAH tree built on the host (lv_sah_host.hpp) is a valid tree for every traversal -- closest hits,
+    AO image (child-pair nodes and the 4-wide collapse of them) and PPLL fragments equal the oracle's bit for bit -- and it really is
+    another tree than the Morton radix tree (other step counts)."""
+    for data, width in (_random(), _helix(), _random(3)):
+        ectx.set_option("b200_bvh_builder", "sah")
+        try:
+            sc = ectx.create_scene(*data, width)
+        finally:
+            ectx.set_option("b200_bvh_builder", "lbvh")
+        sc0, osc = _pair(ectx, oracle, data, width)
+        cam = lv.make_camera(56, 36)
+        hits, st = ectx.trace_primary(sc, cam)
+        hits0, st0 = ectx.trace_primary(sc0, cam)
+        assert np.array_equal(hits, hits0)
+        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 5, "ambient_occlusion_radius": 0.4})
+        try:
+            for wide in (True, False):
+                ectx.set_option("b200_ao_wide", wide)
+                ao, ast = ectx.render_rtao(sc, cam, 0)
+                ao0, ast0 = ectx.render_rtao(sc0, cam, 0)
+                assert ast["rays_ao"] == ast0["rays_ao"] and np.array_equal(ao.view(np.uint32), ao0.view(np.uint32))
+                if data[2].shape[0] > 100:
+                    assert ast["ao_traversal_steps"] != ast0["ao_traversal_steps"]
+        finally:
+            ectx.set_new_settings({"ambient_occlusion_radius": 0.1, "b200_ao_wide": True, "ambient_occlusion_samples_per_frame": 4})
+        ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=5, ao_radius=0.4), 0)
+        assert np.array_equal(ao0.view(np.uint32), ref.view(np.uint32))
+
+
 @pytest.mark.parametrize("radius", [1, 16])
 def test_ploc_builder(ectx, oracle, radius):
     """b200_bvh_builder = ploc: the tree built by parallel locally-ordered clustering is a valid BVH over the same records (every

@@ -39,6 +39,7 @@ for variant in (args.variant or [""]):
     if ref is None:
         ref = img
     k, t = np.min([a for a, _ in ts[1:]]), np.min([b for _, b in ts[1:]])
-    print("%-60s k_rtao_rays %.2f ms  frame %.2f ms  T/ray %.2f I/ray %.2f  rays_ao %d  %s" %
-          (variant or "(defaults)", k, t, st["ao_traversal_steps"] / max(1, st["rays_ao"]), st["ao_intersections"] / max(1, st["rays_ao"]), st["rays_ao"], same), flush=True)
+    print("%-60s k_rtao_rays %.2f ms  frame %.2f ms  T/ray %.2f I/ray %.2f  rays_ao %d  build %.1f ms  %s" %
+          (variant or "(defaults)", k, t, st["ao_traversal_steps"] / max(1, st["rays_ao"]), st["ao_intersections"] / max(1, st["rays_ao"]), st["rays_ao"],
+           sc.info()["build_ms"], same), flush=True)
     sc.close(); ctx.close()
