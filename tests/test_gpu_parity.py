@@ -587,3 +587,29 @@ def test_ao_sample_batch_shards_one_gpu_plays_the_ranks(ctx, oracle, world):
     finally:
         ctx.set_tile_shard(0, 1, 64)
         ctx.set_new_settings({"ambient_occlusion_strength": 0.0, "num_samples_per_frame": 1, "ambient_occlusion_samples_per_frame": 4, "ambient_occlusion_iterations": 64})
+
+
+def test_host_sah_builder_same_results(ctx, oracle):
+    """b200_bvh_builder = sah (binned SAH on the host threads): another tree, the same closest hits and the same AO image bit for bit."""
+    data, width = DATASETS["random"]()
+    ctx.set_option("b200_bvh_builder", "sah")
+    try:
+        sc = ctx.create_scene(*data, width)
+    finally:
+        ctx.set_option("b200_bvh_builder", "lbvh")
+    sc0, osc = _scene_pair(ctx, oracle, data, width)
+    cam = lv.make_camera(120, 80)
+    h, _ = ctx.trace_primary(sc, cam)
+    h0, _ = ctx.trace_primary(sc0, cam)
+    assert np.array_equal(h, h0)
+    ctx.set_new_settings({"ambient_occlusion_samples_per_frame": 8, "ambient_occlusion_distance_based": True, "use_jittered_primary_rays": True,
+                          "ambient_occlusion_radius": 0.3})
+    try:
+        ao, st = ctx.render_rtao(sc, cam, 0)
+        ao0, st0 = ctx.render_rtao(sc0, cam, 0)
+    finally:
+        ctx.set_new_settings({"ambient_occlusion_radius": 0.1})
+    assert st["rays_ao"] == st0["rays_ao"] > 0 and np.array_equal(ao.view(np.uint32), ao0.view(np.uint32))
+    assert st["ao_traversal_steps"] != st0["ao_traversal_steps"]
+    ref, _ = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=8, ao_use_distance=1, ao_jitter_primary=1, ao_radius=0.3), 0)
+    assert np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
