@@ -816,7 +816,7 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
                        **({"frames_in_flight": 2, "ms_one_frame_in_flight": ms_single, "frames_in_flight_equal_to_single": fif_equal} if fif is not None else {}),
                        "scene_bytes": int(scene_bytes), "l2": "inputs larger than L2 (segments + BVH = %.2f GB)" % (scene_bytes / 1e9)
                        if scene_bytes > 200e6 else "scene fits L2; the 126 MB L2 is not flushed between frames",
-                       "parallelism": parallelism_note(world, peer, args.shard),
+                       "parallelism": parallelism_note(world, peer, args.shard) + ("; two frames in flight (two contexts on two streams share the scene)" if fif is not None else ""),
                        "rays_per_step": tot_rays, "rays_primary": tot_rp, "rays_ao": tot_ra,
                        "T_per_ao_ray": ao_T / max(tot_ra, 1), "I_per_ao_ray": ao_I / max(tot_ra, 1),
                        "primary_packet_steps_per_ray": (tot_T - ao_T) / max(tot_rp, 1), "primary_packet_records_per_ray": (tot_I - ao_I) / max(tot_rp, 1),
