@@ -130,7 +130,7 @@ struct lv_ctx {
 
 struct lv_scene {
     lv_ctx* ctx = nullptr;
-    DevBuf<SegRec> segs; DevBuf<uint32_t> prim_ids; DevBuf<Node64> nodes;
+    DevBuf<SegRec> segs; DevBuf<float4> seg_axes; DevBuf<uint32_t> prim_ids; DevBuf<Node64> nodes;
     uint64_t n_seg = 0, n_nodes = 0, n_pt = 0;
     float line_width = 0.0f, build_ms = 0.0f;
     uint32_t depth = 0, leaf_size = 1;
@@ -155,7 +155,7 @@ struct lv_scene {
     float param_len = 0.0f;
     bool has_lines = false;
     SceneDev dev() const {
-        SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
+        SceneDev s; s.segs = segs.p; s.prim_ids = prim_ids.p; s.seg_axes = seg_axes.p; s.nodes = nodes.p; s.n_seg = uint32_t(n_seg);
         s.seg_aux = has_lines ? seg_aux.p : nullptr;
         s.qnodes = qnodes.p;
         for (int k = 0; k < 3; k++) { s.q_origin[k] = q_origin[k]; s.q_scale[k] = q_scale[k]; s.w_origin[k] = w_origin[k]; s.w_scale[k] = w_scale[k]; }
@@ -1279,6 +1279,8 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     LV_BUILD(cubtmp.ensure(cub_bytes + 16));
     LV_BUILD(cub::DeviceRadixSort::SortPairs(cubtmp.p, cub_bytes, keys.p, keys2.p, vals.p, s->prim_ids.p, n, 0, 63, st));
     k_pack_segments<<<(n + 255) / 256, 256, 0, st>>>(d_pos, d_attr, d_idx, s->prim_ids.p, uint32_t(n), s->segs.p);
+    LV_BUILD(s->seg_axes.ensure(size_t(n) + 1));
+    k_seg_axes<<<(n + 1 + 255) / 256, 256, 0, st>>>(s->segs.p, uint32_t(n) + 1u, s->seg_axes.p);   // incl. the dummy record (NaN)
     const int n_inner = std::max(1, n - 1);
     LV_BUILD(children.ensure(n_inner)); LV_BUILD(ranges.ensure(n_inner)); LV_BUILD(parent.ensure(2 * size_t(n)));
     LV_BUILD(boxes.ensure(6 * (2 * size_t(n)))); LV_BUILD(flags.ensure(n_inner));
@@ -1345,7 +1347,7 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
     LV_BUILD(cudaStreamSynchronize(st));
     if (s->depth + 1 > uint32_t(kStackSize) || s->depth + 1 > uint32_t(kAoStack)) {
         const uint32_t depth = s->depth;
-        cleanup(); s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release(); delete s;
+        cleanup(); s->segs.release(); s->seg_axes.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release(); delete s;
         return fail(c, LV_ERR_STATE, "BVH depth " + std::to_string(depth) + " exceeds the traversal stack (" + std::to_string(kAoStack) + ")");
     }
     s->build_ms = elapsed(c->ev[0], c->ev[1]);
@@ -1392,7 +1394,7 @@ int lv_scene_create(lv_ctx* c, lv_scene** out, const float* pos, const float* at
 int lv_scene_destroy(lv_scene* s) {
     if (!s) return LV_OK;
     if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
-    s->segs.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release();
+    s->segs.release(); s->seg_axes.release(); s->prim_ids.release(); s->nodes.release(); s->seg_idx.release();
     s->pt_pos.release(); s->pt_tan.release(); s->pt_nrm.release(); s->seg_aux.release();
     s->sampling.release(); s->weights.release(); s->factors.release();
     s->qnodes.release(); s->wnodes.release();

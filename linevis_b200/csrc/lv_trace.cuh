@@ -135,7 +135,8 @@ __device__ __forceinline__ void packet_flush(const SceneDev& S, PacketScratch& s
     if (lane < n) {
         const SegRec s = load_seg(S.segs + rec);
         float t;
-        if (seg_box_hit(b2, s, S.radius, tmin2, tmax) && capsule_hit(r2, s, S.radius, capped, t, kind) && t >= tmin2 && t <= tmax) {
+        const float4 ax4 = __ldg(S.seg_axes + rec);   // = seg_axis(s), stored at scene creation
+        if (seg_box_hit(b2, s, S.radius, tmin2, tmax) && capsule_hit(r2, s, v3(ax4.x, ax4.y, ax4.z), S.radius, capped, t, kind) && t >= tmin2 && t <= tmax) {
             mykey = (static_cast<unsigned long long>(__float_as_uint(t)) << 32) | __ldg(S.prim_ids + rec);   // t > 0: the bit pattern orders like the value
             atomicMin(&sc.key[owner], mykey);
         }

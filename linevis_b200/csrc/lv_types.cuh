@@ -72,6 +72,7 @@ struct __align__(64) NodeW4 {
 struct SceneDev {
     const SegRec* segs;        // [n_seg] BVH order
     const uint32_t* prim_ids;  // [n_seg] BVH order -> caller's segment index
+    const float4* seg_axes;    // [n_seg + 1] BVH order: normalize(p1 - p0) of the record (cylinder_hit's axis), computed once at scene creation
     const Node64* nodes;       // [n_nodes], root = 0
     const SegAux* seg_aux;     // [n_seg] BVH order, or nullptr (no line frames attached)
     const NodeQ* qnodes;       // [n_nodes] quantised copy of `nodes` (b200_ao_qnodes), or nullptr
