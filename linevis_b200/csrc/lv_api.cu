@@ -57,7 +57,6 @@ struct Options {
     bool ao_raybuf = true;              // b200_ao_raybuf: the AO stream generates rays 32 at a time by the whole warp into a shared batch
     bool ao_wide = true;                // b200_ao_wide: the AO ray stream traverses the 4-wide quantised tree (NodeW4)
     uint32_t ao_tq_bits = 0;            // b200_ao_tq_bits: bits of the packed stream's stack entry distances (0 = what the scene's index range allows: 7 or 4)
-    bool ao_direct_queue = false;       // b200_ao_direct_queue: k_rtao_rays_w queues every hit leaf child at the step instead of descending into / pushing it
     int packet_carveout = -1;           // b200_packet_carveout (see lv_set_option)
     bool ao_packed = true;              // b200_ao_packed: ... with k_rtao_rays_w (lv_aostream.cuh: packed fp32x2 box tests, rays in shared memory)
     uint32_t ao_wide_reps = 1;          // ... node steps per pass of the traversal loop
@@ -591,8 +590,6 @@ int launch_ao_rays(lv_ctx* c, const FrameParams& P, const SceneDev& S, bool one_
     if (queue && c->opt.ao_raybuf && c->opt.ao_packed && default_tuning && c->opt.ao_wide && S.wnodes && !S.w_top && max_rays < 0xFF000000ull)
         {
         const bool seven = S.w_tq_bits == 7u && c->opt.ao_tq_bits != 4u;
-        // experiment, measured slower (25.2 against 24.45 ms on config 5, 6.59 against 6.19 ms on config 3): only the screen-space pass, 7-bit entries
-        if (c->opt.ao_direct_queue && seven && !BAKE) return launch(k_rtao_rays_w<8, false, 7, true>);
         return seven ? launch(k_rtao_rays_w<8, BAKE, 7>) : launch(k_rtao_rays_w<8, BAKE, 4>);
     }
     if (queue && c->opt.ao_raybuf && default_tuning && !(c->opt.ao_wide && S.wnodes && S.w_top))   // warp-wide ray generation into a shared batch (default tuning only)
@@ -974,7 +971,6 @@ int lv_set_option(lv_ctx* c, const char* key, const char* value) {
     else if (k == "b200_ao_wide") o.ao_wide = parse_bool(value);
     else if (k == "b200_ao_raybuf") o.ao_raybuf = parse_bool(value);
     else if (k == "b200_ao_packed") o.ao_packed = parse_bool(value);
-    else if (k == "b200_ao_direct_queue") o.ao_direct_queue = parse_bool(value);
     else if (k == "b200_ao_tq_bits") { if (u() != 0 && u() != 4 && u() != 7) return fail(c, LV_ERR_INVALID_ARGUMENT, "b200_ao_tq_bits must be 0 (automatic), 4 or 7"); o.ao_tq_bits = u(); }
     else if (k == "b200_packet_carveout") {
         // shared-memory carveout (percent of the SM's L1 / shared array) the packet kernels of the tube + RTAO frame ask for.  An SM has
@@ -1061,7 +1057,6 @@ int lv_get_option(const lv_ctx* c, const char* key, char* buf, size_t cap) {
     else if (k == "b200_ao_packed") v = b(o.ao_packed);
     else if (k == "b200_packet_carveout") v = std::to_string(o.packet_carveout);
     else if (k == "b200_ao_tq_bits") v = std::to_string(o.ao_tq_bits);
-    else if (k == "b200_ao_direct_queue") v = b(o.ao_direct_queue);
     else if (k == "b200_frame_format") v = o.frame_rgba8 ? "rgba8" : "rgba32f";
     else if (k == "b200_async_delivery") v = b(o.async_delivery);
     else if (k == "b200_tube_prepass") v = b(o.tube_prepass);

@@ -635,7 +635,7 @@ def test_host_sah_builder(ectx, oracle):
         hits, st = ectx.trace_primary(sc, cam)
         hits0, st0 = ectx.trace_primary(sc0, cam)
         assert np.array_equal(hits, hits0)
-        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 5, "ambient_occlusion_radius": 0.4})
+        ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 5, "ambient_occlusion_radius": 0.4, "ambient_occlusion_distance_based": True})
         try:
             for wide in (True, False):
                 ectx.set_option("b200_ao_wide", wide)
@@ -646,7 +646,7 @@ def test_host_sah_builder(ectx, oracle):
                     assert ast["ao_traversal_steps"] != ast0["ao_traversal_steps"]
         finally:
             ectx.set_new_settings({"ambient_occlusion_radius": 0.1, "b200_ao_wide": True, "ambient_occlusion_samples_per_frame": 4})
-        ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=5, ao_radius=0.4), 0)
+        ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=5, ao_radius=0.4, ao_use_distance=1), 0)
         assert np.array_equal(ao0.view(np.uint32), ref.view(np.uint32))
 
 
@@ -709,7 +709,7 @@ def test_rtao_ray_batches(ectx, oracle, use_distance, wide):
             assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
 
 
-@pytest.mark.parametrize("top,packed", [(0, True), (0, 4), (0, "dq"), (0, False), (85, True), (341, True)])
+@pytest.mark.parametrize("top,packed", [(0, True), (0, 4), (0, False), (85, True), (341, True)])
 @pytest.mark.parametrize("use_distance", [True, False])
 def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top, packed):
     """b200_ao_wide: the AO ray stream over the 4-wide quantised tree (NodeW4: collapse of the child-pair nodes, 16-bit outward-rounded
@@ -721,14 +721,13 @@ def test_rtao_wide_quantised_tree(ectx, oracle, use_distance, top, packed):
         cam = lv.make_camera(56, 36)
         ectx.set_new_settings({"ambient_occlusion_samples_per_frame": 6, "ambient_occlusion_distance_based": use_distance,
                                "ambient_occlusion_radius": 0.4, "b200_ao_wide": True, "b200_ao_wide_top": top, "b200_ao_packed": bool(packed),
-                               "b200_ao_tq_bits": 4 if packed == 4 else 0, "b200_ao_direct_queue": packed == "dq"})
+                               "b200_ao_tq_bits": 4 if packed == 4 else 0})
         try:
             ao, st = ectx.render_rtao(sc, cam, 0)
             ectx.set_option("b200_ao_wide", False)
             ao2, st2 = ectx.render_rtao(sc, cam, 0)
         finally:
-            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1, "b200_ao_packed": True, "b200_ao_tq_bits": 0,
-                                   "b200_ao_direct_queue": False})
+            ectx.set_new_settings({"b200_ao_wide": True, "b200_ao_wide_top": 0, "ambient_occlusion_radius": 0.1, "b200_ao_packed": True, "b200_ao_tq_bits": 0})
         ref, ost = osc.render_rtao(cam, lvo.default_options(ao_strength=1.0, ao_spp=6, ao_use_distance=int(use_distance), ao_radius=0.4), 0)
         assert st["rays_ao"] == ost["rays_ao"] and np.array_equal(ao.view(np.uint32), ref.view(np.uint32))
         if data[2].shape[0] > 100:   # the wide tree really is another tree: fewer steps per ray than the child-pair nodes

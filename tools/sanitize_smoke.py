@@ -11,7 +11,7 @@ cam = lv.make_camera(64, 48)
 tf = lv.scenes.standard_transfer_function(opacity=(0.3, 0.8))
 variants = [{}] if fast else [{}, {"b200_ao_queue": False, "b200_bvh_leaf_size": 4}, {"b200_ao_qnodes": True, "b200_ao_wide": False, "b200_ao_raybuf": False},
                               {"b200_ao_wide": False, "b200_ao_raybuf": False, "b200_tube_prepass": False, "b200_ppll_gather_mode": "raycast", "b200_ppll_reg_sort": False},
-                              {"b200_ao_wide_top": 85}, {"b200_ao_packed": False}, {"b200_ao_tq_bits": 4}, {"b200_ao_direct_queue": True}, {"b200_bvh_builder": "ploc"}, {"b200_frame_format": "rgba8", "b200_async_delivery": True},
+                              {"b200_ao_wide_top": 85}, {"b200_ao_packed": False}, {"b200_ao_tq_bits": 4}, {"b200_bvh_builder": "ploc"}, {"b200_frame_format": "rgba8", "b200_async_delivery": True},
                               {"b200_ppll_gather_mode": "raster_contiguous"}, {"b200_ppll_binned_resolve": True}, {"depth_cue_strength": 0.8},
                               {"geometry_mode": "Triangle Mesh", "b200_rtao_geometry": "triangles"}]
 d = lv.scenes.helix_polylines(12, 41)
