@@ -678,6 +678,8 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
     # --shard samples (N > 1): the AO rays are split by SAMPLE instead of by tile (lv_sao_*, sharding.SampleShards): every rank traces
     # spp / N samples of every hit pixel of the frame; two more collectives per frame (hit lists, per-sample results)
     ss = None
+    if args.frames_in_flight == 0:
+        args.frames_in_flight = 2 if world > 1 else 1
     if world > 1 and args.shard == "samples":
         from linevis_b200.sharding import SampleShards
         ss = SampleShards(ctx, rank, world, wl["ao_spp"], dev)
@@ -707,7 +709,7 @@ def measure_tubes(D, args, name, extra_opts, hbm_peak, peak_src, ppll_names):
         st["ao_traversal_steps"], st["ao_intersections"]])
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, CUDA events, max over ranks.
-    # --frames-in-flight 2 (default): frames alternate between two contexts on two streams that share the scene, so frame i + 1's packet
+    # --frames-in-flight 2 (default on several GPUs): frames alternate between two contexts on two streams that share the scene, so frame i + 1's packet
     # kernels run in the tail of frame i's persistent AO stream (linevis_b200.sharding.FramesInFlight; every frame is still one complete
     # lv_render_tubes frame, the frames are independent: no temporal accumulation in this workload).  ms_one_frame_in_flight is the
     # same loop with a single context, i.e. the latency of a frame.
@@ -912,10 +914,11 @@ def main():
                          "--impl reference shrinks it to fit --ref-budget")
     ap.add_argument("--ppll-sample", type=int, nargs=2, default=[480, 270], help="centre crop of the PPLL headline's CPU baseline / parity leg")
     ap.add_argument("--ref-budget", type=float, default=80.0, help="--impl reference: seconds of CPU rendering for warm-up + steps together")
-    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2],
-                    help="tube + RTAO headline: 2 (default) = frames alternate between two contexts / streams sharing the scene, so one frame's fence, "
-                         "launch gaps and stream tail overlap the next frame's kernels (config 5: nothing on one GPU, 27.86 vs 27.83 ms; 4.10 vs 4.49 ms "
-                         "on 8); 1 = one context.  The line always carries ms_one_frame_in_flight as well")
+    ap.add_argument("--frames-in-flight", type=int, default=0, choices=[0, 1, 2],
+                    help="tube + RTAO headline: 2 = frames alternate between two contexts / streams sharing the scene, so one frame's fence, launch "
+                         "gaps and stream tail overlap the next frame's kernels (config 5: 4.02 vs 4.45 ms on 8 GPUs; nothing on one GPU: 27.56 vs 27.55 ms, "
+                         "and the pipelined e2e leg gets noisier, 28.2-28.9 vs 27.7 ms); 1 = one context; 0 (default) = 2 on several GPUs, 1 on one.  "
+                         "With 2 the line carries ms_one_frame_in_flight as well")
     ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"],
                     help="N > 1, tube + RTAO: tiles = image tiles only (default); samples = tiles for the pixels, AO rays split by sample batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
