@@ -1318,17 +1318,24 @@ int lv_scene_create_device(lv_ctx* c, lv_scene** out, const float* d_pos, const 
         LV_PLOC(cudaStreamSynchronize(st));
         pcleanup();
 #undef LV_PLOC
-    } else if (c->opt.bvh_sah_host && c->opt.bvh_leaf_size == 1 && n >= 2) {
-        // binned SAH on the host (lv_sah_host.hpp): the Morton-ordered records come back, the finished nodes go up
+    }
+    bool sah_done = false;
+    if (!ploc && c->opt.bvh_sah_host && c->opt.bvh_leaf_size == 1 && n >= 2) {
+        // binned SAH on the host (lv_sah_host.hpp): the Morton-ordered records come back, the finished nodes go up.  A SAH tree can be
+        // deep where the Morton tree is not; one that would not fit the traversal stacks is dropped for the Morton tree below.
         std::vector<float> h_segs; h_segs.resize(size_t(n) * 8);
         std::vector<Node64> h_nodes; h_nodes.resize(size_t(n_inner));
         LV_BUILD(cudaMemcpyAsync(h_segs.data(), s->segs.p, size_t(n) * sizeof(SegRec), cudaMemcpyDeviceToHost, st));
         LV_BUILD(cudaStreamSynchronize(st));
         const uint32_t depth = lvsah::build(h_segs.data(), uint32_t(n), r, h_nodes.data());
-        LV_BUILD(cudaMemcpyAsync(s->nodes.p, h_nodes.data(), size_t(n_inner) * sizeof(Node64), cudaMemcpyHostToDevice, st));
-        LV_BUILD(cudaMemcpyAsync(flags.p, &depth, 4, cudaMemcpyHostToDevice, st));
-        LV_BUILD(cudaStreamSynchronize(st));
-    } else {
+        if (depth + 1 <= uint32_t(kStackSize) && depth + 1 <= uint32_t(kAoStack)) {
+            LV_BUILD(cudaMemcpyAsync(s->nodes.p, h_nodes.data(), size_t(n_inner) * sizeof(Node64), cudaMemcpyHostToDevice, st));
+            LV_BUILD(cudaMemcpyAsync(flags.p, &depth, 4, cudaMemcpyHostToDevice, st));
+            LV_BUILD(cudaStreamSynchronize(st));
+            sah_done = true;
+        }
+    }
+    if (!ploc && !sah_done) {
         if (n > 1) k_radix_tree<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys2.p, n, children.p, ranges.p, parent.p);
         k_fit<<<(n + 255) / 256, 256, 0, st>>>(s->segs.p, n, r, children.p, parent.p, boxes.p, flags.p);
         k_emit_nodes<<<(n_inner + 255) / 256, 256, 0, st>>>(n, int(c->opt.bvh_leaf_size), children.p, ranges.p, boxes.p, s->nodes.p);

@@ -78,19 +78,21 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     leaf = int(rng.choice([1, 1, 2, 4]))
     if args.verbose:
         print("case %d seed %d: n_seg %d, %dx%d, width %g, eye %s" % (it - 1, seed, data[2].shape[0], W, H, width, eye), flush=True)
-    ctx.set_option("b200_bvh_leaf_size", leaf)
+    builder = str(rng.choice(["lbvh", "lbvh", "sah", "ploc"])) if leaf == 1 else "lbvh"
+    ctx.set_option("b200_bvh_leaf_size", leaf); ctx.set_option("b200_bvh_builder", builder)
     sc = ctx.create_scene(*data, width); osc = o.scene(*data, width)
-    ctx.set_option("b200_bvh_leaf_size", 1)
+    ctx.set_option("b200_bvh_leaf_size", 1); ctx.set_option("b200_bvh_builder", "lbvh")
     spp = int(rng.integers(1, 7)); dist = bool(rng.integers(0, 2)); jit = bool(rng.integers(0, 2)); radius = float(rng.choice([0.05, 0.1, 0.5]))
     queue = bool(rng.integers(0, 2)); stack = int(rng.choice([0, 1, 8, 12, 16])); qn = bool(rng.integers(0, 2))
     wide = bool(rng.integers(0, 2)); raybuf = bool(rng.integers(0, 2)); wtop = int(rng.choice([0, 0, 85, 341])); wreps = int(rng.choice([1, 1, 2]))
     refill = int(rng.choice([24, 24, 28, 32, 8]))
+    packed = bool(rng.integers(0, 3) > 0); tqb = int(rng.choice([0, 0, 4]))
     capped = bool(rng.integers(0, 4) > 0); halos = bool(rng.integers(0, 2))
     tf = scenes.standard_transfer_function(opacity=(float(rng.random()), float(rng.random())))
     ctx.set_transfer_function(tf)
     ctx.set_new_settings({"ambient_occlusion_samples_per_frame": spp, "ambient_occlusion_distance_based": dist, "use_jittered_primary_rays": jit,
                           "ambient_occlusion_radius": radius, "b200_ao_queue": queue, "b200_ao_stack": stack, "b200_ao_qnodes": qn,
-                          "b200_ao_wide": wide, "b200_ao_raybuf": raybuf, "b200_tube_prepass": bool(rng.integers(0, 2)), "b200_ao_wide_top": wtop, "b200_ao_wide_reps": wreps, "b200_ao_refill_below": refill,
+                          "b200_ao_wide": wide, "b200_ao_raybuf": raybuf, "b200_ao_packed": packed, "b200_ao_tq_bits": tqb, "b200_tube_prepass": bool(rng.integers(0, 2)), "b200_ao_wide_top": wtop, "b200_ao_wide_reps": wreps, "b200_ao_refill_below": refill,
                           "use_capped_tubes": capped, "use_halos": halos, "ambient_occlusion_strength": 1.0, "num_samples_per_frame": 1,
                           "num_accumulated_frames": 1, "depth_cue_strength": 0.0, "b200_rtao_geometry": "capsules", "ambient_occlusion_mode": "RTAO (Screen Space)"})
     opts = lvo.default_options(ao_strength=1.0, ao_spp=spp, ao_use_distance=int(dist), ao_jitter_primary=int(jit), ao_radius=radius,
@@ -111,6 +113,26 @@ while time.time() < t_end and (args.cases == 0 or it < args.start + args.cases):
     img, _ = ctx.render_tubes(sc, cam, 0); rimg, _ = osc.render_tubes(cam, opts, tf, ao_tex=rao)
     if not same(img, rimg):
         fails.append("tubes")
+    if spp % 2 == 0 and ctx.get_option("b200_ao_packed") == "true" and wide and raybuf and queue and stack == 12 and not qn and wtop == 0 and leaf == 1:
+        # AO-sample-batch stages: one context plays two sample batches of the whole frame (lv_sao_*), exchanges by hand
+        import ctypes
+        ptr, n = ctx.sao_primary(sc, cam, 0)
+        hl = np.ctypeslib.as_array((ctypes.c_float * max(n * 12, 1)).from_address(ptr))[:n * 12].reshape(n, 12).copy() if n else np.zeros((0, 12), np.float32)
+        parts = np.zeros((2, n, spp // 2), np.float32)
+        for part in range(2):
+            occ = np.zeros(max(n * (spp // 2), 1), np.float32)
+            ctx.sao_trace(sc, cam, 0, hl, n, part * (spp // 2), spp // 2, occ); ctx.synchronize()
+            parts[part] = occ[:n * (spp // 2)].reshape(n, spp // 2)
+        ptr2, n2 = ctx.sao_primary(sc, cam, 0)
+        now = np.ctypeslib.as_array((ctypes.c_float * max(n2 * 12, 1)).from_address(ptr2))[:n2 * 12].reshape(n2, 12)
+        if n2 != n:
+            fails.append("sample shards: hit count")
+        else:
+            pt, pn = hl[:, 7].view(np.uint32), now[:, 7].view(np.uint32)
+            order = np.argsort(pt, kind="stable")[np.searchsorted(np.sort(pt), pn)] if n else np.zeros(0, np.int64)
+            simg, _ = ctx.sao_finish(sc, cam, 0, np.ascontiguousarray(parts[:, order]), 2, np.zeros((H, W, 4), np.float32))
+            if not same(simg, rimg):
+                fails.append("sample shards")
     ctx.set_option("ambient_occlusion_strength", 0.0)
     if args.verbose:
         print("   phase ppll", flush=True)
