@@ -398,6 +398,38 @@ def test_ao_sample_batch_shards(ectx, oracle, world, jitter):
                                "ambient_occlusion_iterations": 64})
 
 
+def test_ao_sample_batch_stage_errors(ectx):
+    """The staged entry points refuse what they cannot do: sample ranges that are not one of spp / count equal batches, a part count that
+    does not divide spp, lv_sao_finish before lv_sao_primary of that frame size, the stages with screen-space RTAO switched off."""
+    data, width = _helix()
+    sc = ectx.create_scene(*data, width)
+    cam = lv.make_camera(48, 32)
+    ectx.set_transfer_function(scenes.standard_transfer_function())
+    ectx.set_new_settings({"ambient_occlusion_strength": 1.0, "ambient_occlusion_samples_per_frame": 6})
+    try:
+        ptr, n = ectx.sao_primary(sc, cam, 0)
+        assert n > 0
+        occ = np.zeros(n * 6, np.float32)
+        hits = _host_floats(ptr, n * 12).reshape(n, 12).copy()
+        for first, count in ((0, 4), (1, 2), (4, 3), (0, 0), (6, 6)):
+            with pytest.raises(lv.LineVisError):
+                ectx.sao_trace(sc, cam, 0, hits, n, first, count, occ)
+        ectx.sao_trace(sc, cam, 0, hits, n, 0, 6, occ); ectx.synchronize()
+        out = np.zeros((32, 48, 4), np.float32)
+        with pytest.raises(lv.LineVisError):
+            ectx.sao_finish(sc, cam, 0, occ, 4, out)                       # 6 samples in 4 parts
+        with pytest.raises(lv.LineVisError):
+            ectx.sao_finish(sc, lv.make_camera(40, 24), 0, occ, 1, np.zeros((24, 40, 4), np.float32))   # no primary pass of that frame size
+        img, _ = ectx.sao_finish(sc, cam, 0, occ, 1, out)
+        full, _ = ectx.render_tubes(sc, cam)
+        assert np.array_equal(img.view(np.uint32), full.view(np.uint32))
+        ectx.set_option("ambient_occlusion_strength", 0.0)
+        with pytest.raises(lv.LineVisError):
+            ectx.sao_primary(sc, cam, 0)
+    finally:
+        ectx.set_new_settings({"ambient_occlusion_strength": 0.0, "ambient_occlusion_samples_per_frame": 4})
+
+
 def _sample_shard_worker(rank, world, port, lib_path, q):
     import torch
     import torch.distributed as dist
